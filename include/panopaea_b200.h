@@ -1,0 +1,216 @@
+/*
+ * panopaea_b200.h -- C ABI of the B200-native grid fluid step.
+ *
+ * This is the drop-in boundary for ONE hot path of msiglreith/panopaea: the
+ * 2D staggered-grid (MAC) fluid step driven by examples/dec_fluid.rs.  The
+ * reference has no FFI of its own (it is a pure-Rust crate); every entry point
+ * below names the Rust item (file:line under the reference tree) it replaces,
+ * and INTEGRATION.md shows the `extern "C"` block + safe wrappers a maintainer
+ * adds on the Rust side.
+ *
+ * Conventions
+ *  - plain C types only; every function returns int: 0 = PANO_OK, else a
+ *    PANO_ERR_* code.  Nothing throws or aborts across the boundary;
+ *    pano_last_error() returns a thread-local human-readable message.
+ *  - field handles own DEVICE memory laid out exactly like the reference's
+ *    containers (panopaea/src/dec/grid.rs:10, 37-62, 76):
+ *       Simplex2 (h,w): row-major (y,x), h*w values
+ *       Simplex1 (h,w): ONE flat buffer, vy (h+1,w) first, then vx (h,w+1)
+ *                       at element offset w*(h+1)
+ *       Simplex0 (h,w): row-major (h+1, w+1)
+ *    so upload/download of the flat `view_linear()` slice is a single copy.
+ *  - dtype: PANO_F64 (the example's type) or PANO_F32 (the crate is generic;
+ *    one reference test runs in f32).  Scalars cross the ABI as double.
+ *  - calls are asynchronous on the context's stream unless they return a scalar
+ *    or copy to host memory.  One host thread per context.
+ *  - there is NO CPU fallback: every compute entry point fails with
+ *    PANO_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef PANOPAEA_B200_H
+#define PANOPAEA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PANO_API __attribute__((visibility("default")))
+#else
+#define PANO_API
+#endif
+
+enum {
+    PANO_OK = 0,
+    PANO_ERR_INVALID = 1,        /* null handle, bad enum, bad argument            */
+    PANO_ERR_SHAPE = 2,          /* shape/dtype mismatch (the reference panics in ndarray Zip/assign) */
+    PANO_ERR_CUDA = 3,           /* CUDA runtime/driver failure, or no device       */
+    PANO_ERR_UNIMPLEMENTED = 4,  /* mirrors `unimplemented!()` in the reference     */
+    PANO_ERR_TIMEOUT = 5,        /* a device-side wait exceeded its bound           */
+    PANO_ERR_COMM = 6            /* multi-GPU setup/exchange failure                */
+};
+
+enum { PANO_F64 = 0, PANO_F32 = 1 };
+enum { PANO_SIMPLEX0 = 0, PANO_SIMPLEX1 = 1, PANO_SIMPLEX2 = 2 };
+/* component selector for rectangle fills on a Simplex1 (split(): dec/grid.rs:48-61) */
+enum { PANO_COMP_ALL = 0, PANO_COMP_VY = 1, PANO_COMP_VX = 2 };
+/* Preconditioner kinds (panopaea/src/pcg.rs:4-12).  Only `()` exists in the reference. */
+enum { PANO_PRECOND_IDENTITY = 0 };
+
+typedef struct pano_ctx pano_ctx;      /* device + stream + scratch                  */
+typedef struct pano_field pano_field;  /* device-resident Simplex0/1/2               */
+
+/* half-open index rectangle rows [y0,y1) x cols [x0,x1); empty if y0>=y1 or x0>=x1 */
+typedef struct pano_rect { int64_t y0, y1, x0, x1; } pano_rect;
+
+/* what the reference only prints (pcg.rs:36, 61) */
+typedef struct pano_pcg_info {
+    int32_t iterations;      /* index i at the `break` (pcg.rs:60-63); == max_iterations if the loop ran out; -1 on the early-out (pcg.rs:35-38) */
+    int32_t applies;         /* number of operator applications                                 */
+    double final_residual;   /* last max|r| evaluated (max|b| on the early-out)                 */
+    double rhs_max;          /* max|b| (pcg.rs:35)                                              */
+} pano_pcg_info;
+
+/* every literal of examples/dec_fluid.rs:27, 43-44, 51-54, 72-73, 95 */
+typedef struct pano_step_params {
+    double timestep;          /* :43  0.05 */
+    double threshold;         /* :44  0.1  */
+    int32_t max_iterations;   /* :95  100  */
+    int32_t precond;          /* PANO_PRECOND_IDENTITY (:92 `&()`) */
+    pano_rect inflow;         /* :51-52  rows 5..20, cols 54..64 */
+    double inflow_density;    /* :53  1.0  */
+    double inflow_vy;         /* :54  20.0 */
+    pano_rect obstacle;       /* :72-73, :106-107  rows 70..80, cols 50..70 */
+} pano_step_params;
+
+/* ------------------------------------------------------------------ library */
+PANO_API const char *pano_version(void);
+PANO_API const char *pano_last_error(void);
+/* number of CUDA devices visible; 0 (and PANO_OK) when there is no driver */
+PANO_API int pano_device_count(int *count);
+
+/* ------------------------------------------------------------------ context */
+/* stream: a cudaStream_t to enqueue on, or NULL to create a private one. */
+PANO_API int pano_ctx_create(int device, void *stream, pano_ctx **out);
+PANO_API int pano_ctx_destroy(pano_ctx *ctx);
+PANO_API int pano_ctx_sync(pano_ctx *ctx);
+PANO_API int pano_ctx_stream(pano_ctx *ctx, void **stream);
+PANO_API int pano_ctx_num_sms(pano_ctx *ctx, int *n);
+/* kernels launched by this library on this context since creation */
+PANO_API int pano_ctx_launch_count(pano_ctx *ctx, uint64_t *n);
+/* CUDA-event timing on the context's stream (the stream the kernels run on) */
+PANO_API int pano_timer_start(pano_ctx *ctx);
+PANO_API int pano_timer_stop_ms(pano_ctx *ctx, double *ms);   /* records, synchronises, returns elapsed */
+/* Per-phase device time of pano_fluid_step, measured with CUDA events on the context's
+ * stream while option "step_timing" is 1.  phases: 0 inflow fills, 1 advect_all,
+ * 2 neg_divergence, 3 CG solve, 4 project.  Returns the accumulated milliseconds and the
+ * number of steps accumulated since the last reset (this call synchronises, then resets). */
+#define PANO_STEP_PHASES 5
+PANO_API int pano_ctx_step_times(pano_ctx *ctx, double ms_out[PANO_STEP_PHASES], int64_t *steps);
+/* tuning knobs: "cg_ldcg" 0/1, "cg_blocks_per_sm" n, "step_timing" 0/1 */
+PANO_API int pano_ctx_set_option(pano_ctx *ctx, const char *key, int64_t value);
+PANO_API int pano_ctx_get_option(pano_ctx *ctx, const char *key, int64_t *value);
+
+/* pinned host memory for the caller-owned mirrors of the fields */
+PANO_API int pano_host_alloc(size_t bytes, void **out);
+PANO_API int pano_host_free(void *p);
+
+/* ------------------------------------------------------------------- fields
+ * Manifold2d::new_simplex_0/1/2 (dec/grid.rs:358-371): zero-initialised.
+ * Manifold2d::num_elem_0/1/2 (dec/grid.rs:346-356). */
+PANO_API int pano_field_new(pano_ctx *ctx, int kind, int dtype, size_t h, size_t w, pano_field **out);
+PANO_API int pano_field_free(pano_field *f);
+PANO_API int pano_field_num_elem(int kind, size_t h, size_t w, size_t *n);
+PANO_API int pano_field_info(const pano_field *f, int *kind, int *dtype, size_t *h, size_t *w, size_t *n);
+PANO_API int pano_field_device_ptr(const pano_field *f, void **ptr);
+/* host <-> device over the flat view (math/linear_view.rs:5-10); n_elems must equal num_elem */
+PANO_API int pano_field_upload(pano_field *f, const void *host, size_t n_elems);
+PANO_API int pano_field_download(const pano_field *f, void *host, size_t n_elems);
+/* view_linear_mut().fill(v)  (dec_fluid.rs:65-66, 89; pcg.rs:32) */
+PANO_API int pano_field_fill(pano_field *f, double value);
+/* the example's index loops over a rectangle (dec_fluid.rs:48-57, 70-78, 104-112):
+ * comp selects vy / vx / both for a Simplex1 (both: the same (y,x) in each array) */
+PANO_API int pano_field_fill_rect(pano_field *f, int comp, pano_rect rect, double value);
+/* view_linear_mut().assign(&src.view_linear())  (dec_fluid.rs:62-63, pcg.rs:10, 40, 42) */
+PANO_API int pano_field_assign(pano_field *dst, const pano_field *src);
+/* O(1) exchange of the device buffers of two same-shaped fields (replaces copy-back :62-63) */
+PANO_API int pano_field_swap(pano_field *a, pano_field *b);
+/* y = y + alpha * x   (ndarray scaled_add; pcg.rs:55-56, dec_fluid.rs:126) */
+PANO_API int pano_field_scaled_add(pano_field *y, double alpha, const pano_field *x);
+/* x = x * alpha       (dec_fluid.rs:81-83 with alpha=-1, :116-118 with alpha=timestep) */
+PANO_API int pano_field_scale(pano_field *x, double alpha);
+/* dst = a + beta * dst  (the search update, pcg.rs:75-77) */
+PANO_API int pano_field_xpby(pano_field *dst, const pano_field *a, double beta);
+/* LinearViewReal::dot_linear / norm_max (math/linear_view.rs:12-30) */
+PANO_API int pano_field_dot(const pano_field *a, const pano_field *b, double *out);
+PANO_API int pano_field_norm_max(const pano_field *a, double *out);
+
+/* ------------------------------------------- Manifold2d operators, one to one
+ * (dec/manifold.rs:46-83 dispatch; impls in dec/grid.rs) */
+PANO_API int pano_hodge_0_primal(pano_field *dual, const pano_field *primal);      /* grid.rs:106-148 */
+PANO_API int pano_hodge_2_dual(pano_field *primal, const pano_field *dual);        /* grid.rs:149-191 */
+PANO_API int pano_hodge_1_primal(pano_field *dual, const pano_field *primal);      /* grid.rs:206-221 */
+PANO_API int pano_hodge_1_dual(pano_field *primal, const pano_field *dual);        /* grid.rs:223-238 */
+PANO_API int pano_hodge_2_primal(pano_field *dual, const pano_field *primal);      /* grid.rs:253-255 */
+PANO_API int pano_hodge_0_dual(pano_field *primal, const pano_field *dual);        /* grid.rs:257-259 */
+PANO_API int pano_derivative_0_primal(pano_field *edges, const pano_field *vertices);  /* grid.rs:274-288 */
+PANO_API int pano_derivative_1_primal(pano_field *faces, const pano_field *edges);     /* grid.rs:295-305 */
+PANO_API int pano_derivative_0_dual(pano_field *edges, const pano_field *faces);       /* grid.rs:318-334, interior edges only */
+PANO_API int pano_derivative_1_dual(pano_field *vertices, const pano_field *edges);    /* grid.rs:308-312: always PANO_ERR_UNIMPLEMENTED */
+
+/* ----------------------------------------------------------- fused hot path */
+/* advect (dec_fluid.rs:173-211).  dst must not alias src. */
+PANO_API int pano_advect(pano_field *dst, const pano_field *src, double timestep, const pano_field *vel);
+/* advect_mac (dec_fluid.rs:213-291).  dst must not alias src or vel. */
+PANO_API int pano_advect_mac(pano_field *dst, const pano_field *src, double timestep, const pano_field *vel);
+/* both of the above in ONE pass over the grid (self-advection, dec_fluid.rs:59-60):
+ * q_dst <- advect(q_src, vel), vel_dst <- advect_mac(vel, vel). */
+PANO_API int pano_advect_all(pano_field *q_dst, pano_field *vel_dst, const pano_field *q_src,
+                             const pano_field *vel, double timestep);
+/* b = -div(vel) with the obstacle's edges treated as zero (dec_fluid.rs:69-83).
+ * rhs_max (nullable) receives max|b|; when non-null the call synchronises. */
+PANO_API int pano_neg_divergence(pano_field *b, const pano_field *vel, pano_rect obstacle, double *rhs_max);
+/* z = A(s): the matrix-free Laplacian closure (dec_fluid.rs:100-119) in one pass */
+PANO_API int pano_laplacian_apply(pano_field *z, const pano_field *s, double timestep, pano_rect obstacle);
+/* vel += dt * d0_dual(p) on interior edges, then the wall loops (dec_fluid.rs:124-141) */
+PANO_API int pano_project(pano_field *vel, const pano_field *pressure, double timestep);
+
+/* ------------------------------------------------------------------ solver
+ * pcg::precond_conjugate_gradient (pcg.rs:14-82), argument order kept, with the
+ * operator fixed to the dec_fluid Laplacian closure (timestep, obstacle).
+ * Caller owns x, b and the three scratch fields, exactly as in the reference.
+ * On return x, residual and search hold what the reference leaves in them;
+ * `auxiliary` is scratch (contents unspecified).  info (nullable): when non-null
+ * the call synchronises and fills it. */
+PANO_API int pano_pcg_solve(int precond, pano_field *x, const pano_field *b, int32_t max_iterations,
+                            double threshold, pano_field *residual, pano_field *auxiliary,
+                            pano_field *search, double timestep, pano_rect obstacle, pano_pcg_info *info);
+
+/* --------------------------------------------------------------------- step
+ * One pass of the example's loop body (dec_fluid.rs:46-141, PNG dump excluded)
+ * entirely on the device.  temp / vel_temp / residual / auxiliary / search are
+ * the caller-owned scratch fields of dec_fluid.rs:33-41.  The copy-backs of
+ * :62-63 are buffer swaps, so after the call `density`/`vel` hold the new state
+ * and the scratch contents are unspecified.  info nullable as above. */
+PANO_API int pano_fluid_step(const pano_step_params *params, pano_field *density, pano_field *vel,
+                             pano_field *pressure, pano_field *temp, pano_field *vel_temp,
+                             pano_field *residual, pano_field *auxiliary, pano_field *search,
+                             pano_pcg_info *info);
+
+/* The same step for callers that keep the fields in HOST memory, as the Rust
+ * crate does: uploads density and vel (flat views), runs pano_fluid_step,
+ * downloads density, vel and pressure.  All scratch lives in a workspace the
+ * context caches per (h, w).  Host buffers should come from pano_host_alloc. */
+PANO_API int pano_fluid_step_host(pano_ctx *ctx, const pano_step_params *params, size_t h, size_t w,
+                                  double *density, double *vel, double *pressure, pano_pcg_info *info);
+
+/* u8 transfer of a Simplex2 for the PNG dump (panopaea_utils/src/imgproc.rs:2-5 with the
+ * vertical flip of png.rs:12): out[h*w] bytes on the host. */
+PANO_API int pano_density_to_u8(const pano_field *density, double lower, double upper, uint8_t *host_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANOPAEA_B200_H */

@@ -1,0 +1,359 @@
+// pano_cg.cu -- the pressure solve: pcg::precond_conjugate_gradient (panopaea/src/pcg.rs:14-82)
+// with the identity preconditioner `()` (pcg.rs:8-12) and the matrix-free Laplacian closure of
+// examples/dec_fluid.rs:100-119, as ONE persistent cooperative kernel.
+//
+// Reference iteration (pcg.rs:48-80)                 This kernel
+//   z = A s                                            phase P1: s' = r + beta*s (previous iteration's
+//   alpha = sigma / (z . s)                                      search update, folded in), z = A s' is
+//   x += alpha s ; r -= alpha z                                   evaluated but NOT stored, z.s' reduced
+//   if max|r| < threshold: break                       -- grid barrier, every CTA reduces the partials --
+//   sigma' = r . r ; beta = sigma'/sigma               phase P2: z recomputed from s', x += alpha s',
+//   s = r + beta s                                               r -= alpha z, r.r and max|r| reduced
+//                                                      -- grid barrier, convergence test --
+// HBM traffic per cell and iteration: P1 reads r, s and writes s' (24 B), P2 reads s', r, x and
+// writes r, x (40 B) = 64 B, against 240 B for the reference's 12 passes and 88 B for the
+// three-kernel split of SURVEY.md 8(d).  s is double-buffered (search <-> auxiliary) because P1
+// recomputes s' on the one-cell halo of every tile from the neighbours' OLD values.
+//
+// All scalars (sigma, alpha, beta, the convergence decision) stay on the device; every CTA
+// reduces the per-CTA partials in the same fixed order, so all CTAs hold bit-identical scalars
+// and the result is deterministic run to run.
+#include <cooperative_groups.h>
+
+#include "pano_cell_math.h"
+#include "pano_internal.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kTileX = 32, kTileY = 32;             // generic kernel: 32 x 32 cells per tile, 4 rows per thread
+constexpr long long kSpinLimit = 40LL * 1000 * 1000;   // bounded wait: a few seconds, then PANO_ERR_TIMEOUT
+
+template <class T>
+struct CgArgs {
+    T *x;
+    const T *b;
+    T *r;
+    T *s0;   // `search`
+    T *s1;   // `auxiliary`, the second search buffer
+    int h, w;
+    T dt, threshold;
+    int max_iter;
+    RectI m;
+    double *partials;   // 5 * G doubles
+    PanoCgControl *ctl;
+    int tiles_x, tiles_y;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Grid-wide barrier on a monotonically increasing arrival counter.  Returns false when the
+// bounded wait expired somewhere (ctl->error set): every CTA then leaves the kernel.
+__device__ __forceinline__ bool grid_barrier(PanoCgControl *ctl, unsigned long long target, int *s_flag) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&ctl->barrier, 1ULL);
+        long long spins = 0;
+        int ok = 1;
+        while (ld_acquire_u64(&ctl->barrier) < target) {
+            if (*(volatile unsigned int *)&ctl->error) { ok = 0; break; }
+            if (++spins > kSpinLimit) {
+                atomicExch(&ctl->error, 1u);
+                ok = 0;
+                break;
+            }
+        }
+        __threadfence();
+        if (*(volatile unsigned int *)&ctl->error) ok = 0;
+        *s_flag = ok;
+    }
+    __syncthreads();
+    return *s_flag != 0;
+}
+
+template <class T>
+__device__ __forceinline__ T sum_partials(const double *p, int n, T *scratch) {
+    T acc = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (T)__ldcg(p + i);
+    return block_sum(acc, scratch);
+}
+template <class T>
+__device__ __forceinline__ T max_partials(const double *p, int n, T *scratch) {
+    T acc = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        T v = (T)__ldcg(p + i);
+        acc = v > acc ? v : acc;
+    }
+    return block_max(acc, scratch);
+}
+
+template <bool kCg, class T>
+__device__ __forceinline__ T ld(const T *p) {
+    if (kCg) return __ldcg(p);
+    return *p;
+}
+
+// kCg: route every field load through L2 only (ld.global.cg); otherwise rely on the barrier's
+// gpu-scope fence to invalidate L1 (same contract as cooperative_groups::grid_group::sync()).
+template <class T, bool kCg>
+__global__ void __launch_bounds__(kThreads) k_cg_generic(CgArgs<T> a) {
+    __shared__ T scratch[32];
+    __shared__ int s_flag;
+    const int G = gridDim.x;
+    const int h = a.h, w = a.w;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const int ntiles = a.tiles_x * a.tiles_y;
+    double *pA = a.partials, *pB = a.partials + G, *pC = a.partials + 2 * G;       // P1: z.s, b.b, max|b|
+    double *pD = a.partials + 3 * G, *pE = a.partials + 4 * G;                     // P2: r.r, max|r|
+    unsigned long long nbar = 0;
+
+    T sigma = 0, alpha = 0, beta = 0, rmax = 0, bmax = 0;
+    int it = 0, applies = 0;
+    bool converged = false;
+    T *s_cur = a.s0;   // buffer that receives s' in the current P1
+    T *s_old = a.s1;
+
+    for (it = 0; it < a.max_iter; ++it) {
+        const bool first = it == 0;
+        const T *r_src = first ? a.b : a.r;
+        // ------------------------------------------------------------------ P1
+        T acc_zs = 0, acc_bb = 0, acc_bmax = 0;
+        for (int t = blockIdx.x; t < ntiles; t += G) {
+            const int x = (t % a.tiles_x) * kTileX + tx;
+            const int ybase = (t / a.tiles_x) * kTileY + ty;
+            if (x >= w) continue;
+#pragma unroll
+            for (int k = 0; k < kTileY / 8; ++k) {
+                const int y = ybase + k * 8;
+                if (y >= h) break;
+                const size_t i = (size_t)y * w + x;
+                const bool oN = y > 0 && !in_rect(a.m, y, x), oS = y < h - 1 && !in_rect(a.m, y + 1, x);
+                const bool oW = x > 0 && !in_rect(a.m, y, x), oE = x < w - 1 && !in_rect(a.m, y, x + 1);
+                T c, n = 0, s = 0, l = 0, e = 0;
+                if (first) {
+                    c = ld<kCg>(r_src + i);
+                    if (oN) n = ld<kCg>(r_src + i - w);
+                    if (oS) s = ld<kCg>(r_src + i + w);
+                    if (oW) l = ld<kCg>(r_src + i - 1);
+                    if (oE) e = ld<kCg>(r_src + i + 1);
+                    T ab = c < 0 ? -c : c;
+                    acc_bmax = ab > acc_bmax ? ab : acc_bmax;
+                    acc_bb = acc_bb + c * c;
+                } else {
+                    c = ld<kCg>(r_src + i) + beta * ld<kCg>(s_old + i);
+                    if (oN) n = ld<kCg>(r_src + i - w) + beta * ld<kCg>(s_old + i - w);
+                    if (oS) s = ld<kCg>(r_src + i + w) + beta * ld<kCg>(s_old + i + w);
+                    if (oW) l = ld<kCg>(r_src + i - 1) + beta * ld<kCg>(s_old + i - 1);
+                    if (oE) e = ld<kCg>(r_src + i + 1) + beta * ld<kCg>(s_old + i + 1);
+                }
+                if (!first) s_cur[i] = c;   // iteration 0: s = b is materialised in P2, after the early-out test
+                const T z = pano::laplacian_cell<T>(c, n, s, l, e, oN, oS, oW, oE, a.dt);
+                acc_zs = acc_zs + z * c;
+            }
+        }
+        {
+            T v = block_sum(acc_zs, scratch);
+            if (threadIdx.x == 0) pA[blockIdx.x] = (double)v;
+            if (first) {
+                T v2 = block_sum(acc_bb, scratch);
+                T v3 = block_max(acc_bmax, scratch);
+                if (threadIdx.x == 0) {
+                    pB[blockIdx.x] = (double)v2;
+                    pC[blockIdx.x] = (double)v3;
+                }
+            }
+        }
+        if (!grid_barrier(a.ctl, (++nbar) * (unsigned long long)G, &s_flag)) return;
+        const T zs = sum_partials<T>(pA, G, scratch);
+        if (first) {
+            sigma = sum_partials<T>(pB, G, scratch);          // pcg.rs:46  (aux = r = b)
+            bmax = max_partials<T>(pC, G, scratch);           // pcg.rs:35
+            rmax = bmax;
+            if (bmax < a.threshold) {                         // early out: x stays zero, nothing else is touched
+                for (int t = blockIdx.x; t < ntiles; t += G) {
+                    const int x = (t % a.tiles_x) * kTileX + tx;
+                    const int ybase = (t / a.tiles_x) * kTileY + ty;
+                    if (x >= w) continue;
+                    for (int k = 0; k < kTileY / 8; ++k) {
+                        const int y = ybase + k * 8;
+                        if (y < h) a.x[(size_t)y * w + x] = (T)0;
+                    }
+                }
+                if (blockIdx.x == 0 && threadIdx.x == 0) {
+                    a.ctl->iterations = -1;
+                    a.ctl->applies = 0;
+                    a.ctl->final_residual = (double)bmax;
+                    a.ctl->rhs_max = (double)bmax;
+                }
+                return;
+            }
+        }
+        ++applies;
+        alpha = sigma / zs;                                   // pcg.rs:53
+        const T nalpha = -alpha;
+        // ------------------------------------------------------------------ P2
+        T acc_rr = 0, acc_rmax = 0;
+        const T *s_rd = first ? a.b : s_cur;                  // pcg.rs:40-42: s = aux = r = b
+        for (int t = blockIdx.x; t < ntiles; t += G) {
+            const int x = (t % a.tiles_x) * kTileX + tx;
+            const int ybase = (t / a.tiles_x) * kTileY + ty;
+            if (x >= w) continue;
+#pragma unroll
+            for (int k = 0; k < kTileY / 8; ++k) {
+                const int y = ybase + k * 8;
+                if (y >= h) break;
+                const size_t i = (size_t)y * w + x;
+                const bool oN = y > 0 && !in_rect(a.m, y, x), oS = y < h - 1 && !in_rect(a.m, y + 1, x);
+                const bool oW = x > 0 && !in_rect(a.m, y, x), oE = x < w - 1 && !in_rect(a.m, y, x + 1);
+                const T c = ld<kCg>(s_rd + i);
+                const T n = oN ? ld<kCg>(s_rd + i - w) : (T)0, s = oS ? ld<kCg>(s_rd + i + w) : (T)0;
+                const T l = oW ? ld<kCg>(s_rd + i - 1) : (T)0, e = oE ? ld<kCg>(s_rd + i + 1) : (T)0;
+                const T z = pano::laplacian_cell<T>(c, n, s, l, e, oN, oS, oW, oE, a.dt);
+                if (first) a.s0[i] = c;
+                const T xo = first ? (T)0 : ld<kCg>(a.x + i);
+                a.x[i] = xo + alpha * c;                      // pcg.rs:55
+                const T rn = ld<kCg>(r_src + i) + nalpha * z; // pcg.rs:56
+                a.r[i] = rn;
+                const T ar = rn < 0 ? -rn : rn;
+                acc_rmax = ar > acc_rmax ? ar : acc_rmax;
+                acc_rr = acc_rr + rn * rn;
+            }
+        }
+        {
+            T v = block_sum(acc_rr, scratch);
+            T v2 = block_max(acc_rmax, scratch);
+            if (threadIdx.x == 0) {
+                pD[blockIdx.x] = (double)v;
+                pE[blockIdx.x] = (double)v2;
+            }
+        }
+        if (!grid_barrier(a.ctl, (++nbar) * (unsigned long long)G, &s_flag)) return;
+        const T rr = sum_partials<T>(pD, G, scratch);
+        rmax = max_partials<T>(pE, G, scratch);               // pcg.rs:58
+        if (rmax < a.threshold) {                             // pcg.rs:60-63
+            converged = true;
+            break;
+        }
+        beta = rr / sigma;                                    // pcg.rs:67-68
+        sigma = rr;                                           // pcg.rs:79
+        T *tmp = s_cur;
+        s_cur = s_old;
+        s_old = tmp;
+    }
+    // After the loop `s_fin` is the buffer holding the last search direction that was applied.
+    // converged: it is s_cur.  exhausted: the swap already happened, so it is s_old, and the
+    // reference still performs the search update (pcg.rs:72-77) before leaving the loop.
+    const T *s_fin = converged ? s_cur : s_old;
+    if (a.max_iter > 0 && (!converged || s_fin != a.s0)) {
+        for (int t = blockIdx.x; t < ntiles; t += G) {
+            const int x = (t % a.tiles_x) * kTileX + tx;
+            const int ybase = (t / a.tiles_x) * kTileY + ty;
+            if (x >= w) continue;
+            for (int k = 0; k < kTileY / 8; ++k) {
+                const int y = ybase + k * 8;
+                if (y >= h) break;
+                const size_t i = (size_t)y * w + x;
+                const T sv = ld<kCg>(s_fin + i);
+                a.s0[i] = converged ? sv : ld<kCg>(a.r + i) + beta * sv;
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.ctl->iterations = converged ? it : a.max_iter;
+        a.ctl->applies = applies;
+        a.ctl->final_residual = (double)rmax;
+        a.ctl->rhs_max = (double)bmax;
+    }
+}
+
+template <class T>
+int launch_generic(pano_ctx *ctx, CgArgs<T> &args, bool use_cg_loads) {
+    const void *fn = use_cg_loads ? (const void *)k_cg_generic<T, true> : (const void *)k_cg_generic<T, false>;
+    int per_sm = 0;
+    PANO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
+    if (per_sm < 1) PANO_FAIL(PANO_ERR_CUDA, "cg: kernel does not fit on an SM");
+    int64_t cap = pano_option(ctx, "cg_blocks_per_sm", 0);
+    if (cap > 0 && cap < per_sm) per_sm = (int)cap;
+    const int ntiles = args.tiles_x * args.tiles_y;
+    int G = ctx->num_sms * per_sm;
+    if (G > ntiles) G = ntiles;
+    if (G < 1) G = 1;
+    PANO_TRY(pano_ensure_partials(ctx, 5 * (size_t)G));
+    args.partials = ctx->d_partials;
+    PANO_CUDA(cudaMemsetAsync(ctx->d_cg, 0, sizeof(PanoCgControl), ctx->stream));
+    void *kargs[] = {(void *)&args};
+    PANO_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)G), dim3(kThreads), kargs, 0, ctx->stream));
+    return pano_after_launch(ctx, "cg_generic");
+}
+
+}  // namespace
+
+// Solve on raw device pointers.  s0 = search, s1 = auxiliary.  info nullable (non-null => sync).
+int pano_cg_solve_raw(pano_ctx *ctx, int dtype, void *x, const void *b, void *r, void *s0, void *s1, size_t h, size_t w,
+                      int max_iterations, double threshold, double timestep, pano_rect obstacle, pano_pcg_info *info) {
+    if (h == 0 || w == 0) {
+        if (info) *info = pano_pcg_info{-1, 0, 0.0, 0.0};
+        return PANO_OK;
+    }
+    if (max_iterations <= 0) {
+        // pcg.rs:32-46 with an empty loop: x = 0; unless max|b| < threshold, r = s = b
+        const size_t bytes = h * w * pano_dtype_size(dtype);
+        PANO_CUDA(cudaMemsetAsync(x, 0, bytes, ctx->stream));
+        PANO_CUDA(cudaMemcpyAsync(r, b, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        PANO_CUDA(cudaMemcpyAsync(s0, b, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (info) {
+            PANO_CUDA(cudaStreamSynchronize(ctx->stream));
+            *info = pano_pcg_info{0, 0, 0.0, 0.0};
+        }
+        return PANO_OK;
+    }
+    const bool cg_loads = pano_option(ctx, "cg_ldcg", 0) != 0;
+    const RectI m = pano_clip_rect(obstacle, h + 1, w + 1);
+    if (dtype == PANO_F64) {
+        CgArgs<double> a{(double *)x, (const double *)b, (double *)r, (double *)s0, (double *)s1, (int)h, (int)w,
+                         timestep, threshold, max_iterations, m, nullptr, ctx->d_cg,
+                         ((int)w + kTileX - 1) / kTileX, ((int)h + kTileY - 1) / kTileY};
+        PANO_TRY(launch_generic<double>(ctx, a, cg_loads));
+    } else {
+        CgArgs<float> a{(float *)x, (const float *)b, (float *)r, (float *)s0, (float *)s1, (int)h, (int)w,
+                        (float)timestep, (float)threshold, max_iterations, m, nullptr, ctx->d_cg,
+                        ((int)w + kTileX - 1) / kTileX, ((int)h + kTileY - 1) / kTileY};
+        PANO_TRY(launch_generic<float>(ctx, a, cg_loads));
+    }
+    if (info) {
+        PANO_CUDA(cudaMemcpyAsync(ctx->h_cg, ctx->d_cg, sizeof(PanoCgControl), cudaMemcpyDeviceToHost, ctx->stream));
+        PANO_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_cg->error) PANO_FAIL(PANO_ERR_TIMEOUT, "pano_pcg_solve: a grid barrier timed out inside the CG kernel");
+        info->iterations = ctx->h_cg->iterations;
+        info->applies = ctx->h_cg->applies;
+        info->final_residual = ctx->h_cg->final_residual;
+        info->rhs_max = ctx->h_cg->rhs_max;
+    }
+    return PANO_OK;
+}
+
+extern "C" int pano_pcg_solve(int precond, pano_field *x, const pano_field *b, int32_t max_iterations, double threshold,
+                              pano_field *residual, pano_field *auxiliary, pano_field *search, double timestep,
+                              pano_rect obstacle, pano_pcg_info *info) {
+    if (precond != PANO_PRECOND_IDENTITY)
+        PANO_FAIL(PANO_ERR_UNIMPLEMENTED, "pano_pcg_solve: only the identity preconditioner `()` exists (pcg.rs:8-12)");
+    const pano_field *all[] = {x, b, residual, auxiliary, search};
+    const char *names[] = {"x", "b", "residual", "auxiliary", "search"};
+    for (int i = 0; i < 5; ++i) {
+        char nm[64];
+        snprintf(nm, sizeof(nm), "pano_pcg_solve(%s)", names[i]);
+        PANO_TRY(pano_check_kind(all[i], PANO_SIMPLEX2, nm));
+        PANO_TRY(pano_check_same(all[0], all[i], "pano_pcg_solve"));
+        for (int j = 0; j < i; ++j)
+            if (all[i]->d == all[j]->d) PANO_FAIL(PANO_ERR_INVALID, "pano_pcg_solve: %s aliases %s", names[i], names[j]);
+    }
+    pano_ctx *ctx = x->ctx;
+    PANO_TRY(pano_activate(ctx));
+    return pano_cg_solve_raw(ctx, x->dtype, x->d, b->d, residual->d, search->d, auxiliary->d, x->h, x->w, max_iterations,
+                             threshold, timestep, obstacle, info);
+}

@@ -1,0 +1,306 @@
+// pano_fused.cu -- the non-solver passes of the step, each fused into one kernel:
+//   K1 advect_all      examples/dec_fluid.rs:59-66   (advect + both advect_mac loops, one pass)
+//   K3 neg_divergence  examples/dec_fluid.rs:69-83   (hodge_1_dual -> box zero -> d1 -> negate, + max|b|)
+//   K5 laplacian_apply examples/dec_fluid.rs:100-119 (stand-alone form of the CG operator)
+//   K8 project         examples/dec_fluid.rs:124-141 (hodge_2 -> d0_dual -> scaled_add -> walls)
+// All are HBM-bound; see DESIGN.md for bytes per cell.
+#include "pano_cell_math.h"
+#include "pano_internal.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <class T>
+struct View2 {   // row-major (rows, pitch) array in global memory
+    const T *p;
+    int pitch;
+    __device__ __forceinline__ T operator()(int y, int x) const { return p[(size_t)y * pitch + x]; }
+};
+
+// ------------------------------------------------------------------ K1: advection
+// Tile = 32 x 8 cells per 256-thread block; index space (h+1) x (w+1) covers q (h,w),
+// vx (h,w+1) and vy (h+1,w) in one sweep.  Gathers go through L1/L2 (the backtrace lands
+// within ~2 cells of the thread's own cell for CFL-bounded flow).
+template <class T, bool kScalar, bool kMac>
+__global__ void __launch_bounds__(kThreads)
+k_advect(T *__restrict__ q_dst, T *__restrict__ vel_dst, const T *__restrict__ q_src, const T *__restrict__ mac_src,
+         const T *__restrict__ vel, int h, int w, T dt) {
+    const size_t off = (size_t)w * (h + 1);
+    const View2<T> vy{vel, w}, vx{vel + off, w + 1};
+    const View2<T> qy{mac_src, w}, qx{mac_src + off, w + 1};
+    const View2<T> q{q_src, w};
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    if (x > w) return;
+    for (int y = blockIdx.y * 8 + (threadIdx.x >> 5); y <= h; y += gridDim.y * 8) {
+        if (kScalar && y < h && x < w) q_dst[(size_t)y * w + x] = pano::advect_cell<T>(y, x, h, w, dt, q, vy, vx);
+        if (kMac) {
+            if (y < h) vel_dst[off + (size_t)y * (w + 1) + x] = pano::advect_mac_x<T>(y, x, h, w, dt, qx, vy, vx);
+            if (x < w) vel_dst[(size_t)y * w + x] = pano::advect_mac_y<T>(y, x, h, w, dt, qy, vy, vx);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K3: -divergence (+ max|b|, b.b)
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+k_neg_divergence(T *__restrict__ b, const T *__restrict__ vel, int h, int w, RectI m, double *__restrict__ partial_max,
+                 double *__restrict__ partial_dot) {
+    __shared__ T scratch[32];
+    const T *vy = vel, *vx = vel + (size_t)w * (h + 1);
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    T amax = 0, adot = 0;
+    if (x < w) {
+        for (int y = blockIdx.y * 8 + (threadIdx.x >> 5); y < h; y += gridDim.y * 8) {
+            T vy0 = in_rect(m, y, x) ? (T)0 : vy[(size_t)y * w + x];
+            T vy1 = in_rect(m, y + 1, x) ? (T)0 : vy[(size_t)(y + 1) * w + x];
+            T vx0 = in_rect(m, y, x) ? (T)0 : vx[(size_t)y * (w + 1) + x];
+            T vx1 = in_rect(m, y, x + 1) ? (T)0 : vx[(size_t)y * (w + 1) + x + 1];
+            T v = pano::neg_divergence_cell<T>(vy0, vy1, vx0, vx1);
+            b[(size_t)y * w + x] = v;
+            T a = v < 0 ? -v : v;
+            amax = a > amax ? a : amax;
+            adot = adot + v * v;
+        }
+    }
+    T bm = block_max(amax, scratch);
+    T bd = block_sum(adot, scratch);
+    if (threadIdx.x == 0) {
+        const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+        partial_max[bid] = (double)bm;
+        partial_dot[bid] = (double)bd;
+    }
+}
+
+__global__ void k_reduce_max_dot(const double *__restrict__ pmax, const double *__restrict__ pdot, int n,
+                                 double *__restrict__ out) {
+    __shared__ double scratch[32];
+    double m = 0, d = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        m = pmax[i] > m ? pmax[i] : m;
+        d += pdot[i];
+    }
+    m = block_max(m, scratch);
+    d = block_sum(d, scratch);
+    if (threadIdx.x == 0) {
+        out[0] = m;
+        out[1] = d;
+    }
+}
+
+// ------------------------------------------------------------------ K5: stand-alone Laplacian
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+k_laplacian(T *__restrict__ z, const T *__restrict__ p, int h, int w, T dt, RectI m) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    if (x >= w) return;
+    for (int y = blockIdx.y * 8 + (threadIdx.x >> 5); y < h; y += gridDim.y * 8) {
+        const bool oN = y > 0 && !in_rect(m, y, x), oS = y < h - 1 && !in_rect(m, y + 1, x);
+        const bool oW = x > 0 && !in_rect(m, y, x), oE = x < w - 1 && !in_rect(m, y, x + 1);
+        const size_t i = (size_t)y * w + x;
+        const T c = p[i];
+        const T n = oN ? p[i - w] : (T)0, s = oS ? p[i + w] : (T)0;
+        const T l = oW ? p[i - 1] : (T)0, r = oE ? p[i + 1] : (T)0;
+        z[i] = pano::laplacian_cell<T>(c, n, s, l, r, oN, oS, oW, oE, dt);
+    }
+}
+
+// ------------------------------------------------------------------ K8: projection + walls
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+k_project(T *__restrict__ vel, const T *__restrict__ p, int h, int w, T dt) {
+    T *vy = vel, *vx = vel + (size_t)w * (h + 1);
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    if (x > w) return;
+    for (int y = blockIdx.y * 8 + (threadIdx.x >> 5); y <= h; y += gridDim.y * 8) {
+        const T c = (y < h && x < w) ? p[(size_t)y * w + x] : (T)0;
+        if (x < w) {   // vy[y, x]
+            const size_t i = (size_t)y * w + x;
+            if (y == 0 || y == h) vy[i] = (T)0;                                   // walls :137-140
+            else vy[i] = vy[i] + dt * (-(c - p[(size_t)(y - 1) * w + x]));        // d0_dual :322-326, scaled_add :126
+        }
+        if (y < h) {   // vx[y, x]
+            const size_t i = (size_t)y * (w + 1) + x;
+            if (x == 0 || x == w) vx[i] = (T)0;                                   // walls :132-135
+            else vx[i] = vx[i] + dt * (p[(size_t)y * w + x - 1] - c);             // d0_dual :329-333
+        }
+    }
+}
+
+template <class T>
+__global__ void k_to_u8(uint8_t *__restrict__ out, const T *__restrict__ d, int h, int w, T lower, T upper) {
+    const size_t n = (size_t)h * w;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i / w), x = (int)(i % w);
+        T v = d[(size_t)(h - 1 - y) * w + x];                    // vertical flip, png.rs:12
+        v = pano::tmax(pano::tmin(v, upper), lower);             // imgproc.rs:3
+        T s = (v - lower) / (upper - lower) * (T)255;            // imgproc.rs:4
+        out[i] = (uint8_t)(s < (T)0 ? (T)0 : (s > (T)255 ? (T)255 : s));   // Rust `as u8` saturates
+    }
+}
+
+inline dim3 grid2d(int rows, int cols) {
+    int gy = (rows + 7) / 8;
+    if (gy > 8192) gy = 8192;
+    if (gy < 1) gy = 1;
+    int gx = (cols + 31) / 32;
+    if (gx < 1) gx = 1;
+    return dim3((unsigned)gx, (unsigned)gy);
+}
+
+}  // namespace
+
+// internal: advection on raw pointers (used by pano_step.cu as well)
+int pano_advect_launch(pano_ctx *ctx, int dtype, void *q_dst, void *vel_dst, const void *q_src, const void *mac_src,
+                       const void *vel, size_t h, size_t w, double dt) {
+    dim3 g = grid2d((int)h + 1, (int)w + 1);
+    const bool sc = q_dst != nullptr, mac = vel_dst != nullptr;
+#define PANO_LAUNCH_ADV(T, S, M)                                                                                     \
+    k_advect<T, S, M><<<g, kThreads, 0, ctx->stream>>>((T *)q_dst, (T *)vel_dst, (const T *)q_src, (const T *)mac_src, \
+                                                       (const T *)vel, (int)h, (int)w, (T)dt)
+    if (dtype == PANO_F64) {
+        if (sc && mac) PANO_LAUNCH_ADV(double, true, true);
+        else if (sc) PANO_LAUNCH_ADV(double, true, false);
+        else PANO_LAUNCH_ADV(double, false, true);
+    } else {
+        if (sc && mac) PANO_LAUNCH_ADV(float, true, true);
+        else if (sc) PANO_LAUNCH_ADV(float, true, false);
+        else PANO_LAUNCH_ADV(float, false, true);
+    }
+#undef PANO_LAUNCH_ADV
+    return pano_after_launch(ctx, "advect");
+}
+
+// internal: b = -div(vel); d_scalars[0] = max|b|, d_scalars[1] = b.b  (no sync)
+int pano_neg_divergence_launch(pano_ctx *ctx, int dtype, void *b, const void *vel, size_t h, size_t w, pano_rect obstacle) {
+    dim3 g = grid2d((int)h, (int)w);
+    const int nb = (int)(g.x * g.y);
+    PANO_TRY(pano_ensure_partials(ctx, 2 * (size_t)nb));
+    // the obstacle rectangle indexes vy (h+1, w) and vx (h, w+1) alike; clip to the union
+    RectI m = pano_clip_rect(obstacle, h + 1, w + 1);
+    if (dtype == PANO_F64)
+        k_neg_divergence<double><<<g, kThreads, 0, ctx->stream>>>((double *)b, (const double *)vel, (int)h, (int)w, m,
+                                                                  ctx->d_partials, ctx->d_partials + nb);
+    else
+        k_neg_divergence<float><<<g, kThreads, 0, ctx->stream>>>((float *)b, (const float *)vel, (int)h, (int)w, m,
+                                                                 ctx->d_partials, ctx->d_partials + nb);
+    PANO_TRY(pano_after_launch(ctx, "neg_divergence"));
+    k_reduce_max_dot<<<1, kThreads, 0, ctx->stream>>>(ctx->d_partials, ctx->d_partials + nb, nb, ctx->d_scalars);
+    return pano_after_launch(ctx, "neg_divergence(reduce)");
+}
+
+int pano_project_launch(pano_ctx *ctx, int dtype, void *vel, const void *p, size_t h, size_t w, double dt) {
+    dim3 g = grid2d((int)h + 1, (int)w + 1);
+    if (dtype == PANO_F64) k_project<double><<<g, kThreads, 0, ctx->stream>>>((double *)vel, (const double *)p, (int)h, (int)w, dt);
+    else k_project<float><<<g, kThreads, 0, ctx->stream>>>((float *)vel, (const float *)p, (int)h, (int)w, (float)dt);
+    return pano_after_launch(ctx, "project");
+}
+
+extern "C" {
+
+int pano_advect(pano_field *dst, const pano_field *src, double timestep, const pano_field *vel) {
+    PANO_TRY(pano_check_kind(dst, PANO_SIMPLEX2, "pano_advect(dst)"));
+    PANO_TRY(pano_check_kind(src, PANO_SIMPLEX2, "pano_advect(src)"));
+    PANO_TRY(pano_check_kind(vel, PANO_SIMPLEX1, "pano_advect(vel)"));
+    PANO_TRY(pano_check_same(dst, src, "pano_advect"));
+    PANO_TRY(pano_check_grid(dst, vel, "pano_advect"));
+    if (dst->d == src->d) PANO_FAIL(PANO_ERR_INVALID, "pano_advect: dst aliases src (the reference forbids it: &mut vs &)");
+    if (dst->h < 2 || dst->w < 2)
+        PANO_FAIL(PANO_ERR_SHAPE, "pano_advect: grid %zux%zu; the reference indexes q[iy+1, ix+1] and panics below 2x2", dst->h, dst->w);
+    PANO_TRY(pano_activate(dst->ctx));
+    return pano_advect_launch(dst->ctx, dst->dtype, dst->d, nullptr, src->d, nullptr, vel->d, dst->h, dst->w, timestep);
+}
+
+int pano_advect_mac(pano_field *dst, const pano_field *src, double timestep, const pano_field *vel) {
+    PANO_TRY(pano_check_kind(dst, PANO_SIMPLEX1, "pano_advect_mac(dst)"));
+    PANO_TRY(pano_check_kind(src, PANO_SIMPLEX1, "pano_advect_mac(src)"));
+    PANO_TRY(pano_check_kind(vel, PANO_SIMPLEX1, "pano_advect_mac(vel)"));
+    PANO_TRY(pano_check_same(dst, src, "pano_advect_mac"));
+    PANO_TRY(pano_check_same(dst, vel, "pano_advect_mac"));
+    if (dst->d == src->d || dst->d == vel->d) PANO_FAIL(PANO_ERR_INVALID, "pano_advect_mac: dst aliases an input");
+    if (dst->h < 1 || dst->w < 1) PANO_FAIL(PANO_ERR_SHAPE, "pano_advect_mac: empty grid");
+    PANO_TRY(pano_activate(dst->ctx));
+    return pano_advect_launch(dst->ctx, dst->dtype, nullptr, dst->d, nullptr, src->d, vel->d, dst->h, dst->w, timestep);
+}
+
+int pano_advect_all(pano_field *q_dst, pano_field *vel_dst, const pano_field *q_src, const pano_field *vel, double timestep) {
+    PANO_TRY(pano_check_kind(q_dst, PANO_SIMPLEX2, "pano_advect_all(q_dst)"));
+    PANO_TRY(pano_check_kind(q_src, PANO_SIMPLEX2, "pano_advect_all(q_src)"));
+    PANO_TRY(pano_check_kind(vel_dst, PANO_SIMPLEX1, "pano_advect_all(vel_dst)"));
+    PANO_TRY(pano_check_kind(vel, PANO_SIMPLEX1, "pano_advect_all(vel)"));
+    PANO_TRY(pano_check_same(q_dst, q_src, "pano_advect_all"));
+    PANO_TRY(pano_check_same(vel_dst, vel, "pano_advect_all"));
+    PANO_TRY(pano_check_grid(q_dst, vel, "pano_advect_all"));
+    if (q_dst->d == q_src->d || vel_dst->d == vel->d) PANO_FAIL(PANO_ERR_INVALID, "pano_advect_all: an output aliases its input");
+    if (q_dst->h < 2 || q_dst->w < 2) PANO_FAIL(PANO_ERR_SHAPE, "pano_advect_all: grid %zux%zu below 2x2", q_dst->h, q_dst->w);
+    PANO_TRY(pano_activate(q_dst->ctx));
+    return pano_advect_launch(q_dst->ctx, q_dst->dtype, q_dst->d, vel_dst->d, q_src->d, vel->d, vel->d, q_dst->h, q_dst->w, timestep);
+}
+
+int pano_neg_divergence(pano_field *b, const pano_field *vel, pano_rect obstacle, double *rhs_max) {
+    PANO_TRY(pano_check_kind(b, PANO_SIMPLEX2, "pano_neg_divergence(b)"));
+    PANO_TRY(pano_check_kind(vel, PANO_SIMPLEX1, "pano_neg_divergence(vel)"));
+    PANO_TRY(pano_check_grid(b, vel, "pano_neg_divergence"));
+    pano_ctx *ctx = b->ctx;
+    PANO_TRY(pano_activate(ctx));
+    if (b->n == 0) {
+        if (rhs_max) *rhs_max = 0.0;
+        return PANO_OK;
+    }
+    PANO_TRY(pano_neg_divergence_launch(ctx, b->dtype, b->d, vel->d, b->h, b->w, obstacle));
+    if (rhs_max) {
+        PANO_CUDA(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        PANO_CUDA(cudaStreamSynchronize(ctx->stream));
+        *rhs_max = ctx->h_scalars[0];
+    }
+    return PANO_OK;
+}
+
+int pano_laplacian_apply(pano_field *z, const pano_field *s, double timestep, pano_rect obstacle) {
+    PANO_TRY(pano_check_kind(z, PANO_SIMPLEX2, "pano_laplacian_apply(z)"));
+    PANO_TRY(pano_check_kind(s, PANO_SIMPLEX2, "pano_laplacian_apply(s)"));
+    PANO_TRY(pano_check_same(z, s, "pano_laplacian_apply"));
+    if (z->d == s->d) PANO_FAIL(PANO_ERR_INVALID, "pano_laplacian_apply: z aliases s");
+    pano_ctx *ctx = z->ctx;
+    PANO_TRY(pano_activate(ctx));
+    if (z->n == 0) return PANO_OK;
+    RectI m = pano_clip_rect(obstacle, z->h + 1, z->w + 1);
+    dim3 g = grid2d((int)z->h, (int)z->w);
+    if (z->dtype == PANO_F64)
+        k_laplacian<double><<<g, kThreads, 0, ctx->stream>>>((double *)z->d, (const double *)s->d, (int)z->h, (int)z->w, timestep, m);
+    else
+        k_laplacian<float><<<g, kThreads, 0, ctx->stream>>>((float *)z->d, (const float *)s->d, (int)z->h, (int)z->w, (float)timestep, m);
+    return pano_after_launch(ctx, "pano_laplacian_apply");
+}
+
+int pano_project(pano_field *vel, const pano_field *pressure, double timestep) {
+    PANO_TRY(pano_check_kind(vel, PANO_SIMPLEX1, "pano_project(vel)"));
+    PANO_TRY(pano_check_kind(pressure, PANO_SIMPLEX2, "pano_project(pressure)"));
+    PANO_TRY(pano_check_grid(vel, pressure, "pano_project"));
+    PANO_TRY(pano_activate(vel->ctx));
+    if (vel->n == 0) return PANO_OK;
+    return pano_project_launch(vel->ctx, vel->dtype, vel->d, pressure->d, vel->h, vel->w, timestep);
+}
+
+int pano_density_to_u8(const pano_field *density, double lower, double upper, uint8_t *host_out) {
+    PANO_TRY(pano_check_kind(density, PANO_SIMPLEX2, "pano_density_to_u8"));
+    if (!host_out) PANO_FAIL(PANO_ERR_INVALID, "pano_density_to_u8: null output");
+    pano_ctx *ctx = density->ctx;
+    PANO_TRY(pano_activate(ctx));
+    if (density->n == 0) return PANO_OK;
+    uint8_t *d_out = nullptr;
+    PANO_CUDA(cudaMallocAsync((void **)&d_out, density->n, ctx->stream));
+    size_t blocks = (density->n + kThreads - 1) / kThreads;
+    int g = (int)(blocks < (size_t)ctx->num_sms * 8 ? blocks : (size_t)ctx->num_sms * 8);
+    if (density->dtype == PANO_F64)
+        k_to_u8<double><<<g, kThreads, 0, ctx->stream>>>(d_out, (const double *)density->d, (int)density->h, (int)density->w, lower, upper);
+    else
+        k_to_u8<float><<<g, kThreads, 0, ctx->stream>>>(d_out, (const float *)density->d, (int)density->h, (int)density->w, (float)lower, (float)upper);
+    PANO_TRY(pano_after_launch(ctx, "pano_density_to_u8"));
+    PANO_CUDA(cudaMemcpyAsync(host_out, d_out, density->n, cudaMemcpyDeviceToHost, ctx->stream));
+    PANO_CUDA(cudaFreeAsync(d_out, ctx->stream));
+    PANO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PANO_OK;
+}
+
+}  // extern "C"

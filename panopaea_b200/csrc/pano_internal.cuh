@@ -1,0 +1,169 @@
+// pano_internal.cuh -- shared declarations of the B200 grid-fluid library (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/panopaea_b200.h"
+
+// ---------------------------------------------------------------------------------- errors
+void pano_set_error(const char *fmt, ...);
+
+#define PANO_FAIL(code, ...)        \
+    do {                            \
+        pano_set_error(__VA_ARGS__); \
+        return (code);              \
+    } while (0)
+
+#define PANO_CUDA(expr)                                                                         \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            pano_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return PANO_ERR_CUDA;                                                               \
+        }                                                                                       \
+    } while (0)
+
+#define PANO_TRY(expr)             \
+    do {                           \
+        int _rc = (expr);          \
+        if (_rc != PANO_OK) return _rc; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------- handles
+// Device-side control block of the persistent CG kernel (one per context).
+struct PanoCgControl {
+    unsigned long long barrier;   // monotonically increasing arrival counter
+    unsigned int error;           // != 0: a bounded wait expired; everybody leaves
+    int iterations;               // as pano_pcg_info
+    int applies;
+    double final_residual;
+    double rhs_max;
+    double pad[2];
+};
+
+struct PanoWorkspace;   // cached scratch of pano_fluid_step_host
+
+struct pano_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t smem_optin = 0;
+    uint64_t launches = 0;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    // reductions: block partials (device) + final scalars (device, pinned host mirror)
+    double *d_partials = nullptr;
+    size_t partials_cap = 0;      // in doubles
+    double *d_scalars = nullptr;  // 8 doubles
+    double *h_scalars = nullptr;  // pinned, 8 doubles
+    PanoCgControl *d_cg = nullptr;
+    PanoCgControl *h_cg = nullptr;   // pinned
+    // optional per-phase timing of pano_fluid_step ("step_timing" option)
+    std::vector<cudaEvent_t> phase_events;   // ring of (PANO_STEP_PHASES + 1) events per slot
+    int phase_slots = 0, phase_used = 0;
+    double phase_ms[PANO_STEP_PHASES] = {0, 0, 0, 0, 0};
+    int64_t phase_steps = 0;
+    std::map<std::string, int64_t> options;
+    std::map<std::pair<size_t, size_t>, PanoWorkspace *> workspaces;
+};
+
+struct pano_field {
+    pano_ctx *ctx = nullptr;
+    int kind = 0, dtype = 0;
+    size_t h = 0, w = 0, n = 0;
+    void *d = nullptr;
+};
+
+inline size_t pano_dtype_size(int dtype) { return dtype == PANO_F32 ? 4 : 8; }
+inline size_t pano_num_elem(int kind, size_t h, size_t w) {
+    switch (kind) {
+        case PANO_SIMPLEX0: return (h + 1) * (w + 1);
+        case PANO_SIMPLEX1: return (h + 1) * w + h * (w + 1);
+        default: return h * w;
+    }
+}
+
+int pano_check_field(const pano_field *f, const char *name);
+int pano_check_same(const pano_field *a, const pano_field *b, const char *what);
+int pano_check_kind(const pano_field *f, int kind, const char *name);
+int pano_check_grid(const pano_field *a, const pano_field *b, const char *what);   // same ctx/dtype/(h,w)
+int pano_activate(pano_ctx *ctx);                                                  // cudaSetDevice
+int pano_after_launch(pano_ctx *ctx, const char *what);                            // cudaGetLastError + counter
+int pano_ensure_partials(pano_ctx *ctx, size_t doubles);
+int64_t pano_option(pano_ctx *ctx, const char *key, int64_t dflt);
+
+// internal (non-ABI) entry points shared between translation units
+int pano_cg_solve_fused(pano_ctx *ctx, double *x, const double *b, double *r, double *s, size_t h, size_t w,
+                        int max_iterations, double threshold, double timestep, pano_rect obstacle,
+                        pano_pcg_info *info);
+void pano_workspace_free_all(pano_ctx *ctx);
+int pano_phase_mark(pano_ctx *ctx, int phase);     // record event #phase of the current step (no-op unless step_timing)
+int pano_phase_drain(pano_ctx *ctx);               // synchronise and fold recorded events into phase_ms
+
+// ---------------------------------------------------------------------------------- device helpers
+struct RectI {
+    int y0, y1, x0, x1;
+};
+inline RectI pano_clip_rect(pano_rect r, size_t hmax, size_t wmax) {
+    RectI o;
+    auto clip = [](int64_t v, size_t hi) -> int { return v < 0 ? 0 : (v > (int64_t)hi ? (int)hi : (int)v); };
+    o.y0 = clip(r.y0, hmax); o.y1 = clip(r.y1, hmax);
+    o.x0 = clip(r.x0, wmax); o.x1 = clip(r.x1, wmax);
+    if (o.y1 <= o.y0 || o.x1 <= o.x0) o = RectI{0, 0, 0, 0};
+    return o;
+}
+
+__device__ __forceinline__ bool in_rect(const RectI &r, int y, int x) {
+    return y >= r.y0 && y < r.y1 && x >= r.x0 && x < r.x1;
+}
+
+template <class T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <class T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        T u = __shfl_xor_sync(0xffffffffu, v, o);
+        v = u > v ? u : v;
+    }
+    return v;
+}
+
+// Deterministic block reductions (fixed shuffle tree, fixed warp order). `scratch` holds >= 32 T.
+// Result valid in every thread.
+template <class T>
+__device__ __forceinline__ T block_sum(T v, T *scratch) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    T t = 0;
+    for (int i = 0; i < nw; ++i) t += scratch[i];
+    return t;
+}
+template <class T>
+__device__ __forceinline__ T block_max(T v, T *scratch) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    T t = 0;
+    for (int i = 0; i < nw; ++i) t = scratch[i] > t ? scratch[i] : t;
+    return t;
+}

@@ -1,0 +1,64 @@
+// Host build of panopaea_b200/csrc/pano_cell_math.h: lets the CPU test-suite compare the
+// exact per-cell expressions the CUDA kernels use against the oracle, without a GPU.
+// TEST INFRASTRUCTURE ONLY (built by tests/test_cell_math_host.py with g++ -ffp-contract=off).
+#include <cstddef>
+
+#include "../../panopaea_b200/csrc/pano_cell_math.h"
+
+template <class T>
+struct HView {
+    const T *p;
+    int pitch;
+    T operator()(int y, int x) const { return p[(size_t)y * pitch + x]; }
+};
+
+struct RectI { int y0, y1, x0, x1; };
+static inline bool in_rect(const RectI &r, int y, int x) { return y >= r.y0 && y < r.y1 && x >= r.x0 && x < r.x1; }
+
+template <class T>
+static void advect_all(int h, int w, T *q_dst, T *vel_dst, const T *q_src, const T *vel, T dt) {
+    const size_t off = (size_t)w * (h + 1);
+    HView<T> vy{vel, w}, vx{vel + off, w + 1}, q{q_src, w};
+    for (int y = 0; y <= h; ++y)
+        for (int x = 0; x <= w; ++x) {
+            if (y < h && x < w) q_dst[(size_t)y * w + x] = pano::advect_cell<T>(y, x, h, w, dt, q, vy, vx);
+            if (y < h) vel_dst[off + (size_t)y * (w + 1) + x] = pano::advect_mac_x<T>(y, x, h, w, dt, vx, vy, vx);
+            if (x < w) vel_dst[(size_t)y * w + x] = pano::advect_mac_y<T>(y, x, h, w, dt, vy, vy, vx);
+        }
+}
+
+template <class T>
+static void laplacian(int h, int w, T *z, const T *p, T dt, RectI m) {
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const bool oN = y > 0 && !in_rect(m, y, x), oS = y < h - 1 && !in_rect(m, y + 1, x);
+            const bool oW = x > 0 && !in_rect(m, y, x), oE = x < w - 1 && !in_rect(m, y, x + 1);
+            const size_t i = (size_t)y * w + x;
+            const T c = p[i];
+            const T n = oN ? p[i - w] : (T)0, s = oS ? p[i + w] : (T)0;
+            const T l = oW ? p[i - 1] : (T)0, r = oE ? p[i + 1] : (T)0;
+            z[i] = pano::laplacian_cell<T>(c, n, s, l, r, oN, oS, oW, oE, dt);
+        }
+}
+
+template <class T>
+static void neg_divergence(int h, int w, T *b, const T *vel, RectI m) {
+    const T *vy = vel, *vx = vel + (size_t)w * (h + 1);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            T vy0 = in_rect(m, y, x) ? (T)0 : vy[(size_t)y * w + x];
+            T vy1 = in_rect(m, y + 1, x) ? (T)0 : vy[(size_t)(y + 1) * w + x];
+            T vx0 = in_rect(m, y, x) ? (T)0 : vx[(size_t)y * (w + 1) + x];
+            T vx1 = in_rect(m, y, x + 1) ? (T)0 : vx[(size_t)y * (w + 1) + x + 1];
+            b[(size_t)y * w + x] = pano::neg_divergence_cell<T>(vy0, vy1, vx0, vx1);
+        }
+}
+
+extern "C" {
+void hc_advect_all_f64(int h, int w, double *qd, double *vd, const double *q, const double *v, double dt) { advect_all<double>(h, w, qd, vd, q, v, dt); }
+void hc_advect_all_f32(int h, int w, float *qd, float *vd, const float *q, const float *v, float dt) { advect_all<float>(h, w, qd, vd, q, v, dt); }
+void hc_laplacian_f64(int h, int w, double *z, const double *p, double dt, int y0, int y1, int x0, int x1) { laplacian<double>(h, w, z, p, dt, RectI{y0, y1, x0, x1}); }
+void hc_laplacian_f32(int h, int w, float *z, const float *p, float dt, int y0, int y1, int x0, int x1) { laplacian<float>(h, w, z, p, dt, RectI{y0, y1, x0, x1}); }
+void hc_neg_divergence_f64(int h, int w, double *b, const double *v, int y0, int y1, int x0, int x1) { neg_divergence<double>(h, w, b, v, RectI{y0, y1, x0, x1}); }
+void hc_neg_divergence_f32(int h, int w, float *b, const float *v, int y0, int y1, int x0, int x1) { neg_divergence<float>(h, w, b, v, RectI{y0, y1, x0, x1}); }
+}

@@ -1,0 +1,63 @@
+"""The per-cell expressions shared by every CUDA kernel (panopaea_b200/csrc/pano_cell_math.h),
+compiled for the HOST and compared bit for bit with the oracle.  This checks the arithmetic
+the GPU executes without needing a GPU; the kernels' indexing is covered by the -m gpu tests."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "hostcheck", "cell_math_host.cpp")
+HDR = os.path.join(os.path.dirname(HERE), "panopaea_b200", "csrc", "pano_cell_math.h")
+SO = os.path.join(HERE, "hostcheck", "libcell_math_host.so")
+
+
+@pytest.fixture(scope="module")
+def hc():
+    if not os.path.exists(SO) or max(os.path.getmtime(SRC), os.path.getmtime(HDR)) > os.path.getmtime(SO):
+        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", SRC, "-o", SO], check=True)
+    return C.CDLL(SO)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+CASES = [(2, 2, 50.0), (3, 3, 30.0), (5, 5, 30.0), (17, 33, 30.0), (33, 17, 200.0), (64, 48, 200.0), (40, 40, 1e4)]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("h,w,vmax", CASES)
+def test_advect_all(hc, oracle, dtype, h, w, vmax):
+    rng = np.random.default_rng(11)
+    q = rng.uniform(-1, 1, (h, w)).astype(dtype)
+    vel = rng.uniform(-vmax, vmax, oracle.num_elem_1(h, w)).astype(dtype)
+    qd, vd = np.zeros_like(q), np.zeros_like(vel)
+    real = C.c_double if dtype == np.float64 else C.c_float
+    getattr(hc, "hc_advect_all_" + ("f64" if dtype == np.float64 else "f32"))(h, w, _p(qd), _p(vd), _p(q), _p(vel), real(0.05))
+    assert np.array_equal(qd, oracle.advect(h, w, q, 0.05, vel))
+    assert np.array_equal(vd, oracle.advect_mac(h, w, vel, 0.05, vel))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("h,w", [(2, 2), (3, 3), (5, 7), (16, 16), (17, 33)])
+def test_laplacian_and_divergence(hc, oracle, dtype, h, w):
+    rng = np.random.default_rng(12)
+    p = rng.uniform(-3, 3, (h, w)).astype(dtype)
+    vel = rng.uniform(-5, 5, oracle.num_elem_1(h, w)).astype(dtype)
+    for obstacle in [(0, 0, 0, 0), (h // 2, min(h, h // 2 + 2), w // 3, min(w, w // 3 + 3)), (0, 1, 0, 2), (h - 1, h, w - 2, w)]:
+        sfx = "f64" if dtype == np.float64 else "f32"
+        real = C.c_double if dtype == np.float64 else C.c_float
+        z = np.zeros_like(p)
+        getattr(hc, "hc_laplacian_" + sfx)(h, w, _p(z), _p(p), real(0.05), *obstacle)
+        assert np.array_equal(z, oracle.laplacian_closure(h, w, p, 0.05, obstacle))
+        b = np.zeros_like(p)
+        getattr(hc, "hc_neg_divergence_" + sfx)(h, w, _p(b), _p(vel), *obstacle)
+        e = oracle.hodge_1_dual(h, w, vel)
+        ey, ex = oracle.split(e, h, w)
+        y0, y1, x0, x1 = obstacle
+        ey[y0:y1, x0:x1] = 0
+        ex[y0:y1, x0:x1] = 0
+        assert np.array_equal(b, -oracle.derivative_1_primal(h, w, e))

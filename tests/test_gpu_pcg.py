@@ -1,0 +1,154 @@
+"""-m gpu: the pressure solve.  The fused persistent CG kernel against the oracle's restatement of
+pcg.rs:14-82 driven with the dec_fluid Laplacian closure, and against the generic host-driven
+loop over device primitives.
+
+Tolerances (BASELINE.json north_star): same residual threshold reached within +-2 iterations.
+Dot products are reduced in a different order than ndarray's 8-lane loop, so alpha/beta differ
+in the last bits; x is compared at 1e-6 relative to max|x| when the iteration counts agree."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(3, 3), (5, 7), (17, 33), (24, 20), (64, 48), (128, 128), (300, 200)]
+
+
+def _solve(grid, b, max_it, thr, dt, obstacle):
+    from tests import gpu_util as U
+    from panopaea_b200 import pcg
+    x, r, aux, s = (grid.new_simplex_2() for _ in range(4))
+    for f in (x, r, aux, s):
+        f.fill(123.0)   # the solver must not depend on what the scratch fields held
+    info = pcg.solve_grid_laplacian(x, U.s2(grid, b), max_it, thr, r, aux, s, dt, obstacle)
+    return info, x.to_host(), r.to_host(), s.to_host()
+
+
+@pytest.mark.parametrize("ldcg", [0, 1])
+@pytest.mark.parametrize("h,w", SIZES)
+def test_fused_cg_vs_oracle(oracle, h, w, ldcg):
+    from tests import gpu_util as U
+    U.ctx().set_option("cg_ldcg", ldcg)
+    try:
+        grid = U.grid(h, w)
+        obstacle = U.default_obstacle(h, w) if h > 4 else (0, 0, 0, 0)
+        b = U.consistent_rhs(oracle, h, w, obstacle, seed=h + w)
+        want = oracle.pcg_grid_laplacian(h, w, b, 100, 0.1, 0.05, obstacle)
+        info, x, r, s = _solve(grid, b, 100, 0.1, 0.05, obstacle)
+        assert want.iterations >= 0
+        assert abs(info["iterations"] - want.iterations) <= 2
+        assert info["applies"] == (info["iterations"] + 1 if info["iterations"] < 100 else 100)
+        assert info["rhs_max"] == oracle.norm_max(b)
+        assert info["final_residual"] < 0.1 or info["iterations"] == 100
+        # the returned residual field is the true residual of the returned x:  r == b - A x
+        true_r = b - oracle.laplacian_closure(h, w, x, 0.05, obstacle)
+        assert np.allclose(r, true_r, rtol=0, atol=1e-9 * max(1.0, np.abs(b).max()))
+        assert info["final_residual"] == pytest.approx(np.abs(r).max(), rel=1e-12)
+        if info["iterations"] == want.iterations:
+            scale = max(1.0, np.abs(want.x).max())
+            assert np.allclose(x, want.x, rtol=0, atol=1e-6 * scale)
+            assert np.allclose(r, want.residual, rtol=0, atol=1e-6 * max(1.0, np.abs(b).max()))
+            assert np.allclose(s, want.search, rtol=0, atol=1e-6 * max(1.0, np.abs(want.search).max()))
+    finally:
+        U.ctx().set_option("cg_ldcg", 0)
+
+
+def test_early_out_leaves_scratch_untouched(oracle):
+    """pcg.rs:35-38: max|b| < threshold -> x = 0 and nothing else is written."""
+    from tests import gpu_util as U
+    h, w = 40, 24
+    grid = U.grid(h, w)
+    b = np.random.default_rng(1).uniform(-0.05, 0.05, (h, w))
+    info, x, r, s = _solve(grid, b, 100, 0.1, 0.05, (0, 0, 0, 0))
+    assert info["iterations"] == -1 and info["applies"] == 0
+    assert info["final_residual"] == np.abs(b).max() == info["rhs_max"]
+    assert not x.any()
+    assert np.all(r == 123.0) and np.all(s == 123.0)
+
+
+@pytest.mark.parametrize("max_it", [1, 2, 3, 7])
+def test_exhausted_iterations_match_reference_state(oracle, max_it):
+    """When the loop runs out (pcg.rs:48), the reference has still updated `search` (pcg.rs:72-77)."""
+    from tests import gpu_util as U
+    h, w = 33, 47
+    grid = U.grid(h, w)
+    obstacle = U.default_obstacle(h, w)
+    b = U.consistent_rhs(oracle, h, w, obstacle, seed=3)
+    want = oracle.pcg_grid_laplacian(h, w, b, max_it, 1e-9, 0.05, obstacle)
+    info, x, r, s = _solve(grid, b, max_it, 1e-9, 0.05, obstacle)
+    assert want.iterations == max_it and info["iterations"] == max_it and info["applies"] == max_it
+    sc = np.abs(b).max()
+    assert np.allclose(x, want.x, rtol=0, atol=1e-9 * max(1.0, np.abs(want.x).max()))
+    assert np.allclose(r, want.residual, rtol=0, atol=1e-9 * sc)
+    assert np.allclose(s, want.search, rtol=0, atol=1e-9 * max(sc, np.abs(want.search).max()))
+
+
+def test_zero_iterations(oracle):
+    from tests import gpu_util as U
+    h, w = 16, 16
+    grid = U.grid(h, w)
+    b = U.consistent_rhs(oracle, h, w, (0, 0, 0, 0), seed=4)
+    info, x, r, s = _solve(grid, b, 0, 0.1, 0.05, (0, 0, 0, 0))
+    assert info["iterations"] == 0 and not x.any()
+    assert np.array_equal(r, b) and np.array_equal(s, b)
+
+
+def test_generic_driver_matches_fused(oracle):
+    """precond_conjugate_gradient with an arbitrary closure over device primitives (the reference's
+    generic signature) walks the same iterates as the fused kernel."""
+    from tests import gpu_util as U
+    from panopaea_b200 import pcg, fluid
+    h, w = 96, 80
+    grid = U.grid(h, w)
+    obstacle = U.default_obstacle(h, w)
+    b = U.consistent_rhs(oracle, h, w, obstacle, seed=5)
+    B = U.s2(grid, b)
+    x, r, aux, s = (grid.new_simplex_2() for _ in range(4))
+    calls = []
+
+    def closure(dst, src):
+        calls.append(1)
+        fluid.laplacian_apply(dst, src, 0.05, obstacle)
+
+    gi = pcg.precond_conjugate_gradient((), x, B, 100, 0.1, r, aux, s, closure)
+    fi, fx, fr, fs = _solve(grid, b, 100, 0.1, 0.05, obstacle)
+    assert len(calls) == gi["applies"]
+    assert abs(gi["iterations"] - fi["iterations"]) <= 1
+    if gi["iterations"] == fi["iterations"]:
+        assert np.allclose(x.to_host(), fx, rtol=0, atol=1e-7 * max(1.0, np.abs(fx).max()))
+        assert np.allclose(s.to_host(), fs, rtol=0, atol=1e-7 * max(1.0, np.abs(fs).max()))
+
+
+def test_deterministic(oracle):
+    from tests import gpu_util as U
+    h, w = 200, 136
+    grid = U.grid(h, w)
+    obstacle = U.default_obstacle(h, w)
+    b = U.consistent_rhs(oracle, h, w, obstacle, seed=6)
+    a = _solve(grid, b, 100, 0.1, 0.05, obstacle)
+    c = _solve(grid, b, 100, 0.1, 0.05, obstacle)
+    assert a[0] == c[0]
+    assert all(np.array_equal(u, v) for u, v in zip(a[1:], c[1:]))
+
+
+def test_large_grid_capped_solve(oracle):
+    """1024^2 (BASELINE configs[1] size): the cap of 100 iterations is hit, as SURVEY.md 6 observes
+    for N >= 512; compare the full iterate with the oracle after a fixed 100 iterations."""
+    from tests import gpu_util as U
+    n = 1024
+    grid = U.grid(n, n)
+    k = n // 128
+    obstacle = (70 * k, 80 * k, 50 * k, 70 * k)
+    rng = np.random.default_rng(7)
+    b = oracle.laplacian_closure(n, n, rng.normal(size=(n, n)) * 40.0, 0.05, obstacle)
+    oracle.set_threading(oracle.ALL_PARALLEL)
+    try:
+        want = oracle.pcg_grid_laplacian(n, n, b, 100, 0.1, 0.05, obstacle)
+    finally:
+        oracle.set_threading(oracle.SERIAL)
+    info, x, r, s = _solve(grid, b, 100, 0.1, 0.05, obstacle)
+    assert abs(info["iterations"] - want.iterations) <= 2
+    if info["iterations"] == want.iterations:
+        assert np.allclose(x, want.x, rtol=0, atol=1e-5 * np.abs(want.x).max())
+        assert info["final_residual"] == pytest.approx(want.final_residual, rel=1e-5)
+    true_r = b - oracle.laplacian_closure(n, n, x, 0.05, obstacle)
+    assert np.allclose(r, true_r, rtol=0, atol=1e-9 * np.abs(b).max())

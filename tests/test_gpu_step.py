@@ -1,0 +1,128 @@
+"""-m gpu: the whole step (examples/dec_fluid.rs:46-141) on the device against the oracle."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _fields(sim):
+    vy, vx = sim.vel.split()
+    return sim.density.to_host(), vy, vx, sim.pressure.to_host()
+
+
+def _close(a, b, rel):
+    scale = max(np.abs(b).max(), 1e-300)
+    return np.abs(a - b).max() <= rel * scale
+
+
+def test_dec_fluid_128_free_running(oracle):
+    """configs[0]: the shipped example (128^2), run freely from the zero state for 60 steps.
+    Iteration counts must match the oracle within +-2; fields within 1e-5 relative (north_star)."""
+    from tests import gpu_util as U
+    from panopaea_b200 import fluid
+    sim = fluid.DecFluid(**fluid.smoke_params(128), ctx=U.ctx())
+    ref = oracle.FluidState(**oracle.smoke_params(128))
+    z = np.load(os.path.join(GOLD, "oracle_vectors.npz"))
+    same = True
+    for i in range(60):
+        g, o = sim.step(), ref.step()
+        assert abs(g["iterations"] - o["iterations"]) <= 2, (i, g, o)
+        if i < 25:
+            assert abs(g["iterations"] - int(z["dec_fluid_128_iterations"][i])) <= 2
+        if g["iterations"] != o["iterations"]:
+            same = False      # allowed (+-2); the two trajectories separate from here, stop comparing
+            break
+    assert i >= 10, "trajectories separated suspiciously early"
+    if same:
+        d, vy, vx, p = _fields(sim)
+        ovy, ovx = oracle.split(ref.field("vel"), 128, 128)
+        assert _close(d, ref.field("density"), 1e-5)
+        assert _close(vy, ovy, 1e-5) and _close(vx, ovx, 1e-5)
+        assert _close(p, ref.field("pressure"), 1e-5)
+
+
+@pytest.mark.parametrize("n", [128, 256, 1024])
+def test_step_resynchronised(oracle, n):
+    """Per-step parity: before every step the device state is overwritten with the oracle's, so
+    each step is compared on identical inputs (configs[1] at n = 1024)."""
+    from tests import gpu_util as U
+    from panopaea_b200 import fluid
+    sim = fluid.DecFluid(**fluid.smoke_params(n), ctx=U.ctx())
+    ref = oracle.FluidState(**oracle.smoke_params(n))
+    oracle.set_threading(oracle.ALL_PARALLEL if n >= 512 else oracle.SERIAL)
+    try:
+        steps = 12 if n <= 256 else 3
+        for i in range(steps):
+            sim.density.upload(ref.field("density"))
+            sim.vel.upload(ref.field("vel"))
+            g, o = sim.step(), ref.step(want_rhs=True)
+            assert abs(g["iterations"] - o["iterations"]) <= 2, (i, g, o)
+            assert g["rhs_max"] == np.abs(o["rhs"]).max()                     # -div is bit-exact
+            d, vy, vx, p = _fields(sim)
+            ovy, ovx = oracle.split(ref.field("vel"), n, n)
+            assert np.array_equal(d, ref.field("density"))                     # advection is bit-exact
+            if g["iterations"] == o["iterations"]:
+                assert _close(p, ref.field("pressure"), 1e-5), i
+                assert _close(vy, ovy, 1e-5) and _close(vx, ovx, 1e-5), i
+                assert g["final_residual"] == pytest.approx(o["final_residual"], rel=1e-5)
+    finally:
+        oracle.set_threading(oracle.SERIAL)
+
+
+def test_composed_sequence_matches_fused(oracle):
+    """The reference's own call sequence (one kernel per Manifold2d call, generic CG with the
+    Laplacian closure) and the fused step advance the same state."""
+    from tests import gpu_util as U
+    from panopaea_b200 import fluid
+    a = fluid.DecFluid(**fluid.smoke_params(128), ctx=U.ctx())
+    b = fluid.DecFluid(**fluid.smoke_params(128), ctx=U.ctx())
+    for i in range(8):
+        ia, ib = a.step(), b.step_composed()
+        assert abs(ia["iterations"] - ib["iterations"]) <= 1, i
+        if ia["iterations"] != ib["iterations"]:
+            return
+    for u, v in zip(_fields(a), _fields(b)):
+        assert _close(u, v, 1e-7)
+
+
+def test_step_host_buffers(oracle):
+    """pano_fluid_step_host: fields owned by the caller in host memory, as the Rust crate keeps them."""
+    from tests import gpu_util as U
+    from panopaea_b200 import _lib, fluid
+    n = 128
+    prm = fluid.smoke_params(n)
+    params = _lib.StepParams(prm["timestep"], prm["threshold"], prm["max_iterations"], 0, _lib.Rect(*prm["inflow"]),
+                             prm["inflow_density"], prm["inflow_vy"], _lib.Rect(*prm["obstacle"]))
+    ref = oracle.FluidState(**oracle.smoke_params(n))
+    density = np.zeros((n, n))
+    vel = np.zeros((n + 1) * n + n * (n + 1))
+    pressure = np.zeros((n, n))
+    L = _lib.load()
+    for i in range(5):
+        info = _lib.PcgInfo()
+        density[...] = ref.field("density")
+        vel[...] = ref.field("vel")
+        _lib.check(L.pano_fluid_step_host(U.ctx().handle, C.byref(params), n, n, density.ctypes.data_as(C.c_void_p),
+                                          vel.ctypes.data_as(C.c_void_p), pressure.ctypes.data_as(C.c_void_p), C.byref(info)))
+        o = ref.step()
+        assert abs(info.iterations - o["iterations"]) <= 2
+        assert np.array_equal(density, ref.field("density"))
+        if info.iterations == o["iterations"]:
+            assert _close(vel, ref.field("vel"), 1e-5) and _close(pressure, ref.field("pressure"), 1e-5)
+
+
+def test_step_argument_errors():
+    from tests import gpu_util as U
+    import panopaea_b200 as P
+    from panopaea_b200 import fluid
+    with pytest.raises(P.PanoError):
+        fluid.DecFluid(h=64, w=64, ctx=U.ctx()).step()       # default rectangles exceed a 64^2 grid -> index panic
+    sim = fluid.DecFluid(**fluid.smoke_params(128), ctx=U.ctx())
+    sim.params.precond = 7
+    with pytest.raises(P.PanoError):
+        sim.step()
