@@ -213,8 +213,15 @@ def advect_mac(h, w, src, timestep, vel):
     return dst
 
 
+def _check_rect(h, w, rect):
+    y0, y1, x0, x1 = rect
+    if y1 > y0 and x1 > x0 and (y1 > h or x1 > w or y0 < 0 or x0 < 0):
+        raise IndexError(f"rectangle {rect} exceeds the {h}x{w} grid: the reference's vy[(y,x)] / vx[(y,x)] would panic")
+
+
 def laplacian_closure(h, w, p, timestep, obstacle=(0, 0, 0, 0)):
     """A(p) of examples/dec_fluid.rs:100-119 (vel_temp boundary edges zero as after :89)."""
+    _check_rect(h, w, obstacle)
     p = _arr(p)
     sfx, real = _sfx(p.dtype)
     n1 = num_elem_1(h, w)
@@ -238,6 +245,7 @@ class PcgResult:
 
 def pcg_grid_laplacian(h, w, b, max_iterations, threshold, timestep, obstacle=(0, 0, 0, 0)):
     """pcg.rs:14-82 driven with the dec_fluid Laplacian closure."""
+    _check_rect(h, w, obstacle)
     b = _arr(b)
     sfx, real = _sfx(b.dtype)
     L = lib()
@@ -275,6 +283,8 @@ class FluidState:
         self.sfx, self.real = _sfx(dtype)
         self.dtype = np.dtype(dtype)
         self.h, self.w = h, w
+        _check_rect(h, w, inflow)
+        _check_rect(h, w, obstacle)
         P = _params_type(self.real)
         self._params = P(h, w, timestep, threshold, max_iterations, Rect(*inflow), inflow_density,
                          inflow_vy, Rect(*obstacle))

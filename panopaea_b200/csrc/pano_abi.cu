@@ -314,6 +314,14 @@ int pano_check_grid(const pano_field *a, const pano_field *b, const char *what) 
     return PANO_OK;
 }
 
+int pano_check_rect_within(const pano_rect &r, size_t rows, size_t cols, const char *what) {
+    if (r.y0 < 0 || r.x0 < 0 || r.y1 < r.y0 || r.x1 < r.x0) PANO_FAIL(PANO_ERR_INVALID, "%s: malformed rectangle", what);
+    if (r.y1 > r.y0 && r.x1 > r.x0 && ((size_t)r.y1 > rows || (size_t)r.x1 > cols))
+        PANO_FAIL(PANO_ERR_SHAPE, "%s: rectangle [%lld,%lld)x[%lld,%lld) exceeds the %zux%zu grid (the reference would panic on the index)",
+                  what, (long long)r.y0, (long long)r.y1, (long long)r.x0, (long long)r.x1, rows, cols);
+    return PANO_OK;
+}
+
 int pano_activate(pano_ctx *ctx) {
     PANO_CUDA(cudaSetDevice(ctx->device));
     return PANO_OK;

@@ -352,6 +352,7 @@ extern "C" int pano_pcg_solve(int precond, pano_field *x, const pano_field *b, i
         for (int j = 0; j < i; ++j)
             if (all[i]->d == all[j]->d) PANO_FAIL(PANO_ERR_INVALID, "pano_pcg_solve: %s aliases %s", names[i], names[j]);
     }
+    PANO_TRY(pano_check_rect_within(obstacle, x->h, x->w, "pano_pcg_solve(obstacle)"));
     pano_ctx *ctx = x->ctx;
     PANO_TRY(pano_activate(ctx));
     return pano_cg_solve_raw(ctx, x->dtype, x->d, b->d, residual->d, search->d, auxiliary->d, x->h, x->w, max_iterations,

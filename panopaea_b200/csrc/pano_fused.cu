@@ -171,8 +171,10 @@ int pano_advect_launch(pano_ctx *ctx, int dtype, void *q_dst, void *vel_dst, con
     return pano_after_launch(ctx, "advect");
 }
 
-// internal: b = -div(vel); d_scalars[0] = max|b|, d_scalars[1] = b.b  (no sync)
-int pano_neg_divergence_launch(pano_ctx *ctx, int dtype, void *b, const void *vel, size_t h, size_t w, pano_rect obstacle) {
+// internal: b = -div(vel).  want_scalars: also d_scalars[0] = max|b|, d_scalars[1] = b.b (no sync); the
+// step does not need them because the CG kernel reduces max|b| and b.b itself in its first pass.
+int pano_neg_divergence_launch(pano_ctx *ctx, int dtype, void *b, const void *vel, size_t h, size_t w, pano_rect obstacle,
+                               bool want_scalars) {
     dim3 g = grid2d((int)h, (int)w);
     const int nb = (int)(g.x * g.y);
     PANO_TRY(pano_ensure_partials(ctx, 2 * (size_t)nb));
@@ -185,6 +187,7 @@ int pano_neg_divergence_launch(pano_ctx *ctx, int dtype, void *b, const void *ve
         k_neg_divergence<float><<<g, kThreads, 0, ctx->stream>>>((float *)b, (const float *)vel, (int)h, (int)w, m,
                                                                  ctx->d_partials, ctx->d_partials + nb);
     PANO_TRY(pano_after_launch(ctx, "neg_divergence"));
+    if (!want_scalars) return PANO_OK;
     k_reduce_max_dot<<<1, kThreads, 0, ctx->stream>>>(ctx->d_partials, ctx->d_partials + nb, nb, ctx->d_scalars);
     return pano_after_launch(ctx, "neg_divergence(reduce)");
 }
@@ -241,13 +244,14 @@ int pano_neg_divergence(pano_field *b, const pano_field *vel, pano_rect obstacle
     PANO_TRY(pano_check_kind(b, PANO_SIMPLEX2, "pano_neg_divergence(b)"));
     PANO_TRY(pano_check_kind(vel, PANO_SIMPLEX1, "pano_neg_divergence(vel)"));
     PANO_TRY(pano_check_grid(b, vel, "pano_neg_divergence"));
+    PANO_TRY(pano_check_rect_within(obstacle, b->h, b->w, "pano_neg_divergence(obstacle)"));
     pano_ctx *ctx = b->ctx;
     PANO_TRY(pano_activate(ctx));
     if (b->n == 0) {
         if (rhs_max) *rhs_max = 0.0;
         return PANO_OK;
     }
-    PANO_TRY(pano_neg_divergence_launch(ctx, b->dtype, b->d, vel->d, b->h, b->w, obstacle));
+    PANO_TRY(pano_neg_divergence_launch(ctx, b->dtype, b->d, vel->d, b->h, b->w, obstacle, rhs_max != nullptr));
     if (rhs_max) {
         PANO_CUDA(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         PANO_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -261,6 +265,7 @@ int pano_laplacian_apply(pano_field *z, const pano_field *s, double timestep, pa
     PANO_TRY(pano_check_kind(s, PANO_SIMPLEX2, "pano_laplacian_apply(s)"));
     PANO_TRY(pano_check_same(z, s, "pano_laplacian_apply"));
     if (z->d == s->d) PANO_FAIL(PANO_ERR_INVALID, "pano_laplacian_apply: z aliases s");
+    PANO_TRY(pano_check_rect_within(obstacle, z->h, z->w, "pano_laplacian_apply(obstacle)"));
     pano_ctx *ctx = z->ctx;
     PANO_TRY(pano_activate(ctx));
     if (z->n == 0) return PANO_OK;

@@ -103,9 +103,9 @@ int pano_ensure_partials(pano_ctx *ctx, size_t doubles);
 int64_t pano_option(pano_ctx *ctx, const char *key, int64_t dflt);
 
 // internal (non-ABI) entry points shared between translation units
-int pano_cg_solve_fused(pano_ctx *ctx, double *x, const double *b, double *r, double *s, size_t h, size_t w,
-                        int max_iterations, double threshold, double timestep, pano_rect obstacle,
-                        pano_pcg_info *info);
+// the example's rectangle loops index vy[(y,x)] / vx[(y,x)] / d[(y,x)] directly: a rectangle that
+// leaves the (rows, cols) grid panics in the reference, so it is an error here too
+int pano_check_rect_within(const pano_rect &r, size_t rows, size_t cols, const char *what);
 void pano_workspace_free_all(pano_ctx *ctx);
 int pano_phase_mark(pano_ctx *ctx, int phase);     // record event #phase of the current step (no-op unless step_timing)
 int pano_phase_drain(pano_ctx *ctx);               // synchronise and fold recorded events into phase_ms

@@ -13,7 +13,8 @@
 
 int pano_advect_launch(pano_ctx *ctx, int dtype, void *q_dst, void *vel_dst, const void *q_src, const void *mac_src,
                        const void *vel, size_t h, size_t w, double dt);
-int pano_neg_divergence_launch(pano_ctx *ctx, int dtype, void *b, const void *vel, size_t h, size_t w, pano_rect obstacle);
+int pano_neg_divergence_launch(pano_ctx *ctx, int dtype, void *b, const void *vel, size_t h, size_t w, pano_rect obstacle,
+                               bool want_scalars);
 int pano_project_launch(pano_ctx *ctx, int dtype, void *vel, const void *p, size_t h, size_t w, double dt);
 int pano_cg_solve_raw(pano_ctx *ctx, int dtype, void *x, const void *b, void *r, void *s0, void *s1, size_t h, size_t w,
                       int max_iterations, double threshold, double timestep, pano_rect obstacle, pano_pcg_info *info);
@@ -57,13 +58,6 @@ static int get_workspace(pano_ctx *ctx, size_t h, size_t w, PanoWorkspace **out)
     return PANO_OK;
 }
 
-static int check_rect_within(const pano_rect &r, size_t rows, size_t cols, const char *what) {
-    if (r.y0 < 0 || r.x0 < 0 || r.y1 < r.y0 || r.x1 < r.x0) PANO_FAIL(PANO_ERR_INVALID, "%s: malformed rectangle", what);
-    if (r.y1 > r.y0 && r.x1 > r.x0 && ((size_t)r.y1 > rows || (size_t)r.x1 > cols))
-        PANO_FAIL(PANO_ERR_SHAPE, "%s: rectangle exceeds the %zux%zu grid (the reference would panic on the index)", what, rows, cols);
-    return PANO_OK;
-}
-
 extern "C" {
 
 int pano_fluid_step(const pano_step_params *params, pano_field *density, pano_field *vel, pano_field *pressure,
@@ -90,8 +84,8 @@ int pano_fluid_step(const pano_step_params *params, pano_field *density, pano_fi
     const size_t h = density->h, w = density->w;
     if (h < 2 || w < 2) PANO_FAIL(PANO_ERR_SHAPE, "pano_fluid_step: grid %zux%zu below 2x2", h, w);
     // inflow writes density[(y,x)] and vy[(y,x)]; the obstacle zeroes vy[(y,x)] and vx[(y,x)]
-    PANO_TRY(check_rect_within(params->inflow, h, w, "pano_fluid_step(inflow)"));
-    PANO_TRY(check_rect_within(params->obstacle, h, w, "pano_fluid_step(obstacle)"));
+    PANO_TRY(pano_check_rect_within(params->inflow, h, w, "pano_fluid_step(inflow)"));
+    PANO_TRY(pano_check_rect_within(params->obstacle, h, w, "pano_fluid_step(obstacle)"));
     pano_ctx *ctx = density->ctx;
     PANO_TRY(pano_activate(ctx));
     const int dt_ = density->dtype;
@@ -108,7 +102,7 @@ int pano_fluid_step(const pano_step_params *params, pano_field *density, pano_fi
     PANO_TRY(pano_field_swap(vel, vel_temp));
     PANO_TRY(pano_phase_mark(ctx, 2));
     // b = -div  :69-83   (b lives in `temp`, as in the reference)
-    PANO_TRY(pano_neg_divergence_launch(ctx, dt_, temp->d, vel->d, h, w, params->obstacle));
+    PANO_TRY(pano_neg_divergence_launch(ctx, dt_, temp->d, vel->d, h, w, params->obstacle, false));
     PANO_TRY(pano_phase_mark(ctx, 3));
     // pressure solve  :91-119
     PANO_TRY(pano_cg_solve_raw(ctx, dt_, pressure->d, temp->d, residual->d, search->d, auxiliary->d, h, w,

@@ -30,7 +30,7 @@ def main():
         tag = f"{h}x{w}_v{int(vmax)}"
         out[f"advect_{tag}"] = O.advect(h, w, q, 0.05, vel)
         out[f"advect_mac_{tag}"] = O.advect_mac(h, w, vel, 0.05, vel)
-        obstacle = (h // 2, h // 2 + 2, w // 3, w // 3 + 3)
+        obstacle = (h // 2, min(h, h // 2 + 2), w // 3, min(w, w // 3 + 3))
         out[f"lap_{tag}"] = O.laplacian_closure(h, w, q, 0.05, obstacle)
     # shipped example: 128^2, 25 steps; keep iteration counts and field checksums + one row of each field
     S = O.FluidState(**O.smoke_params(128))

@@ -73,7 +73,7 @@ def test_committed_golden_vectors():
         fluid.advect_all(dq, dv, Q, V, 0.05)
         assert np.array_equal(dq.to_host(), z[f"advect_{tag}"])
         assert np.array_equal(dv.view_linear(), z[f"advect_mac_{tag}"])
-        fluid.laplacian_apply(lap, Q, 0.05, (h // 2, h // 2 + 2, w // 3, w // 3 + 3))
+        fluid.laplacian_apply(lap, Q, 0.05, (h // 2, min(h, h // 2 + 2), w // 3, min(w, w // 3 + 3)))
         assert np.array_equal(lap.to_host(), z[f"lap_{tag}"])
 
 
