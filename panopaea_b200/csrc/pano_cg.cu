@@ -293,6 +293,10 @@ int launch_generic(pano_ctx *ctx, CgArgs<T> &args, bool use_cg_loads) {
 
 }  // namespace
 
+bool pano_cg_stream_supported(size_t h, size_t w, const void *x, const void *b, const void *r, const void *s0, const void *s1);
+int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, double *s0, double *s1, size_t h, size_t w,
+                          int max_iterations, double threshold, double timestep, RectI m);
+
 // Solve on raw device pointers.  s0 = search, s1 = auxiliary.  info nullable (non-null => sync).
 int pano_cg_solve_raw(pano_ctx *ctx, int dtype, void *x, const void *b, void *r, void *s0, void *s1, size_t h, size_t w,
                       int max_iterations, double threshold, double timestep, pano_rect obstacle, pano_pcg_info *info) {
@@ -314,7 +318,15 @@ int pano_cg_solve_raw(pano_ctx *ctx, int dtype, void *x, const void *b, void *r,
     }
     const bool cg_loads = pano_option(ctx, "cg_ldcg", 0) != 0;
     const RectI m = pano_clip_rect(obstacle, h + 1, w + 1);
-    if (dtype == PANO_F64) {
+    // kernel choice: "cg_kernel" 0 = auto, 1 = generic (any shape / dtype), 2 = TMA streaming (f64, even width)
+    const int64_t want = pano_option(ctx, "cg_kernel", 0);
+    const bool stream_ok = dtype == PANO_F64 && pano_cg_stream_supported(h, w, x, b, r, s0, s1);
+    if (want == 2 && !stream_ok)
+        PANO_FAIL(PANO_ERR_INVALID, "cg_kernel=2 (TMA streaming) needs f64 fields with an even width (%zux%zu given)", h, w);
+    if (stream_ok && want != 1) {
+        PANO_TRY(pano_cg_stream_launch(ctx, (double *)x, (const double *)b, (double *)r, (double *)s0, (double *)s1, h, w,
+                                       max_iterations, threshold, timestep, m));
+    } else if (dtype == PANO_F64) {
         CgArgs<double> a{(double *)x, (const double *)b, (double *)r, (double *)s0, (double *)s1, (int)h, (int)w,
                          timestep, threshold, max_iterations, m, nullptr, ctx->d_cg,
                          ((int)w + kTileX - 1) / kTileX, ((int)h + kTileY - 1) / kTileY};

@@ -68,6 +68,8 @@ struct pano_ctx {
     double *h_scalars = nullptr;  // pinned, 8 doubles
     PanoCgControl *d_cg = nullptr;
     PanoCgControl *h_cg = nullptr;   // pinned
+    void *d_units = nullptr;         // publish+poll all-reduce units of the persistent kernels
+    unsigned long long launch_epoch = 0;
     // optional per-phase timing of pano_fluid_step ("step_timing" option)
     std::vector<cudaEvent_t> phase_events;   // ring of (PANO_STEP_PHASES + 1) events per slot
     int phase_slots = 0, phase_used = 0;

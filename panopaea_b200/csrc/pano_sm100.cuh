@@ -1,0 +1,117 @@
+// pano_sm100.cuh -- sm_100a building blocks shared by the persistent kernels:
+//   * mbarrier + TMA (cp.async.bulk.tensor) wrappers, written as inline PTX
+//   * bounded waits (a stuck wait raises an error flag instead of hanging the GPU)
+//   * the grid-wide "publish + poll" all-reduce that replaces counter barriers
+#pragma once
+
+#include <cuda.h>   // CUtensorMap (types only; the encode entry point is fetched at run time)
+
+#include "pano_internal.cuh"
+
+namespace pano_sm100 {
+
+constexpr long long kSpinLimit = 1LL << 27;   // polls before a wait gives up (seconds), never reached in a healthy run
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---------------------------------------------------------------------------------- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Returns false if the bounded wait expired or somebody else raised the error flag.
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, volatile unsigned int *err) {
+    long long spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > kSpinLimit || ((spins & 0x3ff) == 0 && *err)) {
+            atomicExch((unsigned int *)err, 1u);
+            return false;
+        }
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------- TMA
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// 2-D tiled load global -> shared, completion signalled on `bar` (complete_tx::bytes).
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+// orders generic-proxy accesses (ld/st) against async-proxy accesses (TMA) of the same memory
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---------------------------------------------------------------------------------- grid all-reduce
+// One 16-byte unit per (value, CTA): {double value, u64 sequence}.  A CTA publishes its partials
+// with single 16-byte stores; every CTA polls every unit until the sequence matches, then reduces
+// the values in a fixed order, so all CTAs obtain bit-identical results.  Publishing, the barrier
+// and the data movement are one L2 round trip (no atomics, no second read of a partials array).
+struct __align__(16) ReduceUnit {
+    double v;
+    unsigned long long seq;
+};
+
+__device__ __forceinline__ void unit_store(ReduceUnit *u, double v, unsigned long long seq) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(u), "l"(__double_as_longlong(v)), "l"(seq) : "memory");
+}
+__device__ __forceinline__ void unit_load(const ReduceUnit *u, double &v, unsigned long long &seq) {
+    long long bits;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(bits), "=l"(seq) : "l"(u) : "memory");
+    v = __longlong_as_double(bits);
+}
+// polls one unit; false on timeout / raised error flag
+__device__ __forceinline__ bool unit_poll(const ReduceUnit *u, unsigned long long seq, double &v, volatile unsigned int *err) {
+    unsigned long long got;
+    long long spins = 0;
+    for (;;) {
+        unit_load(u, v, got);
+        if (got == seq) return true;
+        if (++spins > kSpinLimit || ((spins & 0x3ff) == 0 && *err)) {
+            atomicExch((unsigned int *)err, 1u);
+            return false;
+        }
+    }
+}
+
+// fixed-order sum / max of n values held in shared memory, executed by one full warp
+__device__ __forceinline__ double warp_fixed_sum(const double *vals, int n, int lane) {
+    double a = 0;
+    for (int i = lane; i < n; i += 32) a += vals[i];
+    return warp_sum(a);
+}
+__device__ __forceinline__ double warp_fixed_max(const double *vals, int n, int lane) {
+    double a = 0;
+    for (int i = lane; i < n; i += 32) a = vals[i] > a ? vals[i] : a;
+    return warp_max(a);
+}
+
+}  // namespace pano_sm100
+
+// host side: fetch cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+int pano_make_tensor_map_2d(CUtensorMap *map, const void *base, size_t elem_bytes, uint64_t width, uint64_t height,
+                            uint64_t row_pitch_bytes, uint32_t box_w, uint32_t box_h);

@@ -10,7 +10,16 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-SIZES = [(3, 3), (5, 7), (17, 33), (24, 20), (64, 48), (128, 128), (300, 200)]
+SIZES = [(3, 3), (5, 7), (17, 33), (24, 20), (64, 48), (128, 128), (300, 200), (97, 130), (520, 776)]
+# kernel variants: the generic persistent kernel (any shape), the same with L2-only loads, and "auto"
+# (the TMA streaming kernel whenever the width is even, else generic)
+VARIANTS = {"generic": dict(cg_kernel=1, cg_ldcg=0), "generic_ldcg": dict(cg_kernel=1, cg_ldcg=1), "auto": dict(cg_kernel=0, cg_ldcg=0)}
+
+
+def _set_variant(name):
+    from tests import gpu_util as U
+    for k, v in VARIANTS[name].items():
+        U.ctx().set_option(k, v)
 
 
 def _solve(grid, b, max_it, thr, dt, obstacle):
@@ -23,11 +32,11 @@ def _solve(grid, b, max_it, thr, dt, obstacle):
     return info, x.to_host(), r.to_host(), s.to_host()
 
 
-@pytest.mark.parametrize("ldcg", [0, 1])
+@pytest.mark.parametrize("variant", list(VARIANTS))
 @pytest.mark.parametrize("h,w", SIZES)
-def test_fused_cg_vs_oracle(oracle, h, w, ldcg):
+def test_fused_cg_vs_oracle(oracle, h, w, variant):
     from tests import gpu_util as U
-    U.ctx().set_option("cg_ldcg", ldcg)
+    _set_variant(variant)
     try:
         grid = U.grid(h, w)
         obstacle = U.default_obstacle(h, w) if h > 4 else (0, 0, 0, 0)
@@ -49,32 +58,75 @@ def test_fused_cg_vs_oracle(oracle, h, w, ldcg):
             assert np.allclose(r, want.residual, rtol=0, atol=1e-6 * max(1.0, np.abs(b).max()))
             assert np.allclose(s, want.search, rtol=0, atol=1e-6 * max(1.0, np.abs(want.search).max()))
     finally:
-        U.ctx().set_option("cg_ldcg", 0)
+        _set_variant("auto")
 
 
-def test_early_out_leaves_scratch_untouched(oracle):
+def test_streaming_kernel_requires_even_width():
+    from tests import gpu_util as U
+    import panopaea_b200 as P
+    grid = U.grid(16, 33)
+    U.ctx().set_option("cg_kernel", 2)
+    try:
+        with pytest.raises(P.PanoError):
+            _solve(grid, np.ones((16, 33)), 10, 0.1, 0.05, (0, 0, 0, 0))
+    finally:
+        U.ctx().set_option("cg_kernel", 0)
+
+
+@pytest.mark.parametrize("h,w", [(128, 128), (300, 200), (520, 776)])
+def test_kernel_variants_agree(oracle, h, w):
+    """generic and TMA-streaming kernels run the same arithmetic; only the reduction order differs."""
+    from tests import gpu_util as U
+    grid = U.grid(h, w)
+    obstacle = U.default_obstacle(h, w)
+    b = U.consistent_rhs(oracle, h, w, obstacle, seed=11)
+    out = {}
+    try:
+        for name in ("generic", "auto"):
+            _set_variant(name)
+            out[name] = _solve(grid, b, 100, 0.1, 0.05, obstacle)
+    finally:
+        _set_variant("auto")
+    (ia, xa, ra, sa), (ib, xb, rb, sb) = out["generic"], out["auto"]
+    assert abs(ia["iterations"] - ib["iterations"]) <= 1
+    if ia["iterations"] == ib["iterations"]:
+        for u, v in ((xa, xb), (ra, rb), (sa, sb)):
+            assert np.allclose(u, v, rtol=0, atol=1e-8 * max(1.0, np.abs(u).max()))
+
+
+@pytest.mark.parametrize("variant", ["generic", "auto"])
+def test_early_out_leaves_scratch_untouched(oracle, variant):
     """pcg.rs:35-38: max|b| < threshold -> x = 0 and nothing else is written."""
     from tests import gpu_util as U
-    h, w = 40, 24
+    h, w = 40, 136
     grid = U.grid(h, w)
     b = np.random.default_rng(1).uniform(-0.05, 0.05, (h, w))
-    info, x, r, s = _solve(grid, b, 100, 0.1, 0.05, (0, 0, 0, 0))
+    _set_variant(variant)
+    try:
+        info, x, r, s = _solve(grid, b, 100, 0.1, 0.05, (0, 0, 0, 0))
+    finally:
+        _set_variant("auto")
     assert info["iterations"] == -1 and info["applies"] == 0
     assert info["final_residual"] == np.abs(b).max() == info["rhs_max"]
     assert not x.any()
     assert np.all(r == 123.0) and np.all(s == 123.0)
 
 
+@pytest.mark.parametrize("variant", ["generic", "auto"])
 @pytest.mark.parametrize("max_it", [1, 2, 3, 7])
-def test_exhausted_iterations_match_reference_state(oracle, max_it):
+def test_exhausted_iterations_match_reference_state(oracle, max_it, variant):
     """When the loop runs out (pcg.rs:48), the reference has still updated `search` (pcg.rs:72-77)."""
     from tests import gpu_util as U
-    h, w = 33, 47
+    h, w = 70, 136
     grid = U.grid(h, w)
     obstacle = U.default_obstacle(h, w)
     b = U.consistent_rhs(oracle, h, w, obstacle, seed=3)
     want = oracle.pcg_grid_laplacian(h, w, b, max_it, 1e-9, 0.05, obstacle)
-    info, x, r, s = _solve(grid, b, max_it, 1e-9, 0.05, obstacle)
+    _set_variant(variant)
+    try:
+        info, x, r, s = _solve(grid, b, max_it, 1e-9, 0.05, obstacle)
+    finally:
+        _set_variant("auto")
     assert want.iterations == max_it and info["iterations"] == max_it and info["applies"] == max_it
     sc = np.abs(b).max()
     assert np.allclose(x, want.x, rtol=0, atol=1e-9 * max(1.0, np.abs(want.x).max()))
