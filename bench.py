@@ -217,6 +217,9 @@ def run_ours(args, rank, world, local_rank):
 
     n = args.n or 1024
     ctx = P.Context(local_rank)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     sim = fluid.DecFluid(**fluid.smoke_params(n), ctx=ctx)
     cells = n * n
     K, W = args.steps, max(args.warmup, 3)
@@ -322,7 +325,7 @@ def run_ours(args, rank, world, local_rank):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"2D smoke plume {n}x{n} MAC grid, advect + pressure projection (dec_fluid.rs loop body)",
                            "grid": [n, n], "cg_iterations_per_step": iters, "cg_max_iterations": 100,
-                           "threshold": 0.1, "timestep": 0.05, "parallelism": f"slab{world}" if multi else "single",
+                           "threshold": 0.1, "timestep": 0.05, "options": args.opt, "parallelism": f"slab{world}" if multi else "single",
                            "l2": "flushed before every timed step (302 MB memset); within a step the CG re-reads its working set"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "steps": e2e_steps,
                         "h2d_bytes_per_step": (cells + n1) * 8, "d2h_bytes_per_step": (2 * cells + n1) * 8,
@@ -345,6 +348,7 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="grid size override (multiple of 128)")
     ap.add_argument("--cpu-variant", default="faithful", choices=["faithful", "parallel"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (e.g. cg_kernel=1)")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":

@@ -5,12 +5,17 @@
 //   P1: s' = r + beta*s on every tile INCLUDING its one-cell halo, z = A s' (not stored), z.s'
 //   P2: z recomputed from s', x += alpha s', r -= alpha z, r.r, max|r|
 // What changes is the data movement:
-//   * a producer warp streams (TH+2)x(TW+2) halo boxes of r / s and TH x TW boxes of r / x into a
+//   * a producer warp streams (TH+2)x(TW+4) halo boxes of r / s and TH x TW boxes of r / x into a
 //     4-stage shared-memory ring with cp.async.bulk.tensor (TMA), completion on mbarriers;
 //     out-of-range box elements are zero-filled by the TMA unit, which is exactly what a closed
 //     (Neumann) wall edge needs
-//   * 8 consumer warps run the stencil out of shared memory with a vertical register window
-//     (3 shared loads per cell) and write results with coalesced global stores
+//   * 8 consumer warps run the stencil out of shared memory: each thread owns 2 adjacent columns
+//     x 4 rows with a vertical register window, 128-bit shared loads and 128-bit global stores;
+//     s' is formed in registers (the staged boxes are never written, so no proxy fence is needed
+//     before the TMA unit refills a stage)
+//   * boxes that do not depend on the other CTAs' work of the current phase (s_old in P1, r and x
+//     in P2) are prefetched BEFORE the grid-wide reduction completes, so the pipeline does not
+//     drain at phase boundaries
 //   * tiles that touch neither a wall nor the obstacle take a branch-free path
 //   * the two grid-wide reductions per iteration use the publish+poll all-reduce of
 //     pano_sm100.cuh: one L2 round trip, deterministic, no atomics
@@ -25,12 +30,17 @@ using namespace pano_sm100;
 namespace {
 
 constexpr int TH = 32, TW = 64;                 // tile (cells)
-constexpr int BH = TH + 2, BW = TW + 2;         // halo box
-constexpr int kBoxElems = BH * BW;              // 2244 (even)
-constexpr int kHaloBoxBytes = kBoxElems * 8;    // 17952 = TMA transaction size
-constexpr int kHaloSlot = 18048;                // rounded up to a multiple of 128
+// Halo box: one row above/below, TWO columns left/right.  Measured on B200: cp.async.bulk.tensor
+// traps ("illegal instruction") unless coordinate0 * sizeof(element) is a multiple of 16 bytes, so
+// an f64 box must start on an even column; tx0 - 2 is even, tx0 - 1 is not.  The interior then
+// starts at box column kHX = 2, which also keeps it 16-byte aligned in shared memory.
+constexpr int kHX = 2;
+constexpr int BH = TH + 2, BW = TW + 2 * kHX;   // 34 x 68
+constexpr int kBoxElems = BH * BW;              // 2312 (even)
+constexpr int kHaloBoxBytes = kBoxElems * 8;    // 18496 = TMA transaction size
+constexpr int kHaloSlot = 18560;                // rounded up to a multiple of 128
 constexpr int kIntBoxBytes = TH * TW * 8;       // 16384
-constexpr int kStageBytes = 2 * kHaloSlot + kIntBoxBytes;   // 52480
+constexpr int kStageBytes = 2 * kHaloSlot + kIntBoxBytes;   // 53504
 constexpr int kStages = 4;
 constexpr int kConsumers = 256, kConsumerWarps = 8;
 constexpr int kThreads = kConsumers + 32;       // + one producer warp
@@ -126,85 +136,128 @@ __device__ __forceinline__ bool grid_allreduce(const StreamArgs &a, Tail *tl, un
 }
 
 // ------------------------------------------------------------------------------ tile kernels
-// Consumer warp `wid` owns columns 32*(wid&1) + lane and rows 8*(wid>>1) .. +7 of the tile.
-// S: halo box (BH x BW), cell (ty, tx) at S[(ty+1)*BW + tx+1].
+// Consumer warp `wid` owns rows kRows*wid .. +kRows-1 of the tile; lane owns columns 2*lane, 2*lane+1.
+// S / R: halo boxes (BH x BW), cell (ty, tx) at [(ty+1)*BW + tx + kHX]; 16-byte aligned pairs.
+constexpr int kRows = TH / kConsumerWarps;   // 4
+
+struct Open4 { bool n, s, w, e; };
+__device__ __forceinline__ Open4 open_edges(const StreamArgs &a, int gy, int gx) {
+    Open4 o;
+    o.n = gy > 0 && !in_rect(a.m, gy, gx);
+    o.s = gy < a.h - 1 && !in_rect(a.m, gy + 1, gx);
+    o.w = gx > 0 && !in_rect(a.m, gy, gx);
+    o.e = gx < a.w - 1 && !in_rect(a.m, gy, gx + 1);
+    return o;
+}
+
+// P1: s' = r + beta*s (kFirst: s' = b, nothing stored), z = A s', accumulate z.s' (+ b.b, max|b|)
 template <bool kFast, bool kFirst>
-__device__ __forceinline__ void tile_p1(const StreamArgs &a, const double *S, double *s_dst, int ty0, int tx0,
-                                        double &acc_zs, double &acc_bb, double &acc_bmax) {
+__device__ __forceinline__ void tile_p1(const StreamArgs &a, const double *S, const double *R, double *s_dst, int ty0,
+                                        int tx0, double beta, double &acc_zs, double &acc_bb, double &acc_bmax) {
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int col = (wid & 1) * 32 + lane, row0 = (wid >> 1) * 8;
+    const int col = 2 * lane, row0 = wid * kRows;
     const int gx = tx0 + col;
-    const double *p = S + (row0 + 1) * BW + col + 1;
-    double up = p[-BW], c = p[0];
+    const double *ps = S + (row0 + 1) * BW + col + kHX;
+    const double *pr = R + (row0 + 1) * BW + col + kHX;
+    auto sp2 = [&](int off) -> double2 {
+        double2 sv = *reinterpret_cast<const double2 *>(ps + off);
+        if (kFirst) return sv;
+        const double2 rv = *reinterpret_cast<const double2 *>(pr + off);
+        sv.x = rv.x + beta * sv.x;
+        sv.y = rv.y + beta * sv.y;
+        return sv;
+    };
+    auto sp1 = [&](int off) -> double {
+        const double sv = ps[off];
+        if (kFirst) return sv;
+        return pr[off] + beta * sv;
+    };
+    double2 up = sp2(-BW), c = sp2(0);
 #pragma unroll
-    for (int k = 0; k < 8; ++k, p += BW) {
-        const double dn = p[BW], wv = p[-1], ev = p[1];
+    for (int k = 0; k < kRows; ++k) {
+        const double2 dn = sp2((k + 1) * BW);
+        const double wv = sp1(k * BW - 1), ev = sp1(k * BW + 2);
         const int gy = ty0 + row0 + k;
-        double z;
+        double z0, z1;
+        bool valid = true;
         if (kFast) {
-            z = pano::laplacian_cell<double>(c, up, dn, wv, ev, true, true, true, true, a.dt);
+            z0 = pano::laplacian_cell<double>(c.x, up.x, dn.x, wv, c.y, true, true, true, true, a.dt);
+            z1 = pano::laplacian_cell<double>(c.y, up.y, dn.y, c.x, ev, true, true, true, true, a.dt);
         } else {
-            const bool valid = gy < a.h && gx < a.w;
-            if (!valid) {
-                up = c;
-                c = dn;
-                continue;
-            }
-            const bool oN = gy > 0 && !in_rect(a.m, gy, gx), oS = gy < a.h - 1 && !in_rect(a.m, gy + 1, gx);
-            const bool oW = gx > 0 && !in_rect(a.m, gy, gx), oE = gx < a.w - 1 && !in_rect(a.m, gy, gx + 1);
-            z = pano::laplacian_cell<double>(c, up, dn, wv, ev, oN, oS, oW, oE, a.dt);
+            valid = gy < a.h && gx < a.w;          // the width is even: both columns are valid together
+            const Open4 o0 = open_edges(a, gy, gx), o1 = open_edges(a, gy, gx + 1);
+            z0 = pano::laplacian_cell<double>(c.x, up.x, dn.x, wv, c.y, o0.n, o0.s, o0.w, o0.e, a.dt);
+            z1 = pano::laplacian_cell<double>(c.y, up.y, dn.y, c.x, ev, o1.n, o1.s, o1.w, o1.e, a.dt);
         }
-        acc_zs = acc_zs + z * c;
-        if (kFirst) {
-            const double ab = c < 0 ? -c : c;
-            acc_bmax = ab > acc_bmax ? ab : acc_bmax;
-            acc_bb = acc_bb + c * c;
-        } else {
-            s_dst[(size_t)gy * a.w + gx] = c;
+        if (valid) {
+            acc_zs = acc_zs + z0 * c.x;
+            acc_zs = acc_zs + z1 * c.y;
+            if (kFirst) {
+                const double a0 = c.x < 0 ? -c.x : c.x, a1 = c.y < 0 ? -c.y : c.y;
+                acc_bmax = a0 > acc_bmax ? a0 : acc_bmax;
+                acc_bmax = a1 > acc_bmax ? a1 : acc_bmax;
+                acc_bb = acc_bb + c.x * c.x;
+                acc_bb = acc_bb + c.y * c.y;
+            } else {
+                *reinterpret_cast<double2 *>(s_dst + (size_t)gy * a.w + gx) = c;
+            }
         }
         up = c;
         c = dn;
     }
 }
 
+// P2: z recomputed from s', x += alpha s', r -= alpha z, accumulate r.r and max|r|
 template <bool kFast, bool kFirst>
 __device__ __forceinline__ void tile_p2(const StreamArgs &a, const double *S, const double *R, const double *X, int ty0,
                                         int tx0, double alpha, double &acc_rr, double &acc_rmax) {
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int col = (wid & 1) * 32 + lane, row0 = (wid >> 1) * 8;
+    const int col = 2 * lane, row0 = wid * kRows;
     const int gx = tx0 + col;
     const double nalpha = -alpha;
-    const double *p = S + (row0 + 1) * BW + col + 1;
-    double up = p[-BW], c = p[0];
+    const double *ps = S + (row0 + 1) * BW + col + kHX;
+    double2 up = *reinterpret_cast<const double2 *>(ps - BW), c = *reinterpret_cast<const double2 *>(ps);
 #pragma unroll
-    for (int k = 0; k < 8; ++k, p += BW) {
-        const double dn = p[BW], wv = p[-1], ev = p[1];
+    for (int k = 0; k < kRows; ++k) {
+        const double2 dn = *reinterpret_cast<const double2 *>(ps + (k + 1) * BW);
+        const double wv = ps[k * BW - 1], ev = ps[k * BW + 2];
         const int gy = ty0 + row0 + k;
-        double z;
+        double z0, z1;
+        bool valid = true;
         if (kFast) {
-            z = pano::laplacian_cell<double>(c, up, dn, wv, ev, true, true, true, true, a.dt);
+            z0 = pano::laplacian_cell<double>(c.x, up.x, dn.x, wv, c.y, true, true, true, true, a.dt);
+            z1 = pano::laplacian_cell<double>(c.y, up.y, dn.y, c.x, ev, true, true, true, true, a.dt);
         } else {
-            const bool valid = gy < a.h && gx < a.w;
-            if (!valid) {
-                up = c;
-                c = dn;
-                continue;
-            }
-            const bool oN = gy > 0 && !in_rect(a.m, gy, gx), oS = gy < a.h - 1 && !in_rect(a.m, gy + 1, gx);
-            const bool oW = gx > 0 && !in_rect(a.m, gy, gx), oE = gx < a.w - 1 && !in_rect(a.m, gy, gx + 1);
-            z = pano::laplacian_cell<double>(c, up, dn, wv, ev, oN, oS, oW, oE, a.dt);
+            valid = gy < a.h && gx < a.w;
+            const Open4 o0 = open_edges(a, gy, gx), o1 = open_edges(a, gy, gx + 1);
+            z0 = pano::laplacian_cell<double>(c.x, up.x, dn.x, wv, c.y, o0.n, o0.s, o0.w, o0.e, a.dt);
+            z1 = pano::laplacian_cell<double>(c.y, up.y, dn.y, c.x, ev, o1.n, o1.s, o1.w, o1.e, a.dt);
         }
-        const size_t gi = (size_t)gy * a.w + gx;
-        const int ti = (row0 + k) * TW + col;
-        const double xo = kFirst ? 0.0 : X[ti];
-        const double ro = kFirst ? c : R[ti];            // iteration 0: r = s = b (pcg.rs:40-42)
-        a.x[gi] = xo + alpha * c;                        // pcg.rs:55
-        const double rn = ro + nalpha * z;               // pcg.rs:56
-        a.r[gi] = rn;
-        if (kFirst) a.s0[gi] = c;
-        const double ar = rn < 0 ? -rn : rn;
-        acc_rmax = ar > acc_rmax ? ar : acc_rmax;
-        acc_rr = acc_rr + rn * rn;
+        if (valid) {
+            const size_t gi = (size_t)gy * a.w + gx;
+            const int ti = (row0 + k) * TW + col;
+            double2 xo, ro;
+            if (kFirst) {
+                xo = make_double2(0.0, 0.0);
+                ro = c;                                          // iteration 0: r = s = b (pcg.rs:40-42)
+            } else {
+                xo = *reinterpret_cast<const double2 *>(X + ti);
+                ro = *reinterpret_cast<const double2 *>(R + ti);
+            }
+            double2 xn, rn;
+            xn.x = xo.x + alpha * c.x;                           // pcg.rs:55
+            xn.y = xo.y + alpha * c.y;
+            rn.x = ro.x + nalpha * z0;                           // pcg.rs:56
+            rn.y = ro.y + nalpha * z1;
+            *reinterpret_cast<double2 *>(a.x + gi) = xn;
+            *reinterpret_cast<double2 *>(a.r + gi) = rn;
+            if (kFirst) *reinterpret_cast<double2 *>(a.s0 + gi) = c;
+            const double a0 = rn.x < 0 ? -rn.x : rn.x, a1 = rn.y < 0 ? -rn.y : rn.y;
+            acc_rmax = a0 > acc_rmax ? a0 : acc_rmax;
+            acc_rmax = a1 > acc_rmax ? a1 : acc_rmax;
+            acc_rr = acc_rr + rn.x * rn.x;
+            acc_rr = acc_rr + rn.y * rn.y;
+        }
         up = c;
         c = dn;
     }
@@ -249,38 +302,84 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
         tma_prefetch_desc(&a.m_x_int);
         unsigned n = 0, ngo = 0;
         int cur = 0;   // index of the s buffer that RECEIVES s' in P1 (0: s0, 1: s1)
-        for (int it = 0; it < a.max_iter; ++it) {
-            const bool first = it == 0;
-            for (int phase = 0; phase < 2; ++phase) {
-                fence_proxy_async();
-                for (int jj = 0; jj < n_my; ++jj, ++n) {
-                    const int j = (phase == 1 && a.zigzag) ? n_my - 1 - jj : jj;
-                    const int t = blockIdx.x + j * G;
-                    const int tx0 = (t % a.tiles_x) * TW, ty0 = (t / a.tiles_x) * TH;
-                    const int st = n % kStages;
-                    if (!mbar_wait(&tl->empty[st], ((n / kStages) & 1) ^ 1, err)) return;
-                    unsigned char *base = smem + st * kStageBytes;
-                    if (first) {
-                        mbar_arrive_expect_tx(&tl->full[st], kHaloBoxBytes);
-                        tma_load_2d(base, &a.m_b_halo, &tl->full[st], tx0 - 1, ty0 - 1);
-                    } else if (phase == 0) {
-                        mbar_arrive_expect_tx(&tl->full[st], 2 * kHaloBoxBytes);
-                        tma_load_2d(base, cur ? &a.m_s0_halo : &a.m_s1_halo, &tl->full[st], tx0 - 1, ty0 - 1);   // s (old)
-                        tma_load_2d(base + kHaloSlot, &a.m_r_halo, &tl->full[st], tx0 - 1, ty0 - 1);
-                    } else {
-                        mbar_arrive_expect_tx(&tl->full[st], kHaloBoxBytes + 2 * kIntBoxBytes);
-                        tma_load_2d(base, cur ? &a.m_s1_halo : &a.m_s0_halo, &tl->full[st], tx0 - 1, ty0 - 1);   // s'
-                        tma_load_2d(base + kHaloSlot, &a.m_r_int, &tl->full[st], tx0, ty0);
-                        tma_load_2d(base + 2 * kHaloSlot, &a.m_x_int, &tl->full[st], tx0, ty0);
-                    }
+        // Loads of one tile are split in two groups: `indep` boxes do not depend on what other CTAs
+        // write in the phase that is just ending and may be issued before its reduction completes;
+        // `dep` boxes may only be issued after it (mbarrier `go`).
+        auto tile_of = [&](int phase, int jj, int &tx0, int &ty0) {
+            const int j = (phase == 1 && a.zigzag) ? n_my - 1 - jj : jj;
+            const int t = blockIdx.x + j * G;
+            tx0 = (t % a.tiles_x) * TW;
+            ty0 = (t / a.tiles_x) * TH;
+        };
+        auto issue = [&](int it_, int phase, int cur_, unsigned nn, int tx0, int ty0, bool indep, bool dep) {
+            const bool first = it_ == 0;
+            const int st = nn % kStages;
+            unsigned char *base = smem + st * kStageBytes;
+            uint64_t *bar = &tl->full[st];
+            if (first) {                                   // b never changes: everything is independent
+                if (indep) {
+                    mbar_arrive_expect_tx(bar, kHaloBoxBytes);
+                    tma_load_2d(base, &a.m_b_halo, bar, tx0 - kHX, ty0 - 1);
                 }
-                // the next phase reads what other CTAs wrote in this one: wait for the grid-wide reduction
-                if (!mbar_wait(&tl->go, ngo & 1, err)) return;
-                ++ngo;
-                if (!*(volatile int *)&tl->cont) return;
+            } else if (phase == 0) {
+                if (indep) {
+                    mbar_arrive_expect_tx(bar, 2 * kHaloBoxBytes);
+                    // s (old) is not touched by P2 -- except in iteration 0, whose P2 materialises s0 = b;
+                    // iteration 1 therefore reads b itself (s = b, pcg.rs:40-42), which never changes
+                    tma_load_2d(base, it_ == 1 ? &a.m_b_halo : (cur_ ? &a.m_s0_halo : &a.m_s1_halo), bar, tx0 - kHX, ty0 - 1);
+                }
+                if (dep) tma_load_2d(base + kHaloSlot, &a.m_r_halo, bar, tx0 - kHX, ty0 - 1);        // r: ring written by neighbours in P2
+            } else {
+                if (indep) {
+                    mbar_arrive_expect_tx(bar, kHaloBoxBytes + 2 * kIntBoxBytes);
+                    tma_load_2d(base + kHaloSlot, &a.m_r_int, bar, tx0, ty0);                        // own tiles, untouched by P1
+                    tma_load_2d(base + 2 * kHaloSlot, &a.m_x_int, bar, tx0, ty0);
+                }
+                if (dep) tma_load_2d(base, cur_ ? &a.m_s1_halo : &a.m_s0_halo, bar, tx0 - kHX, ty0 - 1);  // s': ring written by neighbours in P1
+            }
+        };
+        bool stop = false;
+        for (int it = 0; it < a.max_iter && !stop; ++it) {
+            for (int phase = 0; phase < 2 && !stop; ++phase) {
+                const bool need_go = !(it == 0 && phase == 0);
+                const int npre = need_go ? (n_my < kStages ? n_my : kStages) : 0;
+                int tx0, ty0;
+                // (1) independent boxes of the first tiles, while the previous phase is still finishing
+                for (int jj = 0; jj < npre; ++jj) {
+                    tile_of(phase, jj, tx0, ty0);
+                    if (!mbar_wait(&tl->empty[(n + jj) % kStages], (((n + jj) / kStages) & 1) ^ 1, err)) return;
+                    issue(it, phase, cur, n + jj, tx0, ty0, true, false);
+                }
+                // (2) the previous phase's grid-wide reduction
+                if (need_go) {
+                    if (!mbar_wait(&tl->go, ngo & 1, err)) return;
+                    ++ngo;
+                    stop = !*(volatile int *)&tl->cont;
+                    fence_proxy_async();
+                }
+                // (3) dependent boxes of those tiles (issued even when stopping, so that every armed
+                //     barrier completes and no bulk copy is left in flight when the CTA exits)
+                for (int jj = 0; jj < npre; ++jj) {
+                    tile_of(phase, jj, tx0, ty0);
+                    issue(it, phase, cur, n + jj, tx0, ty0, false, true);
+                }
+                if (stop) {
+                    for (int jj = 0; jj < npre; ++jj)
+                        if (!mbar_wait(&tl->full[(n + jj) % kStages], ((n + jj) / kStages) & 1, err)) return;
+                    return;
+                }
+                // (4) the rest of the phase
+                for (int jj = npre; jj < n_my; ++jj) {
+                    tile_of(phase, jj, tx0, ty0);
+                    if (!mbar_wait(&tl->empty[(n + jj) % kStages], (((n + jj) / kStages) & 1) ^ 1, err)) return;
+                    issue(it, phase, cur, n + jj, tx0, ty0, true, true);
+                }
+                n += n_my;
             }
             cur ^= 1;
         }
+        // the reduction that ends the last phase (nothing follows it)
+        if (!stop) mbar_wait(&tl->go, ngo & 1, err);
         return;
     }
 
@@ -302,26 +401,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
             const int tx0 = (t % a.tiles_x) * TW, ty0 = (t / a.tiles_x) * TH;
             const int st = n % kStages;
             if (!mbar_wait(&tl->full[st], (n / kStages) & 1, err)) return;
-            double *S = reinterpret_cast<double *>(smem + st * kStageBytes);
+            const double *S = reinterpret_cast<const double *>(smem + st * kStageBytes);
+            const double *R = reinterpret_cast<const double *>(smem + st * kStageBytes + kHaloSlot);
             const bool fast = tile_is_fast(a, ty0, tx0);
             if (first) {
-                if (fast) tile_p1<true, true>(a, S, nullptr, ty0, tx0, acc_zs, acc_bb, acc_bmax);
-                else tile_p1<false, true>(a, S, nullptr, ty0, tx0, acc_zs, acc_bb, acc_bmax);
+                if (fast) tile_p1<true, true>(a, S, R, nullptr, ty0, tx0, 0.0, acc_zs, acc_bb, acc_bmax);
+                else tile_p1<false, true>(a, S, R, nullptr, ty0, tx0, 0.0, acc_zs, acc_bb, acc_bmax);
             } else {
-                // s' = r + beta * s over the whole halo box, in place (16-byte shared accesses)
-                double2 *S2 = reinterpret_cast<double2 *>(S);
-                const double2 *R2 = reinterpret_cast<const double2 *>(smem + st * kStageBytes + kHaloSlot);
-                for (int i = tid; i < kBoxElems / 2; i += kConsumers) {
-                    double2 sv = S2[i];
-                    const double2 rv = R2[i];
-                    sv.x = rv.x + beta * sv.x;
-                    sv.y = rv.y + beta * sv.y;
-                    S2[i] = sv;
-                }
-                consumer_sync();
-                if (fast) tile_p1<true, false>(a, S, s_cur, ty0, tx0, acc_zs, acc_bb, acc_bmax);
-                else tile_p1<false, false>(a, S, s_cur, ty0, tx0, acc_zs, acc_bb, acc_bmax);
-                fence_proxy_async();   // this stage was written with st.shared; the TMA unit overwrites it next
+                if (fast) tile_p1<true, false>(a, S, R, s_cur, ty0, tx0, beta, acc_zs, acc_bb, acc_bmax);
+                else tile_p1<false, false>(a, S, R, s_cur, ty0, tx0, beta, acc_zs, acc_bb, acc_bmax);
             }
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&tl->empty[st]);
