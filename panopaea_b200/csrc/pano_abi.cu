@@ -81,6 +81,7 @@ int pano_ctx_destroy(pano_ctx *ctx) {
     cudaFreeHost(ctx->h_scalars);
     cudaFree(ctx->d_cg);
     cudaFree(ctx->d_units);
+    cudaFree(ctx->d_mail);
     cudaFreeHost(ctx->h_cg);
     for (cudaEvent_t e : ctx->phase_events) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ev_start);

@@ -68,6 +68,8 @@ struct pano_ctx {
     double *h_scalars = nullptr;  // pinned, 8 doubles
     PanoCgControl *d_cg = nullptr;
     PanoCgControl *h_cg = nullptr;   // pinned
+    double *d_mail = nullptr;        // boundary-line mailboxes of the SM-resident CG kernel
+    size_t mail_cap = 0;             // in doubles
     void *d_units = nullptr;         // publish+poll all-reduce units of the persistent kernels
     unsigned long long launch_epoch = 0;
     // optional per-phase timing of pano_fluid_step ("step_timing" option)
