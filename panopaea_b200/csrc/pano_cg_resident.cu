@@ -3,13 +3,16 @@
 // 148 SMs x (256 KB registers + 227 KB shared memory) hold the three CG vectors of a grid of up
 // to ~1.2 M cells (1024^2 = BASELINE configs[1]).  One persistent CTA per SM owns a fixed
 // rectangular tile for the whole solve:
-//   x, r, z   live in REGISTERS (each thread owns one column x KR consecutive rows)
-//   s         lives in SHARED memory with a one-cell halo frame
+//   r, z      live in REGISTERS (each thread owns one column x KR consecutive rows)
+//   s, x      live in SHARED memory (s with a one-cell halo frame)
 // and HBM is touched only to read b once and to write x / r / s once at the end.  Per iteration
 //   P1: s' = r + beta*s on the tile and on its halo frame (the frame needs the neighbours' boundary
 //       r values: a 4-line "mailbox" per tile in global memory, served from L2), z = A s', z.s'
 //   P2: x += alpha s', r -= alpha z, r.r, max|r|; boundary r values are posted to the mailbox
 // with the two grid-wide reductions done by the publish+poll all-reduce of pano_sm100.cuh.
+// Everything that crosses CTAs -- reduction partials AND mailbox values -- travels as 16-byte
+// {value, sequence} units written with one store and polled by the reader, so the loop contains
+// no memory fence at all (the NCCL "LL" idea applied to a stencil halo).
 // Arithmetic (expression order, no FMA contraction) is identical to the other two CG kernels
 // (pcg.rs:14-82 with the closure of dec_fluid.rs:100-119); only the reduction order differs.
 #include "pano_cell_math.h"
@@ -20,7 +23,6 @@ using namespace pano_sm100;
 namespace {
 
 constexpr int kThreads = 512, kWarps = 16;
-constexpr int kMaxCtas = 192;
 
 struct ResArgs {
     double *x;
@@ -32,8 +34,8 @@ struct ResArgs {
     RectI m;
     int tw, tw_log2;        // tile width (power of two, 32..512); row groups RG = 512 / tw; tile height = RG * KR
     int tiles_x, tiles_y;
-    double *mail;           // [tiles][2*tw + 2*th]: top row, bottom row, left column, right column of r
-    ReduceUnit *units;      // [2 banks][3 values][kMaxCtas]
+    ReduceUnit *mail;       // [tiles][2*tw + 2*th] {value, seq}: top row, bottom row, left column, right column of r
+    ReduceUnit *units;      // kUnitsTotal units (pano_sm100.cuh)
     unsigned long long seq_base;
     PanoCgControl *ctl;
 };
@@ -45,61 +47,74 @@ struct ResShared {          // placed behind the s tile
     int ok;
 };
 
-__device__ __forceinline__ double cta_sum(double v, double *wsum) {
-    v = warp_sum(v);
+// deterministic CTA reduction of (sum, sum, max) in one pass: 2 barriers for all three values
+__device__ __forceinline__ void cta_reduce3(double &v0, double &v1, double &v2, int nvals, unsigned max_mask, ResShared *sh) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v0 = (max_mask & 1u) ? warp_max(v0) : warp_sum(v0);
+    if (nvals > 1) v1 = (max_mask & 2u) ? warp_max(v1) : warp_sum(v1);
+    if (nvals > 2) v2 = (max_mask & 4u) ? warp_max(v2) : warp_sum(v2);
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+    if (lane == 0) {
+        sh->wsum[0][wid] = v0;
+        if (nvals > 1) sh->wsum[1][wid] = v1;
+        if (nvals > 2) sh->wsum[2][wid] = v2;
+    }
     __syncthreads();
-    double t = 0;
+    double t0 = 0, t1 = 0, t2 = 0;
 #pragma unroll
-    for (int i = 0; i < kWarps; ++i) t += wsum[i];
-    return t;
-}
-__device__ __forceinline__ double cta_max(double v, double *wsum) {
-    v = warp_max(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = 0;
-#pragma unroll
-    for (int i = 0; i < kWarps; ++i) t = wsum[i] > t ? wsum[i] : t;
-    return t;
+    for (int i = 0; i < kWarps; ++i) {
+        const double a0 = sh->wsum[0][i];
+        t0 = (max_mask & 1u) ? (a0 > t0 ? a0 : t0) : t0 + a0;
+        if (nvals > 1) {
+            const double a1 = sh->wsum[1][i];
+            t1 = (max_mask & 2u) ? (a1 > t1 ? a1 : t1) : t1 + a1;
+        }
+        if (nvals > 2) {
+            const double a2 = sh->wsum[2][i];
+            t2 = (max_mask & 4u) ? (a2 > t2 ? a2 : t2) : t2 + a2;
+        }
+    }
+    v0 = t0; v1 = t1; v2 = t2;
 }
 
 // grid-wide all-reduce of up to 3 CTA totals; bit max_mask<k> selects max for value k
 __device__ __forceinline__ bool grid_allreduce(const ResArgs &a, ResShared *sh, unsigned long long n, int nvals, double v0,
                                                double v1, double v2, unsigned max_mask, double *out) {
-    const int G = gridDim.x, tid = threadIdx.x;
-    const unsigned long long seq = a.seq_base + n;
-    ReduceUnit *bank = a.units + (n & 1) * 3 * kMaxCtas;
-    if (tid == 0) {
-        __threadfence();
-        unit_store(bank + 0 * kMaxCtas + blockIdx.x, v0, seq);
-        if (nvals > 1) unit_store(bank + 1 * kMaxCtas + blockIdx.x, v1, seq);
-        if (nvals > 2) unit_store(bank + 2 * kMaxCtas + blockIdx.x, v2, seq);
-    }
-    if (tid < G) {
-        volatile unsigned int *err = &a.ctl->error;
-        bool ok = true;
-        for (int k = 0; k < nvals && ok; ++k) {
-            double v;
-            ok = unit_poll(bank + k * kMaxCtas + tid, seq, v, err);
-            sh->vals[k][tid] = v;
+    return grid_allreduce_units(a.units, a.seq_base + n, (unsigned)(n & 1), nvals, v0, v1, v2, max_mask, sh->vals, sh->out,
+                                &sh->ok, &a.ctl->error, /*fenced=*/false, [] { __syncthreads(); }, out);
+}
+
+// z = A s for the KR cells of one thread's column strip, read from the shared s tile.
+// kMasked = false: every edge of every cell of the strip is open (no select instructions).
+template <int KR, bool kMasked, bool kFirst>
+__device__ __forceinline__ void strip_p1(const double *S, int own0, int P, double dt, unsigned vmask, unsigned mN, unsigned mS,
+                                         unsigned mW, unsigned mE, double (&z)[KR], double &acc_zs, double &acc_bb,
+                                         double &acc_bmax) {
+    double up = S[own0 - P], cur = S[own0];
+#pragma unroll
+    for (int k = 0; k < KR; ++k) {
+        const double dn = S[own0 + (k + 1) * P], wv = S[own0 + k * P - 1], ev = S[own0 + k * P + 1];
+        double zz;
+        bool valid = true;
+        if (kMasked) {
+            valid = (vmask >> k) & 1u;
+            zz = pano::laplacian_cell<double>(cur, up, dn, wv, ev, (mN >> k) & 1u, (mS >> k) & 1u, (mW >> k) & 1u,
+                                              (mE >> k) & 1u, dt);
+        } else {
+            zz = pano::laplacian_cell<double>(cur, up, dn, wv, ev, true, true, true, true, dt);
         }
-        __threadfence();
-        if (!ok) sh->ok = 0;
+        if (valid) {
+            z[k] = zz;
+            acc_zs = acc_zs + zz * cur;
+            if (kFirst) {
+                const double ab = cur < 0 ? -cur : cur;
+                acc_bmax = ab > acc_bmax ? ab : acc_bmax;
+                acc_bb = acc_bb + cur * cur;
+            }
+        }
+        up = cur;
+        cur = dn;
     }
-    __syncthreads();
-    const int wid = tid >> 5, lane = tid & 31;
-    if (wid < nvals) {
-        double r = ((max_mask >> wid) & 1u) ? warp_fixed_max(sh->vals[wid], G, lane) : warp_fixed_sum(sh->vals[wid], G, lane);
-        if (lane == 0) sh->out[wid] = r;
-    }
-    __syncthreads();
-    out[0] = sh->out[0];
-    if (nvals > 1) out[1] = sh->out[1];
-    if (nvals > 2) out[2] = sh->out[2];
-    return sh->ok != 0;
 }
 
 template <int KR>
@@ -108,16 +123,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_resident(const ResArgs a) {
     const int tid = threadIdx.x;
     const int tw = a.tw, RG = kThreads >> a.tw_log2, th = RG * KR;
     const int P = tw + 2;                                    // pitch of the s tile (with halo frame)
-    double *S = smem;
-    ResShared *sh = reinterpret_cast<ResShared *>(smem + (size_t)(th + 2) * P);
+    double *S = smem;                                        // (th + 2) x P   search direction + halo frame
+    double *X = smem + (size_t)(th + 2) * P;                 // th x tw        solution
+    ResShared *sh = reinterpret_cast<ResShared *>(X + (size_t)th * tw);
     const int tile = blockIdx.x, tcx = tile % a.tiles_x, tcy = tile / a.tiles_x;
     const int x0 = tcx * tw, y0 = tcy * th;
     const int c = tid & (tw - 1), rg = tid >> a.tw_log2;
     const int gx = x0 + c, gy0 = y0 + rg * KR;
     const int h = a.h, w = a.w;
     const int own0 = (rg * KR + 1) * P + c + 1;              // S index of this thread's first cell
+    const int xown0 = rg * KR * tw + c;                      // X index of this thread's first cell
     const int mail_stride = 2 * tw + 2 * th;
-    double *my_mail = a.mail + (size_t)tile * mail_stride;
+    ReduceUnit *my_mail = a.mail + (size_t)tile * mail_stride;
+    volatile unsigned int *err = &a.ctl->error;
     if (tid == 0) sh->ok = 1;
 
     // per-thread cell masks: validity and the four "edge open" flags (walls and obstacle), KR bits each
@@ -134,16 +152,36 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_resident(const ResArgs a) {
             if (gx < w - 1 && !in_rect(a.m, gy, gx + 1)) mE |= 1u << k;
         }
     }
+    constexpr unsigned kFull = (1u << KR) - 1u;
+    const bool all_open = (vmask & mN & mS & mW & mE) == kFull;   // this thread's strip needs no masking
     const bool has_n = tcy > 0, has_s = tcy + 1 < a.tiles_y, has_w = tcx > 0, has_e = tcx + 1 < a.tiles_x;
 
-    // ---- state: r (= b), x, z in registers; s = b in shared memory, halo frame from global b
-    double r[KR], x[KR], z[KR];
+    // Each thread serves at most two entries of the halo frame (2*tw + 2*th <= 2*512 for every plan):
+    // where the boundary r value comes from (a neighbour's mailbox unit) and where s' goes in S.
+    const ReduceUnit *h_src[2] = {nullptr, nullptr};
+    int h_dst[2] = {0, 0};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int i = tid + q * kThreads;
+        if (i < tw) {                                   // top frame row <- north tile's bottom row
+            if (has_n) { h_src[q] = my_mail - (size_t)a.tiles_x * mail_stride + tw + i; h_dst[q] = i + 1; }
+        } else if (i < 2 * tw) {                        // bottom frame row <- south tile's top row
+            if (has_s) { h_src[q] = my_mail + (size_t)a.tiles_x * mail_stride + (i - tw); h_dst[q] = (th + 1) * P + (i - tw) + 1; }
+        } else if (i < 2 * tw + th) {                   // left frame column <- west tile's right column
+            if (has_w) { h_src[q] = my_mail - mail_stride + 2 * tw + th + (i - 2 * tw); h_dst[q] = (i - 2 * tw + 1) * P; }
+        } else if (i < 2 * tw + 2 * th) {               // right frame column <- east tile's left column
+            if (has_e) { h_src[q] = my_mail + mail_stride + 2 * tw + (i - 2 * tw - th); h_dst[q] = (i - 2 * tw - th + 1) * P + tw + 1; }
+        }
+    }
+
+    // ---- state: r (= b) and z in registers; s = b and x = 0 in shared memory, halo frame from global b
+    double r[KR], z[KR];
 #pragma unroll
     for (int k = 0; k < KR; ++k) {
         r[k] = ((vmask >> k) & 1u) ? a.b[(size_t)(gy0 + k) * w + gx] : 0.0;
-        x[k] = 0.0;
         z[k] = 0.0;
         S[own0 + k * P] = r[k];
+        X[xown0 + k * tw] = 0.0;
     }
     for (int i = tid; i < 2 * P + 2 * th; i += kThreads) {   // frame: top row, bottom row, left col, right col
         int fy, fx;
@@ -165,66 +203,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_resident(const ResArgs a) {
 
     for (it = 0; it < a.max_iter; ++it) {
         const bool first = it == 0;
+        double acc_zs = 0, acc_bb = 0, acc_bmax = 0;
         // ------------------------------------------------------------------ P1
-        if (!first) {
-            // s' = r + beta*s: own cells from registers, halo frame from the neighbours' mailboxes
+        if (first) {
+            if (all_open) strip_p1<KR, false, true>(S, own0, P, a.dt, vmask, mN, mS, mW, mE, z, acc_zs, acc_bb, acc_bmax);
+            else strip_p1<KR, true, true>(S, own0, P, a.dt, vmask, mN, mS, mW, mE, z, acc_zs, acc_bb, acc_bmax);
+        } else {
+            // boundary r of the neighbours, posted in their previous P2 (already there: one L2 round trip)
+            const unsigned long long want = a.seq_base + (unsigned long long)it;
+            double hv[2] = {0.0, 0.0};
+            bool ok = true;
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+                if (h_src[q]) ok = unit_poll(h_src[q], want, hv[q], err) && ok;
+            if (!ok) sh->ok = 0;
+            // s' = r + beta*s: own cells from registers, halo frame from the mailbox values
 #pragma unroll
             for (int k = 0; k < KR; ++k) S[own0 + k * P] = r[k] + beta * S[own0 + k * P];
-            for (int i = tid; i < 2 * tw + 2 * th; i += kThreads) {
-                double rv;
-                int si;
-                bool have;
-                if (i < tw) {                     // top frame row <- north tile's bottom row
-                    have = has_n;
-                    rv = have ? __ldcg(my_mail - (size_t)a.tiles_x * mail_stride + tw + i) : 0.0;
-                    si = i + 1;
-                } else if (i < 2 * tw) {          // bottom frame row <- south tile's top row
-                    have = has_s;
-                    rv = have ? __ldcg(my_mail + (size_t)a.tiles_x * mail_stride + (i - tw)) : 0.0;
-                    si = (th + 1) * P + (i - tw) + 1;
-                } else if (i < 2 * tw + th) {     // left frame column <- west tile's right column
-                    have = has_w;
-                    rv = have ? __ldcg(my_mail - mail_stride + 2 * tw + th + (i - 2 * tw)) : 0.0;
-                    si = (i - 2 * tw + 1) * P;
-                } else {                          // right frame column <- east tile's left column
-                    have = has_e;
-                    rv = have ? __ldcg(my_mail + mail_stride + 2 * tw + (i - 2 * tw - th)) : 0.0;
-                    si = (i - 2 * tw - th + 1) * P + tw + 1;
-                }
-                if (have) S[si] = rv + beta * S[si];
-            }
-            __syncthreads();
-        }
-        double acc_zs = 0, acc_bb = 0, acc_bmax = 0;
-        {
-            double up = S[own0 - P], cur = S[own0];
 #pragma unroll
-            for (int k = 0; k < KR; ++k) {
-                const double dn = S[own0 + (k + 1) * P], wv = S[own0 + k * P - 1], ev = S[own0 + k * P + 1];
-                const double zz = pano::laplacian_cell<double>(cur, up, dn, wv, ev, (mN >> k) & 1u, (mS >> k) & 1u,
-                                                               (mW >> k) & 1u, (mE >> k) & 1u, a.dt);
-                if ((vmask >> k) & 1u) {
-                    z[k] = zz;
-                    acc_zs = acc_zs + zz * cur;
-                    if (first) {
-                        const double ab = cur < 0 ? -cur : cur;
-                        acc_bmax = ab > acc_bmax ? ab : acc_bmax;
-                        acc_bb = acc_bb + cur * cur;
-                    }
-                }
-                up = cur;
-                cur = dn;
-            }
+            for (int q = 0; q < 2; ++q)
+                if (h_src[q]) S[h_dst[q]] = hv[q] + beta * S[h_dst[q]];
+            __syncthreads();
+            if (all_open) strip_p1<KR, false, false>(S, own0, P, a.dt, vmask, mN, mS, mW, mE, z, acc_zs, acc_bb, acc_bmax);
+            else strip_p1<KR, true, false>(S, own0, P, a.dt, vmask, mN, mS, mW, mE, z, acc_zs, acc_bb, acc_bmax);
         }
-        {
-            const double v0 = cta_sum(acc_zs, sh->wsum[0]);
-            double v1 = 0, v2 = 0;
-            if (first) {
-                v1 = cta_sum(acc_bb, sh->wsum[1]);
-                v2 = cta_max(acc_bmax, sh->wsum[2]);
-            }
-            if (!grid_allreduce(a, sh, nred++, first ? 3 : 1, v0, v1, v2, 0x4u, red)) { failed = true; break; }
-        }
+        cta_reduce3(acc_zs, acc_bb, acc_bmax, first ? 3 : 1, 0x4u, sh);
+        if (!grid_allreduce(a, sh, nred++, first ? 3 : 1, acc_zs, acc_bb, acc_bmax, 0x4u, red)) { failed = true; break; }
         const double zs = red[0];
         if (first) {
             sigma = red[1];                                    // pcg.rs:46
@@ -236,12 +240,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_resident(const ResArgs a) {
         alpha = sigma / zs;                                    // pcg.rs:53
         const double nalpha = -alpha;
         // ------------------------------------------------------------------ P2
-        double acc_rr = 0, acc_rmax = 0;
+        double acc_rr = 0, acc_rmax = 0, unused = 0;
 #pragma unroll
         for (int k = 0; k < KR; ++k) {
-            if ((vmask >> k) & 1u) {
+            if (all_open || ((vmask >> k) & 1u)) {
                 const double sc = S[own0 + k * P];
-                x[k] = x[k] + alpha * sc;                      // pcg.rs:55 (x = 0 before iteration 0)
+                X[xown0 + k * tw] = X[xown0 + k * tw] + alpha * sc;   // pcg.rs:55 (x = 0 before iteration 0)
                 const double rn = r[k] + nalpha * z[k];        // pcg.rs:56
                 r[k] = rn;
                 const double ar = rn < 0 ? -rn : rn;
@@ -249,22 +253,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_resident(const ResArgs a) {
                 acc_rr = acc_rr + rn * rn;
             }
         }
-        // post the tile's boundary lines of r for the neighbours' next P1
-        if (rg == 0) my_mail[c] = r[0];
-        if (rg == RG - 1) my_mail[tw + c] = r[KR - 1];
-        if (c == 0) {
-#pragma unroll
-            for (int k = 0; k < KR; ++k) my_mail[2 * tw + rg * KR + k] = r[k];
-        }
-        if (c == tw - 1) {
-#pragma unroll
-            for (int k = 0; k < KR; ++k) my_mail[2 * tw + th + rg * KR + k] = r[k];
-        }
+        // post the tile's boundary lines of r for the neighbours' next P1 (tag: next iteration index)
         {
-            const double v0 = cta_sum(acc_rr, sh->wsum[0]);
-            const double v1 = cta_max(acc_rmax, sh->wsum[1]);
-            if (!grid_allreduce(a, sh, nred++, 2, v0, v1, 0.0, 0x2u, red)) { failed = true; break; }
+            const unsigned long long tag = a.seq_base + (unsigned long long)(it + 1);
+            if (rg == 0 && has_n) unit_store(my_mail + c, r[0], tag);
+            if (rg == RG - 1 && has_s) unit_store(my_mail + tw + c, r[KR - 1], tag);
+            if (c == 0 && has_w) {
+#pragma unroll
+                for (int k = 0; k < KR; ++k) unit_store(my_mail + 2 * tw + rg * KR + k, r[k], tag);
+            }
+            if (c == tw - 1 && has_e) {
+#pragma unroll
+                for (int k = 0; k < KR; ++k) unit_store(my_mail + 2 * tw + th + rg * KR + k, r[k], tag);
+            }
         }
+        cta_reduce3(acc_rr, acc_rmax, unused, 2, 0x2u, sh);
+        if (!grid_allreduce(a, sh, nred++, 2, acc_rr, acc_rmax, 0.0, 0x2u, red)) { failed = true; break; }
         const double rr = red[0];
         rmax = red[1];                                         // pcg.rs:58
         if (rmax < a.threshold) { converged = true; break; }   // pcg.rs:60-63
@@ -281,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_resident(const ResArgs a) {
             if (early) {
                 a.x[gi] = 0.0;                                 // nothing else is touched (pcg.rs:35-38)
             } else {
-                a.x[gi] = x[k];
+                a.x[gi] = X[xown0 + k * tw];
                 a.r[gi] = r[k];
                 const double sv = S[own0 + k * P];
                 // exhausted loop: the reference still performs the search update (pcg.rs:72-77)
@@ -359,7 +363,7 @@ int pano_cg_resident_launch(pano_ctx *ctx, double *x, const double *b, double *r
     a.tw = p.tw; a.tw_log2 = p.tw_log2;
     a.tiles_x = p.tiles_x; a.tiles_y = p.tiles_y;
     const int grid = p.tiles_x * p.tiles_y;
-    const size_t mail_doubles = (size_t)grid * (2 * p.tw + 2 * p.th);
+    const size_t mail_doubles = 2 * (size_t)grid * (2 * p.tw + 2 * p.th);   // 16-byte units
     if (mail_doubles > ctx->mail_cap) {
         if (ctx->d_mail) {
             PANO_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -368,16 +372,17 @@ int pano_cg_resident_launch(pano_ctx *ctx, double *x, const double *b, double *r
             ctx->mail_cap = 0;
         }
         PANO_CUDA(cudaMalloc(&ctx->d_mail, mail_doubles * sizeof(double)));
+        PANO_CUDA(cudaMemsetAsync(ctx->d_mail, 0, mail_doubles * sizeof(double), ctx->stream));   // sequence 0 never matches
         ctx->mail_cap = mail_doubles;
     }
-    a.mail = ctx->d_mail;
-    if (!ctx->d_units) PANO_CUDA(cudaMalloc(&ctx->d_units, 2 * 3 * kMaxCtas * sizeof(ReduceUnit)));
-    if (ctx->launch_epoch == 0) PANO_CUDA(cudaMemsetAsync(ctx->d_units, 0, 2 * 3 * kMaxCtas * sizeof(ReduceUnit), ctx->stream));
+    a.mail = reinterpret_cast<ReduceUnit *>(ctx->d_mail);
+    if (!ctx->d_units) PANO_CUDA(cudaMalloc(&ctx->d_units, kUnitsTotal * sizeof(ReduceUnit)));
+    if (ctx->launch_epoch == 0) PANO_CUDA(cudaMemsetAsync(ctx->d_units, 0, kUnitsTotal * sizeof(ReduceUnit), ctx->stream));
     a.units = (ReduceUnit *)ctx->d_units;
     a.seq_base = (++ctx->launch_epoch) << 32;
     a.ctl = ctx->d_cg;
     PANO_CUDA(cudaMemsetAsync(ctx->d_cg, 0, sizeof(PanoCgControl), ctx->stream));
-    const size_t smem_bytes = ((size_t)(p.th + 2) * (p.tw + 2)) * sizeof(double) + sizeof(ResShared) + 16;
+    const size_t smem_bytes = ((size_t)(p.th + 2) * (p.tw + 2) + (size_t)p.th * p.tw) * sizeof(double) + sizeof(ResShared) + 16;
     switch (p.kr) {
         case 1: return launch_kr<1>(ctx, a, grid, smem_bytes);
         case 2: return launch_kr<2>(ctx, a, grid, smem_bytes);

@@ -44,7 +44,6 @@ constexpr int kStageBytes = 2 * kHaloSlot + kIntBoxBytes;   // 53504
 constexpr int kStages = 4;
 constexpr int kConsumers = 256, kConsumerWarps = 8;
 constexpr int kThreads = kConsumers + 32;       // + one producer warp
-constexpr int kMaxCtas = 192;
 constexpr int kTailBytes = 8192;
 constexpr int kSmemBytes = kStages * kStageBytes + kTailBytes;
 
@@ -58,7 +57,7 @@ struct StreamArgs {
     int max_iter;
     RectI m;
     int tiles_x, tiles_y;
-    ReduceUnit *units;            // [2 banks][3 values][kMaxCtas]
+    ReduceUnit *units;            // kUnitsTotal units (pano_sm100.cuh)
     unsigned long long seq_base;
     PanoCgControl *ctl;
     int zigzag;
@@ -97,42 +96,12 @@ __device__ __forceinline__ double consumer_max(double v, double *wsum) {
     return t;
 }
 
-// Grid-wide all-reduce of up to three block totals (kinds: 0/1 sum, 2 max unless max_mask says otherwise).
-// Called by all consumer threads.  Returns false if a bounded wait expired.
+// Grid-wide all-reduce of up to three block totals, called by all consumer threads (pano_sm100.cuh).
+// fenced: the tiles this CTA stored to global memory must be visible to the others afterwards.
 __device__ __forceinline__ bool grid_allreduce(const StreamArgs &a, Tail *tl, unsigned long long n, int nvals, double v0,
                                                double v1, double v2, unsigned max_mask, double *out) {
-    const int G = gridDim.x, tid = threadIdx.x;
-    const unsigned long long seq = a.seq_base + n;
-    ReduceUnit *bank = a.units + (n & 1) * 3 * kMaxCtas;
-    if (tid == 0) {
-        __threadfence();
-        fence_proxy_async();
-        unit_store(bank + 0 * kMaxCtas + blockIdx.x, v0, seq);
-        if (nvals > 1) unit_store(bank + 1 * kMaxCtas + blockIdx.x, v1, seq);
-        if (nvals > 2) unit_store(bank + 2 * kMaxCtas + blockIdx.x, v2, seq);
-    }
-    bool ok = true;
-    if (tid < G) {
-        volatile unsigned int *err = &a.ctl->error;
-        for (int k = 0; k < nvals && ok; ++k) {
-            double v;
-            ok = unit_poll(bank + k * kMaxCtas + tid, seq, v, err);
-            tl->vals[k][tid] = v;
-        }
-        __threadfence();
-        if (!ok) tl->ok = 0;
-    }
-    consumer_sync();
-    const int wid = tid >> 5, lane = tid & 31;
-    if (wid < nvals) {
-        double r = ((max_mask >> wid) & 1u) ? warp_fixed_max(tl->vals[wid], G, lane) : warp_fixed_sum(tl->vals[wid], G, lane);
-        if (lane == 0) tl->out[wid] = r;
-    }
-    consumer_sync();
-    out[0] = tl->out[0];
-    if (nvals > 1) out[1] = tl->out[1];
-    if (nvals > 2) out[2] = tl->out[2];
-    return tl->ok != 0;
+    return grid_allreduce_units(a.units, a.seq_base + n, (unsigned)(n & 1), nvals, v0, v1, v2, max_mask, tl->vals, tl->out,
+                                &tl->ok, &a.ctl->error, /*fenced=*/true, [] { consumer_sync(); }, out);
 }
 
 // ------------------------------------------------------------------------------ tile kernels
@@ -568,8 +537,8 @@ int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, 
     a.tiles_y = ((int)h + TH - 1) / TH;
     a.ctl = ctx->d_cg;
     a.zigzag = pano_option(ctx, "cg_zigzag", 1) != 0;
-    if (!ctx->d_units) PANO_CUDA(cudaMalloc(&ctx->d_units, 2 * 3 * kMaxCtas * sizeof(ReduceUnit)));
-    if (ctx->launch_epoch == 0) PANO_CUDA(cudaMemsetAsync(ctx->d_units, 0, 2 * 3 * kMaxCtas * sizeof(ReduceUnit), ctx->stream));
+    if (!ctx->d_units) PANO_CUDA(cudaMalloc(&ctx->d_units, kUnitsTotal * sizeof(ReduceUnit)));
+    if (ctx->launch_epoch == 0) PANO_CUDA(cudaMemsetAsync(ctx->d_units, 0, kUnitsTotal * sizeof(ReduceUnit), ctx->stream));
     a.units = (ReduceUnit *)ctx->d_units;
     a.seq_base = (++ctx->launch_epoch) << 32;
     int G = ctx->num_sms;
