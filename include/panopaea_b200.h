@@ -210,6 +210,31 @@ PANO_API int pano_fluid_step_host(pano_ctx *ctx, const pano_step_params *params,
  * vertical flip of png.rs:12): out[h*w] bytes on the host. */
 PANO_API int pano_density_to_u8(const pano_field *density, double lower, double upper, uint8_t *host_out);
 
+/* ---------------------------------------------------------------- multi-GPU
+ * The step slab-decomposed along y over the GPUs of one node, one process per GPU.
+ * Rank g owns rows [y0, y1) given by pano_slab_range.  All halo traffic and the CG reductions move
+ * through peer-mapped device memory (CUDA IPC over NVLink) written from inside the kernels; the host
+ * only hands the IPC handles around once.  Collective calls: every rank makes the same calls in the
+ * same order.  pano_dist_step is asynchronous; pano_dist_sync waits and reports. */
+typedef struct pano_dist pano_dist;
+#define PANO_IPC_HANDLE_BYTES 64
+PANO_API int pano_slab_range(size_t h, int rank, int nranks, size_t *y0, size_t *y1);
+PANO_API int pano_dist_create(pano_ctx *ctx, size_t h, size_t w, int rank, int nranks, const pano_step_params *params,
+                              pano_dist **out);
+PANO_API int pano_dist_destroy(pano_dist *d);
+/* this rank's exchange window: raw device pointer (ranks sharing a process) and IPC handle (one process per GPU) */
+PANO_API int pano_dist_window(pano_dist *d, void **ptr, size_t *bytes);
+PANO_API int pano_dist_ipc_handle(pano_dist *d, void *handle_out /* PANO_IPC_HANDLE_BYTES */);
+/* kind 0: peers = void*[nranks] raw window pointers; kind 1: peers = nranks consecutive IPC handles (own entry ignored) */
+PANO_API int pano_dist_connect(pano_dist *d, int kind, const void *peers);
+/* cap on the CTAs of the solver kernel (loop-back tests that run several ranks on one GPU); 0 = one per SM */
+PANO_API int pano_dist_set_max_ctas(pano_dist *d, int max_ctas);
+/* owned rows of a field: which = 0 density, 1 vy, 2 vx, 3 pressure; host points at this rank's first row */
+PANO_API int pano_dist_upload(pano_dist *d, int which, const double *host_rows);
+PANO_API int pano_dist_download(pano_dist *d, int which, double *host_rows, size_t *rows);
+PANO_API int pano_dist_step(pano_dist *d);
+PANO_API int pano_dist_sync(pano_dist *d, pano_pcg_info *info);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,7 +97,19 @@ _SIGS = {
     "pano_fluid_step": (C.c_int, [C.POINTER(StepParams), _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(PcgInfo)]),
     "pano_fluid_step_host": (C.c_int, [_P, C.POINTER(StepParams), C.c_size_t, C.c_size_t, _P, _P, _P, C.POINTER(PcgInfo)]),
     "pano_density_to_u8": (C.c_int, [_P, C.c_double, C.c_double, _P]),
+    "pano_slab_range": (C.c_int, [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "pano_dist_create": (C.c_int, [_P, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.POINTER(StepParams), C.POINTER(_P)]),
+    "pano_dist_destroy": (C.c_int, [_P]),
+    "pano_dist_window": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
+    "pano_dist_ipc_handle": (C.c_int, [_P, _P]),
+    "pano_dist_connect": (C.c_int, [_P, C.c_int, _P]),
+    "pano_dist_set_max_ctas": (C.c_int, [_P, C.c_int]),
+    "pano_dist_upload": (C.c_int, [_P, C.c_int, _P]),
+    "pano_dist_download": (C.c_int, [_P, C.c_int, _P, C.POINTER(C.c_size_t)]),
+    "pano_dist_step": (C.c_int, [_P]),
+    "pano_dist_sync": (C.c_int, [_P, C.POINTER(PcgInfo)]),
 }
+IPC_HANDLE_BYTES = 64
 
 _lib = None
 

@@ -295,7 +295,7 @@ int launch_generic(pano_ctx *ctx, CgArgs<T> &args, bool use_cg_loads) {
 
 bool pano_cg_stream_supported(size_t h, size_t w, const void *x, const void *b, const void *r, const void *s0, const void *s1);
 int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, double *s0, double *s1, size_t h, size_t w,
-                          int max_iterations, double threshold, double timestep, RectI m);
+                          int max_iterations, double threshold, double timestep, RectI m, const PanoCgSlab *slab);
 
 bool pano_cg_resident_supported(pano_ctx *ctx, size_t h, size_t w);
 int pano_cg_resident_launch(pano_ctx *ctx, double *x, const double *b, double *r, double *s0, size_t h, size_t w,
@@ -336,7 +336,7 @@ int pano_cg_solve_raw(pano_ctx *ctx, int dtype, void *x, const void *b, void *r,
                                          threshold, timestep, m));
     } else if (stream_ok && want != 1) {
         PANO_TRY(pano_cg_stream_launch(ctx, (double *)x, (const double *)b, (double *)r, (double *)s0, (double *)s1, h, w,
-                                       max_iterations, threshold, timestep, m));
+                                       max_iterations, threshold, timestep, m, nullptr));
     } else if (dtype == PANO_F64) {
         CgArgs<double> a{(double *)x, (const double *)b, (double *)r, (double *)s0, (double *)s1, (int)h, (int)w,
                          timestep, threshold, max_iterations, m, nullptr, ctx->d_cg,

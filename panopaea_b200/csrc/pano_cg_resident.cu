@@ -80,7 +80,7 @@ __device__ __forceinline__ void cta_reduce3(double &v0, double &v1, double &v2, 
 // grid-wide all-reduce of up to 3 CTA totals; bit max_mask<k> selects max for value k
 __device__ __forceinline__ bool grid_allreduce(const ResArgs &a, ResShared *sh, unsigned long long n, int nvals, double v0,
                                                double v1, double v2, unsigned max_mask, double *out) {
-    return grid_allreduce_units(a.units, a.seq_base + n, (unsigned)(n & 1), nvals, v0, v1, v2, max_mask, sh->vals, sh->out,
+    return grid_allreduce_units(a.units, a.seq_base + n, n, nvals, v0, v1, v2, max_mask, sh->vals, sh->out,
                                 &sh->ok, &a.ctl->error, /*fenced=*/false, [] { __syncthreads(); }, out);
 }
 

@@ -61,6 +61,12 @@ struct StreamArgs {
     unsigned long long seq_base;
     PanoCgControl *ctl;
     int zigzag;
+    // ---- slab of a larger grid (multi-GPU); single GPU: row0 = 0, gy0 = 0, gh = h, no peers
+    int row0;                     // array row of the first owned row (ghost rows sit above it)
+    int gy0, gh;                  // global row of the first owned row; global grid height (walls)
+    double *up_r, *up_s0, *up_s1; // upper neighbour's ghost row BELOW its slab (receives my first row), or null
+    double *dn_r, *dn_s0, *dn_s1; // lower neighbour's ghost row ABOVE its slab (receives my last row), or null
+    XRank xr;
 };
 
 struct Tail {                     // small shared-memory area behind the stage ring
@@ -100,8 +106,8 @@ __device__ __forceinline__ double consumer_max(double v, double *wsum) {
 // fenced: the tiles this CTA stored to global memory must be visible to the others afterwards.
 __device__ __forceinline__ bool grid_allreduce(const StreamArgs &a, Tail *tl, unsigned long long n, int nvals, double v0,
                                                double v1, double v2, unsigned max_mask, double *out) {
-    return grid_allreduce_units(a.units, a.seq_base + n, (unsigned)(n & 1), nvals, v0, v1, v2, max_mask, tl->vals, tl->out,
-                                &tl->ok, &a.ctl->error, /*fenced=*/true, [] { consumer_sync(); }, out);
+    return grid_allreduce_units(a.units, a.seq_base + n, n, nvals, v0, v1, v2, max_mask, tl->vals, tl->out,
+                                &tl->ok, &a.ctl->error, /*fenced=*/true, [] { consumer_sync(); }, out, &a.xr);
 }
 
 // ------------------------------------------------------------------------------ tile kernels
@@ -112,8 +118,8 @@ constexpr int kRows = TH / kConsumerWarps;   // 4
 struct Open4 { bool n, s, w, e; };
 __device__ __forceinline__ Open4 open_edges(const StreamArgs &a, int gy, int gx) {
     Open4 o;
-    o.n = gy > 0 && !in_rect(a.m, gy, gx);
-    o.s = gy < a.h - 1 && !in_rect(a.m, gy + 1, gx);
+    o.n = gy > 0 && !in_rect(a.m, gy, gx);          // gy is the GLOBAL row
+    o.s = gy < a.gh - 1 && !in_rect(a.m, gy + 1, gx);
     o.w = gx > 0 && !in_rect(a.m, gy, gx);
     o.e = gx < a.w - 1 && !in_rect(a.m, gy, gx + 1);
     return o;
@@ -121,8 +127,9 @@ __device__ __forceinline__ Open4 open_edges(const StreamArgs &a, int gy, int gx)
 
 // P1: s' = r + beta*s (kFirst: s' = b, nothing stored), z = A s', accumulate z.s' (+ b.b, max|b|)
 template <bool kFast, bool kFirst>
-__device__ __forceinline__ void tile_p1(const StreamArgs &a, const double *S, const double *R, double *s_dst, int ty0,
-                                        int tx0, double beta, double &acc_zs, double &acc_bb, double &acc_bmax) {
+__device__ __forceinline__ void tile_p1(const StreamArgs &a, const double *S, const double *R, double *s_dst, double *s_up,
+                                        double *s_dn, int ty0, int tx0, double beta, double &acc_zs, double &acc_bb,
+                                        double &acc_bmax) {
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int col = 2 * lane, row0 = wid * kRows;
     const int gx = tx0 + col;
@@ -146,14 +153,14 @@ __device__ __forceinline__ void tile_p1(const StreamArgs &a, const double *S, co
     for (int k = 0; k < kRows; ++k) {
         const double2 dn = sp2((k + 1) * BW);
         const double wv = sp1(k * BW - 1), ev = sp1(k * BW + 2);
-        const int gy = ty0 + row0 + k;
+        const int ly = ty0 + row0 + k, gy = a.gy0 + ly;   // local (owned) row, global row
         double z0, z1;
         bool valid = true;
         if (kFast) {
             z0 = pano::laplacian_cell<double>(c.x, up.x, dn.x, wv, c.y, true, true, true, true, a.dt);
             z1 = pano::laplacian_cell<double>(c.y, up.y, dn.y, c.x, ev, true, true, true, true, a.dt);
         } else {
-            valid = gy < a.h && gx < a.w;          // the width is even: both columns are valid together
+            valid = ly < a.h && gx < a.w;          // the width is even: both columns are valid together
             const Open4 o0 = open_edges(a, gy, gx), o1 = open_edges(a, gy, gx + 1);
             z0 = pano::laplacian_cell<double>(c.x, up.x, dn.x, wv, c.y, o0.n, o0.s, o0.w, o0.e, a.dt);
             z1 = pano::laplacian_cell<double>(c.y, up.y, dn.y, c.x, ev, o1.n, o1.s, o1.w, o1.e, a.dt);
@@ -168,7 +175,9 @@ __device__ __forceinline__ void tile_p1(const StreamArgs &a, const double *S, co
                 acc_bb = acc_bb + c.x * c.x;
                 acc_bb = acc_bb + c.y * c.y;
             } else {
-                *reinterpret_cast<double2 *>(s_dst + (size_t)gy * a.w + gx) = c;
+                *reinterpret_cast<double2 *>(s_dst + (size_t)(a.row0 + ly) * a.w + gx) = c;
+                if (ly == 0 && s_up) *reinterpret_cast<double2 *>(s_up + gx) = c;          // halo rows go straight into
+                if (ly == a.h - 1 && s_dn) *reinterpret_cast<double2 *>(s_dn + gx) = c;    // the neighbours' HBM (NVLink)
             }
         }
         up = c;
@@ -190,20 +199,20 @@ __device__ __forceinline__ void tile_p2(const StreamArgs &a, const double *S, co
     for (int k = 0; k < kRows; ++k) {
         const double2 dn = *reinterpret_cast<const double2 *>(ps + (k + 1) * BW);
         const double wv = ps[k * BW - 1], ev = ps[k * BW + 2];
-        const int gy = ty0 + row0 + k;
+        const int ly = ty0 + row0 + k, gy = a.gy0 + ly;
         double z0, z1;
         bool valid = true;
         if (kFast) {
             z0 = pano::laplacian_cell<double>(c.x, up.x, dn.x, wv, c.y, true, true, true, true, a.dt);
             z1 = pano::laplacian_cell<double>(c.y, up.y, dn.y, c.x, ev, true, true, true, true, a.dt);
         } else {
-            valid = gy < a.h && gx < a.w;
+            valid = ly < a.h && gx < a.w;
             const Open4 o0 = open_edges(a, gy, gx), o1 = open_edges(a, gy, gx + 1);
             z0 = pano::laplacian_cell<double>(c.x, up.x, dn.x, wv, c.y, o0.n, o0.s, o0.w, o0.e, a.dt);
             z1 = pano::laplacian_cell<double>(c.y, up.y, dn.y, c.x, ev, o1.n, o1.s, o1.w, o1.e, a.dt);
         }
         if (valid) {
-            const size_t gi = (size_t)gy * a.w + gx;
+            const size_t gi = (size_t)(a.row0 + ly) * a.w + gx;
             const int ti = (row0 + k) * TW + col;
             double2 xo, ro;
             if (kFirst) {
@@ -220,6 +229,8 @@ __device__ __forceinline__ void tile_p2(const StreamArgs &a, const double *S, co
             rn.y = ro.y + nalpha * z1;
             *reinterpret_cast<double2 *>(a.x + gi) = xn;
             *reinterpret_cast<double2 *>(a.r + gi) = rn;
+            if (ly == 0 && a.up_r) *reinterpret_cast<double2 *>(a.up_r + gx) = rn;
+            if (ly == a.h - 1 && a.dn_r) *reinterpret_cast<double2 *>(a.dn_r + gx) = rn;
             if (kFirst) *reinterpret_cast<double2 *>(a.s0 + gi) = c;
             const double a0 = rn.x < 0 ? -rn.x : rn.x, a1 = rn.y < 0 ? -rn.y : rn.y;
             acc_rmax = a0 > acc_rmax ? a0 : acc_rmax;
@@ -233,9 +244,11 @@ __device__ __forceinline__ void tile_p2(const StreamArgs &a, const double *S, co
 }
 
 __device__ __forceinline__ bool tile_is_fast(const StreamArgs &a, int ty0, int tx0) {
-    if (ty0 < 1 || ty0 + TH > a.h - 1 || tx0 < 1 || tx0 + TW > a.w - 1) return false;
-    if (a.m.y1 > a.m.y0 && a.m.x1 > a.m.x0 && ty0 < a.m.y1 && ty0 + TH > a.m.y0 - 1 && tx0 < a.m.x1 && tx0 + TW > a.m.x0 - 1)
-        return false;
+    const int g0 = a.gy0 + ty0;   // global row of the tile's first row
+    if (ty0 + TH > a.h) return false;                                            // ragged tile at the end of the slab
+    if (g0 < 1 || g0 + TH > a.gh - 1 || tx0 < 1 || tx0 + TW > a.w - 1) return false;   // touches a wall
+    if (a.m.y1 > a.m.y0 && a.m.x1 > a.m.x0 && g0 < a.m.y1 && g0 + TH > a.m.y0 - 1 && tx0 < a.m.x1 && tx0 + TW > a.m.x0 - 1)
+        return false;                                                            // touches the obstacle
     return true;
 }
 
@@ -288,23 +301,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
             if (first) {                                   // b never changes: everything is independent
                 if (indep) {
                     mbar_arrive_expect_tx(bar, kHaloBoxBytes);
-                    tma_load_2d(base, &a.m_b_halo, bar, tx0 - kHX, ty0 - 1);
+                    tma_load_2d(base, &a.m_b_halo, bar, tx0 - kHX, a.row0 + ty0 - 1);
                 }
             } else if (phase == 0) {
                 if (indep) {
                     mbar_arrive_expect_tx(bar, 2 * kHaloBoxBytes);
                     // s (old) is not touched by P2 -- except in iteration 0, whose P2 materialises s0 = b;
                     // iteration 1 therefore reads b itself (s = b, pcg.rs:40-42), which never changes
-                    tma_load_2d(base, it_ == 1 ? &a.m_b_halo : (cur_ ? &a.m_s0_halo : &a.m_s1_halo), bar, tx0 - kHX, ty0 - 1);
+                    tma_load_2d(base, it_ == 1 ? &a.m_b_halo : (cur_ ? &a.m_s0_halo : &a.m_s1_halo), bar, tx0 - kHX, a.row0 + ty0 - 1);
                 }
-                if (dep) tma_load_2d(base + kHaloSlot, &a.m_r_halo, bar, tx0 - kHX, ty0 - 1);        // r: ring written by neighbours in P2
+                if (dep) tma_load_2d(base + kHaloSlot, &a.m_r_halo, bar, tx0 - kHX, a.row0 + ty0 - 1);        // r: ring written by neighbours in P2
             } else {
                 if (indep) {
                     mbar_arrive_expect_tx(bar, kHaloBoxBytes + 2 * kIntBoxBytes);
-                    tma_load_2d(base + kHaloSlot, &a.m_r_int, bar, tx0, ty0);                        // own tiles, untouched by P1
-                    tma_load_2d(base + 2 * kHaloSlot, &a.m_x_int, bar, tx0, ty0);
+                    tma_load_2d(base + kHaloSlot, &a.m_r_int, bar, tx0, a.row0 + ty0);                        // own tiles, untouched by P1
+                    tma_load_2d(base + 2 * kHaloSlot, &a.m_x_int, bar, tx0, a.row0 + ty0);
                 }
-                if (dep) tma_load_2d(base, cur_ ? &a.m_s1_halo : &a.m_s0_halo, bar, tx0 - kHX, ty0 - 1);  // s': ring written by neighbours in P1
+                if (dep) tma_load_2d(base, cur_ ? &a.m_s1_halo : &a.m_s0_halo, bar, tx0 - kHX, a.row0 + ty0 - 1);  // s': ring written by neighbours in P1
             }
         };
         bool stop = false;
@@ -374,11 +387,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
             const double *R = reinterpret_cast<const double *>(smem + st * kStageBytes + kHaloSlot);
             const bool fast = tile_is_fast(a, ty0, tx0);
             if (first) {
-                if (fast) tile_p1<true, true>(a, S, R, nullptr, ty0, tx0, 0.0, acc_zs, acc_bb, acc_bmax);
-                else tile_p1<false, true>(a, S, R, nullptr, ty0, tx0, 0.0, acc_zs, acc_bb, acc_bmax);
+                if (fast) tile_p1<true, true>(a, S, R, nullptr, nullptr, nullptr, ty0, tx0, 0.0, acc_zs, acc_bb, acc_bmax);
+                else tile_p1<false, true>(a, S, R, nullptr, nullptr, nullptr, ty0, tx0, 0.0, acc_zs, acc_bb, acc_bmax);
             } else {
-                if (fast) tile_p1<true, false>(a, S, R, s_cur, ty0, tx0, beta, acc_zs, acc_bb, acc_bmax);
-                else tile_p1<false, false>(a, S, R, s_cur, ty0, tx0, beta, acc_zs, acc_bb, acc_bmax);
+                double *s_up = s_cur == a.s0 ? a.up_s0 : a.up_s1, *s_dn = s_cur == a.s0 ? a.dn_s0 : a.dn_s1;
+                if (fast) tile_p1<true, false>(a, S, R, s_cur, s_up, s_dn, ty0, tx0, beta, acc_zs, acc_bb, acc_bmax);
+                else tile_p1<false, false>(a, S, R, s_cur, s_up, s_dn, ty0, tx0, beta, acc_zs, acc_bb, acc_bmax);
             }
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&tl->empty[st]);
@@ -455,16 +469,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
     }
 
     // ------------------------------------------------------------------ epilogue (flat, once per solve)
-    const size_t ncell = (size_t)a.h * a.w;
-    const size_t stride = (size_t)G * kConsumers, i0 = (size_t)blockIdx.x * kConsumers + tid;
+    const size_t ncell = (size_t)a.h * a.w, base = (size_t)a.row0 * a.w;
+    const size_t stride = (size_t)G * kConsumers, i0 = base + (size_t)blockIdx.x * kConsumers + tid;
     if (early) {
-        for (size_t i = i0; i < ncell; i += stride) a.x[i] = 0.0;
+        for (size_t i = i0; i < base + ncell; i += stride) a.x[i] = 0.0;
     } else {
         // converged: the last applied direction is in s_cur; exhausted: the swap already happened, it is
         // in s_old, and the reference still performs the search update (pcg.rs:72-77) before leaving
         const double *s_fin = converged ? s_cur : s_old;
         if (!converged || s_fin != a.s0) {
-            for (size_t i = i0; i < ncell; i += stride) {
+            for (size_t i = i0; i < base + ncell; i += stride) {
                 const double sv = __ldcg(s_fin + i);
                 a.s0[i] = converged ? sv : __ldcg(a.r + i) + beta * sv;
             }
@@ -518,17 +532,19 @@ bool pano_cg_stream_supported(size_t h, size_t w, const void *x, const void *b, 
 }
 
 int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, double *s0, double *s1, size_t h, size_t w,
-                          int max_iterations, double threshold, double timestep, RectI m) {
+                          int max_iterations, double threshold, double timestep, RectI m, const PanoCgSlab *slab) {
     PANO_CUDA(cudaFuncSetAttribute(k_cg_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     static_assert(sizeof(Tail) <= kTailBytes, "Tail does not fit");
     StreamArgs a;
+    memset(&a, 0, sizeof(a));
     const uint64_t pitch = (uint64_t)w * 8;
-    PANO_TRY(pano_make_tensor_map_2d(&a.m_b_halo, b, 8, w, h, pitch, BW, BH));
-    PANO_TRY(pano_make_tensor_map_2d(&a.m_r_halo, r, 8, w, h, pitch, BW, BH));
-    PANO_TRY(pano_make_tensor_map_2d(&a.m_r_int, r, 8, w, h, pitch, TW, TH));
-    PANO_TRY(pano_make_tensor_map_2d(&a.m_s0_halo, s0, 8, w, h, pitch, BW, BH));
-    PANO_TRY(pano_make_tensor_map_2d(&a.m_s1_halo, s1, 8, w, h, pitch, BW, BH));
-    PANO_TRY(pano_make_tensor_map_2d(&a.m_x_int, x, 8, w, h, pitch, TW, TH));
+    const uint64_t rows = slab ? (uint64_t)slab->rows_total : (uint64_t)h;   // h = owned rows, rows = stored rows
+    PANO_TRY(pano_make_tensor_map_2d(&a.m_b_halo, b, 8, w, rows, pitch, BW, BH));
+    PANO_TRY(pano_make_tensor_map_2d(&a.m_r_halo, r, 8, w, rows, pitch, BW, BH));
+    PANO_TRY(pano_make_tensor_map_2d(&a.m_r_int, r, 8, w, rows, pitch, TW, TH));
+    PANO_TRY(pano_make_tensor_map_2d(&a.m_s0_halo, s0, 8, w, rows, pitch, BW, BH));
+    PANO_TRY(pano_make_tensor_map_2d(&a.m_s1_halo, s1, 8, w, rows, pitch, BW, BH));
+    PANO_TRY(pano_make_tensor_map_2d(&a.m_x_int, x, 8, w, rows, pitch, TW, TH));
     a.x = x; a.b = b; a.r = r; a.s0 = s0; a.s1 = s1;
     a.h = (int)h; a.w = (int)w;
     a.dt = timestep; a.threshold = threshold; a.max_iter = max_iterations;
@@ -537,11 +553,25 @@ int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, 
     a.tiles_y = ((int)h + TH - 1) / TH;
     a.ctl = ctx->d_cg;
     a.zigzag = pano_option(ctx, "cg_zigzag", 1) != 0;
+    a.row0 = 0; a.gy0 = 0; a.gh = (int)h;
+    a.xr.rank = 0; a.xr.nranks = 1;
+    int max_ctas = 0;
+    if (slab) {
+        a.row0 = slab->row0; a.gy0 = slab->gy0; a.gh = slab->gh;
+        a.up_r = slab->up_r; a.up_s0 = slab->up_s0; a.up_s1 = slab->up_s1;
+        a.dn_r = slab->dn_r; a.dn_s0 = slab->dn_s0; a.dn_s1 = slab->dn_s1;
+        a.xr.rank = slab->rank; a.xr.nranks = slab->nranks;
+        a.xr.seq_base = slab->xseq_base;
+        a.xr.local = (ReduceUnit *)slab->xunits_local;
+        for (int i = 0; i < kMaxRanks; ++i) a.xr.peer[i] = (ReduceUnit *)slab->xunits_peer[i];
+        max_ctas = slab->max_ctas;
+    }
     if (!ctx->d_units) PANO_CUDA(cudaMalloc(&ctx->d_units, kUnitsTotal * sizeof(ReduceUnit)));
     if (ctx->launch_epoch == 0) PANO_CUDA(cudaMemsetAsync(ctx->d_units, 0, kUnitsTotal * sizeof(ReduceUnit), ctx->stream));
     a.units = (ReduceUnit *)ctx->d_units;
     a.seq_base = (++ctx->launch_epoch) << 32;
     int G = ctx->num_sms;
+    if (max_ctas > 0 && G > max_ctas) G = max_ctas;
     const int ntiles = a.tiles_x * a.tiles_y;
     if (G > ntiles) G = ntiles;
     if (G > kMaxCtas) G = kMaxCtas;

@@ -18,10 +18,44 @@ struct View2 {   // row-major (rows, pitch) array in global memory
     __device__ __forceinline__ T operator()(int y, int x) const { return p[(size_t)y * pitch + x]; }
 };
 
+// Same, for a slab of a larger grid: `p` is the VIRTUAL address of global row 0 and only rows
+// [lo, hi) are stored.  A gather that leaves the stored window (backtrace longer than the ghost
+// zone) raises *err and is clamped into the window so that it cannot fault.
+template <class T>
+struct View2W {
+    const T *p;
+    int pitch, lo, hi;
+    unsigned int *err;
+    __device__ __forceinline__ T operator()(int y, int x) const {
+        if (y < lo || y >= hi) {
+            *err = 2u;
+            y = y < lo ? lo : hi - 1;
+        }
+        return p[(size_t)y * pitch + x];
+    }
+};
+
 // ------------------------------------------------------------------ K1: advection
 // Tile = 32 x 8 cells per 256-thread block; index space (h+1) x (w+1) covers q (h,w),
 // vx (h,w+1) and vy (h+1,w) in one sweep.  Gathers go through L1/L2 (the backtrace lands
 // within ~2 cells of the thread's own cell for CFL-bounded flow).
+// Rows [ya, yb) of the cell grid are produced (the whole grid on one GPU, a slab otherwise);
+// the vy face row y belongs to the slab that owns cell row y, and face row h to the last slab.
+template <class T, bool kScalar, bool kMac, class VQ, class VY, class VX>
+__device__ __forceinline__ void advect_rows(T *q_dst, T *vy_dst, T *vx_dst, const VQ &q, const VY &qy, const VX &qx,
+                                            const VY &vy, const VX &vx, int h, int w, T dt, int ya, int yb) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    if (x > w) return;
+    const int yf = yb == h ? h + 1 : yb;   // end of the vy face rows of this slab
+    for (int y = ya + blockIdx.y * 8 + (threadIdx.x >> 5); y < yf; y += gridDim.y * 8) {
+        if (kScalar && y < yb && x < w) q_dst[(size_t)y * w + x] = pano::advect_cell<T>(y, x, h, w, dt, q, vy, vx);
+        if (kMac) {
+            if (y < yb) vx_dst[(size_t)y * (w + 1) + x] = pano::advect_mac_x<T>(y, x, h, w, dt, qx, vy, vx);
+            if (x < w) vy_dst[(size_t)y * w + x] = pano::advect_mac_y<T>(y, x, h, w, dt, qy, vy, vx);
+        }
+    }
+}
+
 template <class T, bool kScalar, bool kMac>
 __global__ void __launch_bounds__(kThreads)
 k_advect(T *__restrict__ q_dst, T *__restrict__ vel_dst, const T *__restrict__ q_src, const T *__restrict__ mac_src,
@@ -30,28 +64,30 @@ k_advect(T *__restrict__ q_dst, T *__restrict__ vel_dst, const T *__restrict__ q
     const View2<T> vy{vel, w}, vx{vel + off, w + 1};
     const View2<T> qy{mac_src, w}, qx{mac_src + off, w + 1};
     const View2<T> q{q_src, w};
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    if (x > w) return;
-    for (int y = blockIdx.y * 8 + (threadIdx.x >> 5); y <= h; y += gridDim.y * 8) {
-        if (kScalar && y < h && x < w) q_dst[(size_t)y * w + x] = pano::advect_cell<T>(y, x, h, w, dt, q, vy, vx);
-        if (kMac) {
-            if (y < h) vel_dst[off + (size_t)y * (w + 1) + x] = pano::advect_mac_x<T>(y, x, h, w, dt, qx, vy, vx);
-            if (x < w) vel_dst[(size_t)y * w + x] = pano::advect_mac_y<T>(y, x, h, w, dt, qy, vy, vx);
-        }
-    }
+    advect_rows<T, kScalar, kMac>(q_dst, vel_dst, vel_dst + off, q, qy, qx, vy, vx, h, w, dt, 0, h);
+}
+
+// slab form (self-advection): separate component pointers, all of them virtual global-row-0 addresses;
+// cell rows [wlo, whi) and face rows [wlo, whi + 1) are stored
+__global__ void __launch_bounds__(kThreads)
+k_advect_slab(double *q_dst, double *vy_dst, double *vx_dst, const double *q_src, const double *vy_src, const double *vx_src,
+              int h, int w, double dt, int ya, int yb, int wlo, int whi, unsigned int *err) {
+    // face row whi is stored but only rows below it are ever received from the neighbour; face row h exists on the last slab
+    const View2W<double> vy{vy_src, w, wlo, whi > h + 1 ? h + 1 : whi, err}, vx{vx_src, w + 1, wlo, whi > h ? h : whi, err};
+    const View2W<double> q{q_src, w, wlo, whi > h ? h : whi, err};
+    advect_rows<double, true, true>(q_dst, vy_dst, vx_dst, q, vy, vx, vy, vx, h, w, dt, ya, yb);
 }
 
 // ------------------------------------------------------------------ K3: -divergence (+ max|b|, b.b)
 template <class T>
 __global__ void __launch_bounds__(kThreads)
-k_neg_divergence(T *__restrict__ b, const T *__restrict__ vel, int h, int w, RectI m, double *__restrict__ partial_max,
-                 double *__restrict__ partial_dot) {
+k_neg_divergence(T *__restrict__ b, const T *__restrict__ vy, const T *__restrict__ vx, int h, int w, RectI m, int ya, int yb,
+                 double *__restrict__ partial_max, double *__restrict__ partial_dot) {
     __shared__ T scratch[32];
-    const T *vy = vel, *vx = vel + (size_t)w * (h + 1);
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     T amax = 0, adot = 0;
     if (x < w) {
-        for (int y = blockIdx.y * 8 + (threadIdx.x >> 5); y < h; y += gridDim.y * 8) {
+        for (int y = ya + blockIdx.y * 8 + (threadIdx.x >> 5); y < yb; y += gridDim.y * 8) {
             T vy0 = in_rect(m, y, x) ? (T)0 : vy[(size_t)y * w + x];
             T vy1 = in_rect(m, y + 1, x) ? (T)0 : vy[(size_t)(y + 1) * w + x];
             T vx0 = in_rect(m, y, x) ? (T)0 : vx[(size_t)y * (w + 1) + x];
@@ -65,7 +101,7 @@ k_neg_divergence(T *__restrict__ b, const T *__restrict__ vel, int h, int w, Rec
     }
     T bm = block_max(amax, scratch);
     T bd = block_sum(adot, scratch);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && partial_max) {
         const int bid = blockIdx.y * gridDim.x + blockIdx.x;
         partial_max[bid] = (double)bm;
         partial_dot[bid] = (double)bd;
@@ -108,18 +144,18 @@ k_laplacian(T *__restrict__ z, const T *__restrict__ p, int h, int w, T dt, Rect
 // ------------------------------------------------------------------ K8: projection + walls
 template <class T>
 __global__ void __launch_bounds__(kThreads)
-k_project(T *__restrict__ vel, const T *__restrict__ p, int h, int w, T dt) {
-    T *vy = vel, *vx = vel + (size_t)w * (h + 1);
+k_project(T *__restrict__ vy, T *__restrict__ vx, const T *__restrict__ p, int h, int w, T dt, int ya, int yb) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     if (x > w) return;
-    for (int y = blockIdx.y * 8 + (threadIdx.x >> 5); y <= h; y += gridDim.y * 8) {
+    const int yf = yb == h ? h + 1 : yb;   // vy face rows [ya, yf), vx rows [ya, yb)
+    for (int y = ya + blockIdx.y * 8 + (threadIdx.x >> 5); y < yf; y += gridDim.y * 8) {
         const T c = (y < h && x < w) ? p[(size_t)y * w + x] : (T)0;
         if (x < w) {   // vy[y, x]
             const size_t i = (size_t)y * w + x;
             if (y == 0 || y == h) vy[i] = (T)0;                                   // walls :137-140
             else vy[i] = vy[i] + dt * (-(c - p[(size_t)(y - 1) * w + x]));        // d0_dual :322-326, scaled_add :126
         }
-        if (y < h) {   // vx[y, x]
+        if (y < yb) {   // vx[y, x]
             const size_t i = (size_t)y * (w + 1) + x;
             if (x == 0 || x == w) vx[i] = (T)0;                                   // walls :132-135
             else vx[i] = vx[i] + dt * (p[(size_t)y * w + x - 1] - c);             // d0_dual :329-333
@@ -180,12 +216,13 @@ int pano_neg_divergence_launch(pano_ctx *ctx, int dtype, void *b, const void *ve
     PANO_TRY(pano_ensure_partials(ctx, 2 * (size_t)nb));
     // the obstacle rectangle indexes vy (h+1, w) and vx (h, w+1) alike; clip to the union
     RectI m = pano_clip_rect(obstacle, h + 1, w + 1);
+    const size_t off = w * (h + 1);
     if (dtype == PANO_F64)
-        k_neg_divergence<double><<<g, kThreads, 0, ctx->stream>>>((double *)b, (const double *)vel, (int)h, (int)w, m,
-                                                                  ctx->d_partials, ctx->d_partials + nb);
+        k_neg_divergence<double><<<g, kThreads, 0, ctx->stream>>>((double *)b, (const double *)vel, (const double *)vel + off, (int)h,
+                                                                  (int)w, m, 0, (int)h, ctx->d_partials, ctx->d_partials + nb);
     else
-        k_neg_divergence<float><<<g, kThreads, 0, ctx->stream>>>((float *)b, (const float *)vel, (int)h, (int)w, m,
-                                                                 ctx->d_partials, ctx->d_partials + nb);
+        k_neg_divergence<float><<<g, kThreads, 0, ctx->stream>>>((float *)b, (const float *)vel, (const float *)vel + off, (int)h,
+                                                                 (int)w, m, 0, (int)h, ctx->d_partials, ctx->d_partials + nb);
     PANO_TRY(pano_after_launch(ctx, "neg_divergence"));
     if (!want_scalars) return PANO_OK;
     k_reduce_max_dot<<<1, kThreads, 0, ctx->stream>>>(ctx->d_partials, ctx->d_partials + nb, nb, ctx->d_scalars);
@@ -194,9 +231,35 @@ int pano_neg_divergence_launch(pano_ctx *ctx, int dtype, void *b, const void *ve
 
 int pano_project_launch(pano_ctx *ctx, int dtype, void *vel, const void *p, size_t h, size_t w, double dt) {
     dim3 g = grid2d((int)h + 1, (int)w + 1);
-    if (dtype == PANO_F64) k_project<double><<<g, kThreads, 0, ctx->stream>>>((double *)vel, (const double *)p, (int)h, (int)w, dt);
-    else k_project<float><<<g, kThreads, 0, ctx->stream>>>((float *)vel, (const float *)p, (int)h, (int)w, (float)dt);
+    const size_t off = w * (h + 1);
+    if (dtype == PANO_F64)
+        k_project<double><<<g, kThreads, 0, ctx->stream>>>((double *)vel, (double *)vel + off, (const double *)p, (int)h, (int)w, dt, 0, (int)h);
+    else
+        k_project<float><<<g, kThreads, 0, ctx->stream>>>((float *)vel, (float *)vel + off, (const float *)p, (int)h, (int)w, (float)dt, 0, (int)h);
     return pano_after_launch(ctx, "project");
+}
+
+// ---- slab forms used by the multi-GPU step (pano_dist.cu): f64, rows [ya, yb) of an h x w grid, every pointer is
+// the virtual address of global row 0 of its array
+int pano_advect_slab_launch(pano_ctx *ctx, double *q_dst, double *vy_dst, double *vx_dst, const double *q_src, const double *vy_src,
+                            const double *vx_src, size_t h, size_t w, double dt, int ya, int yb, int wlo, int whi, unsigned int *err) {
+    dim3 g = grid2d(yb - ya + 1, (int)w + 1);
+    k_advect_slab<<<g, kThreads, 0, ctx->stream>>>(q_dst, vy_dst, vx_dst, q_src, vy_src, vx_src, (int)h, (int)w, dt, ya, yb, wlo, whi, err);
+    return pano_after_launch(ctx, "advect_slab");
+}
+
+int pano_neg_divergence_slab_launch(pano_ctx *ctx, double *b, const double *vy, const double *vx, size_t h, size_t w, pano_rect obstacle,
+                                    int ya, int yb) {
+    dim3 g = grid2d(yb - ya, (int)w);
+    RectI m = pano_clip_rect(obstacle, h + 1, w + 1);
+    k_neg_divergence<double><<<g, kThreads, 0, ctx->stream>>>(b, vy, vx, (int)h, (int)w, m, ya, yb, nullptr, nullptr);
+    return pano_after_launch(ctx, "neg_divergence_slab");
+}
+
+int pano_project_slab_launch(pano_ctx *ctx, double *vy, double *vx, const double *p, size_t h, size_t w, double dt, int ya, int yb) {
+    dim3 g = grid2d(yb - ya + 1, (int)w + 1);
+    k_project<double><<<g, kThreads, 0, ctx->stream>>>(vy, vx, p, (int)h, (int)w, dt, ya, yb);
+    return pano_after_launch(ctx, "project_slab");
 }
 
 extern "C" {

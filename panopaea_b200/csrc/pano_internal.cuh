@@ -106,6 +106,20 @@ int pano_after_launch(pano_ctx *ctx, const char *what);                         
 int pano_ensure_partials(pano_ctx *ctx, size_t doubles);
 int64_t pano_option(pano_ctx *ctx, const char *key, int64_t dflt);
 
+// Slab of a larger grid handed to the streaming CG kernel by the multi-GPU step (pano_dist.cu).
+struct PanoCgSlab {
+    int row0;                     // array row of the first owned row (number of ghost rows above)
+    int rows_total;               // rows of every array, ghosts included
+    int gy0, gh;                  // global row of the first owned row, global grid height
+    double *up_r, *up_s0, *up_s1; // upper neighbour's ghost row below its slab (peer memory), or null
+    double *dn_r, *dn_s0, *dn_s1; // lower neighbour's ghost row above its slab (peer memory), or null
+    int rank, nranks;
+    unsigned long long xseq_base; // identical on every rank
+    void *xunits_local;
+    void *xunits_peer[8];
+    int max_ctas;                 // 0: one CTA per SM; loop-back tests share one GPU between ranks
+};
+
 // internal (non-ABI) entry points shared between translation units
 // the example's rectangle loops index vy[(y,x)] / vx[(y,x)] / d[(y,x)] directly: a rectangle that
 // leaves the (rows, cols) grid panics in the reference, so it is an error here too

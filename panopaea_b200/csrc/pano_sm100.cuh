@@ -123,21 +123,38 @@ constexpr int kMaxCtas = 192;
 constexpr int kUnitsPerBank = 4 * kMaxCtas;       // 3 x kMaxCtas partials + results
 constexpr int kUnitsTotal = 2 * kUnitsPerBank;    // double-buffered by exchange parity
 
+// Multi-GPU extension: after CTA 0 has reduced its GPU's partials it writes the GPU total into a slot of
+// EVERY rank's cross-rank unit array (peer-mapped memory, st.volatile = system scope, over NVLink),
+// polls its own array until all ranks have written, and combines them in a fixed lane = rank order, so
+// every GPU obtains the bit-identical value.  One NVLink store latency per reduction, no NCCL call.
+constexpr int kMaxRanks = 8;
+constexpr int kXUnitsTotal = 2 * kMaxRanks * 3;   // [2 banks][rank][value]
+struct XRank {
+    int rank, nranks;
+    unsigned long long seq_base;      // identical on all ranks (incremented once per collective launch)
+    ReduceUnit *local;                // this rank's cross-rank unit array
+    ReduceUnit *peer[kMaxRanks];      // every rank's array as mapped into this process (peer[rank] == local)
+};
+
 template <class SyncFn>
-__device__ __forceinline__ bool grid_allreduce_units(ReduceUnit *units, unsigned long long seq, unsigned parity, int nvals,
+__device__ __forceinline__ bool grid_allreduce_units(ReduceUnit *units, unsigned long long seq, unsigned long long n, int nvals,
                                                      double v0, double v1, double v2, unsigned max_mask,
                                                      double (*vals)[kMaxCtas], double *out_sh, int *ok_sh,
-                                                     volatile unsigned int *err, bool fenced, SyncFn sync, double *out) {
+                                                     volatile unsigned int *err, bool fenced, SyncFn sync, double *out,
+                                                     const XRank *xr = nullptr) {
     const int G = gridDim.x, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const unsigned parity = (unsigned)(n & 1);
+    const bool multi = xr != nullptr && xr->nranks > 1;
     ReduceUnit *bank = units + parity * kUnitsPerBank;
     ReduceUnit *result = bank + 3 * kMaxCtas;
     if (fenced && tid == 0) {
-        __threadfence();
+        if (multi) __threadfence_system();   // halo rows stored into the neighbours' memory must have landed
+        else __threadfence();
         fence_proxy_async();
     }
     if (fenced) sync();   // the publishing threads below must not run ahead of thread 0's fence
     if (tid < nvals) unit_store(bank + tid * kMaxCtas + blockIdx.x, tid == 0 ? v0 : (tid == 1 ? v1 : v2), seq);
-    const bool root_mode = G > 32;
+    const bool root_mode = G > 32 || multi;
     if (!root_mode || blockIdx.x == 0) {
         if (tid < G) {
             bool ok = true;
@@ -151,7 +168,18 @@ __device__ __forceinline__ bool grid_allreduce_units(ReduceUnit *units, unsigned
         }
         sync();
         if (wid < nvals) {
-            const double r = ((max_mask >> wid) & 1u) ? warp_fixed_max(vals[wid], G, lane) : warp_fixed_sum(vals[wid], G, lane);
+            const bool is_max = (max_mask >> wid) & 1u;
+            double r = is_max ? warp_fixed_max(vals[wid], G, lane) : warp_fixed_sum(vals[wid], G, lane);
+            if (multi) {   // cross-rank stage (root CTA only, one warp per value)
+                const unsigned long long xseq = xr->seq_base + n;
+                const int slot = ((int)parity * kMaxRanks + xr->rank) * 3 + wid;
+                if (fenced) __threadfence_system();
+                if (lane < xr->nranks) unit_store(xr->peer[lane] + slot, r, xseq);
+                double v = 0.0;
+                if (lane < xr->nranks && !unit_poll(xr->local + ((int)parity * kMaxRanks + lane) * 3 + wid, xseq, v, err)) *ok_sh = 0;
+                if (fenced) __threadfence_system();
+                r = is_max ? warp_max(v) : warp_sum(v);   // fixed butterfly over lane = rank: same bits on every GPU
+            }
             if (lane == 0) {
                 out_sh[wid] = r;
                 if (root_mode) unit_store(result + wid, r, seq);
