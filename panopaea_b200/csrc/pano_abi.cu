@@ -67,6 +67,9 @@ int pano_ctx_create(int device, void *stream, pano_ctx **out) {
     PANO_CUDA(cudaMemset(c->d_cg, 0, sizeof(PanoCgControl)));
     PANO_CUDA(cudaMallocHost(&c->h_cg, sizeof(PanoCgControl)));
     PANO_TRY(pano_ensure_partials(c, 3 * 4096));
+    // all-reduce units of the persistent kernels: allocated here so that no launch path ever calls cudaMalloc
+    PANO_CUDA(cudaMalloc(&c->d_units, 4096 * 16));
+    PANO_CUDA(cudaMemset(c->d_units, 0, 4096 * 16));
     *out = c;
     return PANO_OK;
 }

@@ -376,8 +376,7 @@ int pano_cg_resident_launch(pano_ctx *ctx, double *x, const double *b, double *r
         ctx->mail_cap = mail_doubles;
     }
     a.mail = reinterpret_cast<ReduceUnit *>(ctx->d_mail);
-    if (!ctx->d_units) PANO_CUDA(cudaMalloc(&ctx->d_units, kUnitsTotal * sizeof(ReduceUnit)));
-    if (ctx->launch_epoch == 0) PANO_CUDA(cudaMemsetAsync(ctx->d_units, 0, kUnitsTotal * sizeof(ReduceUnit), ctx->stream));
+    static_assert(kUnitsTotal * sizeof(ReduceUnit) <= 4096 * 16, "d_units (allocated in pano_ctx_create) is too small");
     a.units = (ReduceUnit *)ctx->d_units;
     a.seq_base = (++ctx->launch_epoch) << 32;
     a.ctl = ctx->d_cg;

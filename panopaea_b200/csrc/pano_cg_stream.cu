@@ -522,6 +522,13 @@ int pano_make_tensor_map_2d(CUtensorMap *map, const void *base, size_t elem_byte
     return PANO_OK;
 }
 
+int pano_preload_cg_stream() {
+    cudaFuncAttributes fa;
+    PANO_CUDA(cudaFuncGetAttributes(&fa, k_cg_stream));
+    PANO_CUDA(cudaFuncSetAttribute(k_cg_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    return PANO_OK;
+}
+
 // TMA needs 16-byte aligned rows: even width, 16-byte aligned base pointers.
 bool pano_cg_stream_supported(size_t h, size_t w, const void *x, const void *b, const void *r, const void *s0, const void *s1) {
     if (w % 2 != 0 || w < 2 || h < 1) return false;
@@ -566,8 +573,7 @@ int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, 
         for (int i = 0; i < kMaxRanks; ++i) a.xr.peer[i] = (ReduceUnit *)slab->xunits_peer[i];
         max_ctas = slab->max_ctas;
     }
-    if (!ctx->d_units) PANO_CUDA(cudaMalloc(&ctx->d_units, kUnitsTotal * sizeof(ReduceUnit)));
-    if (ctx->launch_epoch == 0) PANO_CUDA(cudaMemsetAsync(ctx->d_units, 0, kUnitsTotal * sizeof(ReduceUnit), ctx->stream));
+    static_assert(kUnitsTotal * sizeof(ReduceUnit) <= 4096 * 16, "d_units (allocated in pano_ctx_create) is too small");
     a.units = (ReduceUnit *)ctx->d_units;
     a.seq_base = (++ctx->launch_epoch) << 32;
     int G = ctx->num_sms;

@@ -15,6 +15,9 @@
 // NCCL is not in the data path; torch.distributed is used by the Python harness only to hand the
 // IPC handles around.  The step itself is pano_step.cu's, restricted to the slab:
 // examples/dec_fluid.rs:46-141.
+#include <cstdlib>
+#include <ctime>
+
 #include "pano_sm100.cuh"
 
 using namespace pano_sm100;
@@ -26,6 +29,9 @@ int pano_neg_divergence_slab_launch(pano_ctx *ctx, double *b, const double *vy, 
 int pano_project_slab_launch(pano_ctx *ctx, double *vy, double *vx, const double *p, size_t h, size_t w, double dt, int ya, int yb);
 int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, double *s0, double *s1, size_t h, size_t w,
                           int max_iterations, double threshold, double timestep, RectI m, const PanoCgSlab *slab);
+
+int pano_preload_fused();
+int pano_preload_cg_stream();
 
 namespace {
 
@@ -224,6 +230,14 @@ int pano_dist_create(pano_ctx *ctx, size_t h, size_t w, int rank, int nranks, co
         if (b - a < (size_t)kGhost) PANO_FAIL(PANO_ERR_SHAPE, "pano_dist_create: slab of rank %d has %zu rows, fewer than the %d ghost rows", r, b - a, kGhost);
     }
     PANO_TRY(pano_activate(ctx));
+    {   // load every kernel of the step now (see pano_preload_fused)
+        cudaFuncAttributes fa;
+        PANO_CUDA(cudaFuncGetAttributes(&fa, k_push));
+        PANO_CUDA(cudaFuncGetAttributes(&fa, k_wait));
+        PANO_CUDA(cudaFuncGetAttributes(&fa, k_fill_rows));
+        PANO_TRY(pano_preload_fused());
+        PANO_TRY(pano_preload_cg_stream());
+    }
     pano_dist *d = new pano_dist();
     d->ctx = ctx;
     d->rank = rank;
@@ -362,6 +376,15 @@ int pano_dist_step(pano_dist *d) {
     const int fVX = cur ? F_VX1 : F_VX0, fVXn = nxt ? F_VX1 : F_VX0;
     unsigned int *err = reinterpret_cast<unsigned int *>(d->window + L.err);
     ++d->step_no;
+    static const bool dbg = getenv("PANO_DIST_DEBUG") != nullptr;
+    struct timespec ts0;
+    clock_gettime(CLOCK_MONOTONIC, &ts0);
+    auto mark = [&](const char *what) {
+        if (!dbg) return;
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        fprintf(stderr, "[pano_dist rank %d] %-12s +%.3f ms\n", d->rank, what, (ts.tv_sec - ts0.tv_sec) * 1e3 + (ts.tv_nsec - ts0.tv_nsec) * 1e-6);
+    };
 
     // inflow  (dec_fluid.rs:48-57): the part of the rectangle this rank owns
     PANO_TRY(fill_owned(d, fD, p.inflow, p.inflow_density));
@@ -371,10 +394,12 @@ int pano_dist_step(pano_dist *d) {
         const int fields[3] = {fD, fVY, fVX};
         PANO_TRY(exchange(d, EX_ADV, 3, fields, kGhost));
     }
+    mark("ex_adv");
     // advect + advect_mac on the owned rows, into the other ping-pong buffers  (:59-63)
     const int wlo = ya - kGhost > 0 ? ya - kGhost : 0, whi = yb + kGhost;
     PANO_TRY(pano_advect_slab_launch(ctx, virt(d, fDn), virt(d, fVYn), virt(d, fVXn), virt(d, fD), virt(d, fVY), virt(d, fVX), H, W,
                                      p.timestep, ya, yb, wlo, whi, err));
+    mark("advect");
     // the face row y1 of the new vy belongs to the lower neighbour
     {
         const int fields[1] = {fVYn};
@@ -387,6 +412,7 @@ int pano_dist_step(pano_dist *d) {
         const int fields[1] = {fB};
         PANO_TRY(exchange(d, EX_B, 1, fields, 1));
     }
+    mark("ex_b");
     // pressure solve  (:91-119): streaming CG on the slab, halo rows and reductions over NVLink from inside the kernel
     {
         PanoCgSlab s;
@@ -420,6 +446,7 @@ int pano_dist_step(pano_dist *d) {
         PANO_TRY(pano_cg_stream_launch(ctx, d->window + L.off[F_P], d->window + L.off[fB], d->window + L.off[F_R], d->window + L.off[F_S0],
                                        d->window + L.off[F_S1], L.hl, W, p.max_iterations, p.threshold, p.timestep, m, &s));
     }
+    mark("cg");
     // p[y0 - 1] lives on the upper neighbour
     {
         const int fields[1] = {F_P};
@@ -427,6 +454,7 @@ int pano_dist_step(pano_dist *d) {
     }
     // projection + walls  (:124-141)
     PANO_TRY(pano_project_slab_launch(ctx, virt(d, fVYn), virt(d, fVXn), virt(d, F_P), H, W, p.timestep, ya, yb));
+    mark("project");
     d->cur = nxt;
     return PANO_OK;
 }

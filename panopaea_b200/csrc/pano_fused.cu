@@ -239,6 +239,16 @@ int pano_project_launch(pano_ctx *ctx, int dtype, void *vel, const void *p, size
     return pano_after_launch(ctx, "project");
 }
 
+// CUDA loads kernels lazily, and loading may need the device to go idle: fatal when another stream is parked in a
+// kernel that waits for this very launch.  The multi-GPU step therefore loads everything it will use up front.
+int pano_preload_fused() {
+    cudaFuncAttributes fa;
+    PANO_CUDA(cudaFuncGetAttributes(&fa, k_advect_slab));
+    PANO_CUDA(cudaFuncGetAttributes(&fa, k_neg_divergence<double>));
+    PANO_CUDA(cudaFuncGetAttributes(&fa, k_project<double>));
+    return PANO_OK;
+}
+
 // ---- slab forms used by the multi-GPU step (pano_dist.cu): f64, rows [ya, yb) of an h x w grid, every pointer is
 // the virtual address of global row 0 of its array
 int pano_advect_slab_launch(pano_ctx *ctx, double *q_dst, double *vy_dst, double *vx_dst, const double *q_src, const double *vy_src,

@@ -41,11 +41,17 @@ def test_loopback_matches_single_gpu(nranks, h, w):
         infos = _step_all(ranks)
         assert all(i == infos[0] for i in infos), "every rank must see the same solver outcome"
         assert abs(infos[0]["iterations"] - want["iterations"]) <= 1, (step, infos[0], want)
-        assert infos[0]["rhs_max"] == want["rhs_max"]            # -div is bit-exact, max is order independent
+        # the first step is bit-exact outside the solver; later steps inherit the solver's reduction-order rounding
+        if step == 0:
+            assert infos[0]["rhs_max"] == want["rhs_max"]
+        else:
+            assert infos[0]["rhs_max"] == pytest.approx(want["rhs_max"], rel=1e-9)
         if infos[0]["iterations"] != want["iterations"]:
             break
         d = dist.gather_local(ranks, dist.DENSITY)
-        assert np.array_equal(d, single.density.to_host()), step   # advection is bit-exact across the decomposition
+        if step == 0:
+            assert np.array_equal(d, single.density.to_host())
+        assert np.abs(d - single.density.to_host()).max() <= 1e-9
         vy, vx = single.vel.split()
         p = single.pressure.to_host()
         for got, ref in ((dist.gather_local(ranks, dist.VY), vy), (dist.gather_local(ranks, dist.VX), vx),
@@ -65,7 +71,9 @@ def test_loopback_against_oracle(oracle):
         o = ref.step()
         infos = _step_all(ranks)
         assert abs(infos[0]["iterations"] - o["iterations"]) <= 2
-        assert np.array_equal(dist.gather_local(ranks, dist.DENSITY), ref.field("density"))
+        if step == 0:
+            assert np.array_equal(dist.gather_local(ranks, dist.DENSITY), ref.field("density"))
+        assert np.abs(dist.gather_local(ranks, dist.DENSITY) - ref.field("density")).max() <= 1e-7
         if infos[0]["iterations"] != o["iterations"]:
             break
         ovy, ovx = oracle.split(ref.field("vel"), n, n)
