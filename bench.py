@@ -198,122 +198,218 @@ def run_reference(args, rank, world):
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+class _Single:
+    """One GPU: device-resident fields stepped by pano_fluid_step; e2e through pano_fluid_step_host."""
+
+    def __init__(self, ctx, n, P, fluid, _lib):
+        self.ctx, self.n, self._lib = ctx, n, _lib
+        self.sim = fluid.DecFluid(**fluid.smoke_params(n), ctx=ctx)
+        self.cells = n * n
+        self.n1 = (n + 1) * n + n * (n + 1)
+        self.workload_rows = n
+
+    def step(self):
+        self.sim.step(want_info=False)
+
+    def info(self):
+        self.ctx.sync()
+        return self.sim.step(want_info=True)
+
+    def e2e_setup(self, np):
+        L, _lib = self._lib.load(), self._lib
+        self.bufs = []
+        for count in (self.cells, self.n1, self.cells):
+            p = C.c_void_p()
+            _lib.check(L.pano_host_alloc(count * 8, C.byref(p)))
+            self.bufs.append(p)
+        d = np.ctypeslib.as_array(C.cast(self.bufs[0], C.POINTER(C.c_double)), shape=(self.cells,))
+        v = np.ctypeslib.as_array(C.cast(self.bufs[1], C.POINTER(C.c_double)), shape=(self.n1,))
+        d[:] = self.sim.density.view_linear()
+        v[:] = self.sim.vel.view_linear()
+        self.h2d, self.d2h = (self.cells + self.n1) * 8, (2 * self.cells + self.n1) * 8
+        self.call = "pano_fluid_step_host (pinned host fields in, fields + pressure out, every step)"
+
+    def e2e_step(self):
+        L, _lib = self._lib.load(), self._lib
+        _lib.check(L.pano_fluid_step_host(self.ctx.handle, C.byref(self.sim.params), self.n, self.n, self.bufs[0], self.bufs[1],
+                                          self.bufs[2], None))
+
+    def e2e_teardown(self):
+        L = self._lib.load()
+        for p in self.bufs:
+            L.pano_host_free(p)
+
+
+class _Slab:
+    """N GPUs: this rank's slab of the grid (pano_dist_*); e2e = upload my rows, step, download my rows."""
+
+    def __init__(self, ctx, n, rank, world, dist_t, P, fluid, _lib):
+        from panopaea_b200 import dist
+        self.ctx, self.n, self._lib, self.dist = ctx, n, _lib, dist
+        prm = fluid.smoke_params(n)
+        self.D = dist.DistFluid(ctx, n, n, rank, world, {k: v for k, v in prm.items() if k not in ("h", "w")})
+        handles = [None] * world
+        dist_t.all_gather_object(handles, self.D.ipc_handle())
+        self.D.connect_ipc(handles)
+        dist_t.barrier()
+        self.cells = n * n
+        self.rows = self.D.y1 - self.D.y0
+
+    def step(self):
+        self.D.step()
+
+    def info(self):
+        self.D.step()
+        return self.D.sync()
+
+    def e2e_setup(self, np):
+        L, _lib, D, dist = self._lib.load(), self._lib, self.D, self.dist
+        self.bufs, self.counts = [], []
+        for which in (dist.DENSITY, dist.VY, dist.VX, dist.PRESSURE):
+            count = D._rows(which) * D._pitch(which)
+            p = C.c_void_p()
+            _lib.check(L.pano_host_alloc(count * 8, C.byref(p)))
+            self.bufs.append(p)
+            self.counts.append(count)
+        for which in (dist.DENSITY, dist.VY, dist.VX):
+            _lib.check(L.pano_dist_download(D._h, which, self.bufs[which], None))
+        self.h2d, self.d2h = sum(self.counts[:3]) * 8, sum(self.counts) * 8       # bytes of THIS rank
+        self.call = "pano_dist_upload x3 + pano_dist_step + pano_dist_sync + pano_dist_download x4 (pinned host rows of this rank)"
+
+    def e2e_step(self):
+        L, _lib, D, dist = self._lib.load(), self._lib, self.D, self.dist
+        for which in (dist.DENSITY, dist.VY, dist.VX):
+            _lib.check(L.pano_dist_upload(D._h, which, self.bufs[which]))
+        D.step()
+        D.sync()
+        for which in (dist.DENSITY, dist.VY, dist.VX, dist.PRESSURE):
+            _lib.check(L.pano_dist_download(D._h, which, self.bufs[which], None))
+
+    def e2e_teardown(self):
+        L = self._lib.load()
+        for p in self.bufs:
+            L.pano_host_free(p)
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
-    import torch.distributed as dist
+    import torch.distributed as dist_t
 
     import panopaea_b200 as P
     from panopaea_b200 import _lib, fluid
 
     multi = world > 1
-    if multi:
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if args.gpus != world:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
     if multi:
-        raise SystemExit("multi-GPU slab decomposition is not wired into bench.py yet")
+        dist_t.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    n = args.n or 1024
+    n = args.n or (8192 if multi else 1024)
     ctx = P.Context(local_rank)
     for kv in args.opt:
         k, v = kv.split("=")
         ctx.set_option(k, int(v))
-    sim = fluid.DecFluid(**fluid.smoke_params(n), ctx=ctx)
+    job = _Slab(ctx, n, rank, world, dist_t, P, fluid, _lib) if multi else _Single(ctx, n, P, fluid, _lib)
     cells = n * n
     K, W = args.steps, max(args.warmup, 3)
-    flush = P.Grid2d((6144, 6144), ctx).new_simplex_2()       # 302 MB > 126 MB L2
+    fields_mb = cells * 8 / 1e6 / world
+    l2_resident = 10 * fields_mb < 126.0
+    flush = P.Grid2d((6144, 6144), ctx).new_simplex_2() if l2_resident else None     # 302 MB > 126 MB L2
 
     def barrier():
         ctx.sync()
         if multi:
-            dist.barrier()
+            dist_t.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if not multi:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist_t.all_reduce(t, op=dist_t.ReduceOp.MAX)
+        return float(t.item())
 
     # ---- warm-up
     for _ in range(W):
-        sim.step(want_info=False)
-    info = sim.step(want_info=True)        # part of warm-up; tells us the iteration count of this regime
+        job.step()
+    info = job.info()                      # part of the warm-up; also tells the iteration count of this regime
     barrier()
 
-    # ---- timed region: K steps, L2 flushed before each, device time from CUDA events on the library's stream
+    # ---- timed region: K steps; device time from CUDA events on the library's stream
     ctx.set_option("step_timing", 1)
     ctx.step_times()
     launches0 = ctx.launch_count()
-    iters_total = 0
     total_ms = 0.0
     with ClockSampler(local_rank) as clk:
         barrier()
-        for _ in range(K):
-            flush.fill(0.0)                # cudaMemsetAsync of 302 MB: evicts the fields from L2
+        if flush is not None:              # small grid: evict the fields from L2 before every step, time each step
+            for _ in range(K):
+                flush.fill(0.0)
+                ctx.timer_start()
+                job.step()
+                total_ms += ctx.timer_stop_ms()
+        else:                              # inputs larger than L2: one event pair around the K steps
             ctx.timer_start()
-            sim.step(want_info=False)
-            total_ms += ctx.timer_stop_ms()
+            for _ in range(K):
+                job.step()
+            total_ms = ctx.timer_stop_ms()
         barrier()
     launches = ctx.launch_count() - launches0
     phase_ms, phase_steps = ctx.step_times()
     ctx.set_option("step_timing", 0)
-    last = sim.step(want_info=True)
+    total_ms = max_over_ranks(total_ms)
+    last = job.info()
     iters = last["applies"]
-    if multi:
-        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
     ms_per_step = total_ms / K
     value = cells * K / (total_ms * 1e-3) / 1e6
 
-    # ---- e2e: the same step through the host-buffer entry point (pinned host fields, H2D + D2H every step)
-    L = _lib.load()
-    n1 = (n + 1) * n + n * (n + 1)
-    bufs = []
-    for count in (cells, n1, cells):
-        p = C.c_void_p()
-        _lib.check(L.pano_host_alloc(count * 8, C.byref(p)))
-        bufs.append(p)
-    h_density = np.ctypeslib.as_array(C.cast(bufs[0], C.POINTER(C.c_double)), shape=(cells,))
-    h_vel = np.ctypeslib.as_array(C.cast(bufs[1], C.POINTER(C.c_double)), shape=(n1,))
-    h_density[:] = sim.density.view_linear()
-    h_vel[:] = sim.vel.view_linear()
+    # ---- e2e: the same step with the fields in (pinned) host memory, H2D + D2H inside every step
+    job.e2e_setup(np)
     e2e_steps = max(3, min(K, 10))
     for _ in range(2):
-        _lib.check(L.pano_fluid_step_host(ctx.handle, C.byref(sim.params), n, n, bufs[0], bufs[1], bufs[2], None))
+        job.e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        _lib.check(L.pano_fluid_step_host(ctx.handle, C.byref(sim.params), n, n, bufs[0], bufs[1], bufs[2], None))
+        job.e2e_step()
     barrier()
-    e2e_s = time.perf_counter() - t0
-    if multi:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = cells * e2e_steps / e2e_s / 1e6
-    for p in bufs:
-        L.pano_host_free(p)
+    h2d, d2h = job.h2d, job.d2h
+    if multi:
+        t = torch.tensor([float(h2d), float(d2h)], device="cuda", dtype=torch.float64)
+        dist_t.all_reduce(t)
+        h2d, d2h = int(t[0].item()), int(t[1].item())
+    job.e2e_teardown()
 
-    # ---- roofline of the dominant kernel (the persistent CG kernel: phase 3)
+    # ---- roofline of the dominant kernel (the persistent CG kernel: phase 3), for this rank's share of the grid
     peak, peak_src = load_peaks()
-    cg_ms = phase_ms[3] / max(1, phase_steps)
-    cg_bytes = cells * (BYTES_CG_INIT + BYTES_CG_ITER * iters)
+    cg_ms = max_over_ranks(phase_ms[3] / max(1, phase_steps))
+    my_cells = cells / world
+    cg_bytes = my_cells * (BYTES_CG_INIT + BYTES_CG_ITER * iters)
     achieved = cg_bytes / (cg_ms * 1e-3) / 1e9 if cg_ms > 0 else 0.0
-    step_bytes = cells * (BYTES_ADVECT + BYTES_NEGDIV + BYTES_PROJECT + BYTES_CG_INIT + BYTES_CG_ITER * iters)
-    roofline = {"bound": "hbm", "kernel": "k_cg_generic (persistent CG: init + %d iterations in one launch)" % iters,
+    step_bytes = my_cells * (BYTES_ADVECT + BYTES_NEGDIV + BYTES_PROJECT + BYTES_CG_INIT + BYTES_CG_ITER * iters)
+    kernel = "k_cg_resident" if (not multi and cells <= 1_200_000) else "k_cg_stream"
+    roofline = {"bound": "hbm", "kernel": "%s (persistent CG: init + %d iterations in one launch%s)" % (kernel, iters, ", per GPU" if multi else ""),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": load_traffic(f"cg_{n}"),
+                "peak_source": peak_src, "traffic": load_traffic(f"cg_{n}_x{world}"),
                 "algorithmic_bytes_per_launch": cg_bytes, "kernel_ms": cg_ms,
                 "kernel_share_of_step": cg_ms / ms_per_step if ms_per_step > 0 else None,
                 "step_achieved_gbs": step_bytes / (ms_per_step * 1e-3) / 1e9,
                 "phase_ms": dict(zip(["inflow", "advect_all", "neg_divergence", "cg", "project"],
                                      [m / max(1, phase_steps) for m in phase_ms])),
-                "note": ("working set (10 fields x %.1f MB) %s the 126 MB L2; algorithmic GB/s above the HBM peak means "
-                         "cache residency, not an error" % (cells * 8 / 1e6, "fits in" if cells * 80 < 126e6 else "exceeds"))}
+                "note": ("algorithmic bytes = SURVEY.md 8(d): 32 + 88 B per cell and CG iteration; the kernel's real traffic is 64 B "
+                         "(fused search update, z not stored); per-GPU working set 10 fields x %.1f MB %s the 126 MB L2, and at "
+                         "<= 1.2 Mcell the CG state stays in registers/shared memory for the whole solve, so algorithmic GB/s "
+                         "above the HBM peak means on-chip residency, not an error"
+                         % (fields_mb, "fits in" if l2_resident else "exceeds"))}
 
-    line = None
     if rank == 0:
-        # ---- CPU baseline on this box's cores: bounded sample of the same workload
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and not multi:
+            # CPU baseline on this box's cores: bounded sample of the same workload (N = 1 only)
             from oracle import pano_oracle as O
             v, dt, cores, sample = cpu_step_rate(n, O.REFERENCE_FAITHFUL, 12.0, full_steps_max=4)
             v2, dt2, cores2, sample2 = cpu_step_rate(n, O.ALL_PARALLEL, 8.0, full_steps_max=4)
@@ -325,17 +421,18 @@ def run_ours(args, rank, world, local_rank):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"2D smoke plume {n}x{n} MAC grid, advect + pressure projection (dec_fluid.rs loop body)",
                            "grid": [n, n], "cg_iterations_per_step": iters, "cg_max_iterations": 100,
-                           "threshold": 0.1, "timestep": 0.05, "options": args.opt, "parallelism": f"slab{world}" if multi else "single",
-                           "l2": "flushed before every timed step (302 MB memset); within a step the CG re-reads its working set"},
-                "e2e": {"value": e2e_value, "unit": UNIT, "steps": e2e_steps,
-                        "h2d_bytes_per_step": (cells + n1) * 8, "d2h_bytes_per_step": (2 * cells + n1) * 8,
-                        "call": "pano_fluid_step_host (pinned host fields in, fields + pressure out, every step)"},
+                           "threshold": 0.1, "timestep": 0.05, "options": args.opt,
+                           "parallelism": f"slab{world} (rows split over {world} GPUs, halos + reductions over NVLink peer memory)" if multi else "single",
+                           "l2": ("flushed before every timed step (302 MB memset); within a step the CG re-reads its working set"
+                                  if l2_resident else "not flushed: every rank's fields are larger than the 126 MB L2")},
+                "e2e": {"value": e2e_value, "unit": UNIT, "steps": e2e_steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "call": job.call},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
                 "cg_info_last_step": last, "cg_info_warm_step": info}
         print(json.dumps(line), flush=True)
     if multi:
-        dist.barrier()
-        dist.destroy_process_group()
+        dist_t.barrier()
+        dist_t.destroy_process_group()
     return 0
 
 

@@ -386,6 +386,7 @@ int pano_dist_step(pano_dist *d) {
         fprintf(stderr, "[pano_dist rank %d] %-12s +%.3f ms\n", d->rank, what, (ts.tv_sec - ts0.tv_sec) * 1e3 + (ts.tv_nsec - ts0.tv_nsec) * 1e-6);
     };
 
+    PANO_TRY(pano_phase_mark(ctx, 0));
     // inflow  (dec_fluid.rs:48-57): the part of the rectangle this rank owns
     PANO_TRY(fill_owned(d, fD, p.inflow, p.inflow_density));
     PANO_TRY(fill_owned(d, fVY, p.inflow, p.inflow_vy));
@@ -395,6 +396,7 @@ int pano_dist_step(pano_dist *d) {
         PANO_TRY(exchange(d, EX_ADV, 3, fields, kGhost));
     }
     mark("ex_adv");
+    PANO_TRY(pano_phase_mark(ctx, 1));
     // advect + advect_mac on the owned rows, into the other ping-pong buffers  (:59-63)
     const int wlo = ya - kGhost > 0 ? ya - kGhost : 0, whi = yb + kGhost;
     PANO_TRY(pano_advect_slab_launch(ctx, virt(d, fDn), virt(d, fVYn), virt(d, fVXn), virt(d, fD), virt(d, fVY), virt(d, fVX), H, W,
@@ -405,6 +407,7 @@ int pano_dist_step(pano_dist *d) {
         const int fields[1] = {fVYn};
         PANO_TRY(exchange(d, EX_VY, 1, fields, 1));
     }
+    PANO_TRY(pano_phase_mark(ctx, 2));
     // b = -div  (:69-83); b reuses the old density buffer, as `temp` does in the reference
     const int fB = fD;
     PANO_TRY(pano_neg_divergence_slab_launch(ctx, virt(d, fB), virt(d, fVYn), virt(d, fVXn), H, W, p.obstacle, ya, yb));
@@ -413,6 +416,7 @@ int pano_dist_step(pano_dist *d) {
         PANO_TRY(exchange(d, EX_B, 1, fields, 1));
     }
     mark("ex_b");
+    PANO_TRY(pano_phase_mark(ctx, 3));
     // pressure solve  (:91-119): streaming CG on the slab, halo rows and reductions over NVLink from inside the kernel
     {
         PanoCgSlab s;
@@ -447,6 +451,7 @@ int pano_dist_step(pano_dist *d) {
                                        d->window + L.off[F_S1], L.hl, W, p.max_iterations, p.threshold, p.timestep, m, &s));
     }
     mark("cg");
+    PANO_TRY(pano_phase_mark(ctx, 4));
     // p[y0 - 1] lives on the upper neighbour
     {
         const int fields[1] = {F_P};
@@ -454,6 +459,7 @@ int pano_dist_step(pano_dist *d) {
     }
     // projection + walls  (:124-141)
     PANO_TRY(pano_project_slab_launch(ctx, virt(d, fVYn), virt(d, fVXn), virt(d, F_P), H, W, p.timestep, ya, yb));
+    PANO_TRY(pano_phase_mark(ctx, 5));
     mark("project");
     d->cur = nxt;
     return PANO_OK;
