@@ -1,0 +1,33 @@
+"""-m gpu: examples/dec_fluid.rs re-typed in C++ over the C ABI (panopaea_b200/host/dec_fluid.cpp), both with the
+reference's own call sequence ("composed") and with the fused step, against the oracle."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "panopaea_b200", "host")
+
+
+@pytest.mark.parametrize("mode", ["composed", "fused"])
+def test_dec_fluid_cpp(oracle, tmp_path, mode):
+    subprocess.run(["make", "-C", HOST, "-s"], check=True)
+    steps = 30
+    out = tmp_path / "state.bin"
+    r = subprocess.run([os.path.join(HOST, "dec_fluid"), str(steps), mode, str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    its = [int(m) for m in re.findall(r"Iterations (-?\d+)", r.stdout)]
+    assert len(its) == steps
+    ref = oracle.FluidState(**oracle.smoke_params(128))
+    want = [ref.step()["iterations"] for _ in range(steps)]
+    assert all(abs(a - b) <= 2 for a, b in zip(its, want))
+    if its == want:
+        raw = np.fromfile(out, dtype=np.float64)
+        n2, n1 = 128 * 128, 129 * 128 + 128 * 129
+        d, v, p = raw[:n2], raw[n2:n2 + n1], raw[n2 + n1:]
+        for got, ref_f in ((d, ref.field("density").ravel()), (v, ref.field("vel")), (p, ref.field("pressure").ravel())):
+            assert np.abs(got - ref_f).max() <= 1e-5 * max(1e-300, np.abs(ref_f).max())
