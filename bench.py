@@ -394,7 +394,7 @@ def run_ours(args, rank, world, local_rank):
     kernel = "k_cg_resident" if (not multi and cells <= 1_200_000) else "k_cg_stream"
     roofline = {"bound": "hbm", "kernel": "%s (persistent CG: init + %d iterations in one launch%s)" % (kernel, iters, ", per GPU" if multi else ""),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": load_traffic(f"cg_{n}_x{world}"),
+                "peak_source": peak_src, "traffic": load_traffic(f"cg_{n}_x{world}"),   # ncu dram bytes per launch (profiles/roofline_traffic.json), null if not captured
                 "algorithmic_bytes_per_launch": cg_bytes, "kernel_ms": cg_ms,
                 "kernel_share_of_step": cg_ms / ms_per_step if ms_per_step > 0 else None,
                 "step_achieved_gbs": step_bytes / (ms_per_step * 1e-3) / 1e9,
