@@ -14,7 +14,7 @@ SIZES = [(3, 3), (5, 7), (17, 33), (24, 20), (64, 48), (128, 128), (300, 200), (
 # kernel variants: the generic persistent kernel (any shape), the same with L2-only loads, and "auto"
 # (the TMA streaming kernel whenever the width is even, else generic)
 VARIANTS = {"generic": dict(cg_kernel=1, cg_ldcg=0), "generic_ldcg": dict(cg_kernel=1, cg_ldcg=1), "auto": dict(cg_kernel=0, cg_ldcg=0),
-            "stream": dict(cg_kernel=2, cg_ldcg=0), "resident": dict(cg_kernel=3, cg_ldcg=0)}
+            "stream": dict(cg_kernel=2, cg_ldcg=0), "resident": dict(cg_kernel=3, cg_ldcg=0), "resident_v1": dict(cg_kernel=4, cg_ldcg=0)}
 
 
 def _set_variant(name):
@@ -85,13 +85,13 @@ def test_kernel_variants_agree(oracle, h, w):
     b = U.consistent_rhs(oracle, h, w, obstacle, seed=11)
     out = {}
     try:
-        for name in ("generic", "stream", "resident"):
+        for name in ("generic", "stream", "resident", "resident_v1"):
             _set_variant(name)
             out[name] = _solve(grid, b, 100, 0.1, 0.05, obstacle)
     finally:
         _set_variant("auto")
     ia, xa, ra, sa = out["generic"]
-    for other in ("stream", "resident"):
+    for other in ("stream", "resident", "resident_v1"):
         ib, xb, rb, sb = out[other]
         assert abs(ia["iterations"] - ib["iterations"]) <= 1, other
         if ia["iterations"] == ib["iterations"]:
@@ -99,7 +99,7 @@ def test_kernel_variants_agree(oracle, h, w):
                 assert np.allclose(u, v, rtol=0, atol=1e-8 * max(1.0, np.abs(u).max())), other
 
 
-@pytest.mark.parametrize("variant", ["generic", "stream", "resident"])
+@pytest.mark.parametrize("variant", ["generic", "stream", "resident", "resident_v1"])
 def test_early_out_leaves_scratch_untouched(oracle, variant):
     """pcg.rs:35-38: max|b| < threshold -> x = 0 and nothing else is written."""
     from tests import gpu_util as U
@@ -117,7 +117,7 @@ def test_early_out_leaves_scratch_untouched(oracle, variant):
     assert np.all(r == 123.0) and np.all(s == 123.0)
 
 
-@pytest.mark.parametrize("variant", ["generic", "stream", "resident"])
+@pytest.mark.parametrize("variant", ["generic", "stream", "resident", "resident_v1"])
 @pytest.mark.parametrize("max_it", [1, 2, 3, 7])
 def test_exhausted_iterations_match_reference_state(oracle, max_it, variant):
     """When the loop runs out (pcg.rs:48), the reference has still updated `search` (pcg.rs:72-77)."""
@@ -187,7 +187,7 @@ def test_deterministic(oracle):
     assert all(np.array_equal(u, v) for u, v in zip(a[1:], c[1:]))
 
 
-@pytest.mark.parametrize("variant", ["stream", "resident"])
+@pytest.mark.parametrize("variant", ["stream", "resident", "resident_v1"])
 def test_large_grid_capped_solve(oracle, variant):
     """1024^2 (BASELINE configs[1] size): the cap of 100 iterations is hit, as SURVEY.md 6 observes
     for N >= 512; compare the full iterate with the oracle after a fixed 100 iterations."""
