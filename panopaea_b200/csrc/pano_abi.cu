@@ -150,6 +150,15 @@ int pano_ctx_step_times(pano_ctx *ctx, double ms_out[PANO_STEP_PHASES], int64_t 
     return PANO_OK;
 }
 
+int pano_ctx_cg_profile(pano_ctx *ctx, int64_t cycles_out[8]) {
+    if (!ctx || !cycles_out) PANO_FAIL(PANO_ERR_INVALID, "pano_ctx_cg_profile: null argument");
+    PANO_TRY(pano_activate(ctx));
+    PANO_CUDA(cudaMemcpyAsync(ctx->h_cg, ctx->d_cg, sizeof(PanoCgControl), cudaMemcpyDeviceToHost, ctx->stream));
+    PANO_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 8; ++i) cycles_out[i] = (int64_t)ctx->h_cg->prof[i];
+    return PANO_OK;
+}
+
 int pano_ctx_set_option(pano_ctx *ctx, const char *key, int64_t value) {
     if (!ctx || !key) PANO_FAIL(PANO_ERR_INVALID, "pano_ctx_set_option: null argument");
     ctx->options[key] = value;

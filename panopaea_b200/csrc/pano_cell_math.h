@@ -21,8 +21,11 @@
 
 namespace pano {
 
-template <class T> PANO_HD T tmin(T a, T b) { return a < b ? a : b; }   // no NaNs on this path
-template <class T> PANO_HD T tmax(T a, T b) { return a > b ? a : b; }
+// no NaNs on this path, so fmin/fmax (one instruction on the device) and the ternary agree bit for bit
+PANO_HD double tmin(double a, double b) { return fmin(a, b); }
+PANO_HD double tmax(double a, double b) { return fmax(a, b); }
+PANO_HD float tmin(float a, float b) { return fminf(a, b); }
+PANO_HD float tmax(float a, float b) { return fmaxf(a, b); }
 PANO_HD double tfloor(double v) { return floor(v); }
 PANO_HD float tfloor(float v) { return floorf(v); }
 
@@ -44,10 +47,10 @@ PANO_HD int to_index(T f) {
 }
 
 // ---- advect (cell-centred scalar).  Q, VY, VX are callables (y, x) -> T ------------------
-template <class T, class Q, class VY, class VX>
-PANO_HD T advect_cell(int y, int x, int h, int w, T timestep, const Q &q, const VY &vy, const VX &vx) {
-    const T ucx = (vx(y, x) + vx(y, x + 1)) / (T)2;
-    const T ucy = (vy(y, x) + vy(y + 1, x)) / (T)2;
+// *_uv forms take the already averaged velocity, so that kernels can share velocity loads between
+// the three advected quantities; the wrappers below fix the reference's summation order.
+template <class T, class Q>
+PANO_HD T advect_cell_uv(int y, int x, int h, int w, T timestep, T ucx, T ucy, const Q &q) {
     const T ndt = -timestep;                                   // integrate_euler(pos, vel, -timestep)
     const T ppx = ((T)x + (T)0.5) + ndt * ucx;
     const T ppy = ((T)y + (T)0.5) + ndt * ucy;
@@ -56,6 +59,12 @@ PANO_HD T advect_cell(int y, int x, int h, int w, T timestep, const Q &q, const 
     const int ix = (int)tfloor(px), iy = (int)tfloor(py);
     const T u = px - (T)ix, v = py - (T)iy;
     return bilinear(q(iy, ix), q(iy, ix + 1), q(iy + 1, ix), q(iy + 1, ix + 1), u, v);
+}
+template <class T, class Q, class VY, class VX>
+PANO_HD T advect_cell(int y, int x, int h, int w, T timestep, const Q &q, const VY &vy, const VX &vx) {
+    const T ucx = (vx(y, x) + vx(y, x + 1)) / (T)2;
+    const T ucy = (vy(y, x) + vy(y + 1, x)) / (T)2;
+    return advect_cell_uv<T>(y, x, h, w, timestep, ucx, ucy, q);
 }
 
 // common tail of both advect_mac loops: index-clamped bilinear gather on an (H, W) array
@@ -71,27 +80,35 @@ PANO_HD T mac_gather(T relx, T rely, int H, int W, const Q &q) {
 }
 
 // ---- advect_mac, x component: (y, x) in (h, w+1) ------------------------------------------
-template <class T, class QX, class VY, class VX>
-PANO_HD T advect_mac_x(int y, int x, int h, int w, T timestep, const QX &qx, const VY &vy, const VX &vx) {
-    const int xc = x < w - 1 ? x : w - 1, xm = x > 0 ? x - 1 : 0;
-    const T vvx = vx(y, x);
-    const T vvy = (vy(y, xc) + vy(y + 1, xc) + vy(y, xm) + vy(y + 1, xm)) / (T)4;
+template <class T, class QX>
+PANO_HD T advect_mac_x_uv(int y, int x, int h, int w, T timestep, T vvx, T vvy, const QX &qx) {
     const T ndt = -timestep;
     const T ppx = ((T)x + (T)0.0) + ndt * vvx;
     const T ppy = ((T)y + (T)0.5) + ndt * vvy;
     return mac_gather<T>(ppx - (T)0.0, ppy - (T)0.5, h, w + 1, qx);
 }
+template <class T, class QX, class VY, class VX>
+PANO_HD T advect_mac_x(int y, int x, int h, int w, T timestep, const QX &qx, const VY &vy, const VX &vx) {
+    const int xc = x < w - 1 ? x : w - 1, xm = x > 0 ? x - 1 : 0;
+    const T vvx = vx(y, x);
+    const T vvy = (vy(y, xc) + vy(y + 1, xc) + vy(y, xm) + vy(y + 1, xm)) / (T)4;
+    return advect_mac_x_uv<T>(y, x, h, w, timestep, vvx, vvy, qx);
+}
 
 // ---- advect_mac, y component: (y, x) in (h+1, w) ------------------------------------------
+template <class T, class QY>
+PANO_HD T advect_mac_y_uv(int y, int x, int h, int w, T timestep, T vvx, T vvy, const QY &qy) {
+    const T ndt = -timestep;
+    const T ppx = ((T)x + (T)0.5) + ndt * vvx;
+    const T ppy = ((T)y + (T)0.0) + ndt * vvy;
+    return mac_gather<T>(ppx - (T)0.5, ppy - (T)0.0, h + 1, w, qy);
+}
 template <class T, class QY, class VY, class VX>
 PANO_HD T advect_mac_y(int y, int x, int h, int w, T timestep, const QY &qy, const VY &vy, const VX &vx) {
     const int yc = y < h - 1 ? y : h - 1, ym = y > 0 ? y - 1 : 0;
     const T vvx = (vx(yc, x) + vx(yc, x + 1) + vx(ym, x) + vx(ym, x + 1)) / (T)4;
     const T vvy = vy(y, x);
-    const T ndt = -timestep;
-    const T ppx = ((T)x + (T)0.5) + ndt * vvx;
-    const T ppy = ((T)y + (T)0.0) + ndt * vvy;
-    return mac_gather<T>(ppx - (T)0.5, ppy - (T)0.0, h + 1, w, qy);
+    return advect_mac_y_uv<T>(y, x, h, w, timestep, vvx, vvy, qy);
 }
 
 // ---- Laplacian closure at one cell.  c = p[y,x]; n/s/w_/e = p at (y-1), (y+1), (x-1), (x+1);

@@ -31,6 +31,7 @@ struct Res2Args {
     ReduceUnit *units;
     unsigned long long seq_base;
     PanoCgControl *ctl;
+    long long *dbg;         // optional: per-section clock64 totals of CTA 0 (option "cg_profile")
 };
 
 struct Res2Shared {
@@ -168,6 +169,15 @@ __global__ void __launch_bounds__(T, 1) k_cg_resident2(const Res2Args a) {
                                     &a.ctl->error, /*fenced=*/false, [] { __syncthreads(); }, red);
     };
 
+    const bool prof = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    long long tprev = prof ? clock64() : 0;
+    auto stamp = [&](int slot) {
+        if (prof) {
+            const long long t = clock64();
+            a.dbg[slot] += t - tprev;
+            tprev = t;
+        }
+    };
     for (it = 0; it < a.max_iter; ++it) {
         const bool first = it == 0;
         double acc_zs = 0, acc_bb = 0, acc_bmax = 0;
@@ -182,6 +192,7 @@ __global__ void __launch_bounds__(T, 1) k_cg_resident2(const Res2Args a) {
                 if (h_src[q]) ok = unit_poll(h_src[q], want, hv[q], err) && ok;
             }
             if (!ok) sh->ok = 0;
+            stamp(0);   // mailbox poll
 #pragma unroll
             for (int k = 0; k < KR; ++k) {                         // s' = r + beta*s  (pcg.rs:72-77)
                 double2 sv = *reinterpret_cast<const double2 *>(Sown + k * P);
@@ -193,6 +204,7 @@ __global__ void __launch_bounds__(T, 1) k_cg_resident2(const Res2Args a) {
             for (int q = 0; q < kPerThread; ++q)
                 if (h_src[q]) S[h_dst[q]] = hv[q] + beta * S[h_dst[q]];
             __syncthreads();
+            stamp(1);   // s' update + barrier
         }
         {   // z = A s'  (dec_fluid.rs:100-119), z.s' (+ b.b and max|b| in iteration 0)
             double2 up = *reinterpret_cast<const double2 *>(Sown - P), cur = *reinterpret_cast<const double2 *>(Sown);
@@ -225,8 +237,11 @@ __global__ void __launch_bounds__(T, 1) k_cg_resident2(const Res2Args a) {
                 cur = dn;
             }
         }
+        stamp(2);       // stencil
         cta_reduce3<T>(acc_zs, acc_bb, acc_bmax, first ? 3 : 1, 0x4u, sh);
+        stamp(3);       // CTA reduction
         if (!allreduce(first ? 3 : 1, acc_zs, acc_bb, acc_bmax, 0x4u)) { failed = true; break; }
+        stamp(4);       // grid all-reduce #1
         ++nred;
         const double zs = red[0];
         if (first) {
@@ -272,8 +287,11 @@ __global__ void __launch_bounds__(T, 1) k_cg_resident2(const Res2Args a) {
                 for (int k = 0; k < KR; ++k) unit_store(my_mail + 2 * TW + TH + rg * KR + k, r[k].y, tag);
             }
         }
+        stamp(5);       // P2 update + mailbox post
         cta_reduce3<T>(acc_rr, acc_rmax, unused, 2, 0x2u, sh);
+        stamp(6);       // CTA reduction
         if (!allreduce(2, acc_rr, acc_rmax, 0.0, 0x2u)) { failed = true; break; }
+        stamp(7);       // grid all-reduce #2
         ++nred;
         const double rr = red[0];
         rmax = red[1];                                             // pcg.rs:58
@@ -385,6 +403,7 @@ int pano_cg_resident2_launch(pano_ctx *ctx, double *x, const double *b, double *
     a.units = (ReduceUnit *)ctx->d_units;
     a.seq_base = (++ctx->launch_epoch) << 32;
     a.ctl = ctx->d_cg;
+    a.dbg = pano_option(ctx, "cg_profile", 0) ? ctx->d_cg->prof : nullptr;   // device address of the 8 slots
     PANO_CUDA(cudaMemsetAsync(ctx->d_cg, 0, sizeof(PanoCgControl), ctx->stream));
 #define PANO_CFG(KR, TW, T) \
     if (c.kr == KR && c.tw == TW && c.t == T) return launch_cfg<KR, TW, T>(ctx, a, grid)

@@ -78,6 +78,96 @@ k_advect_slab(double *q_dst, double *vy_dst, double *vx_dst, const double *q_src
     advect_rows<double, true, true>(q_dst, vy_dst, vx_dst, q, vy, vx, vy, vx, h, w, dt, ya, yb);
 }
 
+// ------------------------------------------------------------------ K1, second generation
+// The first kernel above is issue-bound (ncu: 13 warp instructions per cell, 71 % issue-active, DRAM at 44 %):
+// 64-bit index arithmetic for 26 loads per cell and no reuse of the velocity samples shared by the three
+// advected quantities.  Here a thread owns one column and marches down kRows rows: the eight velocity samples
+// around (y, x) are carried in registers (4 new loads per row), indices are 32-bit, clamps are fmin/fmax.
+// Arithmetic is pano_cell_math.h's, so results stay bit-identical.  (Self-advection only: src == vel.)
+template <class T>
+struct V32 {   // row-major array addressed with 32-bit indices (the host checks that every index fits)
+    const T *p;
+    int pitch;
+    __device__ __forceinline__ T operator()(int y, int x) const { return p[y * pitch + x]; }
+};
+
+constexpr int kAdvRows = 4;   // rows per thread; a 256-thread block covers 32 columns x 32 rows
+
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+k_advect_march(T *__restrict__ q_dst, T *__restrict__ vy_dst, T *__restrict__ vx_dst, const T *__restrict__ q_src,
+               const T *__restrict__ vy_src, const T *__restrict__ vx_src, int h, int w, T dt) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ys = (blockIdx.y * 8 + (threadIdx.x >> 5)) * kAdvRows;
+    if (x > w || ys > h) return;
+    const V32<T> q{q_src, w}, vy{vy_src, w}, vx{vx_src, w + 1};
+    const bool xin = x < w, xpos = x > 0;
+    // rows of vy at y (C at x, E at x-1) and of vx at y-1 (G at x, H at x+1)
+    T C = xin ? vy(ys, x) : (T)0, E = xpos ? vy(ys, x - 1) : (T)0;
+    T G = (T)0, H = (T)0;
+    if (ys > 0) {
+        G = vx(ys - 1, x);
+        H = xin ? vx(ys - 1, x + 1) : (T)0;
+    }
+#pragma unroll
+    for (int k = 0; k < kAdvRows; ++k) {
+        const int y = ys + k;
+        if (y > h) break;
+        const bool yin = y < h;
+        T A = (T)0, B = (T)0, D = (T)0, F = (T)0;
+        if (yin) {
+            A = vx(y, x);
+            if (xin) { B = vx(y, x + 1); D = vy(y + 1, x); }
+            if (xpos) F = vy(y + 1, x - 1);
+        }
+        if (yin && xin) {                                   // advect (dec_fluid.rs:180-183)
+            const T ucx = (A + B) / (T)2, ucy = (C + D) / (T)2;
+            q_dst[y * w + x] = pano::advect_cell_uv<T>(y, x, h, w, dt, ucx, ucy, q);
+        }
+        if (yin) {                                          // advect_mac, x component (:220-225): xc = min(x, w-1), xm = max(x-1, 0)
+            const T t0 = xin ? C : E, t1 = xin ? D : F, t2 = xpos ? E : C, t3 = xpos ? F : D;
+            const T vvy = (t0 + t1 + t2 + t3) / (T)4;
+            vx_dst[y * (w + 1) + x] = pano::advect_mac_x_uv<T>(y, x, h, w, dt, A, vvy, vx);
+        }
+        if (xin) {                                          // advect_mac, y component (:257-263): yc = min(y, h-1), ym = max(y-1, 0)
+            const bool ypos = y > 0;
+            const T t0 = yin ? A : G, t1 = yin ? B : H, t2 = ypos ? G : A, t3 = ypos ? H : B;
+            const T vvx = (t0 + t1 + t2 + t3) / (T)4;
+            vy_dst[y * w + x] = pano::advect_mac_y_uv<T>(y, x, h, w, dt, vvx, C, vy);
+        }
+        C = D; E = F; G = A; H = B;
+    }
+}
+
+// ------------------------------------------------------------------ K3, second generation (no reductions: the
+// solver computes max|b| and b.b itself): one column x kDivRows rows per thread, vy carried down in a register
+constexpr int kDivRows = 8;
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+k_neg_divergence_march(T *__restrict__ b, const T *__restrict__ vy, const T *__restrict__ vx, int h, int w, RectI m) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ys = (blockIdx.y * 8 + (threadIdx.x >> 5)) * kDivRows;
+    if (x >= w || ys >= h) return;
+    // block-uniform test: does this 32 x 64 block touch the obstacle's edges?
+    const int bx0 = blockIdx.x * 32, by0 = blockIdx.y * 8 * kDivRows;
+    const bool masked = m.y1 > m.y0 && m.x1 > m.x0 && by0 < m.y1 && by0 + 8 * kDivRows + 1 > m.y0 && bx0 < m.x1 && bx0 + 33 > m.x0;
+    T vy0 = vy[ys * w + x];
+    if (masked && in_rect(m, ys, x)) vy0 = (T)0;
+#pragma unroll
+    for (int k = 0; k < kDivRows; ++k) {
+        const int y = ys + k;
+        if (y >= h) break;
+        T vy1 = vy[(y + 1) * w + x], vx0 = vx[y * (w + 1) + x], vx1 = vx[y * (w + 1) + x + 1];
+        if (masked) {
+            if (in_rect(m, y + 1, x)) vy1 = (T)0;
+            if (in_rect(m, y, x)) vx0 = (T)0;
+            if (in_rect(m, y, x + 1)) vx1 = (T)0;
+        }
+        b[y * w + x] = pano::neg_divergence_cell<T>(vy0, vy1, vx0, vx1);
+        vy0 = vy1;
+    }
+}
+
 // ------------------------------------------------------------------ K3: -divergence (+ max|b|, b.b)
 template <class T>
 __global__ void __launch_bounds__(kThreads)
@@ -189,8 +279,22 @@ inline dim3 grid2d(int rows, int cols) {
 // internal: advection on raw pointers (used by pano_step.cu as well)
 int pano_advect_launch(pano_ctx *ctx, int dtype, void *q_dst, void *vel_dst, const void *q_src, const void *mac_src,
                        const void *vel, size_t h, size_t w, double dt) {
-    dim3 g = grid2d((int)h + 1, (int)w + 1);
     const bool sc = q_dst != nullptr, mac = vel_dst != nullptr;
+    const size_t off1 = w * (h + 1);
+    // the marching kernel: both outputs, self-advection, 32-bit indices
+    if (sc && mac && mac_src == vel && (h + 1) * (w + 1) < ((size_t)1 << 31) && pano_option(ctx, "advect_kernel", 0) != 1) {
+        dim3 gm((unsigned)((w + 1 + 31) / 32), (unsigned)((h + 1 + 8 * kAdvRows - 1) / (8 * kAdvRows)));
+        if (dtype == PANO_F64)
+            k_advect_march<double><<<gm, kThreads, 0, ctx->stream>>>((double *)q_dst, (double *)vel_dst, (double *)vel_dst + off1,
+                                                                     (const double *)q_src, (const double *)vel, (const double *)vel + off1,
+                                                                     (int)h, (int)w, dt);
+        else
+            k_advect_march<float><<<gm, kThreads, 0, ctx->stream>>>((float *)q_dst, (float *)vel_dst, (float *)vel_dst + off1,
+                                                                    (const float *)q_src, (const float *)vel, (const float *)vel + off1,
+                                                                    (int)h, (int)w, (float)dt);
+        return pano_after_launch(ctx, "advect_march");
+    }
+    dim3 g = grid2d((int)h + 1, (int)w + 1);
 #define PANO_LAUNCH_ADV(T, S, M)                                                                                     \
     k_advect<T, S, M><<<g, kThreads, 0, ctx->stream>>>((T *)q_dst, (T *)vel_dst, (const T *)q_src, (const T *)mac_src, \
                                                        (const T *)vel, (int)h, (int)w, (T)dt)
@@ -211,12 +315,20 @@ int pano_advect_launch(pano_ctx *ctx, int dtype, void *q_dst, void *vel_dst, con
 // step does not need them because the CG kernel reduces max|b| and b.b itself in its first pass.
 int pano_neg_divergence_launch(pano_ctx *ctx, int dtype, void *b, const void *vel, size_t h, size_t w, pano_rect obstacle,
                                bool want_scalars) {
-    dim3 g = grid2d((int)h, (int)w);
-    const int nb = (int)(g.x * g.y);
-    PANO_TRY(pano_ensure_partials(ctx, 2 * (size_t)nb));
     // the obstacle rectangle indexes vy (h+1, w) and vx (h, w+1) alike; clip to the union
     RectI m = pano_clip_rect(obstacle, h + 1, w + 1);
     const size_t off = w * (h + 1);
+    if (!want_scalars && (h + 1) * (w + 1) < ((size_t)1 << 31)) {
+        dim3 gm((unsigned)((w + 31) / 32), (unsigned)((h + 8 * kDivRows - 1) / (8 * kDivRows)));
+        if (dtype == PANO_F64)
+            k_neg_divergence_march<double><<<gm, kThreads, 0, ctx->stream>>>((double *)b, (const double *)vel, (const double *)vel + off, (int)h, (int)w, m);
+        else
+            k_neg_divergence_march<float><<<gm, kThreads, 0, ctx->stream>>>((float *)b, (const float *)vel, (const float *)vel + off, (int)h, (int)w, m);
+        return pano_after_launch(ctx, "neg_divergence_march");
+    }
+    dim3 g = grid2d((int)h, (int)w);
+    const int nb = (int)(g.x * g.y);
+    PANO_TRY(pano_ensure_partials(ctx, 2 * (size_t)nb));
     if (dtype == PANO_F64)
         k_neg_divergence<double><<<g, kThreads, 0, ctx->stream>>>((double *)b, (const double *)vel, (const double *)vel + off, (int)h,
                                                                   (int)w, m, 0, (int)h, ctx->d_partials, ctx->d_partials + nb);

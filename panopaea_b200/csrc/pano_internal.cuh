@@ -47,7 +47,7 @@ struct PanoCgControl {
     int applies;
     double final_residual;
     double rhs_max;
-    double pad[2];
+    long long prof[8];            // per-section clock64 totals of CTA 0 (option "cg_profile", SM-resident kernel)
 };
 
 struct PanoWorkspace;   // cached scratch of pano_fluid_step_host
