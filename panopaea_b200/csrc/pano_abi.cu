@@ -61,6 +61,9 @@ int pano_ctx_create(int device, void *stream, pano_ctx **out) {
     }
     PANO_CUDA(cudaEventCreate(&c->ev_start));
     PANO_CUDA(cudaEventCreate(&c->ev_stop));
+    PANO_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    PANO_CUDA(cudaEventCreateWithFlags(&c->ev_advect, cudaEventDisableTiming));
+    PANO_CUDA(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
     PANO_CUDA(cudaMalloc(&c->d_scalars, 8 * sizeof(double)));
     PANO_CUDA(cudaMallocHost(&c->h_scalars, 8 * sizeof(double)));
     PANO_CUDA(cudaMalloc(&c->d_cg, sizeof(PanoCgControl)));
@@ -89,6 +92,9 @@ int pano_ctx_destroy(pano_ctx *ctx) {
     for (cudaEvent_t e : ctx->phase_events) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ev_start);
     cudaEventDestroy(ctx->ev_stop);
+    cudaEventDestroy(ctx->ev_advect);
+    cudaEventDestroy(ctx->ev_copy);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return PANO_OK;

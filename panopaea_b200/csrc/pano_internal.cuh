@@ -61,6 +61,8 @@ struct pano_ctx {
     size_t smem_optin = 0;
     uint64_t launches = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    cudaStream_t copy_stream = nullptr;          // second stream of pano_fluid_step_host (downloads under the solve)
+    cudaEvent_t ev_advect = nullptr, ev_copy = nullptr;
     // reductions: block partials (device) + final scalars (device, pinned host mirror)
     double *d_partials = nullptr;
     size_t partials_cap = 0;      // in doubles

@@ -58,11 +58,13 @@ static int get_workspace(pano_ctx *ctx, size_t h, size_t w, PanoWorkspace **out)
     return PANO_OK;
 }
 
-extern "C" {
+// after_advect (nullable) runs once the new density is final (right after the advection), long before the solve ends:
+// the host-buffer entry point uses it to start the density download on a second stream, under the CG kernel.
+typedef int (*PanoStepHook)(pano_ctx *ctx, void *user);
 
-int pano_fluid_step(const pano_step_params *params, pano_field *density, pano_field *vel, pano_field *pressure,
-                    pano_field *temp, pano_field *vel_temp, pano_field *residual, pano_field *auxiliary,
-                    pano_field *search, pano_pcg_info *info) {
+static int fluid_step_impl(const pano_step_params *params, pano_field *density, pano_field *vel, pano_field *pressure,
+                           pano_field *temp, pano_field *vel_temp, pano_field *residual, pano_field *auxiliary,
+                           pano_field *search, pano_pcg_info *info, PanoStepHook after_advect, void *user) {
     if (!params) PANO_FAIL(PANO_ERR_INVALID, "pano_fluid_step: null params");
     const pano_field *s2[] = {density, pressure, temp, residual, auxiliary, search};
     const char *n2[] = {"density", "pressure", "temp", "residual", "auxiliary", "search"};
@@ -100,6 +102,7 @@ int pano_fluid_step(const pano_step_params *params, pano_field *density, pano_fi
     PANO_TRY(pano_advect_launch(ctx, dt_, temp->d, vel_temp->d, density->d, vel->d, vel->d, h, w, dt));
     PANO_TRY(pano_field_swap(density, temp));
     PANO_TRY(pano_field_swap(vel, vel_temp));
+    if (after_advect) PANO_TRY(after_advect(ctx, user));
     PANO_TRY(pano_phase_mark(ctx, 2));
     // b = -div  :69-83   (b lives in `temp`, as in the reference)
     PANO_TRY(pano_neg_divergence_launch(ctx, dt_, temp->d, vel->d, h, w, params->obstacle, false));
@@ -123,6 +126,29 @@ int pano_fluid_step(const pano_step_params *params, pano_field *density, pano_fi
     return PANO_OK;
 }
 
+extern "C" {
+
+int pano_fluid_step(const pano_step_params *params, pano_field *density, pano_field *vel, pano_field *pressure,
+                    pano_field *temp, pano_field *vel_temp, pano_field *residual, pano_field *auxiliary,
+                    pano_field *search, pano_pcg_info *info) {
+    return fluid_step_impl(params, density, vel, pressure, temp, vel_temp, residual, auxiliary, search, info, nullptr, nullptr);
+}
+
+struct HostStepCopy {
+    PanoWorkspace *ws;
+    double *density_host;
+    size_t bytes;
+};
+
+static int start_density_download(pano_ctx *ctx, void *user) {
+    HostStepCopy *c = static_cast<HostStepCopy *>(user);
+    PANO_CUDA(cudaEventRecord(ctx->ev_advect, ctx->stream));
+    PANO_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_advect, 0));
+    PANO_CUDA(cudaMemcpyAsync(c->density_host, c->ws->density->d, c->bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    PANO_CUDA(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+    return PANO_OK;
+}
+
 int pano_fluid_step_host(pano_ctx *ctx, const pano_step_params *params, size_t h, size_t w, double *density, double *vel,
                          double *pressure, pano_pcg_info *info) {
     if (!ctx || !params || !density || !vel || !pressure) PANO_FAIL(PANO_ERR_INVALID, "pano_fluid_step_host: null argument");
@@ -132,9 +158,10 @@ int pano_fluid_step_host(pano_ctx *ctx, const pano_step_params *params, size_t h
     const size_t n2 = h * w * sizeof(double), n1 = pano_num_elem(PANO_SIMPLEX1, h, w) * sizeof(double);
     PANO_CUDA(cudaMemcpyAsync(ws->density->d, density, n2, cudaMemcpyHostToDevice, ctx->stream));
     PANO_CUDA(cudaMemcpyAsync(ws->vel->d, vel, n1, cudaMemcpyHostToDevice, ctx->stream));
-    PANO_TRY(pano_fluid_step(params, ws->density, ws->vel, ws->pressure, ws->temp, ws->vel_temp, ws->residual,
-                             ws->auxiliary, ws->search, nullptr));
-    PANO_CUDA(cudaMemcpyAsync(density, ws->density->d, n2, cudaMemcpyDeviceToHost, ctx->stream));
+    HostStepCopy hook{ws, density, n2};
+    PANO_TRY(fluid_step_impl(params, ws->density, ws->vel, ws->pressure, ws->temp, ws->vel_temp, ws->residual, ws->auxiliary,
+                             ws->search, nullptr, start_density_download, &hook));   // density goes home under the solve
+    PANO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
     PANO_CUDA(cudaMemcpyAsync(vel, ws->vel->d, n1, cudaMemcpyDeviceToHost, ctx->stream));
     PANO_CUDA(cudaMemcpyAsync(pressure, ws->pressure->d, n2, cudaMemcpyDeviceToHost, ctx->stream));
     PANO_CUDA(cudaMemcpyAsync(ctx->h_cg, ctx->d_cg, sizeof(PanoCgControl), cudaMemcpyDeviceToHost, ctx->stream));
