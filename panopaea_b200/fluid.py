@@ -46,6 +46,27 @@ def density_to_u8(density, lower=-2.0, upper=2.0):
     return out
 
 
+def export_png(path, density_u8):
+    """util::png::export (panopaea_utils/src/png.rs:6-18) for the gray image returned by density_to_u8:
+    RGB8 with the three channels equal, as examples/dec_fluid.rs:150-154 builds it.  The vertical flip
+    already happened on the device.  Pure-Python encoder (zlib + struct): the PNG stays a host job."""
+    import struct
+    import zlib
+    img = np.ascontiguousarray(density_u8, np.uint8)
+    h, w = img.shape
+    rgb = np.repeat(img[:, :, None], 3, axis=2)
+    raw = b"".join(b"\x00" + rgb[y].tobytes() for y in range(h))
+
+    def chunk(tag, data):
+        body = tag + data
+        return struct.pack(">I", len(data)) + body + struct.pack(">I", zlib.crc32(body) & 0xFFFFFFFF)
+
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) + \
+        chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b"")
+    with open(path, "wb") as f:
+        f.write(png)
+
+
 def smoke_params(n: int):
     """Synthetic smoke plume of SURVEY.md 8(d): the shipped example scaled by k = n/128
     (n = 128 is examples/dec_fluid.rs:27-44, 51-54, 72-73 exactly)."""

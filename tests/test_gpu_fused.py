@@ -123,6 +123,27 @@ def test_density_to_u8():
     assert np.array_equal(img, want)
 
 
+def test_export_png_roundtrip(tmp_path):
+    """the output step after the path (dec_fluid.rs:143-164): device transfer + flip, PNG encode on the host"""
+    import struct
+    import zlib
+    from tests import gpu_util as U
+    from panopaea_b200 import fluid
+    h, w = 24, 40
+    grid = U.grid(h, w)
+    d = np.random.default_rng(10).uniform(-3, 3, (h, w))
+    img = fluid.density_to_u8(U.s2(grid, d))
+    path = tmp_path / "density_0.png"
+    fluid.export_png(str(path), img)
+    raw = path.read_bytes()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+    assert struct.unpack(">II", raw[16:24]) == (w, h)
+    i = raw.index(b"IDAT")
+    n = struct.unpack(">I", raw[i - 4:i])[0]
+    pix = np.frombuffer(zlib.decompress(raw[i + 4:i + 4 + n]), np.uint8).reshape(h, 1 + 3 * w)[:, 1:].reshape(h, w, 3)
+    assert np.array_equal(pix[:, :, 0], img) and np.array_equal(pix[:, :, 1], img) and np.array_equal(pix[:, :, 2], img)
+
+
 def test_full_size_properties():
     """4096^2 (BASELINE configs[3]): size-independent properties instead of an oracle run."""
     from tests import gpu_util as U

@@ -64,6 +64,26 @@ def test_fused_cg_vs_oracle(oracle, h, w, variant):
         _set_variant("auto")
 
 
+def test_f32_solve(oracle):
+    """The crate is generic in T; an f32 solve runs on the generic kernel (f32 accumulation, like the reference's)."""
+    from tests import gpu_util as U
+    from panopaea_b200 import pcg
+    h, w = 40, 56
+    grid = U.grid(h, w)
+    obstacle = U.default_obstacle(h, w)
+    b = U.consistent_rhs(oracle, h, w, obstacle, seed=21, scale=40.0).astype(np.float32)
+    want = oracle.pcg_grid_laplacian(h, w, b, 100, 0.1, 0.05, obstacle)
+    x, r, aux, s = (grid.new_simplex_2(np.float32) for _ in range(4))
+    info = pcg.solve_grid_laplacian(x, U.s2(grid, b, np.float32), 100, 0.1, r, aux, s, 0.05, obstacle)
+    assert want.x.dtype == np.float32 and 0 < want.iterations < 100
+    assert abs(info["iterations"] - want.iterations) <= 3          # f32 dots: the summation order matters more
+    assert info["final_residual"] < 0.1
+    xs = x.to_host()
+    assert xs.dtype == np.float32
+    true_r = b.astype(np.float64) - oracle.laplacian_closure(h, w, xs.astype(np.float64), 0.05, obstacle)
+    assert np.abs(true_r).max() < 0.1 + 1e-2                       # the returned x really solves the system to the threshold
+
+
 def test_streaming_kernel_requires_even_width():
     from tests import gpu_util as U
     import panopaea_b200 as P
