@@ -257,11 +257,6 @@ __global__ void __launch_bounds__(T, 1) k_cg_resident2(const Res2Args a) {
         double acc_rr = 0, acc_rmax = 0, unused = 0;
 #pragma unroll
         for (int k = 0; k < KR; ++k) {
-            const double2 sv = *reinterpret_cast<const double2 *>(Sown + k * P);
-            double2 xv = *reinterpret_cast<const double2 *>(Xown + k * TW);
-            xv.x = xv.x + alpha * sv.x;                            // pcg.rs:55 (x = 0 before iteration 0)
-            xv.y = xv.y + alpha * sv.y;
-            *reinterpret_cast<double2 *>(Xown + k * TW) = xv;
             r[k].x = r[k].x + nalpha * z[k].x;                     // pcg.rs:56 (cells outside the grid: 0 + a*0)
             r[k].y = r[k].y + nalpha * z[k].y;
             acc_rmax = fmax(acc_rmax, fmax(fabs(r[k].x), fabs(r[k].y)));
@@ -290,8 +285,23 @@ __global__ void __launch_bounds__(T, 1) k_cg_resident2(const Res2Args a) {
         stamp(5);       // P2 update + mailbox post
         cta_reduce3<T>(acc_rr, acc_rmax, unused, 2, 0x2u, sh);
         stamp(6);       // CTA reduction
-        if (!allreduce(2, acc_rr, acc_rmax, 0.0, 0x2u)) { failed = true; break; }
-        stamp(7);       // grid all-reduce #2
+        // x += alpha s' (pcg.rs:55; x = 0 before iteration 0) is off the critical path: it runs inside the reduction's wait
+        auto update_x = [&] {
+#pragma unroll
+            for (int k = 0; k < KR; ++k) {
+                const double2 sv = *reinterpret_cast<const double2 *>(Sown + k * P);
+                double2 xv = *reinterpret_cast<const double2 *>(Xown + k * TW);
+                xv.x = xv.x + alpha * sv.x;
+                xv.y = xv.y + alpha * sv.y;
+                *reinterpret_cast<double2 *>(Xown + k * TW) = xv;
+            }
+        };
+        if (!grid_allreduce_units(a.units, a.seq_base + nred, nred, 2, acc_rr, acc_rmax, 0.0, 0x2u, sh->vals, sh->out, &sh->ok,
+                                  &a.ctl->error, /*fenced=*/false, [] { __syncthreads(); }, red, nullptr, update_x)) {
+            failed = true;
+            break;
+        }
+        stamp(7);       // grid all-reduce #2 (+ x update)
         ++nred;
         const double rr = red[0];
         rmax = red[1];                                             // pcg.rs:58

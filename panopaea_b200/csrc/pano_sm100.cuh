@@ -136,12 +136,19 @@ struct XRank {
     ReduceUnit *peer[kMaxRanks];      // every rank's array as mapped into this process (peer[rank] == local)
 };
 
-template <class SyncFn>
+struct NoWork {
+    __device__ __forceinline__ void operator()() const {}
+};
+
+// `mid` is work that does not depend on the reduction's result (e.g. the x update of CG): a CTA that only waits
+// runs it between publishing its partials and polling the result; the root, which everybody waits for, runs it
+// after it has published the result, in the head start it has over the others.
+template <class SyncFn, class MidFn = NoWork>
 __device__ __forceinline__ bool grid_allreduce_units(ReduceUnit *units, unsigned long long seq, unsigned long long n, int nvals,
                                                      double v0, double v1, double v2, unsigned max_mask,
                                                      double (*vals)[kMaxCtas], double *out_sh, int *ok_sh,
                                                      volatile unsigned int *err, bool fenced, SyncFn sync, double *out,
-                                                     const XRank *xr = nullptr) {
+                                                     const XRank *xr = nullptr, MidFn mid = MidFn()) {
     const int G = gridDim.x, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const unsigned parity = (unsigned)(n & 1);
     const bool multi = xr != nullptr && xr->nranks > 1;
@@ -185,7 +192,9 @@ __device__ __forceinline__ bool grid_allreduce_units(ReduceUnit *units, unsigned
                 if (root_mode) unit_store(result + wid, r, seq);
             }
         }
+        mid();
     } else {
+        mid();
         if (tid < nvals) {
             double v;
             if (!unit_poll(result + tid, seq, v, err)) *ok_sh = 0;
