@@ -58,6 +58,7 @@ _SIGS = {
     "pano_timer_stop_ms": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "pano_ctx_step_times": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pano_ctx_cg_profile": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "pano_ctx_cg_profile_ctas": (C.c_int, [_P, C.POINTER(C.c_int64), C.c_int]),
     "pano_ctx_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "pano_ctx_get_option": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64)]),
     "pano_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),

@@ -165,6 +165,14 @@ int pano_ctx_cg_profile(pano_ctx *ctx, int64_t cycles_out[8]) {
     return PANO_OK;
 }
 
+int pano_ctx_cg_profile_ctas(pano_ctx *ctx, int64_t *cycles_out, int n) {
+    if (!ctx || !cycles_out || n < 0 || (size_t)n > ctx->partials_cap) PANO_FAIL(PANO_ERR_INVALID, "pano_ctx_cg_profile_ctas: bad argument");
+    PANO_TRY(pano_activate(ctx));
+    PANO_CUDA(cudaMemcpyAsync(cycles_out, ctx->d_partials, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PANO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PANO_OK;
+}
+
 int pano_ctx_set_option(pano_ctx *ctx, const char *key, int64_t value) {
     if (!ctx || !key) PANO_FAIL(PANO_ERR_INVALID, "pano_ctx_set_option: null argument");
     ctx->options[key] = value;

@@ -67,6 +67,8 @@ struct StreamArgs {
     double *up_r, *up_s0, *up_s1; // upper neighbour's ghost row BELOW its slab (receives my first row), or null
     double *dn_r, *dn_s0, *dn_s1; // lower neighbour's ghost row ABOVE its slab (receives my last row), or null
     XRank xr;
+    long long *dbg;               // optional per-section clock64 totals of CTA 0 (option "cg_profile")
+    long long *dbg_cta;           // optional [2][gridDim.x]: per-CTA clock64 totals spent in the P1 / P2 tile loops
 };
 
 struct Tail {                     // small shared-memory area behind the stage ring
@@ -374,6 +376,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
     double *s_cur = a.s0, *s_old = a.s1;
     double red[3];
 
+    const bool prof = a.dbg != nullptr && tid == 0;
+    long long tprev = prof ? clock64() : 0;
+    auto stamp = [&](int slot) {
+        if (prof) {
+            const long long t = clock64();
+            if (blockIdx.x == 0) a.dbg[slot] += t - tprev;
+            if ((slot & 1) == 0) a.dbg_cta[(slot >> 1) * gridDim.x + blockIdx.x] += t - tprev;   // tile loops of every CTA
+            tprev = t;
+        }
+    };
     for (it = 0; it < a.max_iter; ++it) {
         const bool first = it == 0;
         // ------------------------------------------------------------------ P1
@@ -397,6 +409,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&tl->empty[st]);
         }
+        stamp(0);   // P1 tiles
         {
             const double v0 = consumer_sum(acc_zs, tl->wsum[0]);
             double v1 = 0, v2 = 0;
@@ -409,6 +422,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
                 return;
             }
         }
+        stamp(1);   // CTA reduction + grid all-reduce #1
         const double zs = red[0];
         if (first) {
             sigma = red[1];                                    // pcg.rs:46
@@ -445,6 +459,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&tl->empty[st]);
         }
+        stamp(2);   // P2 tiles
         {
             const double v0 = consumer_sum(acc_rr, tl->wsum[0]);
             const double v1 = consumer_max(acc_rmax, tl->wsum[1]);
@@ -453,6 +468,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
                 return;
             }
         }
+        stamp(3);   // CTA reduction + grid all-reduce #2
         const double rr = red[0];
         rmax = red[1];                                         // pcg.rs:58
         if (rmax < a.threshold) {                              // pcg.rs:60-63
@@ -559,6 +575,9 @@ int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, 
     a.tiles_x = ((int)w + TW - 1) / TW;
     a.tiles_y = ((int)h + TH - 1) / TH;
     a.ctl = ctx->d_cg;
+    a.dbg = pano_option(ctx, "cg_profile", 0) ? ctx->d_cg->prof : nullptr;
+    a.dbg_cta = reinterpret_cast<long long *>(ctx->d_partials);   // >= 12288 doubles (pano_ctx_create); zeroed below when profiling
+    if (a.dbg) PANO_CUDA(cudaMemsetAsync(ctx->d_partials, 0, 2 * kMaxCtas * sizeof(long long), ctx->stream));
     a.zigzag = pano_option(ctx, "cg_zigzag", 1) != 0;
     a.row0 = 0; a.gy0 = 0; a.gh = (int)h;
     a.xr.rank = 0; a.xr.nranks = 1;
