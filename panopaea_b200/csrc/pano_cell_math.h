@@ -38,12 +38,12 @@ PANO_HD T bilinear(T a00, T a01, T a10, T a11, T s, T t) {
     return linear(linear(a00, a01, s), linear(a10, a11, s), t);
 }
 
-// Rust `f as usize` for f >= 0 (saturating); bounded so that +1 cannot overflow an int.
+// Rust `f as usize` for f >= 0, then min(., lim): the index stays an int, the weight uses the floored REAL itself
+// ((T)(f as usize) == f for every f below 2^64; beyond that both corners are the last sample and any weight in [0,1]
+// returns it unchanged).
 template <class T>
-PANO_HD int to_index(T f) {
-    if (!(f > (T)0)) return 0;
-    if (f > (T)1.0e9) return 1000000000;
-    return (int)f;
+PANO_HD int to_index_min(T f, int lim) {
+    return f < (T)lim ? (int)f : lim;
 }
 
 // ---- advect (cell-centred scalar).  Q, VY, VX are callables (y, x) -> T ------------------
@@ -70,12 +70,11 @@ PANO_HD T advect_cell(int y, int x, int h, int w, T timestep, const Q &q, const 
 // common tail of both advect_mac loops: index-clamped bilinear gather on an (H, W) array
 template <class T, class Q>
 PANO_HD T mac_gather(T relx, T rely, int H, int W, const Q &q) {
-    const int px = to_index(tmax(tfloor(relx), (T)0));
-    const int py = to_index(tmax(tfloor(rely), (T)0));
-    const int x0 = px < W - 1 ? px : W - 1, x1 = px + 1 < W - 1 ? px + 1 : W - 1;
-    const int y0 = py < H - 1 ? py : H - 1, y1 = py + 1 < H - 1 ? py + 1 : H - 1;
-    const T s = tmax(tmin(relx - (T)px, (T)1), (T)0);
-    const T t = tmax(tmin(rely - (T)py, (T)1), (T)0);
+    const T fpx = tmax(tfloor(relx), (T)0), fpy = tmax(tfloor(rely), (T)0);     // px, py as REALs
+    const int x0 = to_index_min(fpx, W - 1), x1 = x0 + 1 < W - 1 ? x0 + 1 : W - 1;   // min(px, W-1), min(px+1, W-1)
+    const int y0 = to_index_min(fpy, H - 1), y1 = y0 + 1 < H - 1 ? y0 + 1 : H - 1;
+    const T s = tmax(tmin(relx - fpx, (T)1), (T)0);
+    const T t = tmax(tmin(rely - fpy, (T)1), (T)0);
     return bilinear(q(y0, x0), q(y0, x1), q(y1, x0), q(y1, x1), s, t);
 }
 
@@ -109,6 +108,99 @@ PANO_HD T advect_mac_y(int y, int x, int h, int w, T timestep, const QY &qy, con
     const T vvx = (vx(yc, x) + vx(yc, x + 1) + vx(ym, x) + vx(ym, x + 1)) / (T)4;
     const T vvy = vy(y, x);
     return advect_mac_y_uv<T>(y, x, h, w, timestep, vvx, vvy, qy);
+}
+
+// ---- exact fast forms (f64) ----------------------------------------------------------------
+// The straightforward forms above cost ~120 issue slots per advected value on sm_100a: there is no
+// f64 min/max instruction (every clamp is DSETP + 2 FSEL) and FRND / F2I / I2F on 64-bit types run
+// at 1/8 of the FP64 rate.  The forms below give the SAME bits for every input with
+// |coordinate| < 2^32 cells (anything else falls back to the general form), using
+//   * floor of a non-negative value by one add in round-down mode: t = v (+, RD) 2^52 is
+//     2^52 + floor(v) exactly, its low word IS floor(v) as an integer and t - 2^52 is floor(v)
+//     as a double (exact); the high word of t equals that of 2^52 iff v < 2^32.
+//   * advect_mac's three clamps per axis, max(floor(rel), 0), min(rel - p, 1), max(.., 0)
+//     (dec_fluid.rs:232-246), collapse to ONE: with r = max(rel, 0), p = floor(r) and the weight is
+//     r - p.  rel >= 0: floor(rel) >= 0 and rel - floor(rel) lies in [0, 1) and is exact, so both
+//     weight clamps are no-ops; rel < 0: p = 0 and max(min(rel, 1), 0) = 0 = r - p.
+// Only the sign of a zero weight can differ, which no later operation on this path can observe.
+struct FloorNN {
+    double f;          // floor(v)
+    unsigned i;        // floor(v) mod 2^32
+    unsigned hi;       // == kFloorHi iff v < 2^32
+};
+constexpr unsigned kFloorHi = 0x43300000u;
+PANO_HD FloorNN floor_nonneg(double v) {   // requires v >= 0
+    FloorNN r;
+#if defined(__CUDA_ARCH__)
+    const double t = __dadd_rd(v, 4503599627370496.0);
+    r.i = (unsigned)__double2loint(t);
+    r.hi = (unsigned)__double2hiint(t);
+#else
+    const double t = floor(v) + 4503599627370496.0;   // the same value: this sum is exact below 2^52
+    unsigned long long bits;
+    __builtin_memcpy(&bits, &t, 8);
+    r.i = (unsigned)bits;
+    r.hi = (unsigned)(bits >> 32);
+#endif
+    r.f = t - 4503599627370496.0;
+    return r;
+}
+
+// max(v, 0) and min(v, lim) without the compiler's NaN-propagating max/min expansion (6 instructions on sm_100a):
+// the first is three integer instructions on the sign bit, the second one compare and a 64-bit select.
+PANO_HD double clamp_lo0(double v) {          // v <= 0 (or -0.0) -> +0.0
+#if defined(__CUDA_ARCH__)
+    const int hi = __double2hiint(v), lo = __double2loint(v);
+    const int m = ~(hi >> 31);
+    return __hiloint2double(hi & m, lo & m);
+#else
+    return v > 0.0 ? v : 0.0;
+#endif
+}
+PANO_HD double clamp_hi(double v, double lim) {   // v < lim ? v : lim
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(v), "d"(lim));
+    return r;
+#else
+    return v < lim ? v : lim;
+#endif
+}
+
+// returns false (and leaves `out` alone) when a coordinate is beyond 2^32 cells: the caller then uses mac_gather
+template <class Q>
+PANO_HD bool mac_gather_fast(double relx, double rely, int H, int W, const Q &q, double &out) {
+    const double rx = clamp_lo0(relx), ry = clamp_lo0(rely);
+    const FloorNN fx = floor_nonneg(rx), fy = floor_nonneg(ry);
+    if (((fx.hi ^ kFloorHi) | (fy.hi ^ kFloorHi)) != 0u) return false;
+    const unsigned wm = (unsigned)(W - 1), hm = (unsigned)(H - 1);
+    const unsigned x0 = fx.i < wm ? fx.i : wm, x1 = x0 + 1u < wm ? x0 + 1u : wm;   // = min(p, W-1), min(p+1, W-1)
+    const unsigned y0 = fy.i < hm ? fy.i : hm, y1 = y0 + 1u < hm ? y0 + 1u : hm;
+    const double s = rx - fx.f, t = ry - fy.f;
+    out = bilinear(q((int)y0, (int)x0), q((int)y0, (int)x1), q((int)y1, (int)x0), q((int)y1, (int)x1), s, t);
+    return true;
+}
+
+// xh = x + 0.5, yh = y + 0.5 as doubles (the caller carries them instead of converting per cell);
+// wlim = w - 1.00001, hlim = h - 1.00001
+template <class Q>
+PANO_HD double advect_cell_fast(double xh, double yh, double wlim, double hlim, double ndt, double ucx, double ucy, const Q &q) {
+    const double ppx = xh + ndt * ucx, ppy = yh + ndt * ucy;
+    const double px = clamp_hi(clamp_lo0(ppx - 0.5), wlim), py = clamp_hi(clamp_lo0(ppy - 0.5), hlim);
+    const FloorNN fx = floor_nonneg(px), fy = floor_nonneg(py);      // px, py in [0, 2^31): no guard needed
+    const int ix = (int)fx.i, iy = (int)fy.i;
+    return bilinear(q(iy, ix), q(iy, ix + 1), q(iy + 1, ix), q(iy + 1, ix + 1), px - fx.f, py - fy.f);
+}
+// advect_mac: the backtraced position relative to the component's own sample grid.
+// x component at (x, y + 0.5): xd = (double)x, yh = y + 0.5; `ppx - 0.0` of the reference is the identity.
+PANO_HD void mac_x_rel(double xd, double yh, double ndt, double vvx, double vvy, double &relx, double &rely) {
+    relx = xd + ndt * vvx;
+    rely = (yh + ndt * vvy) - 0.5;
+}
+// y component at (x + 0.5, y)
+PANO_HD void mac_y_rel(double xh, double yd, double ndt, double vvx, double vvy, double &relx, double &rely) {
+    relx = (xh + ndt * vvx) - 0.5;
+    rely = yd + ndt * vvy;
 }
 
 // ---- Laplacian closure at one cell.  c = p[y,x]; n/s/w_/e = p at (y-1), (y+1), (x-1), (x+1);

@@ -139,6 +139,108 @@ k_advect_march(T *__restrict__ q_dst, T *__restrict__ vy_dst, T *__restrict__ vx
     }
 }
 
+// ------------------------------------------------------------------ K1, third generation (f64)
+// k_advect_march is issue-bound at ~370 instructions per cell (ncu: 63 % issue-active, DRAM 42 % of the copy peak).
+// Same marching scheme, but (a) the exact fast forms of pano_cell_math.h (floor by a round-down add, one clamp per
+// axis instead of three, no 64-bit conversions), (b) positions carried as doubles and advanced by +1.0 (exact),
+// (c) blocks that touch no domain border skip every border select (kEdge = false).
+__device__ __noinline__ double mac_gather_far(double relx, double rely, int H, int W, const double *p) {   // > 2^32 cells away: never in practice
+    return pano::mac_gather<double>(relx, rely, H, W, V32<double>{p, W});
+}
+
+template <bool kEdge>
+__device__ __forceinline__ void advect_march3_body(double *__restrict__ q_dst, double *__restrict__ vy_dst, double *__restrict__ vx_dst,
+                                                   const double *__restrict__ q_src, const double *__restrict__ vy_src,
+                                                   const double *__restrict__ vx_src, int h, int w, double dt, int x, int ys) {
+    const V32<double> q{q_src, w}, vy{vy_src, w}, vx{vx_src, w + 1};
+    const bool xin = !kEdge || x < w, xpos = !kEdge || x > 0;
+    const double ndt = -dt, xd = (double)x, xh = xd + 0.5;
+    const double wlim = (double)w - 1.00001, hlim = (double)h - 1.00001;
+    double yd = (double)ys;
+    double C = xin ? vy(ys, x) : 0.0, E = xpos ? vy(ys, x - 1) : 0.0;
+    double G = 0.0, H = 0.0;
+    if (!kEdge || ys > 0) {
+        G = vx(ys - 1, x);
+        H = xin ? vx(ys - 1, x + 1) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < kAdvRows; ++k) {
+        const int y = ys + k;
+        if (kEdge && y > h) break;
+        const bool yin = !kEdge || y < h;
+        const double yh = yd + 0.5;
+        double A = 0.0, B = 0.0, D = 0.0, F = 0.0;
+        if (yin) {
+            A = vx(y, x);
+            if (xin) { B = vx(y, x + 1); D = vy(y + 1, x); }
+            if (xpos) F = vy(y + 1, x - 1);
+        }
+        if (yin && xin) {                                   // advect (dec_fluid.rs:180-183)
+            const double ucx = (A + B) / 2.0, ucy = (C + D) / 2.0;
+            q_dst[y * w + x] = pano::advect_cell_fast(xh, yh, wlim, hlim, ndt, ucx, ucy, q);
+        }
+        if (yin) {                                          // advect_mac, x component (:220-225)
+            double vvy;
+            if (kEdge) {
+                const double t0 = xin ? C : E, t1 = xin ? D : F, t2 = xpos ? E : C, t3 = xpos ? F : D;
+                vvy = (t0 + t1 + t2 + t3) / 4.0;
+            } else {
+                vvy = (C + D + E + F) / 4.0;
+            }
+            double rx, ry, v;
+            pano::mac_x_rel(xd, yh, ndt, A, vvy, rx, ry);
+            if (!pano::mac_gather_fast(rx, ry, h, w + 1, vx, v)) v = mac_gather_far(rx, ry, h, w + 1, vx_src);
+            vx_dst[y * (w + 1) + x] = v;
+        }
+        if (xin) {                                          // advect_mac, y component (:257-263)
+            double vvx;
+            if (kEdge) {
+                const bool ypos = y > 0;
+                const double t0 = yin ? A : G, t1 = yin ? B : H, t2 = ypos ? G : A, t3 = ypos ? H : B;
+                vvx = (t0 + t1 + t2 + t3) / 4.0;
+            } else {
+                vvx = (A + B + G + H) / 4.0;
+            }
+            double rx, ry, v;
+            pano::mac_y_rel(xh, yd, ndt, vvx, C, rx, ry);
+            if (!pano::mac_gather_fast(rx, ry, h + 1, w, vy, v)) v = mac_gather_far(rx, ry, h + 1, w, vy_src);
+            vy_dst[y * w + x] = v;
+        }
+        C = D; E = F; G = A; H = B;
+        yd += 1.0;
+    }
+}
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// kPrefetch: 0 none, 1 L1, 2 L2 -- every row of q, vy, vx the block will touch first is requested at kernel entry, so the
+// DRAM latency of the velocity loads AND of the first-touch gathers (two dependent round trips per row otherwise)
+// overlaps across the whole tile instead of being paid row by row.
+template <int kPrefetch, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
+k_advect_march3(double *__restrict__ q_dst, double *__restrict__ vy_dst, double *__restrict__ vx_dst, const double *__restrict__ q_src,
+                const double *__restrict__ vy_src, const double *__restrict__ vx_src, int h, int w, double dt) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ys = (blockIdx.y * 8 + (threadIdx.x >> 5)) * kAdvRows;
+    // block-uniform: columns [bx0, bx0+32) within [1, w-1] and rows [by0, by0 + 8*kAdvRows) within [1, h-1]
+    const int bx0 = blockIdx.x * 32, by0 = blockIdx.y * 8 * kAdvRows;
+    if (bx0 >= 1 && bx0 + 31 <= w - 1 && by0 >= 1 && by0 + 8 * kAdvRows - 1 <= h - 1) {
+        if (kPrefetch) {
+#pragma unroll
+            for (int k = 0; k < kAdvRows; ++k) {
+                const double *a = q_src + (ys + k) * w + x, *b = vy_src + (ys + k + 1) * w + x, *c = vx_src + (ys + k) * (w + 1) + x;
+                if (kPrefetch == 1) { prefetch_l1(a); prefetch_l1(b); prefetch_l1(c); }
+                else { prefetch_l2(a); prefetch_l2(b); prefetch_l2(c); }
+            }
+        }
+        advect_march3_body<false>(q_dst, vy_dst, vx_dst, q_src, vy_src, vx_src, h, w, dt, x, ys);
+    } else {
+        if (x > w || ys > h) return;
+        advect_march3_body<true>(q_dst, vy_dst, vx_dst, q_src, vy_src, vx_src, h, w, dt, x, ys);
+    }
+}
+
 // ------------------------------------------------------------------ K3, second generation (no reductions: the
 // solver computes max|b| and b.b itself): one column x kDivRows rows per thread, vy carried down in a register
 constexpr int kDivRows = 8;
@@ -284,6 +386,16 @@ int pano_advect_launch(pano_ctx *ctx, int dtype, void *q_dst, void *vel_dst, con
     // the marching kernel: both outputs, self-advection, 32-bit indices
     if (sc && mac && mac_src == vel && (h + 1) * (w + 1) < ((size_t)1 << 31) && pano_option(ctx, "advect_kernel", 0) != 1) {
         dim3 gm((unsigned)((w + 1 + 31) / 32), (unsigned)((h + 1 + 8 * kAdvRows - 1) / (8 * kAdvRows)));
+        if (dtype == PANO_F64 && pano_option(ctx, "advect_kernel", 0) != 2) {
+            const int pf = (int)pano_option(ctx, "advect_prefetch", 1), mb = (int)pano_option(ctx, "advect_minblocks", 3);
+#define PANO_ADV3(PF, MB)                                                                                                          \
+    k_advect_march3<PF, MB><<<gm, kThreads, 0, ctx->stream>>>((double *)q_dst, (double *)vel_dst, (double *)vel_dst + off1, (const double *)q_src, \
+                                                              (const double *)vel, (const double *)vel + off1, (int)h, (int)w, dt)
+            if (mb >= 4) { if (pf == 0) PANO_ADV3(0, 4); else if (pf == 1) PANO_ADV3(1, 4); else PANO_ADV3(2, 4); }
+            else         { if (pf == 0) PANO_ADV3(0, 3); else if (pf == 1) PANO_ADV3(1, 3); else PANO_ADV3(2, 3); }
+#undef PANO_ADV3
+            return pano_after_launch(ctx, "advect_march3");
+        }
         if (dtype == PANO_F64)
             k_advect_march<double><<<gm, kThreads, 0, ctx->stream>>>((double *)q_dst, (double *)vel_dst, (double *)vel_dst + off1,
                                                                      (const double *)q_src, (const double *)vel, (const double *)vel + off1,

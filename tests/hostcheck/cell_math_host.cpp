@@ -27,6 +27,37 @@ static void advect_all(int h, int w, T *q_dst, T *vel_dst, const T *q_src, const
         }
 }
 
+// the exact fast forms used by k_advect_march3 (f64), with the kernel's own operand carrying
+static void advect_all_fast(int h, int w, double *q_dst, double *vel_dst, const double *q_src, const double *vel, double dt) {
+    const size_t off = (size_t)w * (h + 1);
+    HView<double> vy{vel, w}, vx{vel + off, w + 1}, q{q_src, w};
+    const double ndt = -dt, wlim = (double)w - 1.00001, hlim = (double)h - 1.00001;
+    for (int y = 0; y <= h; ++y)
+        for (int x = 0; x <= w; ++x) {
+            const double xd = (double)x, xh = xd + 0.5, yd = (double)y, yh = yd + 0.5;
+            if (y < h && x < w) {
+                const double ucx = (vx(y, x) + vx(y, x + 1)) / 2.0, ucy = (vy(y, x) + vy(y + 1, x)) / 2.0;
+                q_dst[(size_t)y * w + x] = pano::advect_cell_fast(xh, yh, wlim, hlim, ndt, ucx, ucy, q);
+            }
+            if (y < h) {
+                const int xc = x < w - 1 ? x : w - 1, xm = x > 0 ? x - 1 : 0;
+                const double vvy = (vy(y, xc) + vy(y + 1, xc) + vy(y, xm) + vy(y + 1, xm)) / 4.0;
+                double rx, ry, v;
+                pano::mac_x_rel(xd, yh, ndt, vx(y, x), vvy, rx, ry);
+                if (!pano::mac_gather_fast(rx, ry, h, w + 1, vx, v)) v = pano::mac_gather<double>(rx, ry, h, w + 1, vx);
+                vel_dst[off + (size_t)y * (w + 1) + x] = v;
+            }
+            if (x < w) {
+                const int yc = y < h - 1 ? y : h - 1, ym = y > 0 ? y - 1 : 0;
+                const double vvx = (vx(yc, x) + vx(yc, x + 1) + vx(ym, x) + vx(ym, x + 1)) / 4.0;
+                double rx, ry, v;
+                pano::mac_y_rel(xh, yd, ndt, vvx, vy(y, x), rx, ry);
+                if (!pano::mac_gather_fast(rx, ry, h + 1, w, vy, v)) v = pano::mac_gather<double>(rx, ry, h + 1, w, vy);
+                vel_dst[(size_t)y * w + x] = v;
+            }
+        }
+}
+
 template <class T>
 static void laplacian(int h, int w, T *z, const T *p, T dt, RectI m) {
     for (int y = 0; y < h; ++y)
@@ -56,6 +87,7 @@ static void neg_divergence(int h, int w, T *b, const T *vel, RectI m) {
 
 extern "C" {
 void hc_advect_all_f64(int h, int w, double *qd, double *vd, const double *q, const double *v, double dt) { advect_all<double>(h, w, qd, vd, q, v, dt); }
+void hc_advect_all_fast_f64(int h, int w, double *qd, double *vd, const double *q, const double *v, double dt) { advect_all_fast(h, w, qd, vd, q, v, dt); }
 void hc_advect_all_f32(int h, int w, float *qd, float *vd, const float *q, const float *v, float dt) { advect_all<float>(h, w, qd, vd, q, v, dt); }
 void hc_laplacian_f64(int h, int w, double *z, const double *p, double dt, int y0, int y1, int x0, int x1) { laplacian<double>(h, w, z, p, dt, RectI{y0, y1, x0, x1}); }
 void hc_laplacian_f32(int h, int w, float *z, const float *p, float dt, int y0, int y1, int x0, int x1) { laplacian<float>(h, w, z, p, dt, RectI{y0, y1, x0, x1}); }

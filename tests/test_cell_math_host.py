@@ -25,7 +25,8 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-CASES = [(2, 2, 50.0), (3, 3, 30.0), (5, 5, 30.0), (17, 33, 30.0), (33, 17, 200.0), (64, 48, 200.0), (40, 40, 1e4)]
+CASES = [(2, 2, 50.0), (3, 3, 30.0), (5, 5, 30.0), (17, 33, 30.0), (33, 17, 200.0), (64, 48, 200.0), (40, 40, 1e4), (9, 11, 1e11), (9, 11, 1e14),
+         (12, 10, 1e25)]
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
@@ -37,6 +38,21 @@ def test_advect_all(hc, oracle, dtype, h, w, vmax):
     qd, vd = np.zeros_like(q), np.zeros_like(vel)
     real = C.c_double if dtype == np.float64 else C.c_float
     getattr(hc, "hc_advect_all_" + ("f64" if dtype == np.float64 else "f32"))(h, w, _p(qd), _p(vd), _p(q), _p(vel), real(0.05))
+    assert np.array_equal(qd, oracle.advect(h, w, q, 0.05, vel))
+    assert np.array_equal(vd, oracle.advect_mac(h, w, vel, 0.05, vel))
+
+
+@pytest.mark.parametrize("h,w,vmax", CASES + [(9, 11, 1e11), (9, 11, 1e14), (6, 5, 1e300), (31, 29, 1e-300)])
+def test_advect_all_fast_forms(hc, oracle, h, w, vmax):
+    """The exact fast forms of k_advect_march3 (one clamp per axis, floor by a magic add) give the oracle's bits,
+    including backtraces far beyond the grid (guarded fall-back above 2^32 cells) and denormal-scale velocities."""
+    rng = np.random.default_rng(13)
+    q = rng.uniform(-1, 1, (h, w))
+    vel = rng.uniform(-vmax, vmax, oracle.num_elem_1(h, w))
+    vel[::7] = 0.0
+    vel[3::11] *= 1e-3
+    qd, vd = np.zeros_like(q), np.zeros_like(vel)
+    hc.hc_advect_all_fast_f64(h, w, _p(qd), _p(vd), _p(q), _p(vel), C.c_double(0.05))
     assert np.array_equal(qd, oracle.advect(h, w, q, 0.05, vel))
     assert np.array_equal(vd, oracle.advect_mac(h, w, vel, 0.05, vel))
 

@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 # (h, w, vmax): vmax 30 -> <=1.5-cell backtrace (every border clamp), 200 -> 10 cells, 1e4 -> leaves any tile
 CASES = [(2, 2, 50.0), (3, 3, 30.0), (5, 5, 30.0), (17, 33, 30.0), (17, 33, 200.0), (33, 17, 200.0),
-         (128, 128, 30.0), (128, 128, 1e4), (257, 511, 200.0), (1024, 1024, 30.0)]
+         (128, 128, 30.0), (128, 128, 1e4), (257, 511, 200.0), (1024, 1024, 30.0), (64, 48, 1e12), (40, 40, 1e300),
+         (70, 130, 1e-300)]
 
 
 @pytest.mark.parametrize("h,w,vmax", CASES)
