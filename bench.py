@@ -406,6 +406,25 @@ def run_ours(args, rank, world, local_rank):
                          "above the HBM peak means on-chip residency, not an error"
                          % (fields_mb, "fits in" if l2_resident else "exceeds"))}
 
+    # ---- N > 1 is a STRONG-scaling run of configs[2] (8192^2), while the N = 1 default is configs[1] (1024^2): so that the
+    # speed-up can be read off one line, rank 0 also steps the same grid alone on its GPU (the other ranks wait at the barrier)
+    same_1gpu = None
+    if multi and not args.no_single:
+        if rank == 0:
+            solo = _Single(ctx, n, P, fluid, _lib)
+            for _ in range(3):
+                solo.step()
+            ctx.sync()
+            ks = max(2, min(K, 5))
+            ctx.timer_start()
+            for _ in range(ks):
+                solo.step()
+            solo_ms = ctx.timer_stop_ms() / ks
+            same_1gpu = {"value": cells / (solo_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": solo_ms, "steps": ks, "warmup": 3,
+                         "note": "the same grid stepped by rank 0 alone (pano_fluid_step, k_cg_stream) right after the timed region"}
+            del solo
+        barrier()
+
     if rank == 0:
         cpu = None
         if not args.no_cpu and not multi:
@@ -429,6 +448,8 @@ def run_ours(args, rank, world, local_rank):
                         "call": job.call},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
                 "cg_info_last_step": last, "cg_info_warm_step": info}
+        if same_1gpu is not None:
+            line["one_gpu_same_workload"] = same_1gpu
         print(json.dumps(line), flush=True)
     if multi:
         dist_t.barrier()
@@ -445,6 +466,7 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="grid size override (multiple of 128)")
     ap.add_argument("--cpu-variant", default="faithful", choices=["faithful", "parallel"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-single", action="store_true", help="N > 1: skip the one-GPU run of the same grid")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (e.g. cg_kernel=1)")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

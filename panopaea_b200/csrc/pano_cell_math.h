@@ -167,29 +167,60 @@ PANO_HD double clamp_hi(double v, double lim) {   // v < lim ? v : lim
 #endif
 }
 
-// returns false (and leaves `out` alone) when a coordinate is beyond 2^32 cells: the caller then uses mac_gather
-template <class Q>
-PANO_HD bool mac_gather_fast(double relx, double rely, int H, int W, const Q &q, double &out) {
+// The gather split in two so that a kernel can compute the coordinates of several values first and then issue all of
+// their loads together.  `bad` != 0 when a coordinate is beyond 2^32 cells: the caller then uses mac_gather.
+struct MacCoord {
+    unsigned x0, x1, y0, y1;
+    double s, t;
+    unsigned bad;
+};
+PANO_HD MacCoord mac_coord_fast(double relx, double rely, int H, int W) {
+    MacCoord c;
     const double rx = clamp_lo0(relx), ry = clamp_lo0(rely);
     const FloorNN fx = floor_nonneg(rx), fy = floor_nonneg(ry);
-    if (((fx.hi ^ kFloorHi) | (fy.hi ^ kFloorHi)) != 0u) return false;
+    c.bad = (fx.hi ^ kFloorHi) | (fy.hi ^ kFloorHi);
     const unsigned wm = (unsigned)(W - 1), hm = (unsigned)(H - 1);
-    const unsigned x0 = fx.i < wm ? fx.i : wm, x1 = x0 + 1u < wm ? x0 + 1u : wm;   // = min(p, W-1), min(p+1, W-1)
-    const unsigned y0 = fy.i < hm ? fy.i : hm, y1 = y0 + 1u < hm ? y0 + 1u : hm;
-    const double s = rx - fx.f, t = ry - fy.f;
-    out = bilinear(q((int)y0, (int)x0), q((int)y0, (int)x1), q((int)y1, (int)x0), q((int)y1, (int)x1), s, t);
+    c.x0 = fx.i < wm ? fx.i : wm; c.x1 = c.x0 + 1u < wm ? c.x0 + 1u : wm;   // = min(p, W-1), min(p+1, W-1)
+    c.y0 = fy.i < hm ? fy.i : hm; c.y1 = c.y0 + 1u < hm ? c.y0 + 1u : hm;
+    c.s = rx - fx.f; c.t = ry - fy.f;
+    return c;
+}
+template <class Q>
+PANO_HD double mac_gather_at(const MacCoord &c, const Q &q) {
+    return bilinear(q((int)c.y0, (int)c.x0), q((int)c.y0, (int)c.x1), q((int)c.y1, (int)c.x0), q((int)c.y1, (int)c.x1), c.s, c.t);
+}
+template <class Q>
+PANO_HD bool mac_gather_fast(double relx, double rely, int H, int W, const Q &q, double &out) {
+    const MacCoord c = mac_coord_fast(relx, rely, H, W);
+    if (c.bad != 0u) return false;
+    out = mac_gather_at(c, q);
     return true;
+}
+
+// advect's coordinates: always in range (clamped), so no `bad`
+struct CellCoord {
+    int ix, iy;
+    double u, v;
+};
+PANO_HD CellCoord advect_coord_fast(double xh, double yh, double wlim, double hlim, double ndt, double ucx, double ucy) {
+    const double ppx = xh + ndt * ucx, ppy = yh + ndt * ucy;
+    const double px = clamp_hi(clamp_lo0(ppx - 0.5), wlim), py = clamp_hi(clamp_lo0(ppy - 0.5), hlim);
+    const FloorNN fx = floor_nonneg(px), fy = floor_nonneg(py);      // px, py in [0, 2^31): no guard needed
+    CellCoord c;
+    c.ix = (int)fx.i; c.iy = (int)fy.i;
+    c.u = px - fx.f; c.v = py - fy.f;
+    return c;
+}
+template <class Q>
+PANO_HD double advect_gather_at(const CellCoord &c, const Q &q) {
+    return bilinear(q(c.iy, c.ix), q(c.iy, c.ix + 1), q(c.iy + 1, c.ix), q(c.iy + 1, c.ix + 1), c.u, c.v);
 }
 
 // xh = x + 0.5, yh = y + 0.5 as doubles (the caller carries them instead of converting per cell);
 // wlim = w - 1.00001, hlim = h - 1.00001
 template <class Q>
 PANO_HD double advect_cell_fast(double xh, double yh, double wlim, double hlim, double ndt, double ucx, double ucy, const Q &q) {
-    const double ppx = xh + ndt * ucx, ppy = yh + ndt * ucy;
-    const double px = clamp_hi(clamp_lo0(ppx - 0.5), wlim), py = clamp_hi(clamp_lo0(ppy - 0.5), hlim);
-    const FloorNN fx = floor_nonneg(px), fy = floor_nonneg(py);      // px, py in [0, 2^31): no guard needed
-    const int ix = (int)fx.i, iy = (int)fy.i;
-    return bilinear(q(iy, ix), q(iy, ix + 1), q(iy + 1, ix), q(iy + 1, ix + 1), px - fx.f, py - fy.f);
+    return advect_gather_at(advect_coord_fast(xh, yh, wlim, hlim, ndt, ucx, ucy), q);
 }
 // advect_mac: the backtraced position relative to the component's own sample grid.
 // x component at (x, y + 0.5): xd = (double)x, yh = y + 0.5; `ppx - 0.0` of the reference is the identity.

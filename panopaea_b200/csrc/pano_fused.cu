@@ -148,7 +148,7 @@ __device__ __noinline__ double mac_gather_far(double relx, double rely, int H, i
     return pano::mac_gather<double>(relx, rely, H, W, V32<double>{p, W});
 }
 
-template <bool kEdge>
+template <bool kEdge, int kRows>
 __device__ __forceinline__ void advect_march3_body(double *__restrict__ q_dst, double *__restrict__ vy_dst, double *__restrict__ vx_dst,
                                                    const double *__restrict__ q_src, const double *__restrict__ vy_src,
                                                    const double *__restrict__ vx_src, int h, int w, double dt, int x, int ys) {
@@ -164,7 +164,7 @@ __device__ __forceinline__ void advect_march3_body(double *__restrict__ q_dst, d
         H = xin ? vx(ys - 1, x + 1) : 0.0;
     }
 #pragma unroll
-    for (int k = 0; k < kAdvRows; ++k) {
+    for (int k = 0; k < kRows; ++k) {
         const int y = ys + k;
         if (kEdge && y > h) break;
         const bool yin = !kEdge || y < h;
@@ -175,36 +175,35 @@ __device__ __forceinline__ void advect_march3_body(double *__restrict__ q_dst, d
             if (xin) { B = vx(y, x + 1); D = vy(y + 1, x); }
             if (xpos) F = vy(y + 1, x - 1);
         }
-        if (yin && xin) {                                   // advect (dec_fluid.rs:180-183)
-            const double ucx = (A + B) / 2.0, ucy = (C + D) / 2.0;
-            q_dst[y * w + x] = pano::advect_cell_fast(xh, yh, wlim, hlim, ndt, ucx, ucy, q);
+        // the three backtraced positions of this row: advect (dec_fluid.rs:180-183), advect_mac x (:220-225) and y (:257-263)
+        double vvy, vvx;
+        if (kEdge) {
+            const bool ypos = y > 0;
+            const double t0 = xin ? C : E, t1 = xin ? D : F, t2 = xpos ? E : C, t3 = xpos ? F : D;
+            vvy = (t0 + t1 + t2 + t3) / 4.0;
+            const double u0 = yin ? A : G, u1 = yin ? B : H, u2 = ypos ? G : A, u3 = ypos ? H : B;
+            vvx = (u0 + u1 + u2 + u3) / 4.0;
+        } else {
+            vvy = (C + D + E + F) / 4.0;
+            vvx = (A + B + G + H) / 4.0;
         }
-        if (yin) {                                          // advect_mac, x component (:220-225)
-            double vvy;
-            if (kEdge) {
-                const double t0 = xin ? C : E, t1 = xin ? D : F, t2 = xpos ? E : C, t3 = xpos ? F : D;
-                vvy = (t0 + t1 + t2 + t3) / 4.0;
-            } else {
-                vvy = (C + D + E + F) / 4.0;
-            }
-            double rx, ry, v;
-            pano::mac_x_rel(xd, yh, ndt, A, vvy, rx, ry);
-            if (!pano::mac_gather_fast(rx, ry, h, w + 1, vx, v)) v = mac_gather_far(rx, ry, h, w + 1, vx_src);
-            vx_dst[y * (w + 1) + x] = v;
-        }
-        if (xin) {                                          // advect_mac, y component (:257-263)
-            double vvx;
-            if (kEdge) {
-                const bool ypos = y > 0;
-                const double t0 = yin ? A : G, t1 = yin ? B : H, t2 = ypos ? G : A, t3 = ypos ? H : B;
-                vvx = (t0 + t1 + t2 + t3) / 4.0;
-            } else {
-                vvx = (A + B + G + H) / 4.0;
-            }
-            double rx, ry, v;
-            pano::mac_y_rel(xh, yd, ndt, vvx, C, rx, ry);
-            if (!pano::mac_gather_fast(rx, ry, h + 1, w, vy, v)) v = mac_gather_far(rx, ry, h + 1, w, vy_src);
-            vy_dst[y * w + x] = v;
+        const pano::CellCoord cq = pano::advect_coord_fast(xh, yh, wlim, hlim, ndt, (A + B) / 2.0, (C + D) / 2.0);
+        double rxx, rxy, ryx, ryy;
+        pano::mac_x_rel(xd, yh, ndt, A, vvy, rxx, rxy);
+        pano::mac_y_rel(xh, yd, ndt, vvx, C, ryx, ryy);
+        const pano::MacCoord cx = pano::mac_coord_fast(rxx, rxy, h, w + 1), cy = pano::mac_coord_fast(ryx, ryy, h + 1, w);
+        if ((cx.bad | cy.bad) == 0u) {
+            // one straight-line block: all twelve gathers can be in flight together
+            const double vq = (yin && xin) ? pano::advect_gather_at(cq, q) : 0.0;
+            const double vxn = yin ? pano::mac_gather_at(cx, vx) : 0.0;
+            const double vyn = xin ? pano::mac_gather_at(cy, vy) : 0.0;
+            if (yin && xin) q_dst[y * w + x] = vq;
+            if (yin) vx_dst[y * (w + 1) + x] = vxn;
+            if (xin) vy_dst[y * w + x] = vyn;
+        } else {                                             // a backtrace beyond 2^32 cells: the general form
+            if (yin && xin) q_dst[y * w + x] = pano::advect_gather_at(cq, q);
+            if (yin) vx_dst[y * (w + 1) + x] = mac_gather_far(rxx, rxy, h, w + 1, vx_src);
+            if (xin) vy_dst[y * w + x] = mac_gather_far(ryx, ryy, h + 1, w, vy_src);
         }
         C = D; E = F; G = A; H = B;
         yd += 1.0;
@@ -214,30 +213,43 @@ __device__ __forceinline__ void advect_march3_body(double *__restrict__ q_dst, d
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// kPrefetch: 0 none, 1 L1, 2 L2 -- every row of q, vy, vx the block will touch first is requested at kernel entry, so the
-// DRAM latency of the velocity loads AND of the first-touch gathers (two dependent round trips per row otherwise)
-// overlaps across the whole tile instead of being paid row by row.
-template <int kPrefetch, int kMinBlocks>
+// kPrefetch: 0 none, 1 L1, 2 L2, 3 L1 + the tile of the block `ahead` launches further on into L2 -- every row of q, vy, vx
+// the block will touch first is requested at kernel entry, so the DRAM latency of the velocity loads AND of the
+// first-touch gathers (two dependent round trips per row otherwise) overlaps across the whole tile instead of being
+// paid row by row.
+template <int kRows, int kPrefetch, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 k_advect_march3(double *__restrict__ q_dst, double *__restrict__ vy_dst, double *__restrict__ vx_dst, const double *__restrict__ q_src,
-                const double *__restrict__ vy_src, const double *__restrict__ vx_src, int h, int w, double dt) {
+                const double *__restrict__ vy_src, const double *__restrict__ vx_src, int h, int w, double dt, int ahead) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int ys = (blockIdx.y * 8 + (threadIdx.x >> 5)) * kAdvRows;
-    // block-uniform: columns [bx0, bx0+32) within [1, w-1] and rows [by0, by0 + 8*kAdvRows) within [1, h-1]
-    const int bx0 = blockIdx.x * 32, by0 = blockIdx.y * 8 * kAdvRows;
-    if (bx0 >= 1 && bx0 + 31 <= w - 1 && by0 >= 1 && by0 + 8 * kAdvRows - 1 <= h - 1) {
-        if (kPrefetch) {
+    const int ys = (blockIdx.y * 8 + (threadIdx.x >> 5)) * kRows;
+    // block-uniform: columns [bx0, bx0+32) within [1, w-1] and rows [by0, by0 + 8*kRows) within [1, h-1]
+    const int bx0 = blockIdx.x * 32, by0 = blockIdx.y * 8 * kRows;
+    if (kPrefetch == 3) {
+        const int nb = blockIdx.y * gridDim.x + blockIdx.x + ahead;
+        const int px = (nb % gridDim.x) * 32 + (threadIdx.x & 31), py = ((nb / gridDim.x) * 8 + (threadIdx.x >> 5)) * kRows;
+        if (px < w && py + kRows < h) {
 #pragma unroll
-            for (int k = 0; k < kAdvRows; ++k) {
-                const double *a = q_src + (ys + k) * w + x, *b = vy_src + (ys + k + 1) * w + x, *c = vx_src + (ys + k) * (w + 1) + x;
-                if (kPrefetch == 1) { prefetch_l1(a); prefetch_l1(b); prefetch_l1(c); }
-                else { prefetch_l2(a); prefetch_l2(b); prefetch_l2(c); }
+            for (int k = 0; k < kRows; ++k) {
+                prefetch_l2(q_src + (py + k) * w + px);
+                prefetch_l2(vy_src + (py + k + 1) * w + px);
+                prefetch_l2(vx_src + (py + k) * (w + 1) + px);
             }
         }
-        advect_march3_body<false>(q_dst, vy_dst, vx_dst, q_src, vy_src, vx_src, h, w, dt, x, ys);
+    }
+    if (bx0 >= 1 && bx0 + 31 <= w - 1 && by0 >= 1 && by0 + 8 * kRows - 1 <= h - 1) {
+        if (kPrefetch) {
+#pragma unroll
+            for (int k = 0; k < kRows; ++k) {
+                const double *a = q_src + (ys + k) * w + x, *b = vy_src + (ys + k + 1) * w + x, *c = vx_src + (ys + k) * (w + 1) + x;
+                if (kPrefetch == 2) { prefetch_l2(a); prefetch_l2(b); prefetch_l2(c); }
+                else { prefetch_l1(a); prefetch_l1(b); prefetch_l1(c); }
+            }
+        }
+        advect_march3_body<false, kRows>(q_dst, vy_dst, vx_dst, q_src, vy_src, vx_src, h, w, dt, x, ys);
     } else {
         if (x > w || ys > h) return;
-        advect_march3_body<true>(q_dst, vy_dst, vx_dst, q_src, vy_src, vx_src, h, w, dt, x, ys);
+        advect_march3_body<true, kRows>(q_dst, vy_dst, vx_dst, q_src, vy_src, vx_src, h, w, dt, x, ys);
     }
 }
 
@@ -387,12 +399,23 @@ int pano_advect_launch(pano_ctx *ctx, int dtype, void *q_dst, void *vel_dst, con
     if (sc && mac && mac_src == vel && (h + 1) * (w + 1) < ((size_t)1 << 31) && pano_option(ctx, "advect_kernel", 0) != 1) {
         dim3 gm((unsigned)((w + 1 + 31) / 32), (unsigned)((h + 1 + 8 * kAdvRows - 1) / (8 * kAdvRows)));
         if (dtype == PANO_F64 && pano_option(ctx, "advect_kernel", 0) != 2) {
-            const int pf = (int)pano_option(ctx, "advect_prefetch", 1), mb = (int)pano_option(ctx, "advect_minblocks", 3);
-#define PANO_ADV3(PF, MB)                                                                                                          \
-    k_advect_march3<PF, MB><<<gm, kThreads, 0, ctx->stream>>>((double *)q_dst, (double *)vel_dst, (double *)vel_dst + off1, (const double *)q_src, \
-                                                              (const double *)vel, (const double *)vel + off1, (int)h, (int)w, dt)
-            if (mb >= 4) { if (pf == 0) PANO_ADV3(0, 4); else if (pf == 1) PANO_ADV3(1, 4); else PANO_ADV3(2, 4); }
-            else         { if (pf == 0) PANO_ADV3(0, 3); else if (pf == 1) PANO_ADV3(1, 3); else PANO_ADV3(2, 3); }
+            const int pf = (int)pano_option(ctx, "advect_prefetch", 1), mb = (int)pano_option(ctx, "advect_minblocks", 4);
+            const int rows = (int)pano_option(ctx, "advect_rows", 4);
+            const int ahead = ctx->num_sms * (int)pano_option(ctx, "advect_ahead", mb);
+            dim3 g3((unsigned)((w + 1 + 31) / 32), (unsigned)((h + 1 + 8 * rows - 1) / (8 * rows)));
+#define PANO_ADV3(R, PF, MB)                                                                                                       \
+    k_advect_march3<R, PF, MB><<<g3, kThreads, 0, ctx->stream>>>((double *)q_dst, (double *)vel_dst, (double *)vel_dst + off1, (const double *)q_src, \
+                                                                 (const double *)vel, (const double *)vel + off1, (int)h, (int)w, dt, ahead)
+#define PANO_ADV3_PF(R, MB)                                                                                     \
+    do {                                                                                                        \
+        if (pf == 0) PANO_ADV3(R, 0, MB); else if (pf == 1) PANO_ADV3(R, 1, MB); else if (pf == 2) PANO_ADV3(R, 2, MB); else PANO_ADV3(R, 3, MB); \
+    } while (0)
+            if (rows == 8) { if (mb >= 4) PANO_ADV3_PF(8, 4); else PANO_ADV3_PF(8, 3); }
+            else if (rows == 2) { if (mb >= 5) PANO_ADV3_PF(2, 5); else PANO_ADV3_PF(2, 4); }
+            else if (mb >= 5) PANO_ADV3_PF(4, 5);
+            else if (mb == 4) PANO_ADV3_PF(4, 4);
+            else PANO_ADV3_PF(4, 3);
+#undef PANO_ADV3_PF
 #undef PANO_ADV3
             return pano_after_launch(ctx, "advect_march3");
         }
