@@ -56,11 +56,13 @@ enum { PANO_F64 = 0, PANO_F32 = 1 };
 enum { PANO_SIMPLEX0 = 0, PANO_SIMPLEX1 = 1, PANO_SIMPLEX2 = 2 };
 /* component selector for rectangle fills on a Simplex1 (split(): dec/grid.rs:48-61) */
 enum { PANO_COMP_ALL = 0, PANO_COMP_VY = 1, PANO_COMP_VX = 2 };
-/* Preconditioner kinds (panopaea/src/pcg.rs:4-12).  Only `()` exists in the reference. */
-enum { PANO_PRECOND_IDENTITY = 0 };
+/* Preconditioner kinds (trait panopaea/src/pcg.rs:4-6).  Only `()` = identity exists in the reference (pcg.rs:8-12);
+ * Jacobi and the multigrid V-cycle are additions behind the same seam, f64 only. */
+enum { PANO_PRECOND_IDENTITY = 0, PANO_PRECOND_JACOBI = 1, PANO_PRECOND_MULTIGRID = 2 };
 
 typedef struct pano_ctx pano_ctx;      /* device + stream + scratch                  */
 typedef struct pano_field pano_field;  /* device-resident Simplex0/1/2               */
+typedef struct pano_mg pano_mg;        /* multigrid preconditioner of one grid        */
 
 /* half-open index rectangle rows [y0,y1) x cols [x0,x1); empty if y0>=y1 or x0>=x1 */
 typedef struct pano_rect { int64_t y0, y1, x0, x1; } pano_rect;
@@ -78,7 +80,7 @@ typedef struct pano_step_params {
     double timestep;          /* :43  0.05 */
     double threshold;         /* :44  0.1  */
     int32_t max_iterations;   /* :95  100  */
-    int32_t precond;          /* PANO_PRECOND_IDENTITY (:92 `&()`) */
+    int32_t precond;          /* PANO_PRECOND_IDENTITY (:92 `&()`), or one of the other kinds */
     pano_rect inflow;         /* :51-52  rows 5..20, cols 54..64 */
     double inflow_density;    /* :53  1.0  */
     double inflow_vy;         /* :54  20.0 */
@@ -194,6 +196,23 @@ PANO_API int pano_project(pano_field *vel, const pano_field *pressure, double ti
 PANO_API int pano_pcg_solve(int precond, pano_field *x, const pano_field *b, int32_t max_iterations,
                             double threshold, pano_field *residual, pano_field *auxiliary,
                             pano_field *search, double timestep, pano_rect obstacle, pano_pcg_info *info);
+
+/* ---------------------------------------------------------- preconditioners
+ * Objects with the reference's `Preconditioner<L>::apply(&self, dst, src)` (pcg.rs:4-6) for the dec_fluid operator
+ * A = timestep * Laplacian(open faces; walls and `obstacle` closed, examples/dec_fluid.rs:100-119).
+ *   pano_jacobi_apply   dst = src / diag(A)   (0 on a cell whose four faces are closed)
+ *   pano_mg_*           geometric multigrid V-cycle from a zero guess (symmetric positive definite): 2x2 aggregation,
+ *                       damped-Jacobi smoothing; specified bit for bit in DESIGN.md 5b.
+ * pano_mg_create builds the level hierarchy once per (grid, timestep, obstacle); the object belongs to `ctx` and is
+ * released by pano_mg_destroy or with the context.  pano_pcg_solve / pano_fluid_step accept the kinds above: the
+ * identity runs the persistent CG kernels, the others run the loop of pcg.rs:32-80 from the host over the same
+ * device primitives (every scalar read back, like the reference's sigma/alpha/beta). */
+PANO_API int pano_jacobi_apply(pano_field *dst, const pano_field *src, double timestep, pano_rect obstacle);
+PANO_API int pano_mg_create(pano_ctx *ctx, size_t h, size_t w, double timestep, pano_rect obstacle, pano_mg **out);
+PANO_API int pano_mg_destroy(pano_mg *mg);
+PANO_API int pano_mg_apply(pano_mg *mg, pano_field *dst, const pano_field *src);
+/* number of levels, and how many of them run inside the single-CTA tail kernel (nullable) */
+PANO_API int pano_mg_levels(const pano_mg *mg, int *levels, int *tail_levels);
 
 /* --------------------------------------------------------------------- step
  * One pass of the example's loop body (dec_fluid.rs:46-141, PNG dump excluded)

@@ -180,3 +180,84 @@ class FluidState:
         self.vy[0, :] = 0.0
         self.vy[-1, :] = 0.0
         return dict(iterations=it, final_residual=err, rhs=b)
+
+
+# ---------------------------------------------------------------------------------------------
+# Multigrid / Jacobi preconditioners (no counterpart in the reference; trait seam pcg.rs:4-6).
+# Array-at-a-time statement of the scheme that oracle/pano_oracle_mg.inc spells out loop by loop;
+# tests/test_oracle_mg.py requires the two to agree to rounding (summation grouping differs).
+def mg_level0_weights(h, w, obstacle):
+    wy, wx = np.ones((h + 1, w)), np.ones((h, w + 1))
+    wy[0, :] = 0
+    wy[h, :] = 0
+    wx[:, 0] = 0
+    wx[:, w] = 0
+    y0, y1, x0, x1 = obstacle
+    wy[y0:y1, x0:x1] = 0
+    wx[y0:y1, x0:x1] = 0
+    return wy, wx
+
+
+def mg_coarsen(wy, wx):
+    h, w = wx.shape[0], wy.shape[1]
+    hc, wc = (h + 1) // 2, (w + 1) // 2
+    wyp = np.zeros((2 * hc + 1, 2 * wc))
+    wyp[:h + 1, :w] = wy
+    wxp = np.zeros((2 * hc, 2 * wc + 1))
+    wxp[:h, :w + 1] = wx
+    return 0.5 * (wyp[0::2, 0::2] + wyp[0::2, 1::2]), 0.5 * (wxp[0::2, 0::2] + wxp[1::2, 0::2])
+
+
+def mg_apply_operator(wy, wx, u, dt):
+    h, w = u.shape
+    up = np.zeros((h + 2, w + 2))
+    up[1:-1, 1:-1] = u
+    c = up[1:-1, 1:-1]
+    return dt * (wy[:-1] * (c - up[:-2, 1:-1]) + wy[1:] * (c - up[2:, 1:-1]) + wx[:, :-1] * (c - up[1:-1, :-2]) + wx[:, 1:] * (c - up[1:-1, 2:]))
+
+
+class Multigrid:
+    def __init__(self, h, w, timestep, obstacle=(0, 0, 0, 0), omega=0.8, nu=2, ncoarse=16, coarsest=8):
+        self.dt, self.omega, self.nu, self.ncoarse = timestep, omega, nu, ncoarse
+        self.W = [mg_level0_weights(h, w, obstacle)]
+        while max(self.W[-1][1].shape[0], self.W[-1][0].shape[1]) > coarsest:
+            self.W.append(mg_coarsen(*self.W[-1]))
+        self.od = []
+        for wy, wx in self.W:
+            d = timestep * (wy[:-1] + wy[1:] + wx[:, :-1] + wx[:, 1:])
+            od = np.zeros_like(d)
+            od[d > 0] = omega / d[d > 0]
+            self.od.append(od)
+
+    def smooth(self, l, u, f, n, from_zero=False):
+        wy, wx = self.W[l]
+        for k in range(n):
+            if from_zero and k == 0:
+                u = self.od[l] * f
+            else:
+                u = u + self.od[l] * (f - mg_apply_operator(wy, wx, u, self.dt))
+        return u
+
+    def vcycle(self, l, f):
+        wy, wx = self.W[l]
+        if l == len(self.W) - 1:
+            return self.smooth(l, None, f, self.ncoarse, True)
+        u = self.smooth(l, None, f, self.nu, True)
+        r = f - mg_apply_operator(wy, wx, u, self.dt)
+        h, w = r.shape
+        hc, wc = (h + 1) // 2, (w + 1) // 2
+        rp = np.zeros((2 * hc, 2 * wc))
+        rp[:h, :w] = r
+        fc = rp[0::2, 0::2] + rp[0::2, 1::2] + rp[1::2, 0::2] + rp[1::2, 1::2]
+        e = np.repeat(np.repeat(self.vcycle(l + 1, fc), 2, 0), 2, 1)[:h, :w]
+        return self.smooth(l, u + e, f, self.nu)
+
+    def apply(self, r):
+        return self.vcycle(0, np.asarray(r, np.float64))
+
+    def jacobi(self, r):
+        wy, wx = self.W[0]
+        d = self.dt * (wy[:-1] + wy[1:] + wx[:, :-1] + wx[:, 1:])
+        out = np.zeros_like(d)
+        out[d > 0] = np.asarray(r)[d > 0] / d[d > 0]
+        return out

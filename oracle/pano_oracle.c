@@ -54,6 +54,8 @@ EXPORT void orc_set_num_threads(int n) { (void)n; }
 #undef FMAX
 #undef FLOOR
 
+#include "pano_oracle_mg.inc"
+
 #define REAL float
 #define FN(x) x##_f32
 #define FMIN fminf

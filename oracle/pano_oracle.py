@@ -23,7 +23,7 @@ SERIAL, REFERENCE_FAITHFUL, ALL_PARALLEL = 0, 1, 2
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("pano_oracle.c", "pano_oracle_body.inc", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("pano_oracle.c", "pano_oracle_body.inc", "pano_oracle_mg.inc", "Makefile")]
     stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-s"] + (["-B"] if force else []), check=True)
@@ -65,6 +65,9 @@ def lib():
             getattr(_lib, f"orc_state_new_{sfx}").restype = C.c_void_p
             getattr(_lib, f"orc_state_field_{sfx}").restype = C.c_void_p
             getattr(_lib, f"orc_num_elem_1_{sfx}").restype = C.c_size_t
+        _lib.orc_mg_new.restype = C.c_void_p
+        _lib.orc_mg_level_wy.restype = C.c_void_p
+        _lib.orc_mg_level_wx.restype = C.c_void_p
     return _lib
 
 
@@ -258,6 +261,76 @@ def pcg_grid_laplacian(h, w, b, max_iterations, threshold, timestep, obstacle=(0
     closure = C.cast(getattr(L, f"orc_laplacian_closure_{sfx}"), C.c_void_p)
     getattr(L, f"orc_pcg_{sfx}")(C.c_size_t(n), _p(x), _p(b), C.c_size_t(max_iterations), real(threshold),
                                  _p(r), _p(aux), _p(s), closure, C.byref(ctx), info, C.byref(fres))
+    return PcgResult(x.reshape(h, w), r.reshape(h, w), s.reshape(h, w), aux.reshape(h, w),
+                     int(info[0]), int(info[1]), float(fres.value))
+
+
+class Multigrid:
+    """The multigrid preconditioner specified in oracle/pano_oracle_mg.inc (f64).  apply(src) -> dst;
+    jacobi(src) is the diagonal preconditioner built from the same face weights."""
+
+    def __init__(self, h, w, timestep, obstacle=(0, 0, 0, 0)):
+        _check_rect(h, w, obstacle)
+        self.h, self.w = h, w
+        self._L = lib()
+        self._m = C.c_void_p(self._L.orc_mg_new(C.c_size_t(h), C.c_size_t(w), C.c_double(timestep), C.byref(Rect(*obstacle))))
+
+    @property
+    def levels(self):
+        return int(self._L.orc_mg_levels(self._m))
+
+    def level_dim(self, l):
+        hh, ww = C.c_size_t(), C.c_size_t()
+        self._L.orc_mg_level_dim(self._m, l, C.byref(hh), C.byref(ww))
+        return hh.value, ww.value
+
+    def level_weights(self, l):
+        hh, ww = self.level_dim(l)
+        wy = np.ctypeslib.as_array(C.cast(self._L.orc_mg_level_wy(self._m, l), C.POINTER(C.c_double)), shape=((hh + 1) * ww,)).copy()
+        wx = np.ctypeslib.as_array(C.cast(self._L.orc_mg_level_wx(self._m, l), C.POINTER(C.c_double)), shape=(hh * (ww + 1),)).copy()
+        return wy.reshape(hh + 1, ww), wx.reshape(hh, ww + 1)
+
+    def apply(self, src):
+        src = np.ascontiguousarray(src, np.float64)
+        dst = np.zeros(self.h * self.w)
+        self._L.orc_mg_apply(self._m, _p(dst), _p(src))
+        return dst.reshape(self.h, self.w)
+
+    def jacobi(self, src):
+        src = np.ascontiguousarray(src, np.float64)
+        dst = np.zeros(self.h * self.w)
+        self._L.orc_jacobi_apply(self._m, _p(dst), _p(src))
+        return dst.reshape(self.h, self.w)
+
+    def close(self):
+        if self._m:
+            self._L.orc_mg_free(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pcg_grid_laplacian_precond(h, w, b, max_iterations, threshold, timestep, obstacle=(0, 0, 0, 0), precond="multigrid"):
+    """pcg.rs:14-82 with the dec_fluid Laplacian closure and a non-identity Preconditioner (f64):
+    "multigrid" | "jacobi" | "identity"."""
+    _check_rect(h, w, obstacle)
+    b = np.ascontiguousarray(b, np.float64)
+    L = lib()
+    n, n1 = h * w, num_elem_1(h, w)
+    x, r, aux, s = (np.zeros(n) for _ in range(4))
+    pt, vt, vpt = np.zeros(n), np.zeros(n1), np.zeros(n1)
+    ctx = _lap_ctx_type(C.c_double)(h, w, timestep, Rect(*obstacle), _p(pt), _p(vt), _p(vpt))
+    info = (C.c_long * 2)()
+    fres = C.c_double(0)
+    closure = C.cast(L.orc_laplacian_closure_f64, C.c_void_p)
+    mg = Multigrid(h, w, timestep, obstacle) if precond != "identity" else None
+    apply = {"multigrid": L.orc_mg_apply, "jacobi": L.orc_jacobi_apply}.get(precond)
+    L.orc_pcg_precond(C.c_size_t(n), _p(x), _p(b), C.c_size_t(max_iterations), C.c_double(threshold), _p(r), _p(aux), _p(s),
+                      closure, C.byref(ctx), C.cast(apply, C.c_void_p) if apply else None, mg._m if mg else None, info, C.byref(fres))
     return PcgResult(x.reshape(h, w), r.reshape(h, w), s.reshape(h, w), aux.reshape(h, w),
                      int(info[0]), int(info[1]), float(fres.value))
 

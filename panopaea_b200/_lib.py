@@ -15,7 +15,7 @@ OK, ERR_INVALID, ERR_SHAPE, ERR_CUDA, ERR_UNIMPLEMENTED, ERR_TIMEOUT, ERR_COMM =
 F64, F32 = 0, 1
 SIMPLEX0, SIMPLEX1, SIMPLEX2 = 0, 1, 2
 COMP_ALL, COMP_VY, COMP_VX = 0, 1, 2
-PRECOND_IDENTITY = 0
+PRECOND_IDENTITY, PRECOND_JACOBI, PRECOND_MULTIGRID = 0, 1, 2
 
 
 class PanoError(RuntimeError):
@@ -96,6 +96,11 @@ _SIGS = {
     "pano_laplacian_apply": (C.c_int, [_P, _P, C.c_double, Rect]),
     "pano_project": (C.c_int, [_P, _P, C.c_double]),
     "pano_pcg_solve": (C.c_int, [C.c_int, _P, _P, C.c_int32, C.c_double, _P, _P, _P, C.c_double, Rect, C.POINTER(PcgInfo)]),
+    "pano_jacobi_apply": (C.c_int, [_P, _P, C.c_double, Rect]),
+    "pano_mg_create": (C.c_int, [_P, C.c_size_t, C.c_size_t, C.c_double, Rect, C.POINTER(_P)]),
+    "pano_mg_destroy": (C.c_int, [_P]),
+    "pano_mg_apply": (C.c_int, [_P, _P, _P]),
+    "pano_mg_levels": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pano_fluid_step": (C.c_int, [C.POINTER(StepParams), _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(PcgInfo)]),
     "pano_fluid_step_host": (C.c_int, [_P, C.POINTER(StepParams), C.c_size_t, C.c_size_t, _P, _P, _P, C.POINTER(PcgInfo)]),
     "pano_density_to_u8": (C.c_int, [_P, C.c_double, C.c_double, _P]),

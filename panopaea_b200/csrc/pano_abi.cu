@@ -82,6 +82,7 @@ int pano_ctx_destroy(pano_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     pano_workspace_free_all(ctx);
+    pano_mg_free_all(ctx);
     cudaFree(ctx->d_partials);
     cudaFree(ctx->d_scalars);
     cudaFreeHost(ctx->h_scalars);

@@ -372,8 +372,8 @@ int pano_cg_solve_raw(pano_ctx *ctx, int dtype, void *x, const void *b, void *r,
 extern "C" int pano_pcg_solve(int precond, pano_field *x, const pano_field *b, int32_t max_iterations, double threshold,
                               pano_field *residual, pano_field *auxiliary, pano_field *search, double timestep,
                               pano_rect obstacle, pano_pcg_info *info) {
-    if (precond != PANO_PRECOND_IDENTITY)
-        PANO_FAIL(PANO_ERR_UNIMPLEMENTED, "pano_pcg_solve: only the identity preconditioner `()` exists (pcg.rs:8-12)");
+    if (precond != PANO_PRECOND_IDENTITY && precond != PANO_PRECOND_JACOBI && precond != PANO_PRECOND_MULTIGRID)
+        PANO_FAIL(PANO_ERR_INVALID, "pano_pcg_solve: unknown preconditioner kind %d", precond);
     const pano_field *all[] = {x, b, residual, auxiliary, search};
     const char *names[] = {"x", "b", "residual", "auxiliary", "search"};
     for (int i = 0; i < 5; ++i) {
@@ -387,6 +387,8 @@ extern "C" int pano_pcg_solve(int precond, pano_field *x, const pano_field *b, i
     PANO_TRY(pano_check_rect_within(obstacle, x->h, x->w, "pano_pcg_solve(obstacle)"));
     pano_ctx *ctx = x->ctx;
     PANO_TRY(pano_activate(ctx));
+    if (precond != PANO_PRECOND_IDENTITY)
+        return pano_pcg_precond_raw(ctx, precond, x, b, max_iterations, threshold, residual, auxiliary, search, timestep, obstacle, info);
     return pano_cg_solve_raw(ctx, x->dtype, x->d, b->d, residual->d, search->d, auxiliary->d, x->h, x->w, max_iterations,
                              threshold, timestep, obstacle, info);
 }

@@ -51,6 +51,7 @@ struct PanoCgControl {
 };
 
 struct PanoWorkspace;   // cached scratch of pano_fluid_step_host
+struct pano_mg;         // multigrid preconditioner (pano_mg.cu)
 
 struct pano_ctx {
     int device = 0;
@@ -81,6 +82,7 @@ struct pano_ctx {
     int64_t phase_steps = 0;
     std::map<std::string, int64_t> options;
     std::map<std::pair<size_t, size_t>, PanoWorkspace *> workspaces;
+    std::vector<pano_mg *> mg_cache;             // preconditioners built on this context (pano_mg_create)
 };
 
 struct pano_field {
@@ -127,6 +129,9 @@ struct PanoCgSlab {
 // leaves the (rows, cols) grid panics in the reference, so it is an error here too
 int pano_check_rect_within(const pano_rect &r, size_t rows, size_t cols, const char *what);
 void pano_workspace_free_all(pano_ctx *ctx);
+void pano_mg_free_all(pano_ctx *ctx);
+int pano_pcg_precond_raw(pano_ctx *ctx, int precond, pano_field *x, const pano_field *b, int max_iterations, double threshold,
+                         pano_field *residual, pano_field *auxiliary, pano_field *search, double dt, pano_rect ob, pano_pcg_info *info);
 int pano_phase_mark(pano_ctx *ctx, int phase);     // record event #phase of the current step (no-op unless step_timing)
 int pano_phase_drain(pano_ctx *ctx);               // synchronise and fold recorded events into phase_ms
 

@@ -81,8 +81,8 @@ static int fluid_step_impl(const pano_step_params *params, pano_field *density, 
     PANO_TRY(pano_check_same(vel, vel_temp, "pano_fluid_step"));
     PANO_TRY(pano_check_grid(density, vel, "pano_fluid_step"));
     if (vel->d == vel_temp->d) PANO_FAIL(PANO_ERR_INVALID, "pano_fluid_step: vel aliases vel_temp");
-    if (params->precond != PANO_PRECOND_IDENTITY)
-        PANO_FAIL(PANO_ERR_UNIMPLEMENTED, "pano_fluid_step: only the identity preconditioner exists (pcg.rs:8-12)");
+    if (params->precond != PANO_PRECOND_IDENTITY && params->precond != PANO_PRECOND_JACOBI && params->precond != PANO_PRECOND_MULTIGRID)
+        PANO_FAIL(PANO_ERR_INVALID, "pano_fluid_step: unknown preconditioner kind %d", params->precond);
     const size_t h = density->h, w = density->w;
     if (h < 2 || w < 2) PANO_FAIL(PANO_ERR_SHAPE, "pano_fluid_step: grid %zux%zu below 2x2", h, w);
     // inflow writes density[(y,x)] and vy[(y,x)]; the obstacle zeroes vy[(y,x)] and vx[(y,x)]
@@ -108,12 +108,22 @@ static int fluid_step_impl(const pano_step_params *params, pano_field *density, 
     PANO_TRY(pano_neg_divergence_launch(ctx, dt_, temp->d, vel->d, h, w, params->obstacle, false));
     PANO_TRY(pano_phase_mark(ctx, 3));
     // pressure solve  :91-119
-    PANO_TRY(pano_cg_solve_raw(ctx, dt_, pressure->d, temp->d, residual->d, search->d, auxiliary->d, h, w,
-                               params->max_iterations, params->threshold, dt, params->obstacle, nullptr));
+    pano_pcg_info pinfo;
+    const bool host_loop = params->precond != PANO_PRECOND_IDENTITY;
+    if (host_loop)   // Jacobi / multigrid: the loop of pcg.rs:32-80 driven from the host (pano_mg.cu)
+        PANO_TRY(pano_pcg_precond_raw(ctx, params->precond, pressure, temp, params->max_iterations, params->threshold, residual,
+                                      auxiliary, search, dt, params->obstacle, &pinfo));
+    else
+        PANO_TRY(pano_cg_solve_raw(ctx, dt_, pressure->d, temp->d, residual->d, search->d, auxiliary->d, h, w,
+                                   params->max_iterations, params->threshold, dt, params->obstacle, nullptr));
     PANO_TRY(pano_phase_mark(ctx, 4));
     // projection + walls  :124-141
     PANO_TRY(pano_project_launch(ctx, dt_, vel->d, pressure->d, h, w, dt));
     PANO_TRY(pano_phase_mark(ctx, 5));
+    if (info && host_loop) {
+        *info = pinfo;
+        return PANO_OK;
+    }
     if (info) {
         PANO_CUDA(cudaMemcpyAsync(ctx->h_cg, ctx->d_cg, sizeof(PanoCgControl), cudaMemcpyDeviceToHost, ctx->stream));
         PANO_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -159,11 +169,18 @@ int pano_fluid_step_host(pano_ctx *ctx, const pano_step_params *params, size_t h
     PANO_CUDA(cudaMemcpyAsync(ws->density->d, density, n2, cudaMemcpyHostToDevice, ctx->stream));
     PANO_CUDA(cudaMemcpyAsync(ws->vel->d, vel, n1, cudaMemcpyHostToDevice, ctx->stream));
     HostStepCopy hook{ws, density, n2};
+    pano_pcg_info hinfo;
+    const bool host_loop = params->precond != PANO_PRECOND_IDENTITY;
     PANO_TRY(fluid_step_impl(params, ws->density, ws->vel, ws->pressure, ws->temp, ws->vel_temp, ws->residual, ws->auxiliary,
-                             ws->search, nullptr, start_density_download, &hook));   // density goes home under the solve
+                             ws->search, host_loop ? &hinfo : nullptr, start_density_download, &hook));   // density goes home under the solve
     PANO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
     PANO_CUDA(cudaMemcpyAsync(vel, ws->vel->d, n1, cudaMemcpyDeviceToHost, ctx->stream));
     PANO_CUDA(cudaMemcpyAsync(pressure, ws->pressure->d, n2, cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_loop) {
+        PANO_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (info) *info = hinfo;
+        return PANO_OK;
+    }
     PANO_CUDA(cudaMemcpyAsync(ctx->h_cg, ctx->d_cg, sizeof(PanoCgControl), cudaMemcpyDeviceToHost, ctx->stream));
     PANO_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->h_cg->error) PANO_FAIL(PANO_ERR_TIMEOUT, "pano_fluid_step_host: a grid barrier timed out inside the CG kernel");
