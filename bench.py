@@ -406,6 +406,27 @@ def run_ours(args, rank, world, local_rank):
                          "above the HBM peak means on-chip residency, not an error"
                          % (fields_mb, "fits in" if l2_resident else "exceeds"))}
 
+    # ---- beyond the reference: the same step with the multigrid preconditioner behind the pcg.rs trait seam (every solve
+    # reaches the threshold; the reference-faithful identity solve above stops at its 100-iteration cap).  Reported aside,
+    # never mixed into `value`.
+    mg_line = None
+    if not multi and not args.no_mg:
+        sim = job.sim
+        sim.params.precond = _lib.PRECOND_MULTIGRID
+        for _ in range(3):
+            sim.step(want_info=False)
+        ctx.sync()
+        km = max(3, min(K, 10))
+        ctx.timer_start()
+        for _ in range(km):
+            sim.step(want_info=False)
+        mg_ms = ctx.timer_stop_ms() / km
+        mg_info = sim.step(want_info=True)
+        sim.params.precond = _lib.PRECOND_IDENTITY
+        mg_line = {"value": cells / (mg_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": mg_ms, "steps": km,
+                   "cg_iterations_per_step": mg_info["applies"], "final_residual": mg_info["final_residual"],
+                   "note": "pano_step_params.precond = PANO_PRECOND_MULTIGRID (DESIGN.md 5b): converged solves, host-driven PCG loop"}
+
     # ---- N > 1 is a STRONG-scaling run of configs[2] (8192^2), while the N = 1 default is configs[1] (1024^2): so that the
     # speed-up can be read off one line, rank 0 also steps the same grid alone on its GPU (the other ranks wait at the barrier)
     same_1gpu = None
@@ -448,6 +469,8 @@ def run_ours(args, rank, world, local_rank):
                         "call": job.call},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
                 "cg_info_last_step": last, "cg_info_warm_step": info}
+        if mg_line is not None:
+            line["multigrid_pcg_step"] = mg_line
         if same_1gpu is not None:
             line["one_gpu_same_workload"] = same_1gpu
         print(json.dumps(line), flush=True)
@@ -466,6 +489,7 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="grid size override (multiple of 128)")
     ap.add_argument("--cpu-variant", default="faithful", choices=["faithful", "parallel"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-mg", action="store_true", help="skip the multigrid-preconditioned step timing")
     ap.add_argument("--no-single", action="store_true", help="N > 1: skip the one-GPU run of the same grid")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (e.g. cg_kernel=1)")
     args = ap.parse_args()

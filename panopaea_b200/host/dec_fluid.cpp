@@ -36,6 +36,16 @@ int main(int argc, char **argv) {
         const pano_rect inflow{5, 20, 54, 64}, obstacle{70, 80, 50, 70};        // :51-52, :72-73
         const size_t h = 128, w = 128;
 
+        pcg::Multigrid multigrid(ctx, {h, w}, timestep, obstacle);              // used by mode "multigrid" only
+        const auto laplacian_closure = [&](Simplex2<double> &laplacian, const Simplex2<double> &p) {   // :100-119
+            grid.hodge_2_primal(pressure_temp, p);
+            grid.derivative_0_dual(vel_temp, pressure_temp);
+            vel_temp.fill_rect(PANO_COMP_ALL, obstacle, 0.0);
+            grid.hodge_1_dual(vel_primal_temp, vel_temp);
+            grid.derivative_1_primal(laplacian, vel_primal_temp);
+            laplacian.scale(timestep);
+        };
+
         for (int i = 0; i < steps; ++i) {                                       // :46
             long iterations = 0;
             if (mode == "fused") {
@@ -58,16 +68,10 @@ int main(int argc, char **argv) {
                 grid.derivative_1_primal(temp, vel_temp);                       // :80
                 temp.scale(-1.0);                                               // :81-83
                 vel_temp.fill(0.0);                                             // :89
-                auto out = pcg::precond_conjugate_gradient(                     // :91-119
-                    pcg::Identity{}, pressure, temp, 100, threshold, residual, auxiliary, search,
-                    [&](Simplex2<double> &laplacian, const Simplex2<double> &p) {
-                        grid.hodge_2_primal(pressure_temp, p);
-                        grid.derivative_0_dual(vel_temp, pressure_temp);
-                        vel_temp.fill_rect(PANO_COMP_ALL, obstacle, 0.0);
-                        grid.hodge_1_dual(vel_primal_temp, vel_temp);
-                        grid.derivative_1_primal(laplacian, vel_primal_temp);
-                        laplacian.scale(timestep);
-                    });
+                // :91-119; mode "multigrid" hands the same generic loop another Preconditioner object instead of `&()`
+                auto out = mode == "multigrid"
+                               ? pcg::precond_conjugate_gradient(multigrid, pressure, temp, 100, threshold, residual, auxiliary, search, laplacian_closure)
+                               : pcg::precond_conjugate_gradient(pcg::Identity{}, pressure, temp, 100, threshold, residual, auxiliary, search, laplacian_closure);
                 iterations = out.iterations;
                 grid.hodge_2_primal(pressure_temp, pressure);                   // :124
                 grid.derivative_0_dual(vel_temp, pressure_temp);                // :125

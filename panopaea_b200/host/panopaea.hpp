@@ -135,6 +135,28 @@ struct Identity {
     template <class L> void apply(L &dst, const L &src) const { dst.assign(src); }
 };
 
+// Two more impls of the trait (not in the reference) for the operator of examples/dec_fluid.rs:100-119
+struct Jacobi {
+    double timestep;
+    pano_rect obstacle;
+    void apply(dec::Simplex2<double> &dst, const dec::Simplex2<double> &src) const {
+        check(pano_jacobi_apply(dst.handle(), src.handle(), timestep, obstacle));
+    }
+};
+class Multigrid {
+public:
+    Multigrid(const Context &ctx, std::pair<size_t, size_t> dim, double timestep, pano_rect obstacle) {
+        check(pano_mg_create(ctx.handle(), dim.first, dim.second, timestep, obstacle, &h_));
+    }
+    ~Multigrid() { pano_mg_destroy(h_); }
+    Multigrid(const Multigrid &) = delete;
+    Multigrid &operator=(const Multigrid &) = delete;
+    void apply(dec::Simplex2<double> &dst, const dec::Simplex2<double> &src) const { check(pano_mg_apply(h_, dst.handle(), src.handle())); }
+
+private:
+    pano_mg *h_ = nullptr;
+};
+
 struct Outcome {   // what the reference only prints (pcg.rs:36, 61)
     long iterations;
     long applies;

@@ -31,3 +31,13 @@ def test_dec_fluid_cpp(oracle, tmp_path, mode):
         d, v, p = raw[:n2], raw[n2:n2 + n1], raw[n2 + n1:]
         for got, ref_f in ((d, ref.field("density").ravel()), (v, ref.field("vel")), (p, ref.field("pressure").ravel())):
             assert np.abs(got - ref_f).max() <= 1e-5 * max(1e-300, np.abs(ref_f).max())
+
+
+def test_dec_fluid_cpp_multigrid_preconditioner():
+    """The same example with `pcg::Multigrid` as the Preconditioner object of the generic loop (trait seam pcg.rs:4-6):
+    every solve reaches the threshold within a few iterations."""
+    subprocess.run(["make", "-C", HOST, "-s"], check=True)
+    r = subprocess.run([os.path.join(HOST, "dec_fluid"), "30", "multigrid"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    its = [int(m) for m in re.findall(r"Iterations (-?\d+)", r.stdout)]
+    assert len(its) == 30 and all(-1 <= i <= 4 for i in its), its
