@@ -63,7 +63,7 @@ def load_traffic(workload_key):
 
 
 class ClockSampler:
-    """Samples SM clock and throttle reasons during the timed region (NVML, 50 ms period)."""
+    """Samples SM clock and throttle reasons during the timed region (NVML, 5 ms period)."""
     REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
@@ -93,7 +93,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.005)
 
     def __enter__(self):
         if self._nv is not None:

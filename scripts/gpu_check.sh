@@ -13,4 +13,4 @@ echo "== bench 4096" ; timeout 600 python bench.py --steps 5 --warmup 5 --n 4096
 echo "== bench 128" ; timeout 600 python bench.py --steps 50 --warmup 50 --n 128 --no-cpu > gpurun_out/bench_128.json 2> gpurun_out/bench_128.err; echo "bench rc=$?"; cat gpurun_out/bench_128.json
 echo "== ncu launch list (1024^2, 2 steps after 3 warm-up)"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_1024.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_launch.log 2>&1; echo "ncu rc=$?"
+    python bench.py --steps 2 --warmup 3 --no-cpu --no-mg > gpurun_out/ncu_launch.log 2>&1; echo "ncu rc=$?"
