@@ -26,6 +26,9 @@ import sys
 import threading
 import time
 
+# stdout carries exactly ONE line (the JSON).  NCCL writes its version banner / NCCL_DEBUG output to stdout unless told otherwise.
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

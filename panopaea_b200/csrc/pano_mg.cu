@@ -139,6 +139,142 @@ k_mg_level(const G g, double *__restrict__ out, const double *__restrict__ uin, 
     }
 }
 
+// ---- fused forms for the levels that live in HBM: a 16 x 64 tile per block, staged in shared memory with a two-cell halo,
+// so that a whole half of the V-cycle is ONE pass over the level:
+//   k_mg_down: f -> u (two sweeps from zero), and the restricted residual f' = R (f - A u)          8 B read, 10 B written per cell
+//   k_mg_up:   u, u' (coarse correction), f -> two more sweeps of u + P u'                           18 B read, 8 B written
+// The halo cells are recomputed by the neighbouring tiles (same expressions, so the same bits); out-of-place (down writes
+// `t`, up reads `t` and writes `u`) because a tile reads its neighbours' cells.
+constexpr int FT_H = 16, FT_W = 64;                       // tile (even, so that 2x2 aggregates never straddle tiles)
+constexpr int F2_H = FT_H + 4, F2_W = FT_W + 4;           // with the two-cell halo
+constexpr int F1_H = FT_H + 2, F1_W = FT_W + 2;           // with the one-cell halo
+
+struct Geom0Fast {   // level 0 away from walls and obstacle: every face open
+    int h, w;
+    double od4;
+    __device__ __forceinline__ void weights(int, int, double &n, double &s, double &w_, double &e) const { n = s = w_ = e = 1.0; }
+    __device__ __forceinline__ double odv(int, int) const { return od4; }
+};
+// true when every cell of [ya, yb] x [xa, xb] has its four faces open
+__device__ __forceinline__ bool region_open(const Geom0 &g, int ya, int yb, int xa, int xb) {
+    if (ya < 1 || yb > g.h - 2 || xa < 1 || xb > g.w - 2) return false;
+    const RectI &m = g.m;
+    return !(m.y1 > m.y0 && m.x1 > m.x0 && ya < m.y1 && yb + 1 >= m.y0 && xa < m.x1 && xb + 1 >= m.x0);
+}
+
+template <class G>
+__device__ __forceinline__ void mg_down_tile(const G &g, int h, int w, double *__restrict__ uout, const double *__restrict__ f,
+                                             double *__restrict__ fc, int wc, double dt, int ty0, int tx0, double *F, double *U1, double *U2) {
+    const int tid = threadIdx.x;
+    // A: f and u1 = od * f on the tile + 2
+    for (int i = tid; i < F2_H * F2_W; i += kThreads) {
+        const int ly = i / F2_W, lx = i % F2_W, y = ty0 - 2 + ly, x = tx0 - 2 + lx;
+        double fv = 0.0, u1 = 0.0;
+        if (y >= 0 && y < h && x >= 0 && x < w) {
+            fv = f[y * w + x];
+            u1 = g.odv(y, x) * fv;
+        }
+        F[i] = fv;
+        U1[i] = u1;
+    }
+    __syncthreads();
+    // B: second sweep on the tile + 1 (pre_cell: c + od * (f - A u1)); the tile itself goes to global memory
+    auto u1 = [&](int yy, int xx) { return U1[(yy - ty0 + 2) * F2_W + (xx - tx0 + 2)]; };
+    for (int i = tid; i < F1_H * F1_W; i += kThreads) {
+        const int ly = i / F1_W, lx = i % F1_W, y = ty0 - 1 + ly, x = tx0 - 1 + lx;
+        double v = 0.0;
+        if (y >= 0 && y < h && x >= 0 && x < w) {
+            const double c = u1(y, x);
+            v = c + g.odv(y, x) * (F[(ly + 1) * F2_W + lx + 1] - mg_au(g, u1, y, x, c, dt));
+            if (ly >= 1 && ly <= FT_H && lx >= 1 && lx <= FT_W) uout[y * w + x] = v;
+        }
+        U2[i] = v;
+    }
+    __syncthreads();
+    // C: residual of the four children of every coarse cell of the tile, summed in the specified order
+    auto u2 = [&](int yy, int xx) { return U2[(yy - ty0 + 1) * F1_W + (xx - tx0 + 1)]; };
+    auto r = [&](int yy, int xx) { return F[(yy - ty0 + 2) * F2_W + (xx - tx0 + 2)] - mg_au(g, u2, yy, xx, u2(yy, xx), dt); };
+    for (int i = tid; i < (FT_H / 2) * (FT_W / 2); i += kThreads) {
+        const int y = ty0 + 2 * (i / (FT_W / 2)), x = tx0 + 2 * (i % (FT_W / 2));
+        if (y < h && x < w) {
+            const double r00 = r(y, x);
+            const double r01 = x + 1 < w ? r(y, x + 1) : 0.0;
+            const double r10 = y + 1 < h ? r(y + 1, x) : 0.0;
+            const double r11 = (y + 1 < h && x + 1 < w) ? r(y + 1, x + 1) : 0.0;
+            fc[(y >> 1) * wc + (x >> 1)] = ((r00 + r01) + r10) + r11;
+        }
+    }
+}
+
+template <class G>
+__device__ __forceinline__ void mg_up_tile(const G &g, int h, int w, double *__restrict__ uout, const double *__restrict__ uin,
+                                           const double *__restrict__ ec, int wc, const double *__restrict__ f, double dt, int ty0, int tx0,
+                                           double *V, double *F, double *T1) {
+    const int tid = threadIdx.x;
+    // A: v = u + P e on the tile + 2, f on the tile + 1
+    for (int i = tid; i < F2_H * F2_W; i += kThreads) {
+        const int ly = i / F2_W, lx = i % F2_W, y = ty0 - 2 + ly, x = tx0 - 2 + lx;
+        double v = 0.0, fv = 0.0;
+        if (y >= 0 && y < h && x >= 0 && x < w) {
+            v = uin[y * w + x] + ec[(y >> 1) * wc + (x >> 1)];
+            fv = f[y * w + x];
+        }
+        V[i] = v;
+        F[i] = fv;
+    }
+    __syncthreads();
+    auto vv = [&](int yy, int xx) { return V[(yy - ty0 + 2) * F2_W + (xx - tx0 + 2)]; };
+    for (int i = tid; i < F1_H * F1_W; i += kThreads) {
+        const int ly = i / F1_W, lx = i % F1_W, y = ty0 - 1 + ly, x = tx0 - 1 + lx;
+        double t = 0.0;
+        if (y >= 0 && y < h && x >= 0 && x < w) {
+            const double c = vv(y, x);
+            t = c + g.odv(y, x) * (F[(ly + 1) * F2_W + lx + 1] - mg_au(g, vv, y, x, c, dt));
+        }
+        T1[i] = t;
+    }
+    __syncthreads();
+    auto t1 = [&](int yy, int xx) { return T1[(yy - ty0 + 1) * F1_W + (xx - tx0 + 1)]; };
+    for (int i = tid; i < FT_H * FT_W; i += kThreads) {
+        const int ly = i / FT_W, lx = i % FT_W, y = ty0 + ly, x = tx0 + lx;
+        if (y < h && x < w) {
+            const double c = t1(y, x);
+            uout[y * w + x] = c + g.odv(y, x) * (F[(ly + 2) * F2_W + lx + 2] - mg_au(g, t1, y, x, c, dt));
+        }
+    }
+}
+
+template <class G> struct FastOf { static constexpr bool has = false; };
+template <> struct FastOf<Geom0> { static constexpr bool has = true; };
+
+template <class G>
+__global__ void __launch_bounds__(kThreads)
+k_mg_down(const G g, double *__restrict__ uout, const double *__restrict__ f, double *__restrict__ fc, int wc, double dt) {
+    __shared__ double F[F2_H * F2_W], U1[F2_H * F2_W], U2[F1_H * F1_W];
+    const int ty0 = blockIdx.y * FT_H, tx0 = blockIdx.x * FT_W;
+    if constexpr (FastOf<G>::has) {
+        if (region_open(g, ty0 - 2, ty0 + FT_H + 1, tx0 - 2, tx0 + FT_W + 1)) {
+            mg_down_tile(Geom0Fast{g.h, g.w, g.od[4]}, g.h, g.w, uout, f, fc, wc, dt, ty0, tx0, F, U1, U2);
+            return;
+        }
+    }
+    mg_down_tile(g, g.h, g.w, uout, f, fc, wc, dt, ty0, tx0, F, U1, U2);
+}
+template <class G>
+__global__ void __launch_bounds__(kThreads)
+k_mg_up(const G g, double *__restrict__ uout, const double *__restrict__ uin, const double *__restrict__ ec, int wc,
+        const double *__restrict__ f, double dt) {
+    __shared__ double V[F2_H * F2_W], F[F2_H * F2_W], T1[F1_H * F1_W];
+    const int ty0 = blockIdx.y * FT_H, tx0 = blockIdx.x * FT_W;
+    if constexpr (FastOf<G>::has) {
+        if (region_open(g, ty0 - 2, ty0 + FT_H + 1, tx0 - 2, tx0 + FT_W + 1)) {
+            mg_up_tile(Geom0Fast{g.h, g.w, g.od[4]}, g.h, g.w, uout, uin, ec, wc, f, dt, ty0, tx0, V, F, T1);
+            return;
+        }
+    }
+    mg_up_tile(g, g.h, g.w, uout, uin, ec, wc, f, dt, ty0, tx0, V, F, T1);
+}
+
 // ---- every level that fits kTailMax^2 cells: one CTA, one thread per cell, block barriers between the operations
 struct TailArgs {
     int nlev;
@@ -337,7 +473,15 @@ int pano_mg_apply_raw(pano_mg *m, double *dst, const double *src) {
         if (l == 0) return mg_level_op(ctx, m->g0, o, out, uin, F(0), ec, hc, wc, m->dt);
         return mg_level_op(ctx, stored(m, l), o, out, uin, F(l), ec, hc, wc, m->dt);
     };
-    for (int l = 0; l < m->tail; ++l) {                         // down: fused pre-sweeps, residual + restriction
+    const bool fused = pano_option(ctx, "mg_fused", 1) != 0;
+    auto tiles = [&](int l) { return dim3((unsigned)((m->ws[l] + FT_W - 1) / FT_W), (unsigned)((m->hs[l] + FT_H - 1) / FT_H)); };
+    for (int l = 0; l < m->tail; ++l) {                         // down: two sweeps from zero, residual + restriction
+        if (fused) {                                            // one pass: f -> t (= u), f'
+            if (l == 0) k_mg_down<Geom0><<<tiles(0), kThreads, 0, ctx->stream>>>(m->g0, m->t[0], F(0), m->f[1], m->ws[1], m->dt);
+            else k_mg_down<GeomStored><<<tiles(l), kThreads, 0, ctx->stream>>>(stored(m, l), m->t[l], F(l), m->f[l + 1], m->ws[l + 1], m->dt);
+            PANO_TRY(pano_after_launch(ctx, "mg_down"));
+            continue;
+        }
         PANO_TRY(op(l, OP_PRE, U(l), nullptr, nullptr));
         PANO_TRY(op(l, OP_RESTRICT, m->f[l + 1], U(l), nullptr));
     }
@@ -356,6 +500,12 @@ int pano_mg_apply_raw(pano_mg *m, double *dst, const double *src) {
     k_mg_tail<<<1, kTailMax * kTailMax, 0, ctx->stream>>>(a);
     PANO_TRY(pano_after_launch(ctx, "mg_tail"));
     for (int l = m->tail - 1; l >= 0; --l) {                    // up: prolongation fused into post-sweep 1, post-sweep 2
+        if (fused) {                                            // one pass: t, u', f -> u
+            if (l == 0) k_mg_up<Geom0><<<tiles(0), kThreads, 0, ctx->stream>>>(m->g0, U(0), m->t[0], U(1), m->ws[1], F(0), m->dt);
+            else k_mg_up<GeomStored><<<tiles(l), kThreads, 0, ctx->stream>>>(stored(m, l), U(l), m->t[l], U(l + 1), m->ws[l + 1], F(l), m->dt);
+            PANO_TRY(pano_after_launch(ctx, "mg_up"));
+            continue;
+        }
         PANO_TRY(op(l, OP_POST1, m->t[l], U(l), U(l + 1)));
         PANO_TRY(op(l, OP_SWEEP, U(l), m->t[l], nullptr));
     }
