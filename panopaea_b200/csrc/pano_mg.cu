@@ -139,17 +139,26 @@ k_mg_level(const G g, double *__restrict__ out, const double *__restrict__ uin, 
     }
 }
 
-// ---- fused forms for the levels that live in HBM: a 16 x 64 tile per block, staged in shared memory with a two-cell halo,
+// ---- fused forms for the levels that live in HBM: a 16 x 64 tile, staged in shared memory with a two-cell halo,
 // so that a whole half of the V-cycle is ONE pass over the level:
 //   k_mg_down: f -> u (two sweeps from zero), and the restricted residual f' = R (f - A u)          8 B read, 10 B written per cell
 //   k_mg_up:   u, u' (coarse correction), f -> two more sweeps of u + P u'                           18 B read, 8 B written
 // The halo cells are recomputed by the neighbouring tiles (same expressions, so the same bits); out-of-place (down writes
 // `t`, up reads `t` and writes `u`) because a tile reads its neighbours' cells.
+// Persistent blocks walk the tiles with a two-stage cp.async pipeline: the loads of tile k+1 are in flight while tile k
+// is computed, so the DRAM latency is not paid once per tile (first version: load -> barrier -> compute, 45 % of what
+// the same kernels reach now).  Tiles whose faces are all open (`regular`: level 0 away from walls / obstacle; coarser
+// levels by a per-tile flag computed at set-up) use constant weights and never read the geometry arrays.
 constexpr int FT_H = 16, FT_W = 64;                       // tile (even, so that 2x2 aggregates never straddle tiles)
 constexpr int F2_H = FT_H + 4, F2_W = FT_W + 4;           // with the two-cell halo
 constexpr int F1_H = FT_H + 2, F1_W = FT_W + 2;           // with the one-cell halo
+constexpr int EC_H = FT_H / 2 + 2, EC_W = FT_W / 2 + 2;   // coarse cells under the tile + 2
+constexpr int kDownStage = F2_H * F2_W;                               // doubles per pipeline stage of k_mg_down: f
+constexpr int kUpStage = 2 * F2_H * F2_W + EC_H * EC_W;               // k_mg_up: u, f, coarse correction
+constexpr int kDownSmem = (2 * kDownStage + F2_H * F2_W + F1_H * F1_W) * 8;
+constexpr int kUpSmem = (2 * kUpStage + F1_H * F1_W) * 8;
 
-struct Geom0Fast {   // level 0 away from walls and obstacle: every face open
+struct GeomRegular {   // every face open: weights 1, od = omega / (dt * 4)
     int h, w;
     double od4;
     __device__ __forceinline__ void weights(int, int, double &n, double &s, double &w_, double &e) const { n = s = w_ = e = 1.0; }
@@ -162,39 +171,67 @@ __device__ __forceinline__ bool region_open(const Geom0 &g, int ya, int yb, int 
     return !(m.y1 > m.y0 && m.x1 > m.x0 && ya < m.y1 && yb + 1 >= m.y0 && xa < m.x1 && xb + 1 >= m.x0);
 }
 
-template <class G>
-__device__ __forceinline__ void mg_down_tile(const G &g, int h, int w, double *__restrict__ uout, const double *__restrict__ f,
-                                             double *__restrict__ fc, int wc, double dt, int ty0, int tx0, double *F, double *U1, double *U2) {
-    const int tid = threadIdx.x;
-    // A: f and u1 = od * f on the tile + 2
-    for (int i = tid; i < F2_H * F2_W; i += kThreads) {
-        const int ly = i / F2_W, lx = i % F2_W, y = ty0 - 2 + ly, x = tx0 - 2 + lx;
-        double fv = 0.0, u1 = 0.0;
-        if (y >= 0 && y < h && x >= 0 && x < w) {
-            fv = f[y * w + x];
-            u1 = g.odv(y, x) * fv;
-        }
-        F[i] = fv;
-        U1[i] = u1;
+// 8-byte asynchronous copy global -> shared; `ok` false: the destination is zero-filled and nothing is read
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, bool ok) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int n = ok ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// fn(ly, lx) for every cell of an H x W region (W = 64 + 0 / 2 / 4) without a division: 256 threads sweep 4 rows x 64
+// columns per pass, the columns beyond 64 are one extra pass of H x (W - 64) threads
+template <int H, int W, class Fn>
+__device__ __forceinline__ void for_region(const Fn &fn) {
+    static_assert(kThreads == 256 && W >= 64 && W <= 68 && (W - 64) * H <= kThreads, "region shape");
+    const int tid = threadIdx.x, lx = tid & 63, r = tid >> 6;
+#pragma unroll
+    for (int k = 0; k < (H + 3) / 4; ++k) {
+        const int ly = r + 4 * k;
+        if (ly < H) fn(ly, lx);
     }
+    constexpr int E = W - 64;
+    if (E > 0 && tid < H * E) fn(tid / (E > 0 ? E : 1), 64 + tid % (E > 0 ? E : 1));
+}
+
+// stage the (tile + 2) box of a level array
+__device__ __forceinline__ void stage_box2(double *dst, const double *__restrict__ src, int h, int w, int ty0, int tx0) {
+    for_region<F2_H, F2_W>([&](int ly, int lx) {
+        const int y = ty0 - 2 + ly, x = tx0 - 2 + lx;
+        const bool ok = y >= 0 && y < h && x >= 0 && x < w;
+        cp_async8(dst + ly * F2_W + lx, ok ? src + y * w + x : src, ok);
+    });
+}
+
+// compute part of k_mg_down for one staged tile: F = f on the tile + 2
+template <class G>
+__device__ __forceinline__ void mg_down_tile(const G &g, int h, int w, double *__restrict__ uout, double *__restrict__ fc, int wc, double dt,
+                                             int ty0, int tx0, const double *F, double *U1, double *U2) {
+    // A: u1 = od * f on the tile + 2 (first sweep from zero)
+    for_region<F2_H, F2_W>([&](int ly, int lx) {
+        const int y = ty0 - 2 + ly, x = tx0 - 2 + lx;
+        U1[ly * F2_W + lx] = (y >= 0 && y < h && x >= 0 && x < w) ? g.odv(y, x) * F[ly * F2_W + lx] : 0.0;
+    });
     __syncthreads();
-    // B: second sweep on the tile + 1 (pre_cell: c + od * (f - A u1)); the tile itself goes to global memory
+    // B: second sweep on the tile + 1 (c + od * (f - A u1)); the tile itself goes to global memory
     auto u1 = [&](int yy, int xx) { return U1[(yy - ty0 + 2) * F2_W + (xx - tx0 + 2)]; };
-    for (int i = tid; i < F1_H * F1_W; i += kThreads) {
-        const int ly = i / F1_W, lx = i % F1_W, y = ty0 - 1 + ly, x = tx0 - 1 + lx;
+    for_region<F1_H, F1_W>([&](int ly, int lx) {
+        const int y = ty0 - 1 + ly, x = tx0 - 1 + lx;
         double v = 0.0;
         if (y >= 0 && y < h && x >= 0 && x < w) {
             const double c = u1(y, x);
             v = c + g.odv(y, x) * (F[(ly + 1) * F2_W + lx + 1] - mg_au(g, u1, y, x, c, dt));
             if (ly >= 1 && ly <= FT_H && lx >= 1 && lx <= FT_W) uout[y * w + x] = v;
         }
-        U2[i] = v;
-    }
+        U2[ly * F1_W + lx] = v;
+    });
     __syncthreads();
     // C: residual of the four children of every coarse cell of the tile, summed in the specified order
     auto u2 = [&](int yy, int xx) { return U2[(yy - ty0 + 1) * F1_W + (xx - tx0 + 1)]; };
     auto r = [&](int yy, int xx) { return F[(yy - ty0 + 2) * F2_W + (xx - tx0 + 2)] - mg_au(g, u2, yy, xx, u2(yy, xx), dt); };
-    for (int i = tid; i < (FT_H / 2) * (FT_W / 2); i += kThreads) {
+    {
+        const int i = threadIdx.x;                        // (FT_H / 2) * (FT_W / 2) == kThreads coarse cells
         const int y = ty0 + 2 * (i / (FT_W / 2)), x = tx0 + 2 * (i % (FT_W / 2));
         if (y < h && x < w) {
             const double r00 = r(y, x);
@@ -205,74 +242,166 @@ __device__ __forceinline__ void mg_down_tile(const G &g, int h, int w, double *_
         }
     }
 }
-
-template <class G>
-__device__ __forceinline__ void mg_up_tile(const G &g, int h, int w, double *__restrict__ uout, const double *__restrict__ uin,
-                                           const double *__restrict__ ec, int wc, const double *__restrict__ f, double dt, int ty0, int tx0,
-                                           double *V, double *F, double *T1) {
-    const int tid = threadIdx.x;
-    // A: v = u + P e on the tile + 2, f on the tile + 1
-    for (int i = tid; i < F2_H * F2_W; i += kThreads) {
-        const int ly = i / F2_W, lx = i % F2_W, y = ty0 - 2 + ly, x = tx0 - 2 + lx;
-        double v = 0.0, fv = 0.0;
-        if (y >= 0 && y < h && x >= 0 && x < w) {
-            v = uin[y * w + x] + ec[(y >> 1) * wc + (x >> 1)];
-            fv = f[y * w + x];
-        }
-        V[i] = v;
-        F[i] = fv;
+// the same for a regular tile (every face of the tile + 2 open, all of it inside the grid): no bounds, no geometry, and all
+// shared-memory offsets are compile-time constants.  Same expressions, so the same bits as the general form above.
+__device__ __forceinline__ void mg_down_tile_regular(double od4, int w, double *__restrict__ uout, double *__restrict__ fc, int wc, double dt,
+                                                     int ty0, int tx0, const double *F, double *U1, double *U2) {
+    const GeomRegular g{0, 0, od4};
+    for_region<F2_H, F2_W>([&](int ly, int lx) { U1[ly * F2_W + lx] = od4 * F[ly * F2_W + lx]; });
+    __syncthreads();
+    for_region<F1_H, F1_W>([&](int ly, int lx) {
+        const double *p = U1 + (ly + 1) * F2_W + lx + 1;
+        auto u1 = [&](int dy, int dx) { return p[dy * F2_W + dx]; };       // offsets relative to the cell
+        const double c = p[0];
+        const double v = c + od4 * (F[(ly + 1) * F2_W + lx + 1] - mg_au(g, [&](int yy, int xx) { return u1(yy, xx); }, 0, 0, c, dt));
+        if (ly >= 1 && ly <= FT_H && lx >= 1 && lx <= FT_W) uout[(ty0 - 1 + ly) * w + tx0 - 1 + lx] = v;
+        U2[ly * F1_W + lx] = v;
+    });
+    __syncthreads();
+    {
+        const int i = threadIdx.x, cy = i / (FT_W / 2), cx = i % (FT_W / 2);
+        auto r = [&](int ly, int lx) {                                      // tile-local cell (ly, lx)
+            const double *p = U2 + (ly + 1) * F1_W + lx + 1;
+            return F[(ly + 2) * F2_W + lx + 2] - mg_au(g, [&](int dy, int dx) { return p[dy * F1_W + dx]; }, 0, 0, p[0], dt);
+        };
+        const double r00 = r(2 * cy, 2 * cx), r01 = r(2 * cy, 2 * cx + 1), r10 = r(2 * cy + 1, 2 * cx), r11 = r(2 * cy + 1, 2 * cx + 1);
+        fc[((ty0 >> 1) + cy) * wc + (tx0 >> 1) + cx] = ((r00 + r01) + r10) + r11;
     }
+}
+
+// compute part of k_mg_up for one staged tile: V = u, Fs = f on the tile + 2, EC = coarse correction under it
+template <class G>
+__device__ __forceinline__ void mg_up_tile(const G &g, int h, int w, double *__restrict__ uout, double dt, int ty0, int tx0, double *V,
+                                           const double *Fs, const double *EC, double *T1) {
+    // A: v = u + P e on the tile + 2, in place (the parent of box cell (ly, lx) is EC cell (ly / 2, lx / 2): the box starts at even - 2)
+    for_region<F2_H, F2_W>([&](int ly, int lx) {
+        const int y = ty0 - 2 + ly, x = tx0 - 2 + lx;
+        if (y >= 0 && y < h && x >= 0 && x < w) V[ly * F2_W + lx] = V[ly * F2_W + lx] + EC[(ly >> 1) * EC_W + (lx >> 1)];
+    });
     __syncthreads();
     auto vv = [&](int yy, int xx) { return V[(yy - ty0 + 2) * F2_W + (xx - tx0 + 2)]; };
-    for (int i = tid; i < F1_H * F1_W; i += kThreads) {
-        const int ly = i / F1_W, lx = i % F1_W, y = ty0 - 1 + ly, x = tx0 - 1 + lx;
+    for_region<F1_H, F1_W>([&](int ly, int lx) {
+        const int y = ty0 - 1 + ly, x = tx0 - 1 + lx;
         double t = 0.0;
         if (y >= 0 && y < h && x >= 0 && x < w) {
             const double c = vv(y, x);
-            t = c + g.odv(y, x) * (F[(ly + 1) * F2_W + lx + 1] - mg_au(g, vv, y, x, c, dt));
+            t = c + g.odv(y, x) * (Fs[(ly + 1) * F2_W + lx + 1] - mg_au(g, vv, y, x, c, dt));
         }
-        T1[i] = t;
-    }
+        T1[ly * F1_W + lx] = t;
+    });
     __syncthreads();
     auto t1 = [&](int yy, int xx) { return T1[(yy - ty0 + 1) * F1_W + (xx - tx0 + 1)]; };
-    for (int i = tid; i < FT_H * FT_W; i += kThreads) {
-        const int ly = i / FT_W, lx = i % FT_W, y = ty0 + ly, x = tx0 + lx;
+    for_region<FT_H, FT_W>([&](int ly, int lx) {
+        const int y = ty0 + ly, x = tx0 + lx;
         if (y < h && x < w) {
             const double c = t1(y, x);
-            uout[y * w + x] = c + g.odv(y, x) * (F[(ly + 2) * F2_W + lx + 2] - mg_au(g, t1, y, x, c, dt));
+            uout[y * w + x] = c + g.odv(y, x) * (Fs[(ly + 2) * F2_W + lx + 2] - mg_au(g, t1, y, x, c, dt));
         }
-    }
+    });
+}
+__device__ __forceinline__ void mg_up_tile_regular(double od4, int w, double *__restrict__ uout, double dt, int ty0, int tx0, double *V,
+                                                   const double *Fs, const double *EC, double *T1) {
+    const GeomRegular g{0, 0, od4};
+    for_region<F2_H, F2_W>([&](int ly, int lx) { V[ly * F2_W + lx] = V[ly * F2_W + lx] + EC[(ly >> 1) * EC_W + (lx >> 1)]; });
+    __syncthreads();
+    for_region<F1_H, F1_W>([&](int ly, int lx) {
+        const double *p = V + (ly + 1) * F2_W + lx + 1;
+        const double c = p[0];
+        T1[ly * F1_W + lx] = c + od4 * (Fs[(ly + 1) * F2_W + lx + 1] - mg_au(g, [&](int dy, int dx) { return p[dy * F2_W + dx]; }, 0, 0, c, dt));
+    });
+    __syncthreads();
+    for_region<FT_H, FT_W>([&](int ly, int lx) {
+        const double *p = T1 + (ly + 1) * F1_W + lx + 1;
+        const double c = p[0];
+        uout[(ty0 + ly) * w + tx0 + lx] = c + od4 * (Fs[(ly + 2) * F2_W + lx + 2] - mg_au(g, [&](int dy, int dx) { return p[dy * F1_W + dx]; }, 0, 0, c, dt));
+    });
 }
 
-template <class G> struct FastOf { static constexpr bool has = false; };
-template <> struct FastOf<Geom0> { static constexpr bool has = true; };
+// is the tile at (ty0, tx0) regular (every face of the tile + 2 open)?  Level 0: from the geometry; stored levels: set-up flag
+__device__ __forceinline__ bool tile_regular(const Geom0 &g, const unsigned char *, int, int ty0, int tx0) {
+    return region_open(g, ty0 - 2, ty0 + FT_H + 1, tx0 - 2, tx0 + FT_W + 1);
+}
+__device__ __forceinline__ bool tile_regular(const GeomStored &, const unsigned char *flags, int t, int, int) { return flags[t] != 0; }
 
 template <class G>
 __global__ void __launch_bounds__(kThreads)
-k_mg_down(const G g, double *__restrict__ uout, const double *__restrict__ f, double *__restrict__ fc, int wc, double dt) {
-    __shared__ double F[F2_H * F2_W], U1[F2_H * F2_W], U2[F1_H * F1_W];
-    const int ty0 = blockIdx.y * FT_H, tx0 = blockIdx.x * FT_W;
-    if constexpr (FastOf<G>::has) {
-        if (region_open(g, ty0 - 2, ty0 + FT_H + 1, tx0 - 2, tx0 + FT_W + 1)) {
-            mg_down_tile(Geom0Fast{g.h, g.w, g.od[4]}, g.h, g.w, uout, f, fc, wc, dt, ty0, tx0, F, U1, U2);
-            return;
-        }
+k_mg_down(const G g, const unsigned char *__restrict__ flags, double od_reg, double *__restrict__ uout, const double *__restrict__ f,
+          double *__restrict__ fc, int wc, double dt) {
+    extern __shared__ __align__(16) double sm[];
+    double *U1 = sm + 2 * kDownStage, *U2 = U1 + F2_H * F2_W;
+    const int tiles_x = (g.w + FT_W - 1) / FT_W, ntiles = tiles_x * ((g.h + FT_H - 1) / FT_H);
+    int t = blockIdx.x, st = 0;
+    if (t < ntiles) stage_box2(sm, f, g.h, g.w, (t / tiles_x) * FT_H, (t % tiles_x) * FT_W);
+    cp_async_commit();
+    for (; t < ntiles; t += gridDim.x, st ^= 1) {
+        const int tn = t + gridDim.x;
+        if (tn < ntiles) stage_box2(sm + (st ^ 1) * kDownStage, f, g.h, g.w, (tn / tiles_x) * FT_H, (tn % tiles_x) * FT_W);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const int ty0 = (t / tiles_x) * FT_H, tx0 = (t % tiles_x) * FT_W;
+        const double *F = sm + st * kDownStage;
+        if (tile_regular(g, flags, t, ty0, tx0)) mg_down_tile_regular(od_reg, g.w, uout, fc, wc, dt, ty0, tx0, F, U1, U2);
+        else mg_down_tile(g, g.h, g.w, uout, fc, wc, dt, ty0, tx0, F, U1, U2);
+        __syncthreads();   // the stage (and U1 / U2) are free again
     }
-    mg_down_tile(g, g.h, g.w, uout, f, fc, wc, dt, ty0, tx0, F, U1, U2);
 }
+
 template <class G>
 __global__ void __launch_bounds__(kThreads)
-k_mg_up(const G g, double *__restrict__ uout, const double *__restrict__ uin, const double *__restrict__ ec, int wc,
-        const double *__restrict__ f, double dt) {
-    __shared__ double V[F2_H * F2_W], F[F2_H * F2_W], T1[F1_H * F1_W];
-    const int ty0 = blockIdx.y * FT_H, tx0 = blockIdx.x * FT_W;
-    if constexpr (FastOf<G>::has) {
-        if (region_open(g, ty0 - 2, ty0 + FT_H + 1, tx0 - 2, tx0 + FT_W + 1)) {
-            mg_up_tile(Geom0Fast{g.h, g.w, g.od[4]}, g.h, g.w, uout, uin, ec, wc, f, dt, ty0, tx0, V, F, T1);
-            return;
+k_mg_up(const G g, const unsigned char *__restrict__ flags, double od_reg, double *__restrict__ uout, const double *__restrict__ uin,
+        const double *__restrict__ ec, int hc, int wc, const double *__restrict__ f, double dt) {
+    extern __shared__ __align__(16) double sm[];
+    double *T1 = sm + 2 * kUpStage;
+    const int tiles_x = (g.w + FT_W - 1) / FT_W, ntiles = tiles_x * ((g.h + FT_H - 1) / FT_H);
+    auto stage = [&](double *dst, int tt) {
+        const int ty0 = (tt / tiles_x) * FT_H, tx0 = (tt % tiles_x) * FT_W;
+        stage_box2(dst, uin, g.h, g.w, ty0, tx0);
+        stage_box2(dst + F2_H * F2_W, f, g.h, g.w, ty0, tx0);
+        const int cy0 = (ty0 >> 1) - 1, cx0 = (tx0 >> 1) - 1;
+        double *E = dst + 2 * F2_H * F2_W;
+        for (int i = threadIdx.x; i < EC_H * EC_W; i += kThreads) {
+            const int y = cy0 + i / EC_W, x = cx0 + i % EC_W;
+            const bool ok = y >= 0 && y < hc && x >= 0 && x < wc;
+            cp_async8(E + i, ok ? ec + y * wc + x : ec, ok);
         }
+    };
+    int t = blockIdx.x, st = 0;
+    if (t < ntiles) stage(sm, t);
+    cp_async_commit();
+    for (; t < ntiles; t += gridDim.x, st ^= 1) {
+        const int tn = t + gridDim.x;
+        if (tn < ntiles) stage(sm + (st ^ 1) * kUpStage, tn);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const int ty0 = (t / tiles_x) * FT_H, tx0 = (t % tiles_x) * FT_W;
+        double *V = sm + st * kUpStage;
+        if (tile_regular(g, flags, t, ty0, tx0)) mg_up_tile_regular(od_reg, g.w, uout, dt, ty0, tx0, V, V + F2_H * F2_W, V + 2 * F2_H * F2_W, T1);
+        else mg_up_tile(g, g.h, g.w, uout, dt, ty0, tx0, V, V + F2_H * F2_W, V + 2 * F2_H * F2_W, T1);
+        __syncthreads();
     }
-    mg_up_tile(g, g.h, g.w, uout, uin, ec, wc, f, dt, ty0, tx0, V, F, T1);
+}
+
+// set-up: flags[t] = 1 when every face of tile t + 2 of a stored level has weight exactly 1 (then od = omega / (dt * 4) there)
+__global__ void k_mg_tile_flags(const GeomStored g, unsigned char *__restrict__ flags) {
+    const int tiles_x = (g.w + FT_W - 1) / FT_W;
+    const int t = blockIdx.x, ty0 = (t / tiles_x) * FT_H, tx0 = (t % tiles_x) * FT_W;
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = (ty0 - 2 < 0 || ty0 + FT_H + 1 > g.h - 1 || tx0 - 2 < 0 || tx0 + FT_W + 1 > g.w - 1) ? 1 : 0;
+    __syncthreads();
+    if (!bad) {
+        int b = 0;
+        for (int i = threadIdx.x; i < F2_H * F2_W; i += blockDim.x) {
+            const int y = ty0 - 2 + i / F2_W, x = tx0 - 2 + i % F2_W;
+            double n, s, w_, e;
+            g.weights(y, x, n, s, w_, e);
+            if (n != 1.0 || s != 1.0 || w_ != 1.0 || e != 1.0) b = 1;
+        }
+        if (b) bad = 1;   // benign race: every writer stores 1
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) flags[t] = bad ? 0 : 1;
 }
 
 // ---- every level that fits kTailMax^2 cells: one CTA, one thread per cell, block barriers between the operations
@@ -383,6 +512,9 @@ struct pano_mg {
     int hs[kMaxLevels], ws[kMaxLevels];
     double *wy[kMaxLevels], *wx[kMaxLevels], *od[kMaxLevels], *u[kMaxLevels], *f[kMaxLevels], *t[kMaxLevels];
     double *pool = nullptr;
+    unsigned char *flags[kMaxLevels];       // per-tile `regular` flags of the stored levels (null for level 0)
+    unsigned char *flag_pool = nullptr;
+    double od_reg = 0;                      // omega / (dt * 4)
     Geom0 g0;
 };
 
@@ -431,6 +563,16 @@ static int mg_build(pano_mg *m) {
         m->f[i] = i > 0 ? m->pool + o_f[i] : nullptr;
         m->t[i] = m->pool + o_t[i];
     }
+    m->od_reg = kOmega / (m->dt * 4.0);
+    auto ntiles = [&](int i) { return (size_t)((m->ws[i] + FT_W - 1) / FT_W) * (size_t)((m->hs[i] + FT_H - 1) / FT_H); };
+    size_t nflags = 0;
+    for (int i = 1; i < m->tail; ++i) nflags += ntiles(i);
+    for (int i = 0; i < kMaxLevels; ++i) m->flags[i] = nullptr;
+    if (nflags) {
+        PANO_CUDA(cudaMalloc((void **)&m->flag_pool, nflags));
+        size_t o = 0;
+        for (int i = 1; i < m->tail; ++i) { m->flags[i] = m->flag_pool + o; o += ntiles(i); }
+    }
     auto flat = [&](size_t n) { size_t b = (n + 255) / 256; return (int)(b < 1 ? 1 : (b > 4096 ? 4096 : b)); };
     if (m->tail == 0) {
         k_mg_store_level0<<<flat((m->h + 1) * (m->w + 1) * 2), 256, 0, ctx->stream>>>(m->g0, m->wy[0], m->wx[0]);
@@ -447,6 +589,14 @@ static int mg_build(pano_mg *m) {
         k_mg_od<<<flat((size_t)hc * wc), 256, 0, ctx->stream>>>(m->wy[i + 1], m->wx[i + 1], m->od[i + 1], hc, wc, m->dt);
         PANO_TRY(pano_after_launch(ctx, "mg_od"));
     }
+    for (int i = 1; i < m->tail; ++i) {
+        k_mg_tile_flags<<<(unsigned)ntiles(i), 128, 0, ctx->stream>>>(stored(m, i), m->flags[i]);
+        PANO_TRY(pano_after_launch(ctx, "mg_tile_flags"));
+    }
+    PANO_CUDA(cudaFuncSetAttribute(k_mg_down<Geom0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDownSmem));
+    PANO_CUDA(cudaFuncSetAttribute(k_mg_down<GeomStored>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDownSmem));
+    PANO_CUDA(cudaFuncSetAttribute(k_mg_up<Geom0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem));
+    PANO_CUDA(cudaFuncSetAttribute(k_mg_up<GeomStored>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem));
     return PANO_OK;
 }
 
@@ -474,11 +624,16 @@ int pano_mg_apply_raw(pano_mg *m, double *dst, const double *src) {
         return mg_level_op(ctx, stored(m, l), o, out, uin, F(l), ec, hc, wc, m->dt);
     };
     const bool fused = pano_option(ctx, "mg_fused", 1) != 0;
-    auto tiles = [&](int l) { return dim3((unsigned)((m->ws[l] + FT_W - 1) / FT_W), (unsigned)((m->hs[l] + FT_H - 1) / FT_H)); };
+    auto nblocks = [&](int l, int per_sm) {   // persistent blocks: a few per SM, never more than there are tiles
+        const size_t nt = (size_t)((m->ws[l] + FT_W - 1) / FT_W) * (size_t)((m->hs[l] + FT_H - 1) / FT_H);
+        const size_t cap = (size_t)ctx->num_sms * per_sm;
+        return (unsigned)(nt < cap ? nt : cap);
+    };
+    const int down_per_sm = (int)pano_option(ctx, "mg_down_blocks", 5), up_per_sm = (int)pano_option(ctx, "mg_up_blocks", 3);
     for (int l = 0; l < m->tail; ++l) {                         // down: two sweeps from zero, residual + restriction
         if (fused) {                                            // one pass: f -> t (= u), f'
-            if (l == 0) k_mg_down<Geom0><<<tiles(0), kThreads, 0, ctx->stream>>>(m->g0, m->t[0], F(0), m->f[1], m->ws[1], m->dt);
-            else k_mg_down<GeomStored><<<tiles(l), kThreads, 0, ctx->stream>>>(stored(m, l), m->t[l], F(l), m->f[l + 1], m->ws[l + 1], m->dt);
+            if (l == 0) k_mg_down<Geom0><<<nblocks(0, down_per_sm), kThreads, kDownSmem, ctx->stream>>>(m->g0, nullptr, m->od_reg, m->t[0], F(0), m->f[1], m->ws[1], m->dt);
+            else k_mg_down<GeomStored><<<nblocks(l, down_per_sm), kThreads, kDownSmem, ctx->stream>>>(stored(m, l), m->flags[l], m->od_reg, m->t[l], F(l), m->f[l + 1], m->ws[l + 1], m->dt);
             PANO_TRY(pano_after_launch(ctx, "mg_down"));
             continue;
         }
@@ -501,8 +656,8 @@ int pano_mg_apply_raw(pano_mg *m, double *dst, const double *src) {
     PANO_TRY(pano_after_launch(ctx, "mg_tail"));
     for (int l = m->tail - 1; l >= 0; --l) {                    // up: prolongation fused into post-sweep 1, post-sweep 2
         if (fused) {                                            // one pass: t, u', f -> u
-            if (l == 0) k_mg_up<Geom0><<<tiles(0), kThreads, 0, ctx->stream>>>(m->g0, U(0), m->t[0], U(1), m->ws[1], F(0), m->dt);
-            else k_mg_up<GeomStored><<<tiles(l), kThreads, 0, ctx->stream>>>(stored(m, l), U(l), m->t[l], U(l + 1), m->ws[l + 1], F(l), m->dt);
+            if (l == 0) k_mg_up<Geom0><<<nblocks(0, up_per_sm), kThreads, kUpSmem, ctx->stream>>>(m->g0, nullptr, m->od_reg, U(0), m->t[0], U(1), m->hs[1], m->ws[1], F(0), m->dt);
+            else k_mg_up<GeomStored><<<nblocks(l, up_per_sm), kThreads, kUpSmem, ctx->stream>>>(stored(m, l), m->flags[l], m->od_reg, U(l), m->t[l], U(l + 1), m->hs[l + 1], m->ws[l + 1], F(l), m->dt);
             PANO_TRY(pano_after_launch(ctx, "mg_up"));
             continue;
         }
@@ -523,6 +678,7 @@ static pano_mg *mg_cached(pano_ctx *ctx, size_t h, size_t w, double dt, pano_rec
 void pano_mg_free_all(pano_ctx *ctx) {
     for (pano_mg *m : ctx->mg_cache) {
         if (m->pool) cudaFree(m->pool);
+        if (m->flag_pool) cudaFree(m->flag_pool);
         delete m;
     }
     ctx->mg_cache.clear();
@@ -600,6 +756,7 @@ int pano_mg_create(pano_ctx *ctx, size_t h, size_t w, double timestep, pano_rect
     const int rc = mg_build(m);
     if (rc != PANO_OK) {
         if (m->pool) cudaFree(m->pool);
+        if (m->flag_pool) cudaFree(m->flag_pool);
         delete m;
         return rc;
     }
@@ -616,6 +773,7 @@ int pano_mg_destroy(pano_mg *m) {
     for (size_t i = 0; i < ctx->mg_cache.size(); ++i)
         if (ctx->mg_cache[i] == m) { ctx->mg_cache.erase(ctx->mg_cache.begin() + i); break; }
     if (m->pool) cudaFree(m->pool);
+    if (m->flag_pool) cudaFree(m->flag_pool);
     delete m;
     return PANO_OK;
 }

@@ -8,7 +8,10 @@ import panopaea_b200 as P
 from panopaea_b200 import fluid, pcg
 
 ctx = P.Context(0)
-for n in [int(a) for a in sys.argv[1:]] or [1024]:
+for a in [a for a in sys.argv[1:] if "=" in a]:      # library options, e.g. mg_down_blocks=6
+    k, v = a.split("=")
+    ctx.set_option(k, int(v))
+for n in [int(a) for a in sys.argv[1:] if "=" not in a] or [1024]:
     prm = fluid.smoke_params(n)
     sim = fluid.DecFluid(**prm, ctx=ctx)
     for _ in range(10):
