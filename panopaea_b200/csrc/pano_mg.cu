@@ -387,21 +387,18 @@ k_mg_up(const G g, const unsigned char *__restrict__ flags, double od_reg, doubl
 __global__ void k_mg_tile_flags(const GeomStored g, unsigned char *__restrict__ flags) {
     const int tiles_x = (g.w + FT_W - 1) / FT_W;
     const int t = blockIdx.x, ty0 = (t / tiles_x) * FT_H, tx0 = (t % tiles_x) * FT_W;
-    __shared__ int bad;
-    if (threadIdx.x == 0) bad = (ty0 - 2 < 0 || ty0 + FT_H + 1 > g.h - 1 || tx0 - 2 < 0 || tx0 + FT_W + 1 > g.w - 1) ? 1 : 0;
-    __syncthreads();
-    if (!bad) {
-        int b = 0;
+    const bool outside = ty0 - 2 < 0 || ty0 + FT_H + 1 > g.h - 1 || tx0 - 2 < 0 || tx0 + FT_W + 1 > g.w - 1;   // block-uniform
+    int b = 0;
+    if (!outside) {
         for (int i = threadIdx.x; i < F2_H * F2_W; i += blockDim.x) {
             const int y = ty0 - 2 + i / F2_W, x = tx0 - 2 + i % F2_W;
             double n, s, w_, e;
             g.weights(y, x, n, s, w_, e);
             if (n != 1.0 || s != 1.0 || w_ != 1.0 || e != 1.0) b = 1;
         }
-        if (b) bad = 1;   // benign race: every writer stores 1
     }
-    __syncthreads();
-    if (threadIdx.x == 0) flags[t] = bad ? 0 : 1;
+    const int any = __syncthreads_or(b);
+    if (threadIdx.x == 0) flags[t] = (outside || any) ? 0 : 1;
 }
 
 // ---- every level that fits kTailMax^2 cells: one CTA, one thread per cell, block barriers between the operations

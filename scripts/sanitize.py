@@ -12,6 +12,17 @@ for n, kern in ((128, 3), (128, 4), (256, 2), (128, 1)):
         info = sim.step()
     print("kernel", kern, "n", n, info, float(np.abs(sim.pressure.to_host()).max()))
 ctx.set_option("cg_kernel", 0)
+# multigrid-preconditioned step: fused half-cycle kernels (regular and irregular tiles), single-CTA tail, unfused path
+from panopaea_b200 import _lib
+for n, fused in ((256, 1), (384, 1), (96, 1), (256, 0)):
+    ctx.set_option("mg_fused", fused)
+    k = n / 128.0
+    sim = fluid.DecFluid(h=n, w=n, ctx=ctx, inflow=(int(5 * k), int(20 * k), int(54 * k), int(64 * k)), obstacle=(int(70 * k), int(80 * k), int(50 * k), int(70 * k)))
+    sim.params.precond = _lib.PRECOND_MULTIGRID
+    for _ in range(2):
+        info = sim.step()
+    print("multigrid n", n, "fused", fused, info)
+ctx.set_option("mg_fused", 1)
 # loop-back multi-rank step
 ctxs = [P.Context(0) for _ in range(2)]
 k = 2
