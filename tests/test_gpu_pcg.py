@@ -234,3 +234,50 @@ def test_large_grid_capped_solve(oracle, variant):
         assert info["final_residual"] == pytest.approx(want.final_residual, rel=1e-5)
     true_r = b - oracle.laplacian_closure(n, n, x, 0.05, obstacle)
     assert np.allclose(r, true_r, rtol=0, atol=1e-9 * np.abs(b).max())
+
+
+@pytest.mark.parametrize("n", [8192, 16384])
+def test_full_size_streamed_solve_properties(n):
+    """BASELINE configs[2] / configs[4] sizes (8192^2, 16384^2): far beyond what the CPU oracle finishes in seconds, so
+    the streaming CG kernel is checked through size-independent properties, entirely on the device:
+      * the residual it returns is b - A x recomputed with the stand-alone Laplacian kernel,
+      * scaling the system by a power of two scales every iterate exactly (alpha, beta are unchanged),
+      * two runs give the same bits."""
+    from tests import gpu_util as U
+    from panopaea_b200 import fluid, pcg
+    grid = U.grid(n, n)
+    k = n // 128
+    obstacle = (70 * k, 80 * k, 50 * k, 70 * k)
+    rng = np.random.default_rng(21)
+    p = grid.new_simplex_2()
+    p.upload(rng.random((n, n)) - 0.5)
+    b = grid.new_simplex_2()
+    fluid.laplacian_apply(b, p, 0.05, obstacle)                  # a consistent right-hand side
+    bmax = b.norm_max()
+    x, r, aux, s = (grid.new_simplex_2() for _ in range(4))
+    iters = 12
+    info = pcg.solve_grid_laplacian(x, b, iters, 1e-30, r, aux, s, 0.05, obstacle)
+    assert info["iterations"] == iters and info["applies"] == iters
+    assert info["final_residual"] == r.norm_max() and info["rhs_max"] == bmax
+    t = p                                                        # reuse as scratch: t = (b - A x) - r
+    fluid.laplacian_apply(t, x, 0.05, obstacle)
+    t.scale(-1.0)
+    t.scaled_add(1.0, b)
+    t.scaled_add(-1.0, r)
+    assert t.norm_max() <= 1e-9 * bmax
+    # the residual of 12 CG iterations is smaller than the right-hand side (the solve makes progress)
+    assert info["final_residual"] < bmax
+    # exact scaling: solve(4 b) == 4 solve(b), bit for bit
+    x1 = t
+    x1.assign(x)
+    b.scale(4.0)
+    info4 = pcg.solve_grid_laplacian(x, b, iters, 1e-30, r, aux, s, 0.05, obstacle)
+    assert info4["final_residual"] == 4.0 * info["final_residual"]
+    x1.scale(4.0)
+    x1.scaled_add(-1.0, x)
+    assert x1.norm_max() == 0.0
+    # determinism
+    x1.assign(x)
+    pcg.solve_grid_laplacian(x, b, iters, 1e-30, r, aux, s, 0.05, obstacle)
+    x1.scaled_add(-1.0, x)
+    assert x1.norm_max() == 0.0
