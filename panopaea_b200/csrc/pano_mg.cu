@@ -155,8 +155,8 @@ constexpr int F1_H = FT_H + 2, F1_W = FT_W + 2;           // with the one-cell h
 constexpr int EC_H = FT_H / 2 + 2, EC_W = FT_W / 2 + 2;   // coarse cells under the tile + 2
 constexpr int kDownStage = F2_H * F2_W;                               // doubles per pipeline stage of k_mg_down: f
 constexpr int kUpStage = 2 * F2_H * F2_W + EC_H * EC_W;               // k_mg_up: u, f, coarse correction
-constexpr int kDownSmem = (2 * kDownStage + F2_H * F2_W + F1_H * F1_W) * 8;
-constexpr int kUpSmem = (2 * kUpStage + F1_H * F1_W) * 8;
+constexpr int kDownSmem = (2 * kDownStage + 2 * F2_H * F2_W) * 8;   // stages, U1, U2 (U2 in the tile + 2 layout)
+constexpr int kUpSmem = (2 * kUpStage + F2_H * F2_W) * 8;
 
 struct GeomRegular {   // every face open: weights 1, od = omega / (dt * 4)
     int h, w;
@@ -242,29 +242,68 @@ __device__ __forceinline__ void mg_down_tile(const G &g, int h, int w, double *_
         }
     }
 }
-// the same for a regular tile (every face of the tile + 2 open, all of it inside the grid): no bounds, no geometry, and all
-// shared-memory offsets are compile-time constants.  Same expressions, so the same bits as the general form above.
+// ---- regular tiles (every face of the tile + 2 open, all of it inside the grid): no bounds, no geometry, two columns per
+// thread with 128-bit shared-memory accesses.  Same expressions as mg_au / the general forms, so the same bits.
+// fn(ly, j) for the H rows x 34 column pairs of a (tile + 2) box: 8 rows x 32 pairs per pass, pairs 32 and 33 in one extra pass
+template <int H0, int H1, class Fn>
+__device__ __forceinline__ void for_pairs(const Fn &fn) {   // rows [H0, H1)
+    constexpr int H = H1 - H0;
+    static_assert(kThreads == 256 && 2 * H <= kThreads, "pair region shape");
+    const int tid = threadIdx.x, j = tid & 31, r = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < (H + 7) / 8; ++k) {
+        const int ly = H0 + r + 8 * k;
+        if (ly < H1) fn(ly, j);
+    }
+    if (tid < 2 * H) fn(H0 + (tid >> 1), 32 + (tid & 1));
+}
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
+// one damped-Jacobi sweep at the two cells of a pair, all weights 1: c + od4 * (f - (((c-n) + (c-s)) + (c-w)) + (c-e)) * dt)
+__device__ __forceinline__ double2 sweep_pair(double2 up, double2 ce, double2 dn, double l, double r, double2 f, double od4, double dt) {
+    double2 v;
+    v.x = ce.x + od4 * (f.x - ((((ce.x - up.x) + (ce.x - dn.x)) + (ce.x - l)) + (ce.x - ce.y)) * dt);
+    v.y = ce.y + od4 * (f.y - ((((ce.y - up.y) + (ce.y - dn.y)) + (ce.y - ce.x)) + (ce.y - r)) * dt);
+    return v;
+}
+// the sweep of box row ly, pair j, reading A (tile + 2 layout) and the right-hand side Fb; pair 0 / 33 touch a column outside
+// the box (their outer element is never used; the neighbouring index stays inside the array for rows >= 1)
+__device__ __forceinline__ double2 sweep_at(const double *A, const double *Fb, int ly, int j, double od4, double dt) {
+    const double *p = A + ly * F2_W + 2 * j;
+    return sweep_pair(ld2(p - F2_W), ld2(p), ld2(p + F2_W), p[-1], p[2], ld2(Fb + ly * F2_W + 2 * j), od4, dt);
+}
+
 __device__ __forceinline__ void mg_down_tile_regular(double od4, int w, double *__restrict__ uout, double *__restrict__ fc, int wc, double dt,
                                                      int ty0, int tx0, const double *F, double *U1, double *U2) {
-    const GeomRegular g{0, 0, od4};
-    for_region<F2_H, F2_W>([&](int ly, int lx) { U1[ly * F2_W + lx] = od4 * F[ly * F2_W + lx]; });
-    __syncthreads();
-    for_region<F1_H, F1_W>([&](int ly, int lx) {
-        const double *p = U1 + (ly + 1) * F2_W + lx + 1;
-        auto u1 = [&](int dy, int dx) { return p[dy * F2_W + dx]; };       // offsets relative to the cell
-        const double c = p[0];
-        const double v = c + od4 * (F[(ly + 1) * F2_W + lx + 1] - mg_au(g, [&](int yy, int xx) { return u1(yy, xx); }, 0, 0, c, dt));
-        if (ly >= 1 && ly <= FT_H && lx >= 1 && lx <= FT_W) uout[(ty0 - 1 + ly) * w + tx0 - 1 + lx] = v;
-        U2[ly * F1_W + lx] = v;
+    // A: u1 = od4 * f on the whole box
+    for_pairs<0, F2_H>([&](int ly, int j) {
+        const double2 f = ld2(F + ly * F2_W + 2 * j);
+        st2(U1 + ly * F2_W + 2 * j, make_double2(od4 * f.x, od4 * f.y));
     });
     __syncthreads();
+    // B: second sweep on box rows 1..18 (columns 1..66 are meaningful); the tile (rows 2..17, pairs 1..32) goes to global memory
+    const bool vec = (w & 1) == 0;
+    for_pairs<1, F2_H - 1>([&](int ly, int j) {
+        const double2 v = sweep_at(U1, F, ly, j, od4, dt);
+        st2(U2 + ly * F2_W + 2 * j, v);
+        if (ly >= 2 && ly <= FT_H + 1 && j >= 1 && j <= FT_W / 2) {
+            double *g = uout + (ty0 + ly - 2) * w + tx0 + 2 * j - 2;
+            if (vec) st2(g, v);
+            else { g[0] = v.x; g[1] = v.y; }
+        }
+    });
+    __syncthreads();
+    // C: restricted residual; coarse cell (cy, cx) = box rows 2cy+2, 2cy+3, pair cx+1
     {
-        const int i = threadIdx.x, cy = i / (FT_W / 2), cx = i % (FT_W / 2);
-        auto r = [&](int ly, int lx) {                                      // tile-local cell (ly, lx)
-            const double *p = U2 + (ly + 1) * F1_W + lx + 1;
-            return F[(ly + 2) * F2_W + lx + 2] - mg_au(g, [&](int dy, int dx) { return p[dy * F1_W + dx]; }, 0, 0, p[0], dt);
-        };
-        const double r00 = r(2 * cy, 2 * cx), r01 = r(2 * cy, 2 * cx + 1), r10 = r(2 * cy + 1, 2 * cx), r11 = r(2 * cy + 1, 2 * cx + 1);
+        const int i = threadIdx.x, cy = i / (FT_W / 2), cx = i % (FT_W / 2), ly = 2 * cy + 2, j = cx + 1;
+        const double *p = U2 + ly * F2_W + 2 * j;
+        const double2 n = ld2(p - F2_W), a = ld2(p), b = ld2(p + F2_W), s = ld2(p + 2 * F2_W);
+        const double al = p[-1], ar = p[2], bl = p[F2_W - 1], br = p[F2_W + 2];
+        const double2 fa = ld2(F + ly * F2_W + 2 * j), fb = ld2(F + (ly + 1) * F2_W + 2 * j);
+        const double r00 = fa.x - ((((a.x - n.x) + (a.x - b.x)) + (a.x - al)) + (a.x - a.y)) * dt;
+        const double r01 = fa.y - ((((a.y - n.y) + (a.y - b.y)) + (a.y - a.x)) + (a.y - ar)) * dt;
+        const double r10 = fb.x - ((((b.x - a.x) + (b.x - s.x)) + (b.x - bl)) + (b.x - b.y)) * dt;
+        const double r11 = fb.y - ((((b.y - a.y) + (b.y - s.y)) + (b.y - b.x)) + (b.y - br)) * dt;
         fc[((ty0 >> 1) + cy) * wc + (tx0 >> 1) + cx] = ((r00 + r01) + r10) + r11;
     }
 }
@@ -301,20 +340,29 @@ __device__ __forceinline__ void mg_up_tile(const G &g, int h, int w, double *__r
 }
 __device__ __forceinline__ void mg_up_tile_regular(double od4, int w, double *__restrict__ uout, double dt, int ty0, int tx0, double *V,
                                                    const double *Fs, const double *EC, double *T1) {
-    const GeomRegular g{0, 0, od4};
-    for_region<F2_H, F2_W>([&](int ly, int lx) { V[ly * F2_W + lx] = V[ly * F2_W + lx] + EC[(ly >> 1) * EC_W + (lx >> 1)]; });
-    __syncthreads();
-    for_region<F1_H, F1_W>([&](int ly, int lx) {
-        const double *p = V + (ly + 1) * F2_W + lx + 1;
-        const double c = p[0];
-        T1[ly * F1_W + lx] = c + od4 * (Fs[(ly + 1) * F2_W + lx + 1] - mg_au(g, [&](int dy, int dx) { return p[dy * F2_W + dx]; }, 0, 0, c, dt));
+    // A: v = u + P e in place; both columns of pair j have the parent column j
+    for_pairs<0, F2_H>([&](int ly, int j) {
+        const double e = EC[(ly >> 1) * EC_W + j];
+        double2 v = ld2(V + ly * F2_W + 2 * j);
+        v.x = v.x + e;
+        v.y = v.y + e;
+        st2(V + ly * F2_W + 2 * j, v);
     });
     __syncthreads();
-    for_region<FT_H, FT_W>([&](int ly, int lx) {
-        const double *p = T1 + (ly + 1) * F1_W + lx + 1;
-        const double c = p[0];
-        uout[(ty0 + ly) * w + tx0 + lx] = c + od4 * (Fs[(ly + 2) * F2_W + lx + 2] - mg_au(g, [&](int dy, int dx) { return p[dy * F1_W + dx]; }, 0, 0, c, dt));
-    });
+    for_pairs<1, F2_H - 1>([&](int ly, int j) { st2(T1 + ly * F2_W + 2 * j, sweep_at(V, Fs, ly, j, od4, dt)); });
+    __syncthreads();
+    const bool vec = (w & 1) == 0;
+    {   // the tile: box rows 2..17, pairs 1..32 -- 16 x 32 pairs, two passes of 8 rows
+        const int tid = threadIdx.x, j = 1 + (tid & 31), r = tid >> 5;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int ly = 2 + r + 8 * k;
+            const double2 v = sweep_at(T1, Fs, ly, j, od4, dt);
+            double *g = uout + (ty0 + ly - 2) * w + tx0 + 2 * j - 2;
+            if (vec) st2(g, v);
+            else { g[0] = v.x; g[1] = v.y; }
+        }
+    }
 }
 
 // is the tile at (ty0, tx0) regular (every face of the tile + 2 open)?  Level 0: from the geometry; stored levels: set-up flag
@@ -324,11 +372,11 @@ __device__ __forceinline__ bool tile_regular(const Geom0 &g, const unsigned char
 __device__ __forceinline__ bool tile_regular(const GeomStored &, const unsigned char *flags, int t, int, int) { return flags[t] != 0; }
 
 template <class G>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 5)
 k_mg_down(const G g, const unsigned char *__restrict__ flags, double od_reg, double *__restrict__ uout, const double *__restrict__ f,
           double *__restrict__ fc, int wc, double dt) {
     extern __shared__ __align__(16) double sm[];
-    double *U1 = sm + 2 * kDownStage, *U2 = U1 + F2_H * F2_W;
+    double *U1 = sm + 2 * kDownStage, *U2 = U1 + F2_H * F2_W;   // U2: tile + 1 layout (general path) or tile + 2 layout (regular path)
     const int tiles_x = (g.w + FT_W - 1) / FT_W, ntiles = tiles_x * ((g.h + FT_H - 1) / FT_H);
     int t = blockIdx.x, st = 0;
     if (t < ntiles) stage_box2(sm, f, g.h, g.w, (t / tiles_x) * FT_H, (t % tiles_x) * FT_W);
@@ -348,7 +396,7 @@ k_mg_down(const G g, const unsigned char *__restrict__ flags, double od_reg, dou
 }
 
 template <class G>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 k_mg_up(const G g, const unsigned char *__restrict__ flags, double od_reg, double *__restrict__ uout, const double *__restrict__ uin,
         const double *__restrict__ ec, int hc, int wc, const double *__restrict__ f, double dt) {
     extern __shared__ __align__(16) double sm[];
@@ -512,6 +560,7 @@ struct pano_mg {
     unsigned char *flags[kMaxLevels];       // per-tile `regular` flags of the stored levels (null for level 0)
     unsigned char *flag_pool = nullptr;
     double od_reg = 0;                      // omega / (dt * 4)
+    int occ_down = 1, occ_up = 1;           // resident blocks per SM of k_mg_down / k_mg_up (occupancy query)
     Geom0 g0;
 };
 
@@ -594,6 +643,15 @@ static int mg_build(pano_mg *m) {
     PANO_CUDA(cudaFuncSetAttribute(k_mg_down<GeomStored>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDownSmem));
     PANO_CUDA(cudaFuncSetAttribute(k_mg_up<Geom0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem));
     PANO_CUDA(cudaFuncSetAttribute(k_mg_up<GeomStored>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem));
+    int a = 0, b = 0;
+    PANO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_mg_down<Geom0>, kThreads, kDownSmem));
+    PANO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_mg_down<GeomStored>, kThreads, kDownSmem));
+    m->occ_down = a < b ? a : b;
+    PANO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_mg_up<Geom0>, kThreads, kUpSmem));
+    PANO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_mg_up<GeomStored>, kThreads, kUpSmem));
+    m->occ_up = a < b ? a : b;
+    if (m->occ_down < 1) m->occ_down = 1;
+    if (m->occ_up < 1) m->occ_up = 1;
     return PANO_OK;
 }
 
@@ -626,7 +684,10 @@ int pano_mg_apply_raw(pano_mg *m, double *dst, const double *src) {
         const size_t cap = (size_t)ctx->num_sms * per_sm;
         return (unsigned)(nt < cap ? nt : cap);
     };
-    const int down_per_sm = (int)pano_option(ctx, "mg_down_blocks", 5), up_per_sm = (int)pano_option(ctx, "mg_up_blocks", 3);
+    // persistent kernels: exactly as many blocks as are resident at once (more would run as a second, nearly empty wave)
+    int down_per_sm = (int)pano_option(ctx, "mg_down_blocks", 0), up_per_sm = (int)pano_option(ctx, "mg_up_blocks", 0);
+    if (down_per_sm <= 0) down_per_sm = m->occ_down;
+    if (up_per_sm <= 0) up_per_sm = m->occ_up;
     for (int l = 0; l < m->tail; ++l) {                         // down: two sweeps from zero, residual + restriction
         if (fused) {                                            // one pass: f -> t (= u), f'
             if (l == 0) k_mg_down<Geom0><<<nblocks(0, down_per_sm), kThreads, kDownSmem, ctx->stream>>>(m->g0, nullptr, m->od_reg, m->t[0], F(0), m->f[1], m->ws[1], m->dt);

@@ -100,3 +100,41 @@ def test_step_with_multigrid_converges_where_identity_does_not(oracle):
     div = sim.grid.new_simplex_2()
     worst = fluid.neg_divergence(div, sim.vel, fluid.smoke_params(n)["obstacle"])
     assert worst < 0.1 + 1e-9
+
+
+def test_host_buffer_step_with_multigrid():
+    """pano_fluid_step_host with precond = multigrid gives the fields of the device-resident step with the same
+    preconditioner (same kernels, same order), and reports the host-driven loop's info."""
+    import ctypes as C
+    from tests import gpu_util as U
+    from panopaea_b200 import _lib, fluid
+    n = 256
+    prm = fluid.smoke_params(n)
+    params = _lib.StepParams(prm["timestep"], prm["threshold"], prm["max_iterations"], _lib.PRECOND_MULTIGRID, _lib.Rect(*prm["inflow"]),
+                             prm["inflow_density"], prm["inflow_vy"], _lib.Rect(*prm["obstacle"]))
+    sim = fluid.DecFluid(**prm, ctx=U.ctx())
+    sim.params.precond = _lib.PRECOND_MULTIGRID
+    density, vel, pressure = np.zeros((n, n)), np.zeros((n + 1) * n + n * (n + 1)), np.zeros((n, n))
+    L = _lib.load()
+    for _ in range(4):
+        info = _lib.PcgInfo()
+        _lib.check(L.pano_fluid_step_host(U.ctx().handle, C.byref(params), n, n, density.ctypes.data_as(C.c_void_p),
+                                          vel.ctypes.data_as(C.c_void_p), pressure.ctypes.data_as(C.c_void_p), C.byref(info)))
+        want = sim.step()
+        assert info.iterations == want["iterations"] and 0 <= info.iterations <= 4
+        assert info.final_residual == want["final_residual"] < 0.1
+        assert np.array_equal(density, sim.density.to_host())
+        assert np.array_equal(vel, sim.vel.view_linear())
+        assert np.array_equal(pressure, sim.pressure.to_host())
+
+
+def test_multi_gpu_step_rejects_preconditioners():
+    """The slab-decomposed step implements the reference's solver (identity) only; asking for more is an error, not a fallback."""
+    from tests import gpu_util as U
+    import panopaea_b200 as P
+    from panopaea_b200 import _lib, dist
+    prm = dict(timestep=0.05, threshold=0.1, max_iterations=20, inflow=(5, 20, 27, 32), inflow_density=1.0, inflow_vy=20.0, obstacle=(70, 80, 25, 35))
+    params = dist.make_params(**prm)
+    params.precond = _lib.PRECOND_MULTIGRID
+    with pytest.raises(P.PanoError):
+        dist.DistFluid(U.ctx(), 128, 64, 0, 2, params)
