@@ -26,8 +26,10 @@ import sys
 import threading
 import time
 
-# stdout carries exactly ONE line (the JSON).  NCCL writes its version banner / NCCL_DEBUG output to stdout unless told otherwise.
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE line (the JSON).  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
+# version banner there), so the real stdout is kept aside for the JSON line and fd 1 is pointed at stderr for everything else.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -196,7 +198,7 @@ def run_reference(args, rank, world):
                              "note": kind_note},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     return 0
 
 
@@ -476,7 +478,7 @@ def run_ours(args, rank, world, local_rank):
             line["multigrid_pcg_step"] = mg_line
         if same_1gpu is not None:
             line["one_gpu_same_workload"] = same_1gpu
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if multi:
         dist_t.barrier()
         dist_t.destroy_process_group()

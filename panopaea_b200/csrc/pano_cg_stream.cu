@@ -61,6 +61,7 @@ struct StreamArgs {
     unsigned long long seq_base;
     PanoCgControl *ctl;
     int zigzag;
+    int halo_first;               // slab with neighbours: halo tile rows first in every phase (see slot_tile)
     // ---- slab of a larger grid (multi-GPU); single GPU: row0 = 0, gy0 = 0, gh = h, no peers
     int row0;                     // array row of the first owned row (ghost rows sit above it)
     int gy0, gh;                  // global row of the first owned row; global grid height (walls)
@@ -254,6 +255,32 @@ __device__ __forceinline__ bool tile_is_fast(const StreamArgs &a, int ty0, int t
     return true;
 }
 
+// Which tile a CTA works on in its jj-th step of a phase.  Single GPU: tiles blockIdx.x, +G, +2G, ... in P1 and the
+// same list backwards in P2 (zig-zag: the tail of one phase is still in L2 when the next starts).
+// Option "cg_halo_first" (slab of a multi-GPU grid, default OFF): the first and the last tile row are renumbered to the
+// FRONT of the list and taken first in BOTH phases, so that the rows stored into the neighbours' memory over NVLink
+// are long acknowledged when the phase's system-scope fence and reduction come.  Measured on B200s, 8192^2: no gain
+// (2 GPUs: 1605 vs 1602-1612 Mcell-steps/s; 8 GPUs: 5487 vs 5634) -- the posted NVLink stores are not what the
+// cross-GPU reductions wait for; kept as a switch for other topologies.
+__device__ __forceinline__ int slot_tile(const StreamArgs &a, int phase, int jj, int n_my, int G, int ntiles) {
+    const bool halo_first = a.halo_first != 0;
+    int j = jj;
+    if (phase == 1 && a.zigzag) {
+        int nh = 0;                                   // leading steps of this CTA that are halo tiles
+        if (halo_first) {
+            const int nhalo = a.tiles_y > 1 ? 2 * a.tiles_x : a.tiles_x;
+            nh = nhalo > (int)blockIdx.x ? (nhalo - (int)blockIdx.x + G - 1) / G : 0;
+            if (nh > n_my) nh = n_my;
+        }
+        j = jj < nh ? jj : n_my - 1 - (jj - nh);
+    }
+    const int q = blockIdx.x + j * G;
+    if (!halo_first || a.tiles_y <= 2) return q;
+    if (q < a.tiles_x) return q;                                              // first tile row
+    if (q < 2 * a.tiles_x) return ntiles - 2 * a.tiles_x + q;                 // last tile row
+    return q - a.tiles_x;                                                     // rows 1 .. tiles_y - 2
+}
+
 __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant__ StreamArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     Tail *tl = reinterpret_cast<Tail *>(smem + kStages * kStageBytes);
@@ -290,8 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
         // write in the phase that is just ending and may be issued before its reduction completes;
         // `dep` boxes may only be issued after it (mbarrier `go`).
         auto tile_of = [&](int phase, int jj, int &tx0, int &ty0) {
-            const int j = (phase == 1 && a.zigzag) ? n_my - 1 - jj : jj;
-            const int t = blockIdx.x + j * G;
+            const int t = slot_tile(a, phase, jj, n_my, G, ntiles);
             tx0 = (t % a.tiles_x) * TW;
             ty0 = (t / a.tiles_x) * TH;
         };
@@ -391,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
         // ------------------------------------------------------------------ P1
         double acc_zs = 0, acc_bb = 0, acc_bmax = 0;
         for (int jj = 0; jj < n_my; ++jj, ++n) {
-            const int t = blockIdx.x + jj * G;
+            const int t = slot_tile(a, 0, jj, n_my, G, ntiles);
             const int tx0 = (t % a.tiles_x) * TW, ty0 = (t / a.tiles_x) * TH;
             const int st = n % kStages;
             if (!mbar_wait(&tl->full[st], (n / kStages) & 1, err)) return;
@@ -440,8 +466,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
         // ------------------------------------------------------------------ P2
         double acc_rr = 0, acc_rmax = 0;
         for (int jj = 0; jj < n_my; ++jj, ++n) {
-            const int j = a.zigzag ? n_my - 1 - jj : jj;
-            const int t = blockIdx.x + j * G;
+            const int t = slot_tile(a, 1, jj, n_my, G, ntiles);
             const int tx0 = (t % a.tiles_x) * TW, ty0 = (t / a.tiles_x) * TH;
             const int st = n % kStages;
             if (!mbar_wait(&tl->full[st], (n / kStages) & 1, err)) return;
@@ -591,6 +616,7 @@ int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, 
         a.xr.local = (ReduceUnit *)slab->xunits_local;
         for (int i = 0; i < kMaxRanks; ++i) a.xr.peer[i] = (ReduceUnit *)slab->xunits_peer[i];
         max_ctas = slab->max_ctas;
+        a.halo_first = (slab->nranks > 1 && pano_option(ctx, "cg_halo_first", 0) != 0) ? 1 : 0;
     }
     static_assert(kUnitsTotal * sizeof(ReduceUnit) <= 4096 * 16, "d_units (allocated in pano_ctx_create) is too small");
     a.units = (ReduceUnit *)ctx->d_units;
