@@ -396,7 +396,12 @@ def run_ours(args, rank, world, local_rank):
     cg_bytes = my_cells * (BYTES_CG_INIT + BYTES_CG_ITER * iters)
     achieved = cg_bytes / (cg_ms * 1e-3) / 1e9 if cg_ms > 0 else 0.0
     step_bytes = my_cells * (BYTES_ADVECT + BYTES_NEGDIV + BYTES_PROJECT + BYTES_CG_INIT + BYTES_CG_ITER * iters)
-    kernel = "k_cg_resident" if (not multi and cells <= 1_200_000) else "k_cg_stream"
+    if not multi and n <= 1024 and -(-n // 8) * n <= 5120:
+        kernel = "k_cg_cluster"                    # one thread-block cluster (csrc/pano_cg_cluster.cu): grids up to ~40 k cells
+    elif not multi and cells <= 1_200_000:
+        kernel = "k_cg_resident2"
+    else:
+        kernel = "k_cg_stream"
     roofline = {"bound": "hbm", "kernel": "%s (persistent CG: init + %d iterations in one launch%s)" % (kernel, iters, ", per GPU" if multi else ""),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "traffic": load_traffic(f"cg_{n}_x{world}"),   # ncu dram bytes per launch (profiles/roofline_traffic.json), null if not captured

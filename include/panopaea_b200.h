@@ -117,7 +117,7 @@ PANO_API int pano_ctx_step_times(pano_ctx *ctx, double ms_out[PANO_STEP_PHASES],
 PANO_API int pano_ctx_cg_profile(pano_ctx *ctx, int64_t cycles_out[8]);
 /* Same option, streaming kernel: cycles every CTA spent in its P1 tile loop ([0, G)) and P2 tile loop ([G, 2G)), G = CTAs. */
 PANO_API int pano_ctx_cg_profile_ctas(pano_ctx *ctx, int64_t *cycles_out, int n);
-/* tuning knobs: "cg_kernel" 0 auto / 1 generic / 2 TMA streaming / 3 SM-resident / 4 SM-resident v1, "cg_ldcg" 0/1,
+/* tuning knobs: "cg_kernel" 0 auto / 1 generic / 2 TMA streaming / 3 SM-resident / 4 SM-resident v1 / 5 one cluster, "cg_ldcg" 0/1,
  * "cg_zigzag" 0/1, "cg_blocks_per_sm" n, "cg_profile" 0/1, "step_timing" 0/1 */
 PANO_API int pano_ctx_set_option(pano_ctx *ctx, const char *key, int64_t value);
 PANO_API int pano_ctx_get_option(pano_ctx *ctx, const char *key, int64_t *value);

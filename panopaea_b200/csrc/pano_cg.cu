@@ -305,6 +305,10 @@ bool pano_cg_resident2_supported(pano_ctx *ctx, size_t h, size_t w);
 int pano_cg_resident2_launch(pano_ctx *ctx, double *x, const double *b, double *r, double *s0, size_t h, size_t w,
                              int max_iterations, double threshold, double timestep, RectI m);
 
+bool pano_cg_cluster_supported(pano_ctx *ctx, size_t h, size_t w);
+int pano_cg_cluster_launch(pano_ctx *ctx, double *x, const double *b, double *r, double *s0, size_t h, size_t w, int max_iterations,
+                           double threshold, double timestep, RectI m);
+
 // Solve on raw device pointers.  s0 = search, s1 = auxiliary.  info nullable (non-null => sync).
 int pano_cg_solve_raw(pano_ctx *ctx, int dtype, void *x, const void *b, void *r, void *s0, void *s1, size_t h, size_t w,
                       int max_iterations, double threshold, double timestep, pano_rect obstacle, pano_pcg_info *info) {
@@ -327,17 +331,24 @@ int pano_cg_solve_raw(pano_ctx *ctx, int dtype, void *x, const void *b, void *r,
     const bool cg_loads = pano_option(ctx, "cg_ldcg", 0) != 0;
     const RectI m = pano_clip_rect(obstacle, h + 1, w + 1);
     // kernel choice: "cg_kernel" 0 = auto, 1 = generic (any shape / dtype), 2 = TMA streaming (f64, even width),
-    // 3 = SM-resident (f64, grids that fit on chip), 4 = first-generation SM-resident kernel (run-time tile geometry).
-    // auto: resident if it fits, else streaming, else generic.
+    // 3 = SM-resident (f64, grids that fit on chip), 4 = first-generation SM-resident kernel (run-time tile geometry),
+    // 5 = one thread-block cluster (f64, grids up to ~40 k cells).
+    // auto: cluster if it fits, else resident if it fits, else streaming, else generic.
     const int64_t want = pano_option(ctx, "cg_kernel", 0);
     const bool stream_ok = dtype == PANO_F64 && pano_cg_stream_supported(h, w, x, b, r, s0, s1);
     const bool resident_ok = dtype == PANO_F64 && pano_cg_resident_supported(ctx, h, w);
     const bool resident2_ok = dtype == PANO_F64 && pano_cg_resident2_supported(ctx, h, w);
+    const bool cluster_ok = dtype == PANO_F64 && pano_cg_cluster_supported(ctx, h, w);
+    if (want == 5 && !cluster_ok)
+        PANO_FAIL(PANO_ERR_INVALID, "cg_kernel=5 (cluster) needs an f64 grid of at most 8 x 5120 cells and width <= 1024 (%zux%zu given)", h, w);
     if (want == 2 && !stream_ok)
         PANO_FAIL(PANO_ERR_INVALID, "cg_kernel=2 (TMA streaming) needs f64 fields with an even width (%zux%zu given)", h, w);
     if ((want == 3 && !resident2_ok) || (want == 4 && !resident_ok))
         PANO_FAIL(PANO_ERR_INVALID, "cg_kernel=%d (SM-resident) needs an f64 grid that fits on chip (%zux%zu given)", (int)want, h, w);
-    if (resident2_ok && (want == 0 || want == 3)) {
+    if (cluster_ok && (want == 0 || want == 5)) {
+        PANO_TRY(pano_cg_cluster_launch(ctx, (double *)x, (const double *)b, (double *)r, (double *)s0, h, w, max_iterations, threshold,
+                                        timestep, m));
+    } else if (resident2_ok && (want == 0 || want == 3)) {
         PANO_TRY(pano_cg_resident2_launch(ctx, (double *)x, (const double *)b, (double *)r, (double *)s0, h, w, max_iterations,
                                           threshold, timestep, m));
     } else if (resident_ok && (want == 0 || want == 4)) {

@@ -5,7 +5,7 @@ import numpy as np
 import panopaea_b200 as P
 from panopaea_b200 import fluid, pcg, dist
 ctx = P.Context(0)
-for n, kern in ((128, 3), (128, 4), (256, 2), (128, 1)):
+for n, kern in ((128, 5), (128, 3), (128, 4), (256, 2), (128, 1)):
     ctx.set_option("cg_kernel", kern)
     sim = fluid.DecFluid(**fluid.smoke_params(n), ctx=ctx) if n == 128 else fluid.DecFluid(h=n, w=n, ctx=ctx, **{k: v for k, v in fluid.smoke_params(256).items() if k not in ("h", "w")})
     for _ in range(2):

@@ -14,7 +14,13 @@ SIZES = [(3, 3), (5, 7), (17, 33), (24, 20), (64, 48), (128, 128), (300, 200), (
 # kernel variants: the generic persistent kernel (any shape), the same with L2-only loads, and "auto"
 # (the TMA streaming kernel whenever the width is even, else generic)
 VARIANTS = {"generic": dict(cg_kernel=1, cg_ldcg=0), "generic_ldcg": dict(cg_kernel=1, cg_ldcg=1), "auto": dict(cg_kernel=0, cg_ldcg=0),
-            "stream": dict(cg_kernel=2, cg_ldcg=0), "resident": dict(cg_kernel=3, cg_ldcg=0), "resident_v1": dict(cg_kernel=4, cg_ldcg=0)}
+            "stream": dict(cg_kernel=2, cg_ldcg=0), "resident": dict(cg_kernel=3, cg_ldcg=0), "resident_v1": dict(cg_kernel=4, cg_ldcg=0),
+            "cluster": dict(cg_kernel=5, cg_ldcg=0)}
+CLUSTER_MAX_CELLS_PER_CTA, CLUSTER_CTAS = 5120, 8       # csrc/pano_cg_cluster.cu
+
+
+def _cluster_fits(h, w):
+    return w <= 1024 and -(-h // CLUSTER_CTAS) * w <= CLUSTER_MAX_CELLS_PER_CTA
 
 
 def _set_variant(name):
@@ -39,6 +45,8 @@ def test_fused_cg_vs_oracle(oracle, h, w, variant):
     from tests import gpu_util as U
     if variant == "stream" and w % 2:
         pytest.skip("the TMA streaming kernel needs an even width")
+    if variant == "cluster" and not _cluster_fits(h, w):
+        pytest.skip("the cluster kernel holds at most 8 x 5120 cells")
     _set_variant(variant)
     try:
         grid = U.grid(h, w)
@@ -105,13 +113,14 @@ def test_kernel_variants_agree(oracle, h, w):
     b = U.consistent_rhs(oracle, h, w, obstacle, seed=11)
     out = {}
     try:
-        for name in ("generic", "stream", "resident", "resident_v1"):
+        names = ("generic", "stream", "resident", "resident_v1") + (("cluster",) if _cluster_fits(h, w) else ())
+        for name in names:
             _set_variant(name)
             out[name] = _solve(grid, b, 100, 0.1, 0.05, obstacle)
     finally:
         _set_variant("auto")
     ia, xa, ra, sa = out["generic"]
-    for other in ("stream", "resident", "resident_v1"):
+    for other in names[1:]:
         ib, xb, rb, sb = out[other]
         assert abs(ia["iterations"] - ib["iterations"]) <= 1, other
         if ia["iterations"] == ib["iterations"]:
@@ -119,7 +128,7 @@ def test_kernel_variants_agree(oracle, h, w):
                 assert np.allclose(u, v, rtol=0, atol=1e-8 * max(1.0, np.abs(u).max())), other
 
 
-@pytest.mark.parametrize("variant", ["generic", "stream", "resident", "resident_v1"])
+@pytest.mark.parametrize("variant", ["generic", "stream", "resident", "resident_v1", "cluster"])
 def test_early_out_leaves_scratch_untouched(oracle, variant):
     """pcg.rs:35-38: max|b| < threshold -> x = 0 and nothing else is written."""
     from tests import gpu_util as U
@@ -137,7 +146,7 @@ def test_early_out_leaves_scratch_untouched(oracle, variant):
     assert np.all(r == 123.0) and np.all(s == 123.0)
 
 
-@pytest.mark.parametrize("variant", ["generic", "stream", "resident", "resident_v1"])
+@pytest.mark.parametrize("variant", ["generic", "stream", "resident", "resident_v1", "cluster"])
 @pytest.mark.parametrize("max_it", [1, 2, 3, 7])
 def test_exhausted_iterations_match_reference_state(oracle, max_it, variant):
     """When the loop runs out (pcg.rs:48), the reference has still updated `search` (pcg.rs:72-77)."""
