@@ -367,6 +367,36 @@ k_project(T *__restrict__ vy, T *__restrict__ vx, const T *__restrict__ p, int h
     }
 }
 
+// K8, second generation: one column x kProjRows rows per thread, p carried down the column in a register (each p value is
+// loaded once for vy and once per neighbour column for vx instead of three times), 32-bit indices
+constexpr int kProjRows = 8;
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+k_project_march(T *__restrict__ vy, T *__restrict__ vx, const T *__restrict__ p, int h, int w, T dt) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ys = (blockIdx.y * 8 + (threadIdx.x >> 5)) * kProjRows;
+    if (x > w || ys > h) return;
+    const bool xin = x < w;
+    T pn = (xin && ys > 0) ? p[(ys - 1) * w + x] : (T)0;     // p[y-1, x]
+#pragma unroll
+    for (int k = 0; k < kProjRows; ++k) {
+        const int y = ys + k;
+        if (y > h) break;
+        const T c = (y < h && xin) ? p[y * w + x] : (T)0;
+        if (xin) {   // vy[y, x]
+            const int i = y * w + x;
+            if (y == 0 || y == h) vy[i] = (T)0;                                   // walls :137-140
+            else vy[i] = vy[i] + dt * (-(c - pn));                               // d0_dual :322-326, scaled_add :126
+        }
+        if (y < h) {   // vx[y, x]
+            const int i = y * (w + 1) + x;
+            if (x == 0 || x == w) vx[i] = (T)0;                                   // walls :132-135
+            else vx[i] = vx[i] + dt * (p[y * w + x - 1] - c);                     // d0_dual :329-333
+        }
+        pn = c;
+    }
+}
+
 template <class T>
 __global__ void k_to_u8(uint8_t *__restrict__ out, const T *__restrict__ d, int h, int w, T lower, T upper) {
     const size_t n = (size_t)h * w;
@@ -477,8 +507,16 @@ int pano_neg_divergence_launch(pano_ctx *ctx, int dtype, void *b, const void *ve
 }
 
 int pano_project_launch(pano_ctx *ctx, int dtype, void *vel, const void *p, size_t h, size_t w, double dt) {
-    dim3 g = grid2d((int)h + 1, (int)w + 1);
     const size_t off = w * (h + 1);
+    if ((h + 1) * (w + 1) < ((size_t)1 << 31) && pano_option(ctx, "project_kernel", 0) != 1) {
+        dim3 gm((unsigned)((w + 1 + 31) / 32), (unsigned)((h + 1 + 8 * kProjRows - 1) / (8 * kProjRows)));
+        if (dtype == PANO_F64)
+            k_project_march<double><<<gm, kThreads, 0, ctx->stream>>>((double *)vel, (double *)vel + off, (const double *)p, (int)h, (int)w, dt);
+        else
+            k_project_march<float><<<gm, kThreads, 0, ctx->stream>>>((float *)vel, (float *)vel + off, (const float *)p, (int)h, (int)w, (float)dt);
+        return pano_after_launch(ctx, "project_march");
+    }
+    dim3 g = grid2d((int)h + 1, (int)w + 1);
     if (dtype == PANO_F64)
         k_project<double><<<g, kThreads, 0, ctx->stream>>>((double *)vel, (double *)vel + off, (const double *)p, (int)h, (int)w, dt, 0, (int)h);
     else
