@@ -204,6 +204,23 @@ __device__ __forceinline__ void stage_box2(double *dst, const double *__restrict
     });
 }
 
+// the same for a box that lies entirely inside the grid and starts on a 16-byte boundary (regular tile, even width):
+// 16-byte copies, no bounds, no per-element index arithmetic
+__device__ __forceinline__ void cp_async16(double *smem_dst, const double *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void stage_box2_vec(double *dst, const double *__restrict__ src, int w, int ty0, int tx0) {
+    const double *base = src + (ty0 - 2) * w + tx0 - 2;
+    const int tid = threadIdx.x, j = tid & 31, r = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < (F2_H + 7) / 8; ++k) {
+        const int ly = r + 8 * k;
+        if (ly < F2_H) cp_async16(dst + ly * F2_W + 2 * j, base + ly * w + 2 * j);
+    }
+    if (tid < 2 * F2_H) cp_async16(dst + (tid >> 1) * F2_W + 64 + 2 * (tid & 1), base + (tid >> 1) * w + 64 + 2 * (tid & 1));
+}
+
 // compute part of k_mg_down for one staged tile: F = f on the tile + 2
 template <class G>
 __device__ __forceinline__ void mg_down_tile(const G &g, int h, int w, double *__restrict__ uout, double *__restrict__ fc, int wc, double dt,
@@ -378,12 +395,18 @@ k_mg_down(const G g, const unsigned char *__restrict__ flags, double od_reg, dou
     extern __shared__ __align__(16) double sm[];
     double *U1 = sm + 2 * kDownStage, *U2 = U1 + F2_H * F2_W;   // U2: tile + 1 layout (general path) or tile + 2 layout (regular path)
     const int tiles_x = (g.w + FT_W - 1) / FT_W, ntiles = tiles_x * ((g.h + FT_H - 1) / FT_H);
+    const bool even = (g.w & 1) == 0;
+    auto stage = [&](double *dst, int tt) {
+        const int sy0 = (tt / tiles_x) * FT_H, sx0 = (tt % tiles_x) * FT_W;
+        if (even && tile_regular(g, flags, tt, sy0, sx0)) stage_box2_vec(dst, f, g.w, sy0, sx0);
+        else stage_box2(dst, f, g.h, g.w, sy0, sx0);
+    };
     int t = blockIdx.x, st = 0;
-    if (t < ntiles) stage_box2(sm, f, g.h, g.w, (t / tiles_x) * FT_H, (t % tiles_x) * FT_W);
+    if (t < ntiles) stage(sm, t);
     cp_async_commit();
     for (; t < ntiles; t += gridDim.x, st ^= 1) {
         const int tn = t + gridDim.x;
-        if (tn < ntiles) stage_box2(sm + (st ^ 1) * kDownStage, f, g.h, g.w, (tn / tiles_x) * FT_H, (tn % tiles_x) * FT_W);
+        if (tn < ntiles) stage(sm + (st ^ 1) * kDownStage, tn);
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
@@ -402,10 +425,16 @@ k_mg_up(const G g, const unsigned char *__restrict__ flags, double od_reg, doubl
     extern __shared__ __align__(16) double sm[];
     double *T1 = sm + 2 * kUpStage;
     const int tiles_x = (g.w + FT_W - 1) / FT_W, ntiles = tiles_x * ((g.h + FT_H - 1) / FT_H);
+    const bool even = (g.w & 1) == 0;
     auto stage = [&](double *dst, int tt) {
         const int ty0 = (tt / tiles_x) * FT_H, tx0 = (tt % tiles_x) * FT_W;
-        stage_box2(dst, uin, g.h, g.w, ty0, tx0);
-        stage_box2(dst + F2_H * F2_W, f, g.h, g.w, ty0, tx0);
+        if (even && tile_regular(g, flags, tt, ty0, tx0)) {
+            stage_box2_vec(dst, uin, g.w, ty0, tx0);
+            stage_box2_vec(dst + F2_H * F2_W, f, g.w, ty0, tx0);
+        } else {
+            stage_box2(dst, uin, g.h, g.w, ty0, tx0);
+            stage_box2(dst + F2_H * F2_W, f, g.h, g.w, ty0, tx0);
+        }
         const int cy0 = (ty0 >> 1) - 1, cx0 = (tx0 >> 1) - 1;
         double *E = dst + 2 * F2_H * F2_W;
         for (int i = threadIdx.x; i < EC_H * EC_W; i += kThreads) {
