@@ -89,6 +89,8 @@ int pano_ctx_destroy(pano_ctx *ctx) {
     cudaFree(ctx->d_cg);
     cudaFree(ctx->d_units);
     cudaFree(ctx->d_mail);
+    cudaFree(ctx->d_tparts);
+    cudaFree(ctx->d_claim);
     cudaFreeHost(ctx->h_cg);
     for (cudaEvent_t e : ctx->phase_events) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ev_start);

@@ -62,6 +62,9 @@ struct StreamArgs {
     PanoCgControl *ctl;
     int zigzag;
     int halo_first;               // slab with neighbours: halo tile rows first in every phase (see slot_tile)
+    // ---- dynamic tile scheduling (k_cg_stream<true>)
+    unsigned long long *claim;    // 4 claim counters, used round-robin by the phases (zeroed at launch)
+    ReduceUnit *tparts;           // [3 values][ntiles * kConsumerWarps] per-(tile, warp) partials, {value, phase tag}
     // ---- slab of a larger grid (multi-GPU); single GPU: row0 = 0, gy0 = 0, gh = h, no peers
     int row0;                     // array row of the first owned row (ghost rows sit above it)
     int gy0, gh;                  // global row of the first owned row; global grid height (walls)
@@ -78,6 +81,7 @@ struct Tail {                     // small shared-memory area behind the stage r
     double out[4];
     double wsum[3][kConsumerWarps];
     int cont;                     // 1: producer continues with the next phase, 0: stop
+    int tile[kStages];            // dynamic scheduling: the tile staged in each ring slot, -1 = no more tiles in this phase
     int ok;
 };
 
@@ -281,6 +285,15 @@ __device__ __forceinline__ int slot_tile(const StreamArgs &a, int phase, int jj,
     return q - a.tiles_x;                                                     // rows 1 .. tiles_y - 2
 }
 
+// kDyn = false: every CTA owns a fixed list of tiles (slot_tile).
+// kDyn = true:  tiles are claimed from a global counter as ring slots free up, so SMs that stream faster take more
+//   tiles (measured with the fixed lists at 4096^2: the slowest CTA needs 15-20 % longer than the average one in
+//   every phase, and everybody waits for it at the reduction).  The reductions stay deterministic and independent of
+//   who computed what: every consumer warp publishes its partial of every tile as a 16-byte {value, phase tag} unit,
+//   and CTA c adds the units of the FIXED tile range c*ntiles/G .. (c+1)*ntiles/G in a fixed order before the usual
+//   grid all-reduce.  Each phase instance k uses claim counter k mod 4; a counter only grows, by ntiles + G per use
+//   (every CTA makes exactly one failing claim), so it never has to be reset while the kernel runs.
+template <bool kDyn>
 __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant__ StreamArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     Tail *tl = reinterpret_cast<Tail *>(smem + kStages * kStageBytes);
@@ -349,6 +362,65 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
             }
         };
         bool stop = false;
+        if constexpr (kDyn) {
+            const unsigned long long M = (unsigned long long)ntiles + (unsigned long long)G;   // claims per phase instance
+            for (int it = 0; it < a.max_iter && !stop; ++it) {
+                for (int phase = 0; phase < 2 && !stop; ++phase) {
+                    const int k = 2 * it + phase;
+                    bool exhausted = false;
+                    auto claim = [&]() -> int {               // next tile of this phase, or -1 (exactly once per phase)
+                        const unsigned long long v = atomicAdd(&a.claim[k & 3], 1ULL) - (unsigned long long)(k >> 2) * M;
+                        if (v >= (unsigned long long)ntiles) { exhausted = true; return -1; }
+                        return (phase == 1 && a.zigzag) ? ntiles - 1 - (int)v : (int)v;
+                    };
+                    const bool need_go = k != 0;
+                    int pre[kStages], npre = 0;
+                    // (1) claim the first tiles and stage their independent boxes while the previous phase is still finishing
+                    if (need_go) {
+                        while (npre < kStages && !exhausted) {
+                            const int t = claim();
+                            if (t < 0) break;
+                            const unsigned nn = n + npre;
+                            if (!mbar_wait(&tl->empty[nn % kStages], ((nn / kStages) & 1) ^ 1, err)) return;
+                            tl->tile[nn % kStages] = t;
+                            issue(it, phase, cur, nn, (t % a.tiles_x) * TW, (t / a.tiles_x) * TH, true, false);
+                            pre[npre++] = t;
+                        }
+                        // (2) the previous phase's grid-wide reduction
+                        if (!mbar_wait(&tl->go, ngo & 1, err)) return;
+                        ++ngo;
+                        stop = !*(volatile int *)&tl->cont;
+                        fence_proxy_async();
+                    }
+                    // (3) their dependent boxes (also when stopping: every armed barrier must complete)
+                    for (int jj = 0; jj < npre; ++jj)
+                        issue(it, phase, cur, n + jj, (pre[jj] % a.tiles_x) * TW, (pre[jj] / a.tiles_x) * TH, false, true);
+                    if (stop) {
+                        for (int jj = 0; jj < npre; ++jj)
+                            if (!mbar_wait(&tl->full[(n + jj) % kStages], ((n + jj) / kStages) & 1, err)) return;
+                        return;
+                    }
+                    n += npre;
+                    // (4) the rest of the phase
+                    while (!exhausted) {
+                        const int t = claim();
+                        if (t < 0) break;
+                        if (!mbar_wait(&tl->empty[n % kStages], ((n / kStages) & 1) ^ 1, err)) return;
+                        tl->tile[n % kStages] = t;
+                        issue(it, phase, cur, n, (t % a.tiles_x) * TW, (t / a.tiles_x) * TH, true, true);
+                        ++n;
+                    }
+                    // (5) end-of-phase marker for the consumers: an empty slot
+                    if (!mbar_wait(&tl->empty[n % kStages], ((n / kStages) & 1) ^ 1, err)) return;
+                    tl->tile[n % kStages] = -1;
+                    mbar_arrive(&tl->full[n % kStages]);
+                    ++n;
+                }
+                cur ^= 1;
+            }
+            if (!stop) mbar_wait(&tl->go, ngo & 1, err);
+            return;
+        }
         for (int it = 0; it < a.max_iter && !stop; ++it) {
             for (int phase = 0; phase < 2 && !stop; ++phase) {
                 const bool need_go = !(it == 0 && phase == 0);
@@ -416,11 +488,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
         const bool first = it == 0;
         // ------------------------------------------------------------------ P1
         double acc_zs = 0, acc_bb = 0, acc_bmax = 0;
-        for (int jj = 0; jj < n_my; ++jj, ++n) {
-            const int t = slot_tile(a, 0, jj, n_my, G, ntiles);
-            const int tx0 = (t % a.tiles_x) * TW, ty0 = (t / a.tiles_x) * TH;
+        const unsigned long long tag1 = a.seq_base + (unsigned long long)(2 * it) + 1;   // phase tag of the per-tile units
+        for (int jj = 0;; ++jj, ++n) {
             const int st = n % kStages;
-            if (!mbar_wait(&tl->full[st], (n / kStages) & 1, err)) return;
+            int t;
+            if constexpr (kDyn) {
+                if (!mbar_wait(&tl->full[st], (n / kStages) & 1, err)) return;
+                t = *(volatile int *)&tl->tile[st];
+                if (t < 0) {                                    // end-of-phase marker: hand the slot back and leave
+                    __syncwarp();
+                    if ((tid & 31) == 0) mbar_arrive(&tl->empty[st]);
+                    ++n;
+                    break;
+                }
+            } else {
+                if (jj >= n_my) break;
+                t = slot_tile(a, 0, jj, n_my, G, ntiles);
+                if (!mbar_wait(&tl->full[st], (n / kStages) & 1, err)) return;
+            }
+            const int tx0 = (t % a.tiles_x) * TW, ty0 = (t / a.tiles_x) * TH;
             const double *S = reinterpret_cast<const double *>(smem + st * kStageBytes);
             const double *R = reinterpret_cast<const double *>(smem + st * kStageBytes + kHaloSlot);
             const bool fast = tile_is_fast(a, ty0, tx0);
@@ -432,11 +518,40 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
                 if (fast) tile_p1<true, false>(a, S, R, s_cur, s_up, s_dn, ty0, tx0, beta, acc_zs, acc_bb, acc_bmax);
                 else tile_p1<false, false>(a, S, R, s_cur, s_up, s_dn, ty0, tx0, beta, acc_zs, acc_bb, acc_bmax);
             }
+            if constexpr (kDyn) {                               // this warp's partials of THIS tile, then start afresh
+                const size_t plane = (size_t)ntiles * kConsumerWarps, u = (size_t)t * kConsumerWarps + wid;
+                const double p0 = warp_sum(acc_zs);
+                if ((tid & 31) == 0) unit_store(a.tparts + u, p0, tag1);
+                if (first) {
+                    const double p1 = warp_sum(acc_bb), p2 = warp_max(acc_bmax);
+                    if ((tid & 31) == 0) {
+                        unit_store(a.tparts + plane + u, p1, tag1);
+                        unit_store(a.tparts + 2 * plane + u, p2, tag1);
+                    }
+                }
+                acc_zs = 0; acc_bb = 0; acc_bmax = 0;
+            }
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&tl->empty[st]);
         }
         stamp(0);   // P1 tiles
         {
+            if constexpr (kDyn) {   // the units of this CTA's FIXED tile range, whoever computed them, in a fixed order
+                const size_t plane = (size_t)ntiles * kConsumerWarps;
+                const int c0 = (int)((long long)blockIdx.x * ntiles / G), c1 = (int)((long long)(blockIdx.x + 1) * ntiles / G);
+                const ReduceUnit *base = a.tparts + (size_t)c0 * kConsumerWarps;
+                for (int e = tid; e < (c1 - c0) * kConsumerWarps; e += kConsumers) {
+                    double v;
+                    unit_poll(base + e, tag1, v, err);
+                    acc_zs = acc_zs + v;
+                    if (first) {
+                        unit_poll(base + plane + e, tag1, v, err);
+                        acc_bb = acc_bb + v;
+                        unit_poll(base + 2 * plane + e, tag1, v, err);
+                        acc_bmax = v > acc_bmax ? v : acc_bmax;
+                    }
+                }
+            }
             const double v0 = consumer_sum(acc_zs, tl->wsum[0]);
             double v1 = 0, v2 = 0;
             if (first) {
@@ -465,11 +580,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
         alpha = sigma / zs;                                    // pcg.rs:53
         // ------------------------------------------------------------------ P2
         double acc_rr = 0, acc_rmax = 0;
-        for (int jj = 0; jj < n_my; ++jj, ++n) {
-            const int t = slot_tile(a, 1, jj, n_my, G, ntiles);
-            const int tx0 = (t % a.tiles_x) * TW, ty0 = (t / a.tiles_x) * TH;
+        const unsigned long long tag2 = a.seq_base + (unsigned long long)(2 * it + 1) + 1;
+        for (int jj = 0;; ++jj, ++n) {
             const int st = n % kStages;
-            if (!mbar_wait(&tl->full[st], (n / kStages) & 1, err)) return;
+            int t;
+            if constexpr (kDyn) {
+                if (!mbar_wait(&tl->full[st], (n / kStages) & 1, err)) return;
+                t = *(volatile int *)&tl->tile[st];
+                if (t < 0) {
+                    __syncwarp();
+                    if ((tid & 31) == 0) mbar_arrive(&tl->empty[st]);
+                    ++n;
+                    break;
+                }
+            } else {
+                if (jj >= n_my) break;
+                t = slot_tile(a, 1, jj, n_my, G, ntiles);
+                if (!mbar_wait(&tl->full[st], (n / kStages) & 1, err)) return;
+            }
+            const int tx0 = (t % a.tiles_x) * TW, ty0 = (t / a.tiles_x) * TH;
             const double *S = reinterpret_cast<const double *>(smem + st * kStageBytes);
             const double *R = reinterpret_cast<const double *>(smem + st * kStageBytes + kHaloSlot);
             const double *X = reinterpret_cast<const double *>(smem + st * kStageBytes + 2 * kHaloSlot);
@@ -481,11 +610,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
                 if (fast) tile_p2<true, false>(a, S, R, X, ty0, tx0, alpha, acc_rr, acc_rmax);
                 else tile_p2<false, false>(a, S, R, X, ty0, tx0, alpha, acc_rr, acc_rmax);
             }
+            if constexpr (kDyn) {
+                const size_t plane = (size_t)ntiles * kConsumerWarps, u = (size_t)t * kConsumerWarps + wid;
+                const double p0 = warp_sum(acc_rr), p1 = warp_max(acc_rmax);
+                if ((tid & 31) == 0) {
+                    unit_store(a.tparts + u, p0, tag2);
+                    unit_store(a.tparts + plane + u, p1, tag2);
+                }
+                acc_rr = 0; acc_rmax = 0;
+            }
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&tl->empty[st]);
         }
         stamp(2);   // P2 tiles
         {
+            if constexpr (kDyn) {
+                const size_t plane = (size_t)ntiles * kConsumerWarps;
+                const int c0 = (int)((long long)blockIdx.x * ntiles / G), c1 = (int)((long long)(blockIdx.x + 1) * ntiles / G);
+                const ReduceUnit *base = a.tparts + (size_t)c0 * kConsumerWarps;
+                for (int e = tid; e < (c1 - c0) * kConsumerWarps; e += kConsumers) {
+                    double v;
+                    unit_poll(base + e, tag2, v, err);
+                    acc_rr = acc_rr + v;
+                    unit_poll(base + plane + e, tag2, v, err);
+                    acc_rmax = v > acc_rmax ? v : acc_rmax;
+                }
+            }
             const double v0 = consumer_sum(acc_rr, tl->wsum[0]);
             const double v1 = consumer_max(acc_rmax, tl->wsum[1]);
             if (!grid_allreduce(a, tl, nred++, 2, v0, v1, 0.0, 0x2u, red)) {
@@ -565,8 +715,10 @@ int pano_make_tensor_map_2d(CUtensorMap *map, const void *base, size_t elem_byte
 
 int pano_preload_cg_stream() {
     cudaFuncAttributes fa;
-    PANO_CUDA(cudaFuncGetAttributes(&fa, k_cg_stream));
-    PANO_CUDA(cudaFuncSetAttribute(k_cg_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    PANO_CUDA(cudaFuncGetAttributes(&fa, k_cg_stream<false>));
+    PANO_CUDA(cudaFuncSetAttribute(k_cg_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    PANO_CUDA(cudaFuncGetAttributes(&fa, k_cg_stream<true>));
+    PANO_CUDA(cudaFuncSetAttribute(k_cg_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     return PANO_OK;
 }
 
@@ -581,7 +733,8 @@ bool pano_cg_stream_supported(size_t h, size_t w, const void *x, const void *b, 
 
 int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, double *s0, double *s1, size_t h, size_t w,
                           int max_iterations, double threshold, double timestep, RectI m, const PanoCgSlab *slab) {
-    PANO_CUDA(cudaFuncSetAttribute(k_cg_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    PANO_CUDA(cudaFuncSetAttribute(k_cg_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    PANO_CUDA(cudaFuncSetAttribute(k_cg_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     static_assert(sizeof(Tail) <= kTailBytes, "Tail does not fit");
     StreamArgs a;
     memset(&a, 0, sizeof(a));
@@ -627,7 +780,31 @@ int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, 
     if (G > ntiles) G = ntiles;
     if (G > kMaxCtas) G = kMaxCtas;
     PANO_CUDA(cudaMemsetAsync(ctx->d_cg, 0, sizeof(PanoCgControl), ctx->stream));
+    // dynamic tile scheduling pays once a CTA has enough tiles for the imbalance to matter ("cg_dynamic": 0 off, 1 on, -1 auto)
+    const int64_t dyn_opt = pano_option(ctx, "cg_dynamic", -1);
+    const bool dynamic = dyn_opt > 0 || (dyn_opt < 0 && ntiles >= 16 * G);
+    if (dynamic) {
+        const size_t units = 3 * (size_t)ntiles * kConsumerWarps;
+        if (units > ctx->tparts_cap) {
+            if (ctx->d_tparts) {
+                PANO_CUDA(cudaStreamSynchronize(ctx->stream));
+                PANO_CUDA(cudaFree(ctx->d_tparts));
+                ctx->d_tparts = nullptr;
+                ctx->tparts_cap = 0;
+            }
+            PANO_CUDA(cudaMalloc(&ctx->d_tparts, units * sizeof(ReduceUnit)));
+            PANO_CUDA(cudaMemsetAsync(ctx->d_tparts, 0, units * sizeof(ReduceUnit), ctx->stream));   // tag 0 never matches
+            ctx->tparts_cap = units;
+        }
+        if (!ctx->d_claim) PANO_CUDA(cudaMalloc((void **)&ctx->d_claim, 4 * sizeof(unsigned long long)));
+        PANO_CUDA(cudaMemsetAsync(ctx->d_claim, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        a.tparts = (ReduceUnit *)ctx->d_tparts;
+        a.claim = ctx->d_claim;
+    }
     void *kargs[] = {(void *)&a};
-    PANO_CUDA(cudaLaunchCooperativeKernel((const void *)k_cg_stream, dim3((unsigned)G), dim3(kThreads), kargs, kSmemBytes, ctx->stream));
-    return pano_after_launch(ctx, "cg_stream");
+    if (dynamic)
+        PANO_CUDA(cudaLaunchCooperativeKernel((const void *)k_cg_stream<true>, dim3((unsigned)G), dim3(kThreads), kargs, kSmemBytes, ctx->stream));
+    else
+        PANO_CUDA(cudaLaunchCooperativeKernel((const void *)k_cg_stream<false>, dim3((unsigned)G), dim3(kThreads), kargs, kSmemBytes, ctx->stream));
+    return pano_after_launch(ctx, dynamic ? "cg_stream(dynamic)" : "cg_stream");
 }

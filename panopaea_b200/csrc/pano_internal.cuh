@@ -73,6 +73,9 @@ struct pano_ctx {
     PanoCgControl *h_cg = nullptr;   // pinned
     double *d_mail = nullptr;        // boundary-line mailboxes of the SM-resident CG kernel
     size_t mail_cap = 0;             // in doubles
+    void *d_tparts = nullptr;        // per-(tile, warp) reduction units of the dynamically scheduled streaming CG kernel
+    size_t tparts_cap = 0;           // in 16-byte units
+    unsigned long long *d_claim = nullptr;   // 4 tile-claim counters (one per phase in flight)
     void *d_units = nullptr;         // publish+poll all-reduce units of the persistent kernels
     unsigned long long launch_epoch = 0;
     // optional per-phase timing of pano_fluid_step ("step_timing" option)

@@ -27,8 +27,9 @@ def _step_all(ranks):
     return [r.sync() for r in ranks]
 
 
+@pytest.mark.parametrize("dynamic", [0, 1])
 @pytest.mark.parametrize("nranks,h,w", [(2, 256, 256), (4, 256, 128), (3, 250, 192)])
-def test_loopback_matches_single_gpu(nranks, h, w):
+def test_loopback_matches_single_gpu(nranks, h, w, dynamic):
     from tests import gpu_util as U
     from panopaea_b200 import dist, fluid
     k = 2
@@ -36,6 +37,8 @@ def test_loopback_matches_single_gpu(nranks, h, w):
                inflow_vy=20.0, obstacle=(70 * k, 80 * k, 25 * k, 35 * k))
     single = fluid.DecFluid(h=h, w=w, ctx=U.ctx(), **prm)
     ranks = _make_ranks(nranks, h, w, prm)
+    for r in ranks:
+        r.ctx.set_option("cg_dynamic", dynamic)      # 1: tiles claimed from a counter (by default only above 16 tiles per CTA)
     for step in range(6):
         want = single.step()
         infos = _step_all(ranks)
