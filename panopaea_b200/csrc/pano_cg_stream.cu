@@ -64,7 +64,8 @@ struct StreamArgs {
     int halo_first;               // slab with neighbours: halo tile rows first in every phase (see slot_tile)
     // ---- dynamic tile scheduling (k_cg_stream<true>)
     unsigned long long *claim;    // 4 claim counters, used round-robin by the phases (zeroed at launch)
-    ReduceUnit *tparts;           // [3 values][ntiles * kConsumerWarps] per-(tile, warp) partials, {value, phase tag}
+    ReduceUnit *tparts;           // [3 values][nbatch * kConsumerWarps] per-(batch, warp) partials, {value, phase tag}
+    int batch_len, nbatch_long, nbatch;   // claim unit: the first nbatch_long batches have batch_len tiles, the rest one tile
     // ---- slab of a larger grid (multi-GPU); single GPU: row0 = 0, gy0 = 0, gh = h, no peers
     int row0;                     // array row of the first owned row (ghost rows sit above it)
     int gy0, gh;                  // global row of the first owned row; global grid height (walls)
@@ -82,6 +83,7 @@ struct Tail {                     // small shared-memory area behind the stage r
     double wsum[3][kConsumerWarps];
     int cont;                     // 1: producer continues with the next phase, 0: stop
     int tile[kStages];            // dynamic scheduling: the tile staged in each ring slot, -1 = no more tiles in this phase
+    int batch[kStages];           // its batch index if the tile is the LAST of its batch (partials are published then), else -1
     int ok;
 };
 
@@ -289,10 +291,12 @@ __device__ __forceinline__ int slot_tile(const StreamArgs &a, int phase, int jj,
 // kDyn = true:  tiles are claimed from a global counter as ring slots free up, so SMs that stream faster take more
 //   tiles (measured with the fixed lists at 4096^2: the slowest CTA needs 15-20 % longer than the average one in
 //   every phase, and everybody waits for it at the reduction).  The reductions stay deterministic and independent of
-//   who computed what: every consumer warp publishes its partial of every tile as a 16-byte {value, phase tag} unit,
-//   and CTA c adds the units of the FIXED tile range c*ntiles/G .. (c+1)*ntiles/G in a fixed order before the usual
-//   grid all-reduce.  Each phase instance k uses claim counter k mod 4; a counter only grows, by ntiles + G per use
-//   (every CTA makes exactly one failing claim), so it never has to be reset while the kernel runs.
+//   who computed what: the unit of claiming is a BATCH of consecutive tiles from a fixed list (long batches first, single
+//   tiles for the last fifth of a phase, so that the finish is balanced to one tile while only a few claims and
+//   reductions are paid per CTA); every consumer warp publishes its partial of every batch as a 16-byte
+//   {value, phase tag} unit, and CTA c adds the units of the FIXED batch range c*nbatch/G .. (c+1)*nbatch/G in a fixed
+//   order before the usual grid all-reduce.  Each phase instance k uses claim counter k mod 4; a counter only grows, by
+//   nbatch + G per use (every CTA makes exactly one failing claim), so it never has to be reset while the kernel runs.
 template <bool kDyn>
 __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant__ StreamArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -363,26 +367,38 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
         };
         bool stop = false;
         if constexpr (kDyn) {
-            const unsigned long long M = (unsigned long long)ntiles + (unsigned long long)G;   // claims per phase instance
+            const unsigned long long M = (unsigned long long)a.nbatch + (unsigned long long)G;   // claims per phase instance
             for (int it = 0; it < a.max_iter && !stop; ++it) {
                 for (int phase = 0; phase < 2 && !stop; ++phase) {
                     const int k = 2 * it + phase;
                     bool exhausted = false;
-                    auto claim = [&]() -> int {               // next tile of this phase, or -1 (exactly once per phase)
-                        const unsigned long long v = atomicAdd(&a.claim[k & 3], 1ULL) - (unsigned long long)(k >> 2) * M;
-                        if (v >= (unsigned long long)ntiles) { exhausted = true; return -1; }
-                        return (phase == 1 && a.zigzag) ? ntiles - 1 - (int)v : (int)v;
+                    int b_idx = -1, b_next = 0, b_end = 0;    // current batch: index, next claim-order position, end position
+                    // next tile of this phase (and whether it closes its batch), or false when the list is exhausted
+                    auto next_tile = [&](int &t, int &closes) -> bool {
+                        if (b_next == b_end) {
+                            if (exhausted) return false;
+                            const unsigned long long v = atomicAdd(&a.claim[k & 3], 1ULL) - (unsigned long long)(k >> 2) * M;
+                            if (v >= (unsigned long long)a.nbatch) { exhausted = true; return false; }   // exactly once per phase
+                            b_idx = (int)v;
+                            if (b_idx < a.nbatch_long) { b_next = b_idx * a.batch_len; b_end = b_next + a.batch_len; }
+                            else { b_next = a.nbatch_long * a.batch_len + (b_idx - a.nbatch_long); b_end = b_next + 1; }
+                        }
+                        const int pos = b_next++;
+                        t = (phase == 1 && a.zigzag) ? ntiles - 1 - pos : pos;
+                        closes = b_next == b_end ? b_idx : -1;
+                        return true;
                     };
                     const bool need_go = k != 0;
                     int pre[kStages], npre = 0;
                     // (1) claim the first tiles and stage their independent boxes while the previous phase is still finishing
                     if (need_go) {
-                        while (npre < kStages && !exhausted) {
-                            const int t = claim();
-                            if (t < 0) break;
+                        while (npre < kStages) {
+                            int t, closes;
+                            if (!next_tile(t, closes)) break;
                             const unsigned nn = n + npre;
                             if (!mbar_wait(&tl->empty[nn % kStages], ((nn / kStages) & 1) ^ 1, err)) return;
                             tl->tile[nn % kStages] = t;
+                            tl->batch[nn % kStages] = closes;
                             issue(it, phase, cur, nn, (t % a.tiles_x) * TW, (t / a.tiles_x) * TH, true, false);
                             pre[npre++] = t;
                         }
@@ -402,11 +418,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
                     }
                     n += npre;
                     // (4) the rest of the phase
-                    while (!exhausted) {
-                        const int t = claim();
-                        if (t < 0) break;
+                    for (;;) {
+                        int t, closes;
+                        if (!next_tile(t, closes)) break;
                         if (!mbar_wait(&tl->empty[n % kStages], ((n / kStages) & 1) ^ 1, err)) return;
                         tl->tile[n % kStages] = t;
+                        tl->batch[n % kStages] = closes;
                         issue(it, phase, cur, n, (t % a.tiles_x) * TW, (t / a.tiles_x) * TH, true, true);
                         ++n;
                     }
@@ -518,8 +535,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
                 if (fast) tile_p1<true, false>(a, S, R, s_cur, s_up, s_dn, ty0, tx0, beta, acc_zs, acc_bb, acc_bmax);
                 else tile_p1<false, false>(a, S, R, s_cur, s_up, s_dn, ty0, tx0, beta, acc_zs, acc_bb, acc_bmax);
             }
-            if constexpr (kDyn) {                               // this warp's partials of THIS tile, then start afresh
-                const size_t plane = (size_t)ntiles * kConsumerWarps, u = (size_t)t * kConsumerWarps + wid;
+            const int closes = kDyn ? *(volatile int *)&tl->batch[st] : -1;
+            if (kDyn && closes >= 0) {                          // this warp's partials of the batch that ends here, then afresh
+                const size_t plane = (size_t)a.nbatch * kConsumerWarps, u = (size_t)closes * kConsumerWarps + wid;
                 const double p0 = warp_sum(acc_zs);
                 if ((tid & 31) == 0) unit_store(a.tparts + u, p0, tag1);
                 if (first) {
@@ -536,9 +554,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
         }
         stamp(0);   // P1 tiles
         {
-            if constexpr (kDyn) {   // the units of this CTA's FIXED tile range, whoever computed them, in a fixed order
-                const size_t plane = (size_t)ntiles * kConsumerWarps;
-                const int c0 = (int)((long long)blockIdx.x * ntiles / G), c1 = (int)((long long)(blockIdx.x + 1) * ntiles / G);
+            if constexpr (kDyn) {   // the units of this CTA's FIXED batch range, whoever computed them, in a fixed order
+                const size_t plane = (size_t)a.nbatch * kConsumerWarps;
+                const int c0 = (int)((long long)blockIdx.x * a.nbatch / G), c1 = (int)((long long)(blockIdx.x + 1) * a.nbatch / G);
                 const ReduceUnit *base = a.tparts + (size_t)c0 * kConsumerWarps;
                 for (int e = tid; e < (c1 - c0) * kConsumerWarps; e += kConsumers) {
                     double v;
@@ -610,8 +628,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
                 if (fast) tile_p2<true, false>(a, S, R, X, ty0, tx0, alpha, acc_rr, acc_rmax);
                 else tile_p2<false, false>(a, S, R, X, ty0, tx0, alpha, acc_rr, acc_rmax);
             }
-            if constexpr (kDyn) {
-                const size_t plane = (size_t)ntiles * kConsumerWarps, u = (size_t)t * kConsumerWarps + wid;
+            const int closes = kDyn ? *(volatile int *)&tl->batch[st] : -1;
+            if (kDyn && closes >= 0) {
+                const size_t plane = (size_t)a.nbatch * kConsumerWarps, u = (size_t)closes * kConsumerWarps + wid;
                 const double p0 = warp_sum(acc_rr), p1 = warp_max(acc_rmax);
                 if ((tid & 31) == 0) {
                     unit_store(a.tparts + u, p0, tag2);
@@ -625,8 +644,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
         stamp(2);   // P2 tiles
         {
             if constexpr (kDyn) {
-                const size_t plane = (size_t)ntiles * kConsumerWarps;
-                const int c0 = (int)((long long)blockIdx.x * ntiles / G), c1 = (int)((long long)(blockIdx.x + 1) * ntiles / G);
+                const size_t plane = (size_t)a.nbatch * kConsumerWarps;
+                const int c0 = (int)((long long)blockIdx.x * a.nbatch / G), c1 = (int)((long long)(blockIdx.x + 1) * a.nbatch / G);
                 const ReduceUnit *base = a.tparts + (size_t)c0 * kConsumerWarps;
                 for (int e = tid; e < (c1 - c0) * kConsumerWarps; e += kConsumers) {
                     double v;
@@ -784,6 +803,14 @@ int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, 
     const int64_t dyn_opt = pano_option(ctx, "cg_dynamic", -1);
     const bool dynamic = dyn_opt > 0 || (dyn_opt < 0 && ntiles >= 16 * G);
     if (dynamic) {
+        // the fixed batch list: ~80 % of the tiles in batches of up to 8 (about six long batches per CTA), then single tiles
+        int bl = (int)pano_option(ctx, "cg_batch", 0);
+        if (bl <= 0) bl = ntiles / (6 * G);
+        if (bl > 8) bl = 8;
+        if (bl < 1) bl = 1;
+        a.batch_len = bl;
+        a.nbatch_long = bl > 1 ? (int)((long long)ntiles * 4 / 5 / bl) : 0;
+        a.nbatch = a.nbatch_long + (ntiles - a.nbatch_long * bl);
         const size_t units = 3 * (size_t)ntiles * kConsumerWarps;
         if (units > ctx->tparts_cap) {
             if (ctx->d_tparts) {
