@@ -801,7 +801,9 @@ int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, 
     PANO_CUDA(cudaMemsetAsync(ctx->d_cg, 0, sizeof(PanoCgControl), ctx->stream));
     // dynamic tile scheduling pays once a CTA has enough tiles for the imbalance to matter ("cg_dynamic": 0 off, 1 on, -1 auto)
     const int64_t dyn_opt = pano_option(ctx, "cg_dynamic", -1);
-    const bool dynamic = dyn_opt > 0 || (dyn_opt < 0 && ntiles >= 16 * G);
+    // measured on B200 (Mcell-steps/s, static -> dynamic): 2048^2 (14 tiles per CTA) 787 -> 758; 8192^2 over 8 GPUs (28) 5488 ->
+    // 5549, i.e. noise; 4096^2 (55) 893 -> 944; 8192^2 (221) 842 -> 996.  The second reduction stage costs ~1 us per phase.
+    const bool dynamic = dyn_opt > 0 || (dyn_opt < 0 && ntiles >= 40 * G);
     if (dynamic) {
         // the fixed batch list: ~80 % of the tiles in batches of up to 8 (about six long batches per CTA), then single tiles
         int bl = (int)pano_option(ctx, "cg_batch", 0);
