@@ -496,7 +496,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=0, help="grid size override (multiple of 128)")
+    ap.add_argument("--n", "--grid", dest="n", type=int, default=0, help="grid size override (multiple of 128); use --grid under torchrun, whose own parser claims --n")
     ap.add_argument("--cpu-variant", default="faithful", choices=["faithful", "parallel"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-mg", action="store_true", help="skip the multigrid-preconditioned step timing")
