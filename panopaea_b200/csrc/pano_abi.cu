@@ -73,6 +73,8 @@ int pano_ctx_create(int device, void *stream, pano_ctx **out) {
     // all-reduce units of the persistent kernels: allocated here so that no launch path ever calls cudaMalloc
     PANO_CUDA(cudaMalloc(&c->d_units, 4096 * 16));
     PANO_CUDA(cudaMemset(c->d_units, 0, 4096 * 16));
+    PANO_CUDA(cudaMalloc(&c->d_inbox, kPanoInboxBytes));            // push exchange of the SM-resident CG kernel
+    PANO_CUDA(cudaMemset(c->d_inbox, 0, kPanoInboxBytes));          // sequence 0 never matches
     *out = c;
     return PANO_OK;
 }
@@ -88,6 +90,7 @@ int pano_ctx_destroy(pano_ctx *ctx) {
     cudaFreeHost(ctx->h_scalars);
     cudaFree(ctx->d_cg);
     cudaFree(ctx->d_units);
+    cudaFree(ctx->d_inbox);
     cudaFree(ctx->d_mail);
     cudaFree(ctx->d_tparts);
     cudaFree(ctx->d_claim);
@@ -408,7 +411,16 @@ int pano_phase_drain(pano_ctx *ctx) {
     return PANO_OK;
 }
 
+// Look-up order: pano_ctx_set_option, then the environment variable PANO_OPT_<key> (lets a whole test run exercise a
+// non-default kernel variant without touching the callers), then the built-in default.
 int64_t pano_option(pano_ctx *ctx, const char *key, int64_t dflt) {
     auto it = ctx->options.find(key);
-    return it == ctx->options.end() ? dflt : it->second;
+    if (it != ctx->options.end()) return it->second;
+    const std::string name = std::string("PANO_OPT_") + key;
+    if (const char *env = getenv(name.c_str())) {
+        char *end = nullptr;
+        const long long v = strtoll(env, &end, 10);
+        if (end != env) return (int64_t)v;
+    }
+    return dflt;
 }

@@ -29,6 +29,7 @@ struct Res2Args {
     int tiles_x, tiles_y;
     ReduceUnit *mail;       // [tiles][2*TW + 2*TH] {value, seq}: top row, bottom row, left column, right column of r
     ReduceUnit *units;
+    ReduceUnit *inbox;      // push all-reduce (option "cg_push", default on), or null for the root protocol
     unsigned long long seq_base;
     PanoCgControl *ctl;
     long long *dbg;         // optional: per-section clock64 totals of CTA 0 (option "cg_profile")
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(T, 1) k_cg_resident2(const Res2Args a) {
 
     auto allreduce = [&](int nvals, double v0, double v1, double v2, unsigned max_mask) {
         return grid_allreduce_units(a.units, a.seq_base + nred, nred, nvals, v0, v1, v2, max_mask, sh->vals, sh->out, &sh->ok,
-                                    &a.ctl->error, /*fenced=*/false, [] { __syncthreads(); }, red);
+                                    &a.ctl->error, /*fenced=*/false, [] { __syncthreads(); }, red, nullptr, NoWork(), a.inbox);
     };
 
     const bool prof = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(T, 1) k_cg_resident2(const Res2Args a) {
             }
         };
         if (!grid_allreduce_units(a.units, a.seq_base + nred, nred, 2, acc_rr, acc_rmax, 0.0, 0x2u, sh->vals, sh->out, &sh->ok,
-                                  &a.ctl->error, /*fenced=*/false, [] { __syncthreads(); }, red, nullptr, update_x)) {
+                                  &a.ctl->error, /*fenced=*/false, [] { __syncthreads(); }, red, nullptr, update_x, a.inbox)) {
             failed = true;
             break;
         }
@@ -411,6 +412,7 @@ int pano_cg_resident2_launch(pano_ctx *ctx, double *x, const double *b, double *
     }
     a.mail = reinterpret_cast<ReduceUnit *>(ctx->d_mail);
     a.units = (ReduceUnit *)ctx->d_units;
+    a.inbox = pano_option(ctx, "cg_push", 1) ? (ReduceUnit *)ctx->d_inbox : nullptr;
     a.seq_base = (++ctx->launch_epoch) << 32;
     a.ctl = ctx->d_cg;
     a.dbg = pano_option(ctx, "cg_profile", 0) ? ctx->d_cg->prof : nullptr;   // device address of the 8 slots

@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -50,6 +51,8 @@ struct PanoCgControl {
     long long prof[8];            // per-section clock64 totals of CTA 0 (option "cg_profile", SM-resident kernel)
 };
 
+constexpr size_t kPanoInboxBytes = (size_t)2 * 192 * 3 * 192 * 16;   // = pano_sm100::kInboxUnits * sizeof(ReduceUnit)
+
 struct PanoWorkspace;   // cached scratch of pano_fluid_step_host
 struct pano_mg;         // multigrid preconditioner (pano_mg.cu)
 
@@ -77,6 +80,7 @@ struct pano_ctx {
     size_t tparts_cap = 0;           // in 16-byte units
     unsigned long long *d_claim = nullptr;   // 4 tile-claim counters (one per phase in flight)
     void *d_units = nullptr;         // publish+poll all-reduce units of the persistent kernels
+    void *d_inbox = nullptr;         // per-CTA inboxes of the push all-reduce (pano_sm100.cuh), kPanoInboxBytes
     unsigned long long launch_epoch = 0;
     // optional per-phase timing of pano_fluid_step ("step_timing" option)
     std::vector<cudaEvent_t> phase_events;   // ring of (PANO_STEP_PHASES + 1) events per slot

@@ -116,12 +116,17 @@ __device__ __forceinline__ double warp_fixed_max(const double *vals, int n, int 
 //   G  > 32 : root       -- CTA 0 polls all partials, reduces them in a fixed order and publishes the
 //             result; the others poll that one unit (two round trips but no hot-spotting:
 //             measured 1.43 us at G = 148 against 3.5 us all-to-all and 2.5 us for an atomic counter)
+//   G  > 32, `inbox` given, one GPU : push -- every CTA stores its partials into every CTA's private inbox and
+//             polls its own (one round trip, no shared polled lines); see the branch below
 // Every CTA ends up with bit-identical results.  `fenced`: bulk data written with ordinary stores
 // must be visible to the other CTAs afterwards (streaming kernel); the SM-resident kernel moves
 // everything through units and needs no fence.
 constexpr int kMaxCtas = 192;
 constexpr int kUnitsPerBank = 4 * kMaxCtas;       // 3 x kMaxCtas partials + results
 constexpr int kUnitsTotal = 2 * kUnitsPerBank;    // double-buffered by exchange parity
+// "push" exchange (grids above 32 CTAs, one GPU): [2 banks][reader CTA][3 values][writer CTA] units, 3.4 MB
+constexpr size_t kInboxUnits = (size_t)2 * kMaxCtas * 3 * kMaxCtas;
+static_assert(kInboxUnits * 16 == kPanoInboxBytes, "inbox size (pano_internal.cuh)");
 
 // Multi-GPU extension: after CTA 0 has reduced its GPU's partials it writes the GPU total into a slot of
 // EVERY rank's cross-rank unit array (peer-mapped memory, st.volatile = system scope, over NVLink),
@@ -148,7 +153,7 @@ __device__ __forceinline__ bool grid_allreduce_units(ReduceUnit *units, unsigned
                                                      double v0, double v1, double v2, unsigned max_mask,
                                                      double (*vals)[kMaxCtas], double *out_sh, int *ok_sh,
                                                      volatile unsigned int *err, bool fenced, SyncFn sync, double *out,
-                                                     const XRank *xr = nullptr, MidFn mid = MidFn()) {
+                                                     const XRank *xr = nullptr, MidFn mid = MidFn(), ReduceUnit *inbox = nullptr) {
     const int G = gridDim.x, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const unsigned parity = (unsigned)(n & 1);
     const bool multi = xr != nullptr && xr->nranks > 1;
@@ -160,6 +165,42 @@ __device__ __forceinline__ bool grid_allreduce_units(ReduceUnit *units, unsigned
         fence_proxy_async();
     }
     if (fenced) sync();   // the publishing threads below must not run ahead of thread 0's fence
+    if (inbox != nullptr && !multi && G > 32) {
+        // push: thread t hands this CTA's partials (v0..v2 must hold the CTA totals in EVERY thread) to CTA t's
+        // private inbox, then polls the unit CTA t pushed into this CTA's inbox.  Nobody shares a polled line with
+        // another reader, so the exchange is one store + one poll; all CTAs then reduce the same values in the same
+        // order as the root would.  Two banks suffice: a CTA can be at most one exchange ahead of any other, because
+        // it needs everybody's units of exchange n+1 before it can start n+2.
+        if (tid < G) {
+            ReduceUnit *dst = inbox + ((size_t)(parity * kMaxCtas + (unsigned)tid) * 3) * kMaxCtas + blockIdx.x;
+            unit_store(dst, v0, seq);
+            if (nvals > 1) unit_store(dst + kMaxCtas, v1, seq);
+            if (nvals > 2) unit_store(dst + 2 * kMaxCtas, v2, seq);
+        }
+        mid();
+        if (tid < G) {
+            const ReduceUnit *src = inbox + ((size_t)(parity * kMaxCtas + blockIdx.x) * 3) * kMaxCtas + tid;
+            bool ok = true;
+            for (int k = 0; k < nvals && ok; ++k) {
+                double v;
+                ok = unit_poll(src + k * kMaxCtas, seq, v, err);
+                vals[k][tid] = v;
+            }
+            if (fenced) __threadfence();
+            if (!ok) *ok_sh = 0;
+        }
+        sync();
+        if (wid < nvals) {
+            const bool is_max = (max_mask >> wid) & 1u;
+            const double r = is_max ? warp_fixed_max(vals[wid], G, lane) : warp_fixed_sum(vals[wid], G, lane);
+            if (lane == 0) out_sh[wid] = r;
+        }
+        sync();
+        out[0] = out_sh[0];
+        if (nvals > 1) out[1] = out_sh[1];
+        if (nvals > 2) out[2] = out_sh[2];
+        return *ok_sh != 0;
+    }
     if (tid < nvals) unit_store(bank + tid * kMaxCtas + blockIdx.x, tid == 0 ? v0 : (tid == 1 ? v1 : v2), seq);
     const bool root_mode = G > 32 || multi;
     if (!root_mode || blockIdx.x == 0) {
