@@ -62,6 +62,7 @@ struct StreamArgs {
     PanoCgControl *ctl;
     int zigzag;
     int halo_first;               // slab with neighbours: halo tile rows first in every phase (see slot_tile)
+    int fence_mode;               // kFenceLight | kFenceSysIfRemote (pano_sm100.cuh), option "cg_fence"
     // ---- dynamic tile scheduling (k_cg_stream<true>)
     unsigned long long *claim;    // 4 claim counters, used round-robin by the phases (zeroed at launch)
     ReduceUnit *tparts;           // [3 values][nbatch * kConsumerWarps] per-(batch, warp) partials, {value, phase tag}
@@ -113,10 +114,26 @@ __device__ __forceinline__ double consumer_max(double v, double *wsum) {
 
 // Grid-wide all-reduce of up to three block totals, called by all consumer threads (pano_sm100.cuh).
 // fenced: the tiles this CTA stored to global memory must be visible to the others afterwards.
+// remote: this CTA stored rows into a neighbour GPU's memory since the previous exchange.
 __device__ __forceinline__ bool grid_allreduce(const StreamArgs &a, Tail *tl, unsigned long long n, int nvals, double v0,
-                                               double v1, double v2, unsigned max_mask, double *out) {
+                                               double v1, double v2, unsigned max_mask, double *out, bool remote, bool flags_sent) {
     return grid_allreduce_units(a.units, a.seq_base + n, n, nvals, v0, v1, v2, max_mask, tl->vals, tl->out,
-                                &tl->ok, &a.ctl->error, /*fenced=*/true, [] { consumer_sync(); }, out, &a.xr);
+                                &tl->ok, &a.ctl->error, /*fenced=*/true, [] { consumer_sync(); }, out, &a.xr, NoWork(), nullptr,
+                                a.fence_mode, remote && !flags_sent, flags_sent);
+}
+// Static tile lists with halo_first: a CTA's halo tiles are its first `nh` tiles of every phase.  Right after the last of
+// them the CTA fences at system scope and raises its halo flags for the reduction that ends the phase (exchange number
+// `nred`), ~3 us of one warp in the middle of the phase instead of all warps' at its end.
+__device__ __forceinline__ void early_halo_flags(const StreamArgs &a, unsigned long long nred) {
+    consumer_sync();                       // every consumer warp's halo-row stores happen-before thread 0's fence
+    if (threadIdx.x == 0) {
+        fence_sys((a.fence_mode & kFenceLight) != 0);
+        send_halo_flags(&a.xr, nred);
+    }
+}
+// does a tile touch a slab edge whose rows are mirrored into a neighbour's ghost row?
+__device__ __forceinline__ bool tile_stores_remote(const StreamArgs &a, int ty0) {
+    return (ty0 == 0 && a.up_r != nullptr) || (ty0 + TH >= a.h && a.dn_r != nullptr);
 }
 
 // ------------------------------------------------------------------------------ tile kernels
@@ -501,10 +518,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
             tprev = t;
         }
     };
+    // leading halo tiles of this CTA in every phase (slot_tile), when they are flagged early
+    int nh_early = 0;
+    if (!kDyn && a.halo_first && a.tiles_y > 2 && a.xr.nranks > 1 && a.xr.hflags != nullptr) {
+        const int nhalo = 2 * a.tiles_x;
+        nh_early = nhalo > (int)blockIdx.x ? (nhalo - (int)blockIdx.x + G - 1) / G : 0;
+        if (nh_early > n_my) nh_early = n_my;
+    }
     for (it = 0; it < a.max_iter; ++it) {
         const bool first = it == 0;
         // ------------------------------------------------------------------ P1
         double acc_zs = 0, acc_bb = 0, acc_bmax = 0;
+        bool remote = false;      // uniform over the CTA: every consumer warp walks the same tiles
         const unsigned long long tag1 = a.seq_base + (unsigned long long)(2 * it) + 1;   // phase tag of the per-tile units
         for (int jj = 0;; ++jj, ++n) {
             const int st = n % kStages;
@@ -524,6 +549,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
                 if (!mbar_wait(&tl->full[st], (n / kStages) & 1, err)) return;
             }
             const int tx0 = (t % a.tiles_x) * TW, ty0 = (t / a.tiles_x) * TH;
+            remote = remote || tile_stores_remote(a, ty0);
             const double *S = reinterpret_cast<const double *>(smem + st * kStageBytes);
             const double *R = reinterpret_cast<const double *>(smem + st * kStageBytes + kHaloSlot);
             const bool fast = tile_is_fast(a, ty0, tx0);
@@ -551,6 +577,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
             }
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&tl->empty[st]);
+            if (!kDyn && jj == nh_early - 1) early_halo_flags(a, nred);
         }
         stamp(0);   // P1 tiles
         {
@@ -576,7 +603,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
                 v1 = consumer_sum(acc_bb, tl->wsum[1]);
                 v2 = consumer_max(acc_bmax, tl->wsum[2]);
             }
-            if (!grid_allreduce(a, tl, nred++, first ? 3 : 1, v0, v1, v2, 0x4u, red)) {
+            if (!grid_allreduce(a, tl, nred++, first ? 3 : 1, v0, v1, v2, 0x4u, red, remote, nh_early > 0)) {
                 if (tid == 0) { tl->cont = 0; mbar_arrive(&tl->go); }
                 return;
             }
@@ -598,6 +625,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
         alpha = sigma / zs;                                    // pcg.rs:53
         // ------------------------------------------------------------------ P2
         double acc_rr = 0, acc_rmax = 0;
+        remote = false;
         const unsigned long long tag2 = a.seq_base + (unsigned long long)(2 * it + 1) + 1;
         for (int jj = 0;; ++jj, ++n) {
             const int st = n % kStages;
@@ -617,6 +645,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
                 if (!mbar_wait(&tl->full[st], (n / kStages) & 1, err)) return;
             }
             const int tx0 = (t % a.tiles_x) * TW, ty0 = (t / a.tiles_x) * TH;
+            remote = remote || tile_stores_remote(a, ty0);
             const double *S = reinterpret_cast<const double *>(smem + st * kStageBytes);
             const double *R = reinterpret_cast<const double *>(smem + st * kStageBytes + kHaloSlot);
             const double *X = reinterpret_cast<const double *>(smem + st * kStageBytes + 2 * kHaloSlot);
@@ -640,6 +669,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
             }
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&tl->empty[st]);
+            if (!kDyn && jj == nh_early - 1) early_halo_flags(a, nred);
         }
         stamp(2);   // P2 tiles
         {
@@ -657,7 +687,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
             }
             const double v0 = consumer_sum(acc_rr, tl->wsum[0]);
             const double v1 = consumer_max(acc_rmax, tl->wsum[1]);
-            if (!grid_allreduce(a, tl, nred++, 2, v0, v1, 0.0, 0x2u, red)) {
+            if (!grid_allreduce(a, tl, nred++, 2, v0, v1, 0.0, 0x2u, red, remote, nh_early > 0)) {
                 if (tid == 0) { tl->cont = 0; mbar_arrive(&tl->go); }
                 return;
             }
@@ -776,6 +806,7 @@ int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, 
     a.dbg_cta = reinterpret_cast<long long *>(ctx->d_partials);   // >= 12288 doubles (pano_ctx_create); zeroed below when profiling
     if (a.dbg) PANO_CUDA(cudaMemsetAsync(ctx->d_partials, 0, 2 * kMaxCtas * sizeof(long long), ctx->stream));
     a.zigzag = pano_option(ctx, "cg_zigzag", 1) != 0;
+    a.fence_mode = (int)pano_option(ctx, "cg_fence", 0);
     a.row0 = 0; a.gy0 = 0; a.gh = (int)h;
     a.xr.rank = 0; a.xr.nranks = 1;
     int max_ctas = 0;
@@ -787,6 +818,21 @@ int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, 
         a.xr.seq_base = slab->xseq_base;
         a.xr.local = (ReduceUnit *)slab->xunits_local;
         for (int i = 0; i < kMaxRanks; ++i) a.xr.peer[i] = (ReduceUnit *)slab->xunits_peer[i];
+        if (slab->nranks > 1 && pano_option(ctx, "cg_xflags", 1) != 0) {
+            // halo flags (pano_sm100.cuh): behind the cross-rank totals in every rank's unit array.  The neighbours run
+            // the same launch code on their slabs, so their CTA counts follow from the slab split.
+            auto ctas_of = [&](int r) {
+                const long long rows = (long long)slab->gh * (r + 1) / slab->nranks - (long long)slab->gh * r / slab->nranks;
+                long long g = ctx->num_sms, nt = (long long)a.tiles_x * ((rows + TH - 1) / TH);
+                if (slab->max_ctas > 0 && g > slab->max_ctas) g = slab->max_ctas;
+                if (g > nt) g = nt;
+                if (g > kMaxCtas) g = kMaxCtas;
+                return (int)g;
+            };
+            a.xr.hflags = a.xr.local + kXUnitsTotal;
+            if (slab->rank > 0) { a.xr.hflags_up = a.xr.peer[slab->rank - 1] + kXUnitsTotal; a.xr.g_up = ctas_of(slab->rank - 1); }
+            if (slab->rank + 1 < slab->nranks) { a.xr.hflags_dn = a.xr.peer[slab->rank + 1] + kXUnitsTotal; a.xr.g_dn = ctas_of(slab->rank + 1); }
+        }
         max_ctas = slab->max_ctas;
         a.halo_first = (slab->nranks > 1 && pano_option(ctx, "cg_halo_first", 0) != 0) ? 1 : 0;
     }
@@ -803,7 +849,8 @@ int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, 
     const int64_t dyn_opt = pano_option(ctx, "cg_dynamic", -1);
     // measured on B200 (Mcell-steps/s, static -> dynamic): 2048^2 (14 tiles per CTA) 787 -> 758; 8192^2 over 8 GPUs (28) 5488 ->
     // 5549, i.e. noise; 4096^2 (55) 893 -> 944; 8192^2 (221) 842 -> 996.  The second reduction stage costs ~1 us per phase.
-    const bool dynamic = dyn_opt > 0 || (dyn_opt < 0 && ntiles >= 40 * G);
+    // 1024 x 8192 slab (28): one GPU 96.2 -> 94.9 us per iteration, 2 GPUs 105.1 -> 104.0: the auto threshold is 24 tiles per CTA.
+    const bool dynamic = dyn_opt > 0 || (dyn_opt < 0 && ntiles >= 24 * G);
     if (dynamic) {
         // the fixed batch list: ~80 % of the tiles in batches of up to 8 (about six long batches per CTA), then single tiles
         int bl = (int)pano_option(ctx, "cg_batch", 0);

@@ -69,7 +69,7 @@ Layout make_layout(size_t H, size_t W, int rank, int nranks) {
         L.rows[f] = L.hl + 2 * kGhost + (is_vy ? 1 : 0);
         L.off[f] = take(L.rows[f] * L.pitch[f]);
     }
-    L.xunits = take(2 * (size_t)kXUnitsTotal);       // ReduceUnit = 2 doubles
+    L.xunits = take(2 * (size_t)(kXUnitsTotal + kXFlagUnits));   // ReduceUnit = 2 doubles; cross-rank totals, then the halo flags
     L.flags = take(2 * (size_t)EX_COUNT * 2);
     L.err = take(2);
     L.total = off;

@@ -98,6 +98,21 @@ __device__ __forceinline__ bool unit_poll(const ReduceUnit *u, unsigned long lon
     }
 }
 
+// the same poll with ld.acquire.sys: the poller synchronises with a releasing writer on another GPU without paying a
+// system-scope fence afterwards (SASS: LD + CCTL.IVALL; MEMBAR.SYS costs ~3.1 us on a B200 NVLink system)
+__device__ __forceinline__ bool unit_poll_acquire_sys(const ReduceUnit *u, unsigned long long seq, volatile unsigned int *err) {
+    unsigned long long got, bits;
+    long long spins = 0;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(bits), "=l"(got) : "l"(u) : "memory");
+        if (got == seq) return true;
+        if (++spins > kSpinLimit || ((spins & 0x3ff) == 0 && *err)) {
+            atomicExch((unsigned int *)err, 1u);
+            return false;
+        }
+    }
+}
+
 // fixed-order sum / max of n values held in shared memory, executed by one full warp
 __device__ __forceinline__ double warp_fixed_sum(const double *vals, int n, int lane) {
     double a = 0;
@@ -134,12 +149,45 @@ static_assert(kInboxUnits * 16 == kPanoInboxBytes, "inbox size (pano_internal.cu
 // every GPU obtains the bit-identical value.  One NVLink store latency per reduction, no NCCL call.
 constexpr int kMaxRanks = 8;
 constexpr int kXUnitsTotal = 2 * kMaxRanks * 3;   // [2 banks][rank][value]
+// "Halo flags" (XRank::hflags, option cg_xflags): the cross-GPU exchange above needs a system-scope fence on either side
+// of it in the root CTA, because the root vouches for the halo rows OTHER CTAs stored into the neighbours' memory
+// (fence cumulativity) -- measured 2 x 3.1 us per reduction (scripts/probe/xgpu_probe.cu).  With halo flags every CTA
+// vouches for itself: after its own system-scope fence it stores a {0, sequence} unit into a per-CTA slot in each
+// neighbour's memory, and the neighbour's root polls those slots with ld.acquire.sys.  The roots then exchange the GPU
+// totals with plain volatile stores and polls, no fence around them.  [2 banks][from up / from down][CTA] units.
+constexpr int kXFlagUnits = 2 * 2 * kMaxCtas;
 struct XRank {
     int rank, nranks;
     unsigned long long seq_base;      // identical on all ranks (incremented once per collective launch)
     ReduceUnit *local;                // this rank's cross-rank unit array
     ReduceUnit *peer[kMaxRanks];      // every rank's array as mapped into this process (peer[rank] == local)
+    ReduceUnit *hflags;               // this rank's halo-flag array (written by the neighbours' CTAs), or null: fenced exchange
+    ReduceUnit *hflags_up, *hflags_dn;   // the neighbours' arrays as mapped here, or null at the domain walls
+    int g_up, g_dn;                   // CTAs of the upper / lower neighbour's kernel (flags to wait for), 0 at the walls
 };
+
+// Fences of the `fenced` exchange.  Every use is a release (before publishing a unit) or an acquire (after polling
+// one) around relaxed volatile accesses, for which PTX's fence.acq_rel is sufficient; __threadfence*() emit the
+// sequentially consistent fence.sc (SASS MEMBAR.SC.* instead of MEMBAR.ALL.*).  `light` selects fence.acq_rel.
+__device__ __forceinline__ void fence_gpu(bool light) {
+    if (light) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    else __threadfence();
+}
+__device__ __forceinline__ void fence_sys(bool light) {
+    if (light) asm volatile("fence.acq_rel.sys;" ::: "memory");
+    else __threadfence_system();
+}
+constexpr int kFenceLight = 1;        // fence.acq_rel instead of fence.sc
+constexpr int kFenceSysIfRemote = 2;  // multi-GPU: system scope only in CTAs that stored into a peer's memory this phase
+constexpr int kFenceRootGpuOnly = 4;  // DIAGNOSTIC (formally a race): the root's two fences around the cross-GPU exchange at gpu scope
+
+// One thread, after a fence that covers the CTA's stores into the neighbours' memory: this CTA's halo flags of exchange n.
+__device__ __forceinline__ void send_halo_flags(const XRank *xr, unsigned long long n) {
+    const unsigned long long xseq = xr->seq_base + n;
+    const int parity = (int)(n & 1);
+    if (xr->hflags_up) unit_store(xr->hflags_up + (parity * 2 + 1) * kMaxCtas + blockIdx.x, 0.0, xseq);
+    if (xr->hflags_dn) unit_store(xr->hflags_dn + (parity * 2 + 0) * kMaxCtas + blockIdx.x, 0.0, xseq);
+}
 
 struct NoWork {
     __device__ __forceinline__ void operator()() const {}
@@ -153,15 +201,22 @@ __device__ __forceinline__ bool grid_allreduce_units(ReduceUnit *units, unsigned
                                                      double v0, double v1, double v2, unsigned max_mask,
                                                      double (*vals)[kMaxCtas], double *out_sh, int *ok_sh,
                                                      volatile unsigned int *err, bool fenced, SyncFn sync, double *out,
-                                                     const XRank *xr = nullptr, MidFn mid = MidFn(), ReduceUnit *inbox = nullptr) {
+                                                     const XRank *xr = nullptr, MidFn mid = MidFn(), ReduceUnit *inbox = nullptr,
+                                                     int fmode = 0, bool remote = true, bool flags_sent = false) {
     const int G = gridDim.x, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const unsigned parity = (unsigned)(n & 1);
     const bool multi = xr != nullptr && xr->nranks > 1;
     ReduceUnit *bank = units + parity * kUnitsPerBank;
     ReduceUnit *result = bank + 3 * kMaxCtas;
+    const bool light = (fmode & kFenceLight) != 0;
     if (fenced && tid == 0) {
-        if (multi) __threadfence_system();   // halo rows stored into the neighbours' memory must have landed
-        else __threadfence();
+        // halo rows stored into the neighbours' memory must have landed; a CTA that stored none only publishes
+        // tiles that its own GPU reads
+        if (multi && (remote || !(fmode & kFenceSysIfRemote))) fence_sys(light);
+        else fence_gpu(light);
+        // this CTA's halo rows of the ending phase have landed: tell the neighbours' roots (unless send_halo_flags
+        // already ran, right after the CTA's last halo tile of the phase)
+        if (multi && xr->hflags && !flags_sent) send_halo_flags(xr, n);
         fence_proxy_async();
     }
     if (fenced) sync();   // the publishing threads below must not run ahead of thread 0's fence
@@ -186,7 +241,7 @@ __device__ __forceinline__ bool grid_allreduce_units(ReduceUnit *units, unsigned
                 ok = unit_poll(src + k * kMaxCtas, seq, v, err);
                 vals[k][tid] = v;
             }
-            if (fenced) __threadfence();
+            if (fenced) fence_gpu(light);
             if (!ok) *ok_sh = 0;
         }
         sync();
@@ -211,7 +266,7 @@ __device__ __forceinline__ bool grid_allreduce_units(ReduceUnit *units, unsigned
                 ok = unit_poll(bank + k * kMaxCtas + tid, seq, v, err);
                 vals[k][tid] = v;
             }
-            if (fenced) __threadfence();
+            if (fenced) fence_gpu(light);
             if (!ok) *ok_sh = 0;
         }
         sync();
@@ -221,16 +276,30 @@ __device__ __forceinline__ bool grid_allreduce_units(ReduceUnit *units, unsigned
             if (multi) {   // cross-rank stage (root CTA only, one warp per value)
                 const unsigned long long xseq = xr->seq_base + n;
                 const int slot = ((int)parity * kMaxRanks + xr->rank) * 3 + wid;
-                if (fenced) __threadfence_system();
+                const bool root_sys = !(fmode & kFenceRootGpuOnly), fence_here = fenced && xr->hflags == nullptr;
+                if (fence_here) { if (root_sys) fence_sys(light); else fence_gpu(light); }
                 if (lane < xr->nranks) unit_store(xr->peer[lane] + slot, r, xseq);
                 double v = 0.0;
                 if (lane < xr->nranks && !unit_poll(xr->local + ((int)parity * kMaxRanks + lane) * 3 + wid, xseq, v, err)) *ok_sh = 0;
-                if (fenced) __threadfence_system();
+                if (fence_here) { if (root_sys) fence_sys(light); else fence_gpu(light); }
                 r = is_max ? warp_max(v) : warp_sum(v);   // fixed butterfly over lane = rank: same bits on every GPU
             }
             if (lane == 0) {
                 out_sh[wid] = r;
-                if (root_mode) unit_store(result + wid, r, seq);
+                if (root_mode && !(multi && xr->hflags)) unit_store(result + wid, r, seq);
+            }
+        } else if (multi && xr->hflags && wid < nvals + 4) {
+            // four more warps: the halo flags of both neighbours' CTAs (acquire: their rows are visible to this GPU now)
+            const unsigned long long xseq = xr->seq_base + n;
+            const ReduceUnit *from_up = xr->hflags + ((int)parity * 2 + 0) * kMaxCtas, *from_dn = xr->hflags + ((int)parity * 2 + 1) * kMaxCtas;
+            for (int t = tid - 32 * nvals; t < xr->g_up + xr->g_dn; t += 128)
+                if (!unit_poll_acquire_sys(t < xr->g_up ? from_up + t : from_dn + (t - xr->g_up), xseq, err)) *ok_sh = 0;
+        }
+        if (multi && xr->hflags) {   // the result goes out once the totals AND the flags are in
+            sync();
+            if (wid < nvals && lane == 0) {
+                fence_gpu(light);    // release, cumulative over what the flag pollers acquired (ordered by the barrier above)
+                unit_store(result + wid, out_sh[wid], seq);
             }
         }
         mid();
@@ -239,7 +308,7 @@ __device__ __forceinline__ bool grid_allreduce_units(ReduceUnit *units, unsigned
         if (tid < nvals) {
             double v;
             if (!unit_poll(result + tid, seq, v, err)) *ok_sh = 0;
-            if (fenced) __threadfence();
+            if (fenced) fence_gpu(light);
             out_sh[tid] = v;
         }
     }

@@ -27,9 +27,11 @@ def _step_all(ranks):
     return [r.sync() for r in ranks]
 
 
-@pytest.mark.parametrize("dynamic", [0, 1])
+# variants of the cross-rank protocol inside the CG kernel (pano_sm100.cuh): halo flags (default) with static or dynamic tile
+# lists, halo tiles first with the flags raised early, and the fenced root exchange the flags replaced
+@pytest.mark.parametrize("dynamic,halo_first,xflags", [(0, 0, 1), (1, 0, 1), (0, 1, 1), (0, 0, 0), (1, 0, 0), (0, 1, 0)])
 @pytest.mark.parametrize("nranks,h,w", [(2, 256, 256), (4, 256, 128), (3, 250, 192)])
-def test_loopback_matches_single_gpu(nranks, h, w, dynamic):
+def test_loopback_matches_single_gpu(nranks, h, w, dynamic, halo_first, xflags):
     from tests import gpu_util as U
     from panopaea_b200 import dist, fluid
     k = 2
@@ -38,7 +40,9 @@ def test_loopback_matches_single_gpu(nranks, h, w, dynamic):
     single = fluid.DecFluid(h=h, w=w, ctx=U.ctx(), **prm)
     ranks = _make_ranks(nranks, h, w, prm)
     for r in ranks:
-        r.ctx.set_option("cg_dynamic", dynamic)      # 1: tiles claimed from a counter (by default only above 16 tiles per CTA)
+        r.ctx.set_option("cg_dynamic", dynamic)      # 1: tiles claimed from a counter (by default only above 24 tiles per CTA)
+        r.ctx.set_option("cg_halo_first", halo_first)
+        r.ctx.set_option("cg_xflags", xflags)
     for step in range(6):
         want = single.step()
         infos = _step_all(ranks)

@@ -13,13 +13,13 @@ pytestmark = pytest.mark.gpu
 SIZES = [(3, 3), (5, 7), (17, 33), (24, 20), (64, 48), (128, 128), (300, 200), (97, 130), (520, 776)]
 # kernel variants: the generic persistent kernel (any shape), the same with L2-only loads, and "auto"
 # (the TMA streaming kernel whenever the width is even, else generic)
-_BASE = dict(cg_ldcg=0, cg_dynamic=-1, cg_batch=0, cg_push=1)
+_BASE = dict(cg_ldcg=0, cg_dynamic=-1, cg_batch=0, cg_push=0)
 VARIANTS = {"generic": dict(_BASE, cg_kernel=1), "generic_ldcg": dict(_BASE, cg_kernel=1, cg_ldcg=1), "auto": dict(_BASE, cg_kernel=0),
             "stream": dict(_BASE, cg_kernel=2, cg_dynamic=0),
             "stream_dyn": dict(_BASE, cg_kernel=2, cg_dynamic=1),            # tiles claimed from a counter instead of fixed lists
             "stream_dyn_batch": dict(_BASE, cg_kernel=2, cg_dynamic=1, cg_batch=3),   # ... in batches of 3 for the first 80 %
-            "resident": dict(_BASE, cg_kernel=3),                            # grid all-reduce: per-CTA inboxes ("push") above 32 CTAs
-            "resident_root": dict(_BASE, cg_kernel=3, cg_push=0),            # ... the root protocol instead
+            "resident": dict(_BASE, cg_kernel=3),                            # grid all-reduce above 32 CTAs: root protocol
+            "resident_push": dict(_BASE, cg_kernel=3, cg_push=1),            # ... per-CTA inboxes instead (measured slower, kept as an option)
             "resident_v1": dict(_BASE, cg_kernel=4), "cluster": dict(_BASE, cg_kernel=5)}
 CLUSTER_MAX_CELLS_PER_CTA, CLUSTER_CTAS = 5120, 8       # csrc/pano_cg_cluster.cu
 
@@ -218,10 +218,10 @@ def test_push_and_root_allreduce_are_bit_identical(oracle, h, w):
     obstacle = U.default_obstacle(h, w)
     b = U.consistent_rhs(oracle, h, w, obstacle, seed=21)
     try:
-        _set_variant("resident")
+        _set_variant("resident_push")
         a = _solve(grid, b, 100, 0.1, 0.05, obstacle)
         a2 = _solve(grid, b, 100, 0.1, 0.05, obstacle)
-        _set_variant("resident_root")
+        _set_variant("resident")
         c = _solve(grid, b, 100, 0.1, 0.05, obstacle)
     finally:
         _set_variant("auto")
@@ -242,7 +242,7 @@ def test_deterministic(oracle):
     assert all(np.array_equal(u, v) for u, v in zip(a[1:], c[1:]))
 
 
-@pytest.mark.parametrize("variant", ["stream", "stream_dyn", "stream_dyn_batch", "resident", "resident_root", "resident_v1"])
+@pytest.mark.parametrize("variant", ["stream", "stream_dyn", "stream_dyn_batch", "resident", "resident_push", "resident_v1"])
 def test_large_grid_capped_solve(oracle, variant):
     """1024^2 (BASELINE configs[1] size): the cap of 100 iterations is hit, as SURVEY.md 6 observes
     for N >= 512; compare the full iterate with the oracle after a fixed 100 iterations."""
