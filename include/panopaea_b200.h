@@ -253,7 +253,9 @@ PANO_API int pano_dist_window(pano_dist *d, void **ptr, size_t *bytes);
 PANO_API int pano_dist_ipc_handle(pano_dist *d, void *handle_out /* PANO_IPC_HANDLE_BYTES */);
 /* kind 0: peers = void*[nranks] raw window pointers; kind 1: peers = nranks consecutive IPC handles (own entry ignored) */
 PANO_API int pano_dist_connect(pano_dist *d, int kind, const void *peers);
-/* cap on the CTAs of the solver kernel (loop-back tests that run several ranks on one GPU); 0 = one per SM */
+/* cap on the CTAs of the solver kernel (loop-back tests that run several ranks on one GPU); 0 = one per SM.
+ * Must be the same on every rank (like the device type): a rank derives its neighbours' CTA counts, whose halo flags
+ * it waits for, from its own launch parameters. */
 PANO_API int pano_dist_set_max_ctas(pano_dist *d, int max_ctas);
 /* owned rows of a field: which = 0 density, 1 vy, 2 vx, 3 pressure; host points at this rank's first row */
 PANO_API int pano_dist_upload(pano_dist *d, int which, const double *host_rows);

@@ -1,6 +1,6 @@
 #!/bin/bash
-# One gpurun call (round 1, v7): push vs root grid all-reduce of the SM-resident CG kernel (parity, A/B bench, section
-# profile), then the full GPU suite, smoke, the default bench line, the ncu launch list and the 4096^2 / 128^2 lines.
+# One gpurun call (round 1, v7): the full GPU suite, smoke, the default bench line, the ncu launch list and the
+# 4096^2 / 128^2 lines.
 # Everything is bounded by `timeout`; logs land in gpurun_out/.
 set -u
 mkdir -p gpurun_out
@@ -8,20 +8,6 @@ T0=$SECONDS
 stamp() { echo "[t=$((SECONDS - T0))s] $*"; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/nvsmi.txt 2>&1
 timeout 300 python __graft_entry__.py > gpurun_out/build.log 2>&1; stamp "build rc=$?"
-timeout 300 python -m pytest tests/test_gpu_pcg.py -m gpu -x -q -k "push or resident" > gpurun_out/tests_push.log 2>&1; stamp "push tests rc=$?"; tail -4 gpurun_out/tests_push.log
-for MODE in 1 0; do
-  PANO_OPT_cg_push=$MODE timeout 200 python bench.py --steps 20 --warmup 20 --no-cpu --no-mg > gpurun_out/bench_1024_push$MODE.json 2> gpurun_out/bench_1024_push$MODE.err; stamp "bench push=$MODE rc=$?"
-  python - <<PY
-import json
-try:
-    d = json.load(open("gpurun_out/bench_1024_push$MODE.json")); r = d["roofline"]
-    print("   push=$MODE value=%.1f ms/step=%.4f cg_ms=%.4f e2e=%.1f clocks=%s" % (d["value"], d["ms_per_step"], r["kernel_ms"], d["e2e"]["value"], d["clocks"]))
-except Exception as e:
-    print("   bench push=$MODE failed:", e); print(open("gpurun_out/bench_1024_push$MODE.err").read()[-1500:])
-PY
-  PANO_OPT_cg_push=$MODE timeout 120 python scripts/prof_resident.py 1024 > gpurun_out/prof_resident_push$MODE.txt 2>&1; cat gpurun_out/prof_resident_push$MODE.txt
-done
-timeout 120 python scripts/bench_small_cg.py 256 512 1024 > gpurun_out/small_cg.txt 2>&1; cat gpurun_out/small_cg.txt
 stamp "full suite"
 timeout 700 python -m pytest tests -m gpu -x -q > gpurun_out/tests.log 2>&1; stamp "tests rc=$?"; tail -6 gpurun_out/tests.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; stamp "smoke rc=$?"; tail -2 gpurun_out/smoke.log
