@@ -92,3 +92,38 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "pano_oracle" not in text and "np_oracle" not in text and "oracle/" not in text.replace("the CPU oracle", ""), f
+
+
+def _header_prototypes():
+    """name -> number of parameters, from the header."""
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for name, args in re.findall(r"PANO_API\s+[\w\s\*]+?\b(pano_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        args = args.strip()
+        out[name] = 0 if args in ("", "void") else len(args.split(","))
+    return out
+
+
+def test_rust_bindings_match_header():
+    """rust/panopaea-b200-sys cannot be compiled here (no Rust toolchain): at least keep its extern block in step with
+    the header -- same symbols, same parameter counts, same constants."""
+    src = open(os.path.join(ROOT, "rust", "panopaea-b200-sys", "src", "lib.rs")).read()
+    block = src[src.index('extern "C" {'):]
+    block = block[:block.index("\n}\n")]
+    block = re.sub(r"//.*", "", block)
+    rust = {}
+    for name, args in re.findall(r"pub fn (pano_\w+)\s*\(([^)]*)\)", block, flags=re.S):
+        args = args.strip()
+        rust[name] = 0 if not args else len([a for a in args.split(",") if a.strip()])
+    want = _header_prototypes()
+    assert sorted(rust) == sorted(want)
+    assert rust == want
+    header = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    consts = dict(re.findall(r"\b(PANO_[A-Z0-9_]+)\s*=\s*(\d+)", header))
+    consts.update(re.findall(r"#define\s+(PANO_[A-Z0-9_]+)\s+(\d+)", header))
+    assert len(consts) >= 20
+    for k, v in consts.items():
+        m = re.search(r"pub const %s: \w+ = (\d+);" % k, src)
+        assert m, f"{k} missing from the Rust bindings"
+        assert m.group(1) == v, k
