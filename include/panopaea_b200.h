@@ -118,7 +118,11 @@ PANO_API int pano_ctx_cg_profile(pano_ctx *ctx, int64_t cycles_out[8]);
 /* Same option, streaming kernel: cycles every CTA spent in its P1 tile loop ([0, G)) and P2 tile loop ([G, 2G)), G = CTAs. */
 PANO_API int pano_ctx_cg_profile_ctas(pano_ctx *ctx, int64_t *cycles_out, int n);
 /* tuning knobs: "cg_kernel" 0 auto / 1 generic / 2 TMA streaming / 3 SM-resident / 4 SM-resident v1 / 5 one cluster, "cg_ldcg" 0/1,
- * "cg_zigzag" 0/1, "cg_blocks_per_sm" n, "cg_profile" 0/1, "step_timing" 0/1 */
+ * "cg_zigzag" 0/1, "cg_blocks_per_sm" n, "cg_profile" 0/1, "step_timing" 0/1; streaming kernel: "cg_dynamic" -1 auto (from 24
+ * tiles per CTA) / 0 fixed tile lists / 1 claimed tiles, "cg_batch" n (claim unit, 0 auto), "cg_fence" bit 0 fence.acq_rel
+ * instead of fence.sc, bit 1 system scope only in CTAs that stored into a peer; multi-GPU: "cg_xflags" 1 halo flags (default) /
+ * 0 fenced root exchange, "cg_halo_first" 0/1; SM-resident kernel: "cg_push" 0 root all-reduce (default) / 1 per-CTA inboxes.
+ * A key that was not set with this call is looked up in the environment as PANO_OPT_<key> before its default applies. */
 PANO_API int pano_ctx_set_option(pano_ctx *ctx, const char *key, int64_t value);
 PANO_API int pano_ctx_get_option(pano_ctx *ctx, const char *key, int64_t *value);
 
