@@ -90,6 +90,15 @@ struct Tail {                     // small shared-memory area behind the stage r
 
 __device__ __forceinline__ void consumer_sync() { named_bar_sync(1, kConsumers); }
 
+// A ring-slot word written by the producer lane (dynamic scheduling): read by lane 0 and broadcast, so that the thread that
+// reads it is the thread that later hands the slot back with mbarrier.arrive on `empty` -- the write-after-read edge then
+// needs no cumulativity argument (and compute-sanitizer's racecheck can follow it).
+__device__ __forceinline__ int slot_word(const int *p) {
+    int v = 0;
+    if ((threadIdx.x & 31) == 0) v = *(const volatile int *)p;
+    return __shfl_sync(0xffffffffu, v, 0);
+}
+
 // deterministic block reduction among the 256 consumer threads; result in every consumer thread
 __device__ __forceinline__ double consumer_sum(double v, double *wsum) {
     v = warp_sum(v);
@@ -536,7 +545,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
             int t;
             if constexpr (kDyn) {
                 if (!mbar_wait(&tl->full[st], (n / kStages) & 1, err)) return;
-                t = *(volatile int *)&tl->tile[st];
+                t = slot_word(&tl->tile[st]);
                 if (t < 0) {                                    // end-of-phase marker: hand the slot back and leave
                     __syncwarp();
                     if ((tid & 31) == 0) mbar_arrive(&tl->empty[st]);
@@ -561,7 +570,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
                 if (fast) tile_p1<true, false>(a, S, R, s_cur, s_up, s_dn, ty0, tx0, beta, acc_zs, acc_bb, acc_bmax);
                 else tile_p1<false, false>(a, S, R, s_cur, s_up, s_dn, ty0, tx0, beta, acc_zs, acc_bb, acc_bmax);
             }
-            const int closes = kDyn ? *(volatile int *)&tl->batch[st] : -1;
+            const int closes = kDyn ? slot_word(&tl->batch[st]) : -1;
             if (kDyn && closes >= 0) {                          // this warp's partials of the batch that ends here, then afresh
                 const size_t plane = (size_t)a.nbatch * kConsumerWarps, u = (size_t)closes * kConsumerWarps + wid;
                 const double p0 = warp_sum(acc_zs);
@@ -632,7 +641,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
             int t;
             if constexpr (kDyn) {
                 if (!mbar_wait(&tl->full[st], (n / kStages) & 1, err)) return;
-                t = *(volatile int *)&tl->tile[st];
+                t = slot_word(&tl->tile[st]);
                 if (t < 0) {
                     __syncwarp();
                     if ((tid & 31) == 0) mbar_arrive(&tl->empty[st]);
@@ -657,7 +666,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
                 if (fast) tile_p2<true, false>(a, S, R, X, ty0, tx0, alpha, acc_rr, acc_rmax);
                 else tile_p2<false, false>(a, S, R, X, ty0, tx0, alpha, acc_rr, acc_rmax);
             }
-            const int closes = kDyn ? *(volatile int *)&tl->batch[st] : -1;
+            const int closes = kDyn ? slot_word(&tl->batch[st]) : -1;
             if (kDyn && closes >= 0) {
                 const size_t plane = (size_t)a.nbatch * kConsumerWarps, u = (size_t)closes * kConsumerWarps + wid;
                 const double p0 = warp_sum(acc_rr), p1 = warp_max(acc_rmax);
