@@ -105,6 +105,11 @@ PANO_API int pano_ctx_launch_count(pano_ctx *ctx, uint64_t *n);
 /* CUDA-event timing on the context's stream (the stream the kernels run on) */
 PANO_API int pano_timer_start(pano_ctx *ctx);
 PANO_API int pano_timer_stop_ms(pano_ctx *ctx, double *ms);   /* records, synchronises, returns elapsed */
+/* Lap timing without host synchronisation between laps: pano_timer_mark records one more event on
+ * the stream (up to 4096 between two reads); pano_timer_marks_ms synchronises, writes the elapsed
+ * milliseconds between consecutive marks (count - 1 values, at most `cap`) and forgets the marks. */
+PANO_API int pano_timer_mark(pano_ctx *ctx);
+PANO_API int pano_timer_marks_ms(pano_ctx *ctx, double *ms_out, int cap, int *count);
 /* Per-phase device time of pano_fluid_step, measured with CUDA events on the context's
  * stream while option "step_timing" is 1.  phases: 0 inflow fills, 1 advect_all,
  * 2 neg_divergence, 3 CG solve, 4 project.  Returns the accumulated milliseconds and the
@@ -231,8 +236,9 @@ PANO_API int pano_fluid_step(const pano_step_params *params, pano_field *density
 
 /* The same step for callers that keep the fields in HOST memory, as the Rust
  * crate does: uploads density and vel (flat views), runs pano_fluid_step,
- * downloads density, vel and pressure.  All scratch lives in a workspace the
- * context caches per (h, w).  Host buffers should come from pano_host_alloc. */
+ * downloads density, vel and -- unless `pressure` is NULL -- pressure (the example never reads it
+ * between steps, examples/dec_fluid.rs:143-164; the solve starts from zero, pcg.rs:32).  All scratch
+ * lives in a workspace the context caches per (h, w).  Host buffers should come from pano_host_alloc. */
 PANO_API int pano_fluid_step_host(pano_ctx *ctx, const pano_step_params *params, size_t h, size_t w,
                                   double *density, double *vel, double *pressure, pano_pcg_info *info);
 
@@ -265,6 +271,9 @@ PANO_API int pano_dist_set_max_ctas(pano_dist *d, int max_ctas);
 PANO_API int pano_dist_upload(pano_dist *d, int which, const double *host_rows);
 PANO_API int pano_dist_download(pano_dist *d, int which, double *host_rows, size_t *rows);
 PANO_API int pano_dist_step(pano_dist *d);
+/* The pressure solve alone (pcg.rs:14-82 on this rank's slab), again on the right-hand side of the
+ * last step: BASELINE configs[4], "pressure Poisson solve strong scaling".  Collective, asynchronous. */
+PANO_API int pano_dist_solve(pano_dist *d);
 PANO_API int pano_dist_sync(pano_dist *d, pano_pcg_info *info);
 
 #ifdef __cplusplus

@@ -56,6 +56,8 @@ _SIGS = {
     "pano_ctx_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "pano_timer_start": (C.c_int, [_P]),
     "pano_timer_stop_ms": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "pano_timer_mark": (C.c_int, [_P]),
+    "pano_timer_marks_ms": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]),
     "pano_ctx_step_times": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pano_ctx_cg_profile": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "pano_ctx_cg_profile_ctas": (C.c_int, [_P, C.POINTER(C.c_int64), C.c_int]),
@@ -114,6 +116,7 @@ _SIGS = {
     "pano_dist_upload": (C.c_int, [_P, C.c_int, _P]),
     "pano_dist_download": (C.c_int, [_P, C.c_int, _P, C.POINTER(C.c_size_t)]),
     "pano_dist_step": (C.c_int, [_P]),
+    "pano_dist_solve": (C.c_int, [_P]),
     "pano_dist_sync": (C.c_int, [_P, C.POINTER(PcgInfo)]),
 }
 IPC_HANDLE_BYTES = 64

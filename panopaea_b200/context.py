@@ -44,6 +44,16 @@ class Context:
         check(self._L.pano_timer_stop_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def timer_mark(self):
+        check(self._L.pano_timer_mark(self._h))
+
+    def timer_marks_ms(self):
+        """Elapsed ms between consecutive timer_mark() calls since the last read (synchronises)."""
+        buf = (C.c_double * 4096)()
+        n = C.c_int()
+        check(self._L.pano_timer_marks_ms(self._h, buf, 4096, C.byref(n)))
+        return [buf[i] for i in range(max(0, n.value - 1))]
+
     def set_option(self, key: str, value: int):
         check(self._L.pano_ctx_set_option(self._h, key.encode(), int(value)))
 

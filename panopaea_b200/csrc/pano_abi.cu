@@ -1,6 +1,8 @@
 // pano_abi.cu -- context, field handles, copies: the plumbing half of the C ABI
 // (include/panopaea_b200.h).  Compute entry points live in pano_prim.cu,
 // pano_fused.cu, pano_cg.cu and pano_step.cu.
+#include <cstddef>
+
 #include "pano_internal.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -10,6 +12,21 @@ void pano_set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+int pano_cg_control_reset(pano_ctx *ctx) {
+    static_assert(offsetof(PanoCgControl, error) == 0, "the sticky error word leads the control block");
+    const size_t skip = offsetof(PanoCgControl, barrier);
+    PANO_CUDA(cudaMemsetAsync(reinterpret_cast<char *>(ctx->d_cg) + skip, 0, sizeof(PanoCgControl) - skip, ctx->stream));
+    return PANO_OK;
+}
+
+// h_cg holds a fresh copy of (at least) the error word.  A raised flag is reported once and cleared, so the context stays usable.
+int pano_check_device_error(pano_ctx *ctx, const char *where) {
+    if (!ctx->h_cg->error) return PANO_OK;
+    ctx->h_cg->error = 0;
+    cudaMemsetAsync(&ctx->d_cg->error, 0, sizeof(unsigned int), ctx->stream);
+    PANO_FAIL(PANO_ERR_TIMEOUT, "%s: a bounded wait expired inside a persistent kernel (grid barrier / pipeline timeout)", where);
 }
 
 extern "C" {
@@ -29,6 +46,8 @@ int pano_device_count(int *count) {
     return PANO_OK;
 }
 
+static int ctx_init(pano_ctx *c, int device, const cudaDeviceProp &prop, void *stream);
+
 int pano_ctx_create(int device, void *stream, pano_ctx **out) {
     if (!out) PANO_FAIL(PANO_ERR_INVALID, "pano_ctx_create: null out pointer");
     *out = nullptr;
@@ -47,6 +66,16 @@ int pano_ctx_create(int device, void *stream, pano_ctx **out) {
         PANO_FAIL(PANO_ERR_CUDA, "pano_ctx_create: device %d is sm_%d%d; this build targets sm_100a only", device,
                   prop.major, prop.minor);
     pano_ctx *c = new pano_ctx();
+    const int rc = ctx_init(c, device, prop, stream);
+    if (rc != PANO_OK) {   // nothing half-built survives a failed create
+        pano_ctx_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return PANO_OK;
+}
+
+static int ctx_init(pano_ctx *c, int device, const cudaDeviceProp &prop, void *stream) {
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     c->cc_major = prop.major;
@@ -75,14 +104,13 @@ int pano_ctx_create(int device, void *stream, pano_ctx **out) {
     PANO_CUDA(cudaMemset(c->d_units, 0, 4096 * 16));
     PANO_CUDA(cudaMalloc(&c->d_inbox, kPanoInboxBytes));            // push exchange of the SM-resident CG kernel
     PANO_CUDA(cudaMemset(c->d_inbox, 0, kPanoInboxBytes));          // sequence 0 never matches
-    *out = c;
     return PANO_OK;
 }
 
 int pano_ctx_destroy(pano_ctx *ctx) {
     if (!ctx) return PANO_OK;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     pano_workspace_free_all(ctx);
     pano_mg_free_all(ctx);
     cudaFree(ctx->d_partials);
@@ -96,12 +124,11 @@ int pano_ctx_destroy(pano_ctx *ctx) {
     cudaFree(ctx->d_claim);
     cudaFreeHost(ctx->h_cg);
     for (cudaEvent_t e : ctx->phase_events) cudaEventDestroy(e);
-    cudaEventDestroy(ctx->ev_start);
-    cudaEventDestroy(ctx->ev_stop);
-    cudaEventDestroy(ctx->ev_advect);
-    cudaEventDestroy(ctx->ev_copy);
+    for (cudaEvent_t e : ctx->marks) cudaEventDestroy(e);
+    for (cudaEvent_t e : {ctx->ev_start, ctx->ev_stop, ctx->ev_advect, ctx->ev_copy})
+        if (e) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return PANO_OK;
 }
@@ -109,8 +136,10 @@ int pano_ctx_destroy(pano_ctx *ctx) {
 int pano_ctx_sync(pano_ctx *ctx) {
     if (!ctx) PANO_FAIL(PANO_ERR_INVALID, "pano_ctx_sync: null context");
     PANO_TRY(pano_activate(ctx));
+    // the sticky device error word rides along: an asynchronous step whose solver timed out is reported here
+    PANO_CUDA(cudaMemcpyAsync(&ctx->h_cg->error, &ctx->d_cg->error, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
     PANO_CUDA(cudaStreamSynchronize(ctx->stream));
-    return PANO_OK;
+    return pano_check_device_error(ctx, "pano_ctx_sync");
 }
 
 int pano_ctx_stream(pano_ctx *ctx, void **stream) {
@@ -146,6 +175,35 @@ int pano_timer_stop_ms(pano_ctx *ctx, double *ms) {
     float f = 0.f;
     PANO_CUDA(cudaEventElapsedTime(&f, ctx->ev_start, ctx->ev_stop));
     *ms = (double)f;
+    return PANO_OK;
+}
+
+int pano_timer_mark(pano_ctx *ctx) {
+    if (!ctx) PANO_FAIL(PANO_ERR_INVALID, "pano_timer_mark: null context");
+    PANO_TRY(pano_activate(ctx));
+    if (ctx->marks_used >= 4096) PANO_FAIL(PANO_ERR_INVALID, "pano_timer_mark: 4096 marks pending; read them with pano_timer_marks_ms");
+    if (ctx->marks_used == (int)ctx->marks.size()) {
+        cudaEvent_t e;
+        PANO_CUDA(cudaEventCreate(&e));
+        ctx->marks.push_back(e);
+    }
+    PANO_CUDA(cudaEventRecord(ctx->marks[ctx->marks_used++], ctx->stream));
+    return PANO_OK;
+}
+
+int pano_timer_marks_ms(pano_ctx *ctx, double *ms_out, int cap, int *count) {
+    if (!ctx || !ms_out || !count) PANO_FAIL(PANO_ERR_INVALID, "pano_timer_marks_ms: null argument");
+    PANO_TRY(pano_activate(ctx));
+    const int n = ctx->marks_used;
+    *count = n;
+    ctx->marks_used = 0;
+    if (n == 0) return PANO_OK;
+    PANO_CUDA(cudaEventSynchronize(ctx->marks[n - 1]));
+    for (int i = 0; i + 1 < n && i < cap; ++i) {
+        float f = 0.f;
+        PANO_CUDA(cudaEventElapsedTime(&f, ctx->marks[i], ctx->marks[i + 1]));
+        ms_out[i] = (double)f;
+    }
     return PANO_OK;
 }
 

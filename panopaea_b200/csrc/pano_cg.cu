@@ -63,7 +63,7 @@ __device__ __forceinline__ bool grid_barrier(PanoCgControl *ctl, unsigned long l
         while (ld_acquire_u64(&ctl->barrier) < target) {
             if (*(volatile unsigned int *)&ctl->error) { ok = 0; break; }
             if (++spins > kSpinLimit) {
-                atomicExch(&ctl->error, 1u);
+                atomicCAS(&ctl->error, 0u, 1u);
                 ok = 0;
                 break;
             }
@@ -285,7 +285,7 @@ int launch_generic(pano_ctx *ctx, CgArgs<T> &args, bool use_cg_loads) {
     if (G < 1) G = 1;
     PANO_TRY(pano_ensure_partials(ctx, 5 * (size_t)G));
     args.partials = ctx->d_partials;
-    PANO_CUDA(cudaMemsetAsync(ctx->d_cg, 0, sizeof(PanoCgControl), ctx->stream));
+    PANO_TRY(pano_cg_control_reset(ctx));
     void *kargs[] = {(void *)&args};
     PANO_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)G), dim3(kThreads), kargs, 0, ctx->stream));
     return pano_after_launch(ctx, "cg_generic");
@@ -317,14 +317,20 @@ int pano_cg_solve_raw(pano_ctx *ctx, int dtype, void *x, const void *b, void *r,
         return PANO_OK;
     }
     if (max_iterations <= 0) {
-        // pcg.rs:32-46 with an empty loop: x = 0; unless max|b| < threshold, r = s = b
+        // pcg.rs:32-46 with an empty loop: x = 0; then the early-out of :35-38 (scratch untouched) or r = s = b.
+        // Rare enough to afford a host round trip for max|b|.
         const size_t bytes = h * w * pano_dtype_size(dtype);
+        double bmax = 0.0;
+        PANO_TRY(pano_norm_max_raw(ctx, dtype, b, h * w, &bmax));
         PANO_CUDA(cudaMemsetAsync(x, 0, bytes, ctx->stream));
-        PANO_CUDA(cudaMemcpyAsync(r, b, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-        PANO_CUDA(cudaMemcpyAsync(s0, b, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        const bool early = bmax < threshold;
+        if (!early) {
+            PANO_CUDA(cudaMemcpyAsync(r, b, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+            PANO_CUDA(cudaMemcpyAsync(s0, b, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
         if (info) {
             PANO_CUDA(cudaStreamSynchronize(ctx->stream));
-            *info = pano_pcg_info{0, 0, 0.0, 0.0};
+            *info = pano_pcg_info{early ? -1 : 0, 0, bmax, bmax};
         }
         return PANO_OK;
     }
@@ -371,7 +377,7 @@ int pano_cg_solve_raw(pano_ctx *ctx, int dtype, void *x, const void *b, void *r,
     if (info) {
         PANO_CUDA(cudaMemcpyAsync(ctx->h_cg, ctx->d_cg, sizeof(PanoCgControl), cudaMemcpyDeviceToHost, ctx->stream));
         PANO_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (ctx->h_cg->error) PANO_FAIL(PANO_ERR_TIMEOUT, "pano_pcg_solve: a grid barrier timed out inside the CG kernel");
+        PANO_TRY(pano_check_device_error(ctx, "pano_pcg_solve"));
         info->iterations = ctx->h_cg->iterations;
         info->applies = ctx->h_cg->applies;
         info->final_residual = ctx->h_cg->final_residual;

@@ -269,7 +269,7 @@ int pano_cg_cluster_launch(pano_ctx *ctx, double *x, const double *b, double *r,
     ClArgs a{x, b, r, s0, (int)h, (int)w, timestep, threshold, max_iterations, m, ctx->d_cg};
     const size_t smem = cluster_smem(w);
     const int ka = (int)((((h + CL - 1) / CL) * w + CT - 1) / CT);       // cells per thread of the largest slab, 1..kK
-    PANO_CUDA(cudaMemsetAsync(ctx->d_cg, 0, sizeof(PanoCgControl), ctx->stream));
+    PANO_TRY(pano_cg_control_reset(ctx));
 #define PANO_CL_CASE(K)                                                                                              \
     case K:                                                                                                          \
         PANO_CUDA(cudaFuncSetAttribute(k_cg_cluster<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \

@@ -380,7 +380,7 @@ int pano_cg_resident_launch(pano_ctx *ctx, double *x, const double *b, double *r
     a.units = (ReduceUnit *)ctx->d_units;
     a.seq_base = (++ctx->launch_epoch) << 32;
     a.ctl = ctx->d_cg;
-    PANO_CUDA(cudaMemsetAsync(ctx->d_cg, 0, sizeof(PanoCgControl), ctx->stream));
+    PANO_TRY(pano_cg_control_reset(ctx));
     const size_t smem_bytes = ((size_t)(p.th + 2) * (p.tw + 2) + (size_t)p.th * p.tw) * sizeof(double) + sizeof(ResShared) + 16;
     switch (p.kr) {
         case 1: return launch_kr<1>(ctx, a, grid, smem_bytes);

@@ -417,7 +417,7 @@ int pano_cg_resident2_launch(pano_ctx *ctx, double *x, const double *b, double *
     a.seq_base = (++ctx->launch_epoch) << 32;
     a.ctl = ctx->d_cg;
     a.dbg = pano_option(ctx, "cg_profile", 0) ? ctx->d_cg->prof : nullptr;   // device address of the 8 slots
-    PANO_CUDA(cudaMemsetAsync(ctx->d_cg, 0, sizeof(PanoCgControl), ctx->stream));
+    PANO_TRY(pano_cg_control_reset(ctx));
 #define PANO_CFG(KR, TW, T) \
     if (c.kr == KR && c.tw == TW && c.t == T) return launch_cfg<KR, TW, T>(ctx, a, grid)
     PANO_CFG(8, 256, 512);

@@ -791,6 +791,8 @@ bool pano_cg_stream_supported(size_t h, size_t w, const void *x, const void *b, 
 
 int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, double *s0, double *s1, size_t h, size_t w,
                           int max_iterations, double threshold, double timestep, RectI m, const PanoCgSlab *slab) {
+    // the producer of a launch with no iterations would wait on `go` for an arrival that never comes
+    if (max_iterations <= 0) PANO_FAIL(PANO_ERR_INVALID, "pano_cg_stream_launch: max_iterations = %d (callers handle the empty loop on the host)", max_iterations);
     PANO_CUDA(cudaFuncSetAttribute(k_cg_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     PANO_CUDA(cudaFuncSetAttribute(k_cg_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     static_assert(sizeof(Tail) <= kTailBytes, "Tail does not fit");
@@ -853,7 +855,7 @@ int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, 
     const int ntiles = a.tiles_x * a.tiles_y;
     if (G > ntiles) G = ntiles;
     if (G > kMaxCtas) G = kMaxCtas;
-    PANO_CUDA(cudaMemsetAsync(ctx->d_cg, 0, sizeof(PanoCgControl), ctx->stream));
+    PANO_TRY(pano_cg_control_reset(ctx));
     // dynamic tile scheduling pays once a CTA has enough tiles for the imbalance to matter ("cg_dynamic": 0 off, 1 on, -1 auto)
     const int64_t dyn_opt = pano_option(ctx, "cg_dynamic", -1);
     // measured on B200 (Mcell-steps/s, static -> dynamic): 2048^2 (14 tiles per CTA) 787 -> 758; 8192^2 over 8 GPUs (28) 5488 ->

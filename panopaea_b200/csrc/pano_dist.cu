@@ -132,6 +132,7 @@ struct pano_dist {
     bool connected = false;
     int cur = 0;                      // which ping-pong buffer holds the current density / velocity
     unsigned long long step_no = 0;   // identical on all ranks
+    unsigned long long solve_no = 0;  // CG launches so far (steps and stand-alone solves), identical on all ranks
     unsigned int *d_counter = nullptr;
     int max_ctas = 0;
 };
@@ -205,6 +206,49 @@ int fill_owned(pano_dist *d, int f, pano_rect r, double value) {
     return pano_after_launch(d->ctx, "dist_fill");
 }
 
+
+// The persistent CG kernel on this rank's slab, right-hand side in array fB; x lands in F_P.
+int launch_cg(pano_dist *d, int fB) {
+    pano_ctx *ctx = d->ctx;
+    const Layout &L = d->L;
+    const pano_step_params &p = d->prm;
+    const size_t H = d->H, W = d->W;
+    const int ya = (int)L.y0;
+    ++d->solve_no;
+    {
+        PanoCgSlab s;
+        memset(&s, 0, sizeof(s));
+        s.row0 = kGhost;
+        s.rows_total = (int)L.rows[F_P];
+        s.gy0 = ya;
+        s.gh = (int)H;
+        s.rank = d->rank;
+        s.nranks = d->nranks;
+        s.xseq_base = d->solve_no << 32;
+        s.max_ctas = d->max_ctas;
+        if (d->rank > 0) {
+            const Layout Lup = make_layout(H, W, d->rank - 1, d->nranks);
+            s.up_r = peer_row(d, d->rank - 1, Lup, F_R, (ptrdiff_t)L.y0);     // global row y0 = first ghost row below its slab
+            s.up_s0 = peer_row(d, d->rank - 1, Lup, F_S0, (ptrdiff_t)L.y0);
+            s.up_s1 = peer_row(d, d->rank - 1, Lup, F_S1, (ptrdiff_t)L.y0);
+        }
+        if (d->rank + 1 < d->nranks) {
+            const Layout Ldn = make_layout(H, W, d->rank + 1, d->nranks);
+            s.dn_r = peer_row(d, d->rank + 1, Ldn, F_R, (ptrdiff_t)L.y1 - 1); // global row y1-1 = last ghost row above its slab
+            s.dn_s0 = peer_row(d, d->rank + 1, Ldn, F_S0, (ptrdiff_t)L.y1 - 1);
+            s.dn_s1 = peer_row(d, d->rank + 1, Ldn, F_S1, (ptrdiff_t)L.y1 - 1);
+        }
+        for (int r = 0; r < d->nranks; ++r) {
+            const Layout Lr = r == d->rank ? L : make_layout(H, W, r, d->nranks);
+            s.xunits_peer[r] = d->peer[r] + Lr.xunits;
+        }
+        s.xunits_local = d->window + L.xunits;
+        const RectI m = pano_clip_rect(p.obstacle, H + 1, W + 1);
+        PANO_TRY(pano_cg_stream_launch(ctx, d->window + L.off[F_P], d->window + L.off[fB], d->window + L.off[F_R], d->window + L.off[F_S0],
+                                       d->window + L.off[F_S1], L.hl, W, p.max_iterations, p.threshold, p.timestep, m, &s));
+    }
+    return PANO_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -221,6 +265,8 @@ int pano_dist_create(pano_ctx *ctx, size_t h, size_t w, int rank, int nranks, co
     if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks)
         PANO_FAIL(PANO_ERR_INVALID, "pano_dist_create: rank %d of %d (at most %d ranks)", rank, nranks, kMaxRanks);
     if (w % 2 != 0 || w < 2) PANO_FAIL(PANO_ERR_SHAPE, "pano_dist_create: the slab solver needs an even width (TMA rows are 16-byte aligned)");
+    if (params->max_iterations <= 0)
+        PANO_FAIL(PANO_ERR_INVALID, "pano_dist_create: max_iterations = %d; the slab solver runs at least one iteration", (int)params->max_iterations);
     if (params->precond != PANO_PRECOND_IDENTITY) PANO_FAIL(PANO_ERR_UNIMPLEMENTED, "pano_dist_create: only the identity preconditioner exists");
     PANO_TRY(pano_check_rect_within(params->inflow, h, w, "pano_dist_create(inflow)"));
     PANO_TRY(pano_check_rect_within(params->obstacle, h, w, "pano_dist_create(obstacle)"));
@@ -252,10 +298,16 @@ int pano_dist_create(pano_ctx *ctx, size_t h, size_t w, int rank, int nranks, co
         delete d;
         PANO_FAIL(PANO_ERR_CUDA, "pano_dist_create: cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e));
     }
-    PANO_CUDA(cudaMemsetAsync(d->window, 0, d->L.total * sizeof(double), ctx->stream));
-    PANO_CUDA(cudaMalloc(&d->d_counter, sizeof(unsigned int)));
-    PANO_CUDA(cudaMemsetAsync(d->d_counter, 0, sizeof(unsigned int), ctx->stream));
-    PANO_CUDA(cudaStreamSynchronize(ctx->stream));
+    e = cudaMemsetAsync(d->window, 0, d->L.total * sizeof(double), ctx->stream);
+    if (e == cudaSuccess) e = cudaMalloc(&d->d_counter, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d->d_counter, 0, sizeof(unsigned int), ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {   // nothing half-built survives a failed create
+        cudaFree(d->window);
+        cudaFree(d->d_counter);
+        delete d;
+        PANO_FAIL(PANO_ERR_CUDA, "pano_dist_create: %s", cudaGetErrorString(e));
+    }
     d->peer[rank] = d->window;
     d->connected = nranks == 1;
     *out = d;
@@ -418,38 +470,7 @@ int pano_dist_step(pano_dist *d) {
     mark("ex_b");
     PANO_TRY(pano_phase_mark(ctx, 3));
     // pressure solve  (:91-119): streaming CG on the slab, halo rows and reductions over NVLink from inside the kernel
-    {
-        PanoCgSlab s;
-        memset(&s, 0, sizeof(s));
-        s.row0 = kGhost;
-        s.rows_total = (int)L.rows[F_P];
-        s.gy0 = ya;
-        s.gh = (int)H;
-        s.rank = d->rank;
-        s.nranks = d->nranks;
-        s.xseq_base = d->step_no << 32;
-        s.max_ctas = d->max_ctas;
-        if (d->rank > 0) {
-            const Layout Lup = make_layout(H, W, d->rank - 1, d->nranks);
-            s.up_r = peer_row(d, d->rank - 1, Lup, F_R, (ptrdiff_t)L.y0);     // global row y0 = first ghost row below its slab
-            s.up_s0 = peer_row(d, d->rank - 1, Lup, F_S0, (ptrdiff_t)L.y0);
-            s.up_s1 = peer_row(d, d->rank - 1, Lup, F_S1, (ptrdiff_t)L.y0);
-        }
-        if (d->rank + 1 < d->nranks) {
-            const Layout Ldn = make_layout(H, W, d->rank + 1, d->nranks);
-            s.dn_r = peer_row(d, d->rank + 1, Ldn, F_R, (ptrdiff_t)L.y1 - 1); // global row y1-1 = last ghost row above its slab
-            s.dn_s0 = peer_row(d, d->rank + 1, Ldn, F_S0, (ptrdiff_t)L.y1 - 1);
-            s.dn_s1 = peer_row(d, d->rank + 1, Ldn, F_S1, (ptrdiff_t)L.y1 - 1);
-        }
-        for (int r = 0; r < d->nranks; ++r) {
-            const Layout Lr = r == d->rank ? L : make_layout(H, W, r, d->nranks);
-            s.xunits_peer[r] = d->peer[r] + Lr.xunits;
-        }
-        s.xunits_local = d->window + L.xunits;
-        const RectI m = pano_clip_rect(p.obstacle, H + 1, W + 1);
-        PANO_TRY(pano_cg_stream_launch(ctx, d->window + L.off[F_P], d->window + L.off[fB], d->window + L.off[F_R], d->window + L.off[F_S0],
-                                       d->window + L.off[F_S1], L.hl, W, p.max_iterations, p.threshold, p.timestep, m, &s));
-    }
+    PANO_TRY(launch_cg(d, fB));
     mark("cg");
     PANO_TRY(pano_phase_mark(ctx, 4));
     // p[y0 - 1] lives on the upper neighbour
@@ -465,6 +486,15 @@ int pano_dist_step(pano_dist *d) {
     return PANO_OK;
 }
 
+// The solve alone, again on the right-hand side of the last step (it still sits in the old density buffer).
+int pano_dist_solve(pano_dist *d) {
+    if (!d) PANO_FAIL(PANO_ERR_INVALID, "pano_dist_solve: null handle");
+    if (!d->connected) PANO_FAIL(PANO_ERR_COMM, "pano_dist_solve: call pano_dist_connect first");
+    if (d->step_no == 0) PANO_FAIL(PANO_ERR_INVALID, "pano_dist_solve: no step has produced a right-hand side yet");
+    PANO_TRY(pano_activate(d->ctx));
+    return launch_cg(d, (d->cur ^ 1) ? F_D1 : F_D0);
+}
+
 // wait for the enqueued steps; info (nullable) describes the last solve
 int pano_dist_sync(pano_dist *d, pano_pcg_info *info) {
     if (!d) PANO_FAIL(PANO_ERR_INVALID, "pano_dist_sync: null handle");
@@ -474,7 +504,13 @@ int pano_dist_sync(pano_dist *d, pano_pcg_info *info) {
     PANO_CUDA(cudaMemcpyAsync(ctx->h_scalars, d->window + d->L.err, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     PANO_CUDA(cudaStreamSynchronize(ctx->stream));
     const unsigned int derr = *reinterpret_cast<unsigned int *>(ctx->h_scalars);
-    if (ctx->h_cg->error || derr == 1u) PANO_FAIL(PANO_ERR_TIMEOUT, "pano_dist: a bounded device-side wait expired (rank %d)", d->rank);
+    if (derr != 0u) cudaMemsetAsync(d->window + d->L.err, 0, sizeof(unsigned int), ctx->stream);   // reported once; the handle stays usable
+    if (derr == 1u) {
+        ctx->h_cg->error = 0;
+        cudaMemsetAsync(&ctx->d_cg->error, 0, sizeof(unsigned int), ctx->stream);
+        PANO_FAIL(PANO_ERR_TIMEOUT, "pano_dist: a bounded device-side wait expired (rank %d)", d->rank);
+    }
+    PANO_TRY(pano_check_device_error(ctx, "pano_dist_sync"));
     if (derr == 2u)
         PANO_FAIL(PANO_ERR_SHAPE, "pano_dist: an advection backtrace left the %d ghost rows (rank %d): dt*max|v| is too large for the slab", kGhost, d->rank);
     if (info) {

@@ -431,6 +431,10 @@ int pano_advect_launch(pano_ctx *ctx, int dtype, void *q_dst, void *vel_dst, con
         if (dtype == PANO_F64 && pano_option(ctx, "advect_kernel", 0) != 2) {
             const int pf = (int)pano_option(ctx, "advect_prefetch", 1), mb = (int)pano_option(ctx, "advect_minblocks", 4);
             const int rows = (int)pano_option(ctx, "advect_rows", 4);
+            if (rows != 2 && rows != 4 && rows != 8)   // the launch grid is sized from it; only these are instantiated
+                PANO_FAIL(PANO_ERR_INVALID, "option advect_rows = %d: the marching kernel exists for 2, 4 and 8 rows per thread", rows);
+            if (pf < 0 || pf > 3 || mb < 3 || mb > 5)
+                PANO_FAIL(PANO_ERR_INVALID, "option advect_prefetch = %d (0..3) / advect_minblocks = %d (3..5) out of range", pf, mb);
             const int ahead = ctx->num_sms * (int)pano_option(ctx, "advect_ahead", mb);
             dim3 g3((unsigned)((w + 1 + 31) / 32), (unsigned)((h + 1 + 8 * rows - 1) / (8 * rows)));
 #define PANO_ADV3(R, PF, MB)                                                                                                       \

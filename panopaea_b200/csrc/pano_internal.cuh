@@ -42,8 +42,12 @@ void pano_set_error(const char *fmt, ...);
 // ---------------------------------------------------------------------------------- handles
 // Device-side control block of the persistent CG kernel (one per context).
 struct PanoCgControl {
+    // != 0: a bounded wait expired; everybody leaves.  STICKY: launches clear only what follows this word
+    // (pano_cg_control_reset), so that a failure inside an asynchronous step is still there when the host next
+    // synchronises (pano_check_device_error); kernels launched meanwhile see it at their first wait and leave at once.
+    unsigned int error;
+    unsigned int pad_;
     unsigned long long barrier;   // monotonically increasing arrival counter
-    unsigned int error;           // != 0: a bounded wait expired; everybody leaves
     int iterations;               // as pano_pcg_info
     int applies;
     double final_residual;
@@ -65,6 +69,8 @@ struct pano_ctx {
     size_t smem_optin = 0;
     uint64_t launches = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    std::vector<cudaEvent_t> marks;              // pano_timer_mark laps
+    int marks_used = 0;
     cudaStream_t copy_stream = nullptr;          // second stream of pano_fluid_step_host (downloads under the solve)
     cudaEvent_t ev_advect = nullptr, ev_copy = nullptr;
     // reductions: block partials (device) + final scalars (device, pinned host mirror)
@@ -139,6 +145,9 @@ void pano_workspace_free_all(pano_ctx *ctx);
 void pano_mg_free_all(pano_ctx *ctx);
 int pano_pcg_precond_raw(pano_ctx *ctx, int precond, pano_field *x, const pano_field *b, int max_iterations, double threshold,
                          pano_field *residual, pano_field *auxiliary, pano_field *search, double dt, pano_rect ob, pano_pcg_info *info);
+int pano_norm_max_raw(pano_ctx *ctx, int dtype, const void *a, size_t n, double *out);   // max|a[k]| (synchronises)
+int pano_cg_control_reset(pano_ctx *ctx);          // before a CG launch: clear the control block, keep the sticky error word
+int pano_check_device_error(pano_ctx *ctx, const char *where);   // after a stream sync that copied d_cg into h_cg
 int pano_phase_mark(pano_ctx *ctx, int phase);     // record event #phase of the current step (no-op unless step_timing)
 int pano_phase_drain(pano_ctx *ctx);               // synchronise and fold recorded events into phase_ms
 

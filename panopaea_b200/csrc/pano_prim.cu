@@ -193,6 +193,20 @@ int reduce_to_host(pano_ctx *ctx, int dtype, int nblocks, bool is_max, double *o
 
 }  // namespace
 
+// max|a[k]| of a flat device array (synchronises); shared with the solver's empty-loop path (pano_cg.cu)
+int pano_norm_max_raw(pano_ctx *ctx, int dtype, const void *a, size_t n, double *out) {
+    if (n == 0) {
+        *out = 0.0;
+        return PANO_OK;
+    }
+    const int g = flat_grid(ctx, n);
+    PANO_TRY(pano_ensure_partials(ctx, (size_t)g));
+    if (dtype == PANO_F64) k_absmax_partial<double><<<g, kThreads, 0, ctx->stream>>>((const double *)a, n, ctx->d_partials);
+    else k_absmax_partial<float><<<g, kThreads, 0, ctx->stream>>>((const float *)a, n, ctx->d_partials);
+    PANO_TRY(pano_after_launch(ctx, "pano_field_norm_max"));
+    return reduce_to_host(ctx, dtype, g, true, out);
+}
+
 extern "C" {
 
 int pano_field_fill(pano_field *f, double value) {
@@ -316,18 +330,8 @@ int pano_field_dot(const pano_field *a, const pano_field *b, double *out) {
 int pano_field_norm_max(const pano_field *a, double *out) {
     PANO_TRY(pano_check_field(a, "pano_field_norm_max"));
     if (!out) PANO_FAIL(PANO_ERR_INVALID, "pano_field_norm_max: null out pointer");
-    pano_ctx *ctx = a->ctx;
-    PANO_TRY(pano_activate(ctx));
-    if (a->n == 0) {
-        *out = 0.0;
-        return PANO_OK;
-    }
-    const int g = flat_grid(ctx, a->n);
-    PANO_TRY(pano_ensure_partials(ctx, (size_t)g));
-    if (a->dtype == PANO_F64) k_absmax_partial<double><<<g, kThreads, 0, ctx->stream>>>((const double *)a->d, a->n, ctx->d_partials);
-    else k_absmax_partial<float><<<g, kThreads, 0, ctx->stream>>>((const float *)a->d, a->n, ctx->d_partials);
-    PANO_TRY(pano_after_launch(ctx, "pano_field_norm_max"));
-    return reduce_to_host(ctx, a->dtype, g, true, out);
+    PANO_TRY(pano_activate(a->ctx));
+    return pano_norm_max_raw(a->ctx, a->dtype, a->d, a->n, out);
 }
 
 // ------------------------------------------------------------------ Hodge stars

@@ -41,7 +41,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, volati
     long long spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > kSpinLimit || ((spins & 0x3ff) == 0 && *err)) {
-            atomicExch((unsigned int *)err, 1u);
+            atomicCAS((unsigned int *)err, 0u, 1u);   // keep the first error code (View2W raises 2)
             return false;
         }
     }
@@ -92,7 +92,7 @@ __device__ __forceinline__ bool unit_poll(const ReduceUnit *u, unsigned long lon
         unit_load(u, v, got);
         if (got == seq) return true;
         if (++spins > kSpinLimit || ((spins & 0x3ff) == 0 && *err)) {
-            atomicExch((unsigned int *)err, 1u);
+            atomicCAS((unsigned int *)err, 0u, 1u);   // keep the first error code (View2W raises 2)
             return false;
         }
     }
@@ -107,7 +107,7 @@ __device__ __forceinline__ bool unit_poll_acquire_sys(const ReduceUnit *u, unsig
         asm volatile("ld.acquire.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(bits), "=l"(got) : "l"(u) : "memory");
         if (got == seq) return true;
         if (++spins > kSpinLimit || ((spins & 0x3ff) == 0 && *err)) {
-            atomicExch((unsigned int *)err, 1u);
+            atomicCAS((unsigned int *)err, 0u, 1u);   // keep the first error code (View2W raises 2)
             return false;
         }
     }
@@ -148,14 +148,20 @@ static_assert(kInboxUnits * 16 == kPanoInboxBytes, "inbox size (pano_internal.cu
 // polls its own array until all ranks have written, and combines them in a fixed lane = rank order, so
 // every GPU obtains the bit-identical value.  One NVLink store latency per reduction, no NCCL call.
 constexpr int kMaxRanks = 8;
-constexpr int kXUnitsTotal = 2 * kMaxRanks * 3;   // [2 banks][rank][value]
+// Four banks over (launch & 1, exchange & 1): between two solver launches the ranks are ordered only by nearest-neighbour
+// halo exchanges, so a fast rank may store its total of (step+1, n=0) while a rank several hops away has not yet read the
+// value of (step, n=0) -- the launch bit keeps those two apart (seq_base carries the launch number in its high word).
+constexpr int kXBanks = 4;
+constexpr int kXUnitsTotal = kXBanks * kMaxRanks * 3;   // [bank][rank][value]
 // "Halo flags" (XRank::hflags, option cg_xflags): the cross-GPU exchange above needs a system-scope fence on either side
 // of it in the root CTA, because the root vouches for the halo rows OTHER CTAs stored into the neighbours' memory
 // (fence cumulativity) -- measured 2 x 3.1 us per reduction (scripts/probe/xgpu_probe.cu).  With halo flags every CTA
 // vouches for itself: after its own system-scope fence it stores a {0, sequence} unit into a per-CTA slot in each
 // neighbour's memory, and the neighbour's root polls those slots with ld.acquire.sys.  The roots then exchange the GPU
-// totals with plain volatile stores and polls, no fence around them.  [2 banks][from up / from down][CTA] units.
-constexpr int kXFlagUnits = 2 * 2 * kMaxCtas;
+// totals with plain volatile stores and polls, no fence around them.  [bank][from up / from down][CTA] units.
+constexpr int kXFlagUnits = kXBanks * 2 * kMaxCtas;
+struct XRank;
+__device__ __forceinline__ int xbank_of(const XRank *xr, unsigned long long n);
 struct XRank {
     int rank, nranks;
     unsigned long long seq_base;      // identical on all ranks (incremented once per collective launch)
@@ -165,6 +171,10 @@ struct XRank {
     ReduceUnit *hflags_up, *hflags_dn;   // the neighbours' arrays as mapped here, or null at the domain walls
     int g_up, g_dn;                   // CTAs of the upper / lower neighbour's kernel (flags to wait for), 0 at the walls
 };
+
+__device__ __forceinline__ int xbank_of(const XRank *xr, unsigned long long n) {
+    return (int)(n & 1) + 2 * (int)((xr->seq_base >> 32) & 1);
+}
 
 // Fences of the `fenced` exchange.  Every use is a release (before publishing a unit) or an acquire (after polling
 // one) around relaxed volatile accesses, for which PTX's fence.acq_rel is sufficient; __threadfence*() emit the
@@ -184,9 +194,9 @@ constexpr int kFenceRootGpuOnly = 4;  // DIAGNOSTIC (formally a race): the root'
 // One thread, after a fence that covers the CTA's stores into the neighbours' memory: this CTA's halo flags of exchange n.
 __device__ __forceinline__ void send_halo_flags(const XRank *xr, unsigned long long n) {
     const unsigned long long xseq = xr->seq_base + n;
-    const int parity = (int)(n & 1);
-    if (xr->hflags_up) unit_store(xr->hflags_up + (parity * 2 + 1) * kMaxCtas + blockIdx.x, 0.0, xseq);
-    if (xr->hflags_dn) unit_store(xr->hflags_dn + (parity * 2 + 0) * kMaxCtas + blockIdx.x, 0.0, xseq);
+    const int xb = xbank_of(xr, n);
+    if (xr->hflags_up) unit_store(xr->hflags_up + (xb * 2 + 1) * kMaxCtas + blockIdx.x, 0.0, xseq);
+    if (xr->hflags_dn) unit_store(xr->hflags_dn + (xb * 2 + 0) * kMaxCtas + blockIdx.x, 0.0, xseq);
 }
 
 struct NoWork {
@@ -275,12 +285,13 @@ __device__ __forceinline__ bool grid_allreduce_units(ReduceUnit *units, unsigned
             double r = is_max ? warp_fixed_max(vals[wid], G, lane) : warp_fixed_sum(vals[wid], G, lane);
             if (multi) {   // cross-rank stage (root CTA only, one warp per value)
                 const unsigned long long xseq = xr->seq_base + n;
-                const int slot = ((int)parity * kMaxRanks + xr->rank) * 3 + wid;
+                const int xb = xbank_of(xr, n);
+                const int slot = (xb * kMaxRanks + xr->rank) * 3 + wid;
                 const bool root_sys = !(fmode & kFenceRootGpuOnly), fence_here = fenced && xr->hflags == nullptr;
                 if (fence_here) { if (root_sys) fence_sys(light); else fence_gpu(light); }
                 if (lane < xr->nranks) unit_store(xr->peer[lane] + slot, r, xseq);
                 double v = 0.0;
-                if (lane < xr->nranks && !unit_poll(xr->local + ((int)parity * kMaxRanks + lane) * 3 + wid, xseq, v, err)) *ok_sh = 0;
+                if (lane < xr->nranks && !unit_poll(xr->local + (xb * kMaxRanks + lane) * 3 + wid, xseq, v, err)) *ok_sh = 0;
                 if (fence_here) { if (root_sys) fence_sys(light); else fence_gpu(light); }
                 r = is_max ? warp_max(v) : warp_sum(v);   // fixed butterfly over lane = rank: same bits on every GPU
             }
@@ -291,7 +302,8 @@ __device__ __forceinline__ bool grid_allreduce_units(ReduceUnit *units, unsigned
         } else if (multi && xr->hflags && wid < nvals + 4) {
             // four more warps: the halo flags of both neighbours' CTAs (acquire: their rows are visible to this GPU now)
             const unsigned long long xseq = xr->seq_base + n;
-            const ReduceUnit *from_up = xr->hflags + ((int)parity * 2 + 0) * kMaxCtas, *from_dn = xr->hflags + ((int)parity * 2 + 1) * kMaxCtas;
+            const int xb = xbank_of(xr, n);
+            const ReduceUnit *from_up = xr->hflags + (xb * 2 + 0) * kMaxCtas, *from_dn = xr->hflags + (xb * 2 + 1) * kMaxCtas;
             for (int t = tid - 32 * nvals; t < xr->g_up + xr->g_dn; t += 128)
                 if (!unit_poll_acquire_sys(t < xr->g_up ? from_up + t : from_dn + (t - xr->g_up), xseq, err)) *ok_sh = 0;
         }

@@ -45,15 +45,20 @@ static int get_workspace(pano_ctx *ctx, size_t h, size_t w, PanoWorkspace **out)
     PanoWorkspace *ws = new PanoWorkspace();
     ws->h = h;
     ws->w = w;
-    ctx->workspaces[key] = ws;   // owned by the context from here on, even if an allocation below fails
-    PANO_TRY(pano_field_new(ctx, PANO_SIMPLEX2, PANO_F64, h, w, &ws->density));
-    PANO_TRY(pano_field_new(ctx, PANO_SIMPLEX1, PANO_F64, h, w, &ws->vel));
-    PANO_TRY(pano_field_new(ctx, PANO_SIMPLEX2, PANO_F64, h, w, &ws->pressure));
-    PANO_TRY(pano_field_new(ctx, PANO_SIMPLEX2, PANO_F64, h, w, &ws->temp));
-    PANO_TRY(pano_field_new(ctx, PANO_SIMPLEX1, PANO_F64, h, w, &ws->vel_temp));
-    PANO_TRY(pano_field_new(ctx, PANO_SIMPLEX2, PANO_F64, h, w, &ws->residual));
-    PANO_TRY(pano_field_new(ctx, PANO_SIMPLEX2, PANO_F64, h, w, &ws->auxiliary));
-    PANO_TRY(pano_field_new(ctx, PANO_SIMPLEX2, PANO_F64, h, w, &ws->search));
+    // the workspace enters the cache only when all eight fields exist: a half-built entry would be found by the next
+    // call and dereferenced (the header promises that nothing aborts across the FFI boundary)
+    struct { pano_field **f; int kind; } want[] = {
+        {&ws->density, PANO_SIMPLEX2}, {&ws->vel, PANO_SIMPLEX1}, {&ws->pressure, PANO_SIMPLEX2}, {&ws->temp, PANO_SIMPLEX2},
+        {&ws->vel_temp, PANO_SIMPLEX1}, {&ws->residual, PANO_SIMPLEX2}, {&ws->auxiliary, PANO_SIMPLEX2}, {&ws->search, PANO_SIMPLEX2}};
+    for (auto &wf : want) {
+        const int rc = pano_field_new(ctx, wf.kind, PANO_F64, h, w, wf.f);
+        if (rc != PANO_OK) {
+            for (auto &g : want) pano_field_free(*g.f);   // null-safe
+            delete ws;
+            return rc;
+        }
+    }
+    ctx->workspaces[key] = ws;
     *out = ws;
     return PANO_OK;
 }
@@ -127,7 +132,7 @@ static int fluid_step_impl(const pano_step_params *params, pano_field *density, 
     if (info) {
         PANO_CUDA(cudaMemcpyAsync(ctx->h_cg, ctx->d_cg, sizeof(PanoCgControl), cudaMemcpyDeviceToHost, ctx->stream));
         PANO_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (ctx->h_cg->error) PANO_FAIL(PANO_ERR_TIMEOUT, "pano_fluid_step: a grid barrier timed out inside the CG kernel");
+        PANO_TRY(pano_check_device_error(ctx, "pano_fluid_step"));
         info->iterations = ctx->h_cg->iterations;
         info->applies = ctx->h_cg->applies;
         info->final_residual = ctx->h_cg->final_residual;
@@ -161,7 +166,7 @@ static int start_density_download(pano_ctx *ctx, void *user) {
 
 int pano_fluid_step_host(pano_ctx *ctx, const pano_step_params *params, size_t h, size_t w, double *density, double *vel,
                          double *pressure, pano_pcg_info *info) {
-    if (!ctx || !params || !density || !vel || !pressure) PANO_FAIL(PANO_ERR_INVALID, "pano_fluid_step_host: null argument");
+    if (!ctx || !params || !density || !vel) PANO_FAIL(PANO_ERR_INVALID, "pano_fluid_step_host: null argument");
     PANO_TRY(pano_activate(ctx));
     PanoWorkspace *ws = nullptr;
     PANO_TRY(get_workspace(ctx, h, w, &ws));
@@ -175,7 +180,7 @@ int pano_fluid_step_host(pano_ctx *ctx, const pano_step_params *params, size_t h
                              ws->search, host_loop ? &hinfo : nullptr, start_density_download, &hook));   // density goes home under the solve
     PANO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
     PANO_CUDA(cudaMemcpyAsync(vel, ws->vel->d, n1, cudaMemcpyDeviceToHost, ctx->stream));
-    PANO_CUDA(cudaMemcpyAsync(pressure, ws->pressure->d, n2, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pressure) PANO_CUDA(cudaMemcpyAsync(pressure, ws->pressure->d, n2, cudaMemcpyDeviceToHost, ctx->stream));
     if (host_loop) {
         PANO_CUDA(cudaStreamSynchronize(ctx->stream));
         if (info) *info = hinfo;
@@ -183,7 +188,7 @@ int pano_fluid_step_host(pano_ctx *ctx, const pano_step_params *params, size_t h
     }
     PANO_CUDA(cudaMemcpyAsync(ctx->h_cg, ctx->d_cg, sizeof(PanoCgControl), cudaMemcpyDeviceToHost, ctx->stream));
     PANO_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (ctx->h_cg->error) PANO_FAIL(PANO_ERR_TIMEOUT, "pano_fluid_step_host: a grid barrier timed out inside the CG kernel");
+    PANO_TRY(pano_check_device_error(ctx, "pano_fluid_step_host"));
     if (info) {
         info->iterations = ctx->h_cg->iterations;
         info->applies = ctx->h_cg->applies;

@@ -83,6 +83,10 @@ class DistFluid:
     def step(self):
         check(self._L.pano_dist_step(self._h))
 
+    def solve(self):
+        """The pressure solve alone, on the right-hand side of the last step (collective, asynchronous)."""
+        check(self._L.pano_dist_solve(self._h))
+
     def sync(self):
         info = PcgInfo()
         check(self._L.pano_dist_sync(self._h, C.byref(info)))

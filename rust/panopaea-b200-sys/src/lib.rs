@@ -94,6 +94,8 @@ extern "C" {
     pub fn pano_ctx_launch_count(ctx: *mut pano_ctx, n: *mut u64) -> c_int;
     pub fn pano_timer_start(ctx: *mut pano_ctx) -> c_int;
     pub fn pano_timer_stop_ms(ctx: *mut pano_ctx, ms: *mut f64) -> c_int;
+    pub fn pano_timer_mark(ctx: *mut pano_ctx) -> c_int;
+    pub fn pano_timer_marks_ms(ctx: *mut pano_ctx, ms_out: *mut f64, cap: c_int, count: *mut c_int) -> c_int;
     pub fn pano_ctx_step_times(ctx: *mut pano_ctx, ms_out: *mut f64, steps: *mut i64) -> c_int;
     pub fn pano_ctx_cg_profile(ctx: *mut pano_ctx, cycles_out: *mut i64) -> c_int;
     pub fn pano_ctx_cg_profile_ctas(ctx: *mut pano_ctx, cycles_out: *mut i64, n: c_int) -> c_int;
@@ -174,6 +176,7 @@ extern "C" {
     pub fn pano_dist_upload(d: *mut pano_dist, which: c_int, host_rows: *const f64) -> c_int;
     pub fn pano_dist_download(d: *mut pano_dist, which: c_int, host_rows: *mut f64, rows: *mut usize) -> c_int;
     pub fn pano_dist_step(d: *mut pano_dist) -> c_int;
+    pub fn pano_dist_solve(d: *mut pano_dist) -> c_int;
     pub fn pano_dist_sync(d: *mut pano_dist, info: *mut pano_pcg_info) -> c_int;
 }
 

@@ -271,6 +271,34 @@ def test_large_grid_capped_solve(oracle, variant):
     assert np.allclose(r, true_r, rtol=0, atol=1e-9 * np.abs(b).max())
 
 
+def test_4096_capped_solve_auto_kernel(oracle):
+    """4096^2 (BASELINE configs[3]) with the kernel choice left on auto: that is k_cg_stream<true>, the dynamically
+    scheduled streaming kernel every grid from 4096^2 up and every 8-GPU slab runs on.  Full iterate against the
+    all-parallel oracle after the reference's cap of 100 iterations (pcg.rs:48)."""
+    from tests import gpu_util as U
+    n = 4096
+    grid = U.grid(n, n)
+    k = n // 128
+    obstacle = (70 * k, 80 * k, 50 * k, 70 * k)
+    rng = np.random.default_rng(11)
+    oracle.set_threading(oracle.ALL_PARALLEL)
+    try:
+        b = oracle.laplacian_closure(n, n, rng.normal(size=(n, n)) * 40.0, 0.05, obstacle)
+        want = oracle.pcg_grid_laplacian(n, n, b, 100, 0.1, 0.05, obstacle)
+        _set_variant("auto")
+        info, x, r, s = _solve(grid, b, 100, 0.1, 0.05, obstacle)
+        assert abs(info["iterations"] - want.iterations) <= 2
+        if info["iterations"] == want.iterations:
+            assert np.abs(x - want.x).max() <= 1e-5 * np.abs(want.x).max()
+            assert np.abs(r - want.residual).max() <= 1e-5 * np.abs(b).max()
+            assert np.abs(s - want.search).max() <= 1e-5 * np.abs(want.search).max()
+            assert info["final_residual"] == pytest.approx(want.final_residual, rel=1e-5)
+        true_r = b - oracle.laplacian_closure(n, n, x, 0.05, obstacle)
+        assert np.abs(r - true_r).max() <= 1e-9 * np.abs(b).max()
+    finally:
+        oracle.set_threading(oracle.SERIAL)
+
+
 @pytest.mark.parametrize("n", [8192, 16384])
 def test_full_size_streamed_solve_properties(n):
     """BASELINE configs[2] / configs[4] sizes (8192^2, 16384^2): far beyond what the CPU oracle finishes in seconds, so

@@ -74,6 +74,49 @@ def test_step_resynchronised(oracle, n):
         oracle.set_threading(oracle.SERIAL)
 
 
+@pytest.mark.parametrize("n,steps", [(4096, 2), (8192, 1)])
+def test_step_full_size_vs_oracle(oracle, n, steps):
+    """BASELINE configs[3] (4096^2) and configs[2] (8192^2) against the all-parallel oracle on identical inputs: the whole
+    step (examples/dec_fluid.rs:46-141) through the kernels these sizes really run (marching / TMA advection, streaming CG
+    with dynamic tile scheduling).  The state is a developed plume: the oracle first runs the 1024^2 plume for a few steps,
+    which is then upsampled by pixel replication -- no zero fields, backtraces of more than a cell."""
+    from tests import gpu_util as U
+    from panopaea_b200 import fluid
+    oracle.set_threading(oracle.ALL_PARALLEL)
+    try:
+        small = oracle.FluidState(**oracle.smoke_params(1024))
+        for _ in range(3):
+            small.step()
+        f = n // 1024
+        d0 = np.kron(small.field("density"), np.ones((f, f)))
+        vy0, vx0 = oracle.split(small.field("vel"), 1024, 1024)
+        vy = np.zeros((n + 1, n))
+        vy[:n] = np.kron(vy0[:1024], np.ones((f, f)))
+        vx = np.zeros((n, n + 1))
+        vx[:, :n] = np.kron(vx0[:, :1024], np.ones((f, f)))
+        small.close()
+        ref = oracle.FluidState(**oracle.smoke_params(n))
+        ref.field("density")[...] = d0
+        ref.field("vel")[...] = oracle.join(vy, vx)
+        del d0, vy, vx
+        sim = fluid.DecFluid(**fluid.smoke_params(n), ctx=U.ctx())
+        for i in range(steps):
+            sim.density.upload(ref.field("density"))
+            sim.vel.upload(ref.field("vel"))
+            g, o = sim.step(), ref.step(want_rhs=True)
+            assert abs(g["iterations"] - o["iterations"]) <= 2, (i, g, o)
+            assert g["rhs_max"] == np.abs(o["rhs"]).max()                     # -div is bit-exact
+            d, gvy, gvx, p = _fields(sim)
+            ovy, ovx = oracle.split(ref.field("vel"), n, n)
+            assert np.array_equal(d, ref.field("density"))                     # advection is bit-exact
+            if g["iterations"] == o["iterations"]:
+                assert _close(p, ref.field("pressure"), 1e-5), i
+                assert _close(gvy, ovy, 1e-5) and _close(gvx, ovx, 1e-5), i
+                assert g["final_residual"] == pytest.approx(o["final_residual"], rel=1e-5)
+    finally:
+        oracle.set_threading(oracle.SERIAL)
+
+
 def test_composed_sequence_matches_fused(oracle):
     """The reference's own call sequence (one kernel per Manifold2d call, generic CG with the
     Laplacian closure) and the fused step advance the same state."""
