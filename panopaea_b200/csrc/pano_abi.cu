@@ -121,6 +121,7 @@ int pano_ctx_destroy(pano_ctx *ctx) {
     cudaFree(ctx->d_inbox);
     cudaFree(ctx->d_mail);
     cudaFree(ctx->d_tparts);
+    cudaFree(ctx->d_sr_scratch);
     cudaFree(ctx->d_claim);
     cudaFreeHost(ctx->h_cg);
     for (cudaEvent_t e : ctx->phase_events) cudaEventDestroy(e);

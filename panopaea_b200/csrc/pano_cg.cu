@@ -297,6 +297,9 @@ bool pano_cg_stream_supported(size_t h, size_t w, const void *x, const void *b, 
 int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, double *s0, double *s1, size_t h, size_t w,
                           int max_iterations, double threshold, double timestep, RectI m, const PanoCgSlab *slab);
 
+int pano_cg_sr_launch(pano_ctx *ctx, double *x, const double *b, double *r, double *p, double *s0, double *r1, double *s1, size_t h,
+                      size_t w, int max_iterations, double threshold, double timestep, RectI m, const PanoCgSrSlab *slab);
+
 bool pano_cg_resident_supported(pano_ctx *ctx, size_t h, size_t w);
 int pano_cg_resident_launch(pano_ctx *ctx, double *x, const double *b, double *r, double *s0, size_t h, size_t w,
                             int max_iterations, double threshold, double timestep, RectI m);
@@ -338,8 +341,10 @@ int pano_cg_solve_raw(pano_ctx *ctx, int dtype, void *x, const void *b, void *r,
     const RectI m = pano_clip_rect(obstacle, h + 1, w + 1);
     // kernel choice: "cg_kernel" 0 = auto, 1 = generic (any shape / dtype), 2 = TMA streaming (f64, even width),
     // 3 = SM-resident (f64, grids that fit on chip), 4 = first-generation SM-resident kernel (run-time tile geometry),
-    // 5 = one thread-block cluster (f64, grids up to ~40 k cells).
-    // auto: cluster if it fits, else resident if it fits, else streaming, else generic.
+    // 5 = one thread-block cluster (f64, grids up to ~40 k cells), 6 = TMA streaming with ONE reduction per iteration
+    // (pano_cg_sr.cu; f64, even width).
+    // auto: cluster if it fits, else resident if it fits, else streaming (the single-reduction form when option
+    // "cg_single_reduction" is 1, the default), else generic.
     const int64_t want = pano_option(ctx, "cg_kernel", 0);
     const bool stream_ok = dtype == PANO_F64 && pano_cg_stream_supported(h, w, x, b, r, s0, s1);
     const bool resident_ok = dtype == PANO_F64 && pano_cg_resident_supported(ctx, h, w);
@@ -347,6 +352,8 @@ int pano_cg_solve_raw(pano_ctx *ctx, int dtype, void *x, const void *b, void *r,
     const bool cluster_ok = dtype == PANO_F64 && pano_cg_cluster_supported(ctx, h, w);
     if (want == 5 && !cluster_ok)
         PANO_FAIL(PANO_ERR_INVALID, "cg_kernel=5 (cluster) needs an f64 grid of at most 8 x 5120 cells and width <= 1024 (%zux%zu given)", h, w);
+    if (want == 6 && !stream_ok)
+        PANO_FAIL(PANO_ERR_INVALID, "cg_kernel=6 (single-reduction TMA streaming) needs f64 fields with an even width (%zux%zu given)", h, w);
     if (want == 2 && !stream_ok)
         PANO_FAIL(PANO_ERR_INVALID, "cg_kernel=2 (TMA streaming) needs f64 fields with an even width (%zux%zu given)", h, w);
     if ((want == 3 && !resident2_ok) || (want == 4 && !resident_ok))
@@ -360,6 +367,21 @@ int pano_cg_solve_raw(pano_ctx *ctx, int dtype, void *x, const void *b, void *r,
     } else if (resident_ok && (want == 0 || want == 4)) {
         PANO_TRY(pano_cg_resident_launch(ctx, (double *)x, (const double *)b, (double *)r, (double *)s0, h, w, max_iterations,
                                          threshold, timestep, m));
+    } else if (stream_ok && (want == 6 || (want == 0 && pano_option(ctx, "cg_single_reduction", 1) != 0))) {
+        // the second r and s buffers live in a scratch area the context keeps (two h x w arrays, 256-byte aligned)
+        const size_t per = (h * w + 31) & ~(size_t)31;
+        if (ctx->sr_scratch_cap < 2 * per) {
+            if (ctx->d_sr_scratch) {
+                PANO_CUDA(cudaStreamSynchronize(ctx->stream));
+                PANO_CUDA(cudaFree(ctx->d_sr_scratch));
+                ctx->d_sr_scratch = nullptr;
+                ctx->sr_scratch_cap = 0;
+            }
+            PANO_CUDA(cudaMalloc((void **)&ctx->d_sr_scratch, 2 * per * sizeof(double)));
+            ctx->sr_scratch_cap = 2 * per;
+        }
+        PANO_TRY(pano_cg_sr_launch(ctx, (double *)x, (const double *)b, (double *)r, (double *)s0, (double *)s1, ctx->d_sr_scratch,
+                                   ctx->d_sr_scratch + per, h, w, max_iterations, threshold, timestep, m, nullptr));
     } else if (stream_ok && want != 1) {
         PANO_TRY(pano_cg_stream_launch(ctx, (double *)x, (const double *)b, (double *)r, (double *)s0, (double *)s1, h, w,
                                        max_iterations, threshold, timestep, m, nullptr));

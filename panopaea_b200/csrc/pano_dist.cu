@@ -30,15 +30,20 @@ int pano_project_slab_launch(pano_ctx *ctx, double *vy, double *vx, const double
 int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, double *s0, double *s1, size_t h, size_t w,
                           int max_iterations, double threshold, double timestep, RectI m, const PanoCgSlab *slab);
 
+int pano_cg_sr_launch(pano_ctx *ctx, double *x, const double *b, double *r, double *p, double *s0, double *r1, double *s1, size_t h,
+                      size_t w, int max_iterations, double threshold, double timestep, RectI m, const PanoCgSrSlab *slab);
+
 int pano_preload_fused();
 int pano_preload_cg_stream();
+int pano_preload_cg_sr();
 
 namespace {
 
 constexpr int kGhost = 8;          // ghost rows per side; the backtrace reach dt*max|v| + 2 must fit (checked on device)
 constexpr int kThreads = 256;
 enum { EX_ADV = 0, EX_VY = 1, EX_B = 2, EX_P = 3, EX_COUNT = 4 };
-enum { F_D0 = 0, F_D1, F_VY0, F_VY1, F_VX0, F_VX1, F_P, F_R, F_S0, F_S1, F_COUNT };
+// F_S0 is the search direction (p of the single-reduction kernel), F_S1 / F_S2 its s = A p buffers, F_R / F_R1 the residual's
+enum { F_D0 = 0, F_D1, F_VY0, F_VY1, F_VX0, F_VX1, F_P, F_R, F_S0, F_S1, F_R1, F_S2, F_COUNT };
 
 // element offsets (in doubles) of every array inside a rank's window; the same formula on every rank
 struct Layout {
@@ -207,6 +212,9 @@ int fill_owned(pano_dist *d, int f, pano_rect r, double value) {
 }
 
 
+// option "cg_single_reduction" (default 1; must agree on all ranks): the Chronopoulos-Gear kernel of pano_cg_sr.cu
+bool use_single_reduction(pano_dist *d) { return pano_option(d->ctx, "cg_single_reduction", 1) != 0; }
+
 // The persistent CG kernel on this rank's slab, right-hand side in array fB; x lands in F_P.
 int launch_cg(pano_dist *d, int fB) {
     pano_ctx *ctx = d->ctx;
@@ -215,6 +223,43 @@ int launch_cg(pano_dist *d, int fB) {
     const size_t H = d->H, W = d->W;
     const int ya = (int)L.y0;
     ++d->solve_no;
+    if (use_single_reduction(d)) {
+        // one reduction per iteration (pano_cg_sr.cu): r and s double-buffered, two halo rows of r, one of s
+        PanoCgSrSlab s;
+        memset(&s, 0, sizeof(s));
+        s.row0 = kGhost;
+        s.rows_total = (int)L.rows[F_P];
+        s.gy0 = ya;
+        s.gh = (int)H;
+        s.rank = d->rank;
+        s.nranks = d->nranks;
+        s.xseq_base = d->solve_no << 32;
+        s.max_ctas = d->max_ctas;
+        const int fr[2] = {F_R, F_R1}, fs[2] = {F_S1, F_S2};
+        if (d->rank > 0) {
+            const Layout Lup = make_layout(H, W, d->rank - 1, d->nranks);
+            for (int i = 0; i < 2; ++i) {   // my rows y0, y0+1 = its first ghost rows below its slab
+                s.up_r[i] = peer_row(d, d->rank - 1, Lup, fr[i], (ptrdiff_t)L.y0);
+                s.up_s[i] = peer_row(d, d->rank - 1, Lup, fs[i], (ptrdiff_t)L.y0);
+            }
+        }
+        if (d->rank + 1 < d->nranks) {
+            const Layout Ldn = make_layout(H, W, d->rank + 1, d->nranks);
+            for (int i = 0; i < 2; ++i) {   // my rows y1-2, y1-1 = its last ghost rows above its slab
+                s.dn_r[i] = peer_row(d, d->rank + 1, Ldn, fr[i], (ptrdiff_t)L.y1 - 2);
+                s.dn_s[i] = peer_row(d, d->rank + 1, Ldn, fs[i], (ptrdiff_t)L.y1 - 1);
+            }
+        }
+        for (int r = 0; r < d->nranks; ++r) {
+            const Layout Lr = r == d->rank ? L : make_layout(H, W, r, d->nranks);
+            s.xunits_peer[r] = d->peer[r] + Lr.xunits;
+        }
+        s.xunits_local = d->window + L.xunits;
+        const RectI m = pano_clip_rect(p.obstacle, H + 1, W + 1);
+        return pano_cg_sr_launch(ctx, d->window + L.off[F_P], d->window + L.off[fB], d->window + L.off[F_R], d->window + L.off[F_S0],
+                                 d->window + L.off[F_S1], d->window + L.off[F_R1], d->window + L.off[F_S2], L.hl, W, p.max_iterations,
+                                 p.threshold, p.timestep, m, &s);
+    }
     {
         PanoCgSlab s;
         memset(&s, 0, sizeof(s));
@@ -283,6 +328,7 @@ int pano_dist_create(pano_ctx *ctx, size_t h, size_t w, int rank, int nranks, co
         PANO_CUDA(cudaFuncGetAttributes(&fa, k_fill_rows));
         PANO_TRY(pano_preload_fused());
         PANO_TRY(pano_preload_cg_stream());
+        PANO_TRY(pano_preload_cg_sr());
     }
     pano_dist *d = new pano_dist();
     d->ctx = ctx;
@@ -465,7 +511,7 @@ int pano_dist_step(pano_dist *d) {
     PANO_TRY(pano_neg_divergence_slab_launch(ctx, virt(d, fB), virt(d, fVYn), virt(d, fVXn), H, W, p.obstacle, ya, yb));
     {
         const int fields[1] = {fB};
-        PANO_TRY(exchange(d, EX_B, 1, fields, 1));
+        PANO_TRY(exchange(d, EX_B, 1, fields, use_single_reduction(d) ? 2 : 1));   // the single-reduction kernel reads a two-row halo of b
     }
     mark("ex_b");
     PANO_TRY(pano_phase_mark(ctx, 3));

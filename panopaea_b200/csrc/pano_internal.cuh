@@ -82,6 +82,8 @@ struct pano_ctx {
     PanoCgControl *h_cg = nullptr;   // pinned
     double *d_mail = nullptr;        // boundary-line mailboxes of the SM-resident CG kernel
     size_t mail_cap = 0;             // in doubles
+    double *d_sr_scratch = nullptr;  // two more h x w arrays of the single-reduction CG kernel (second r and s buffers)
+    size_t sr_scratch_cap = 0;       // in doubles
     void *d_tparts = nullptr;        // per-(tile, warp) reduction units of the dynamically scheduled streaming CG kernel
     size_t tparts_cap = 0;           // in 16-byte units
     unsigned long long *d_claim = nullptr;   // 4 tile-claim counters (one per phase in flight)
@@ -135,6 +137,18 @@ struct PanoCgSlab {
     void *xunits_local;
     void *xunits_peer[8];
     int max_ctas;                 // 0: one CTA per SM; loop-back tests share one GPU between ranks
+};
+
+// The same for the single-reduction kernel (pano_cg_sr.cu): r and s are double-buffered, r has TWO halo rows.
+struct PanoCgSrSlab {
+    int row0, rows_total, gy0, gh;
+    double *up_r[2], *up_s[2];    // upper neighbour's r / s buffers at the ghost row that mirrors my row 0, or null
+    double *dn_r[2], *dn_s[2];    // lower neighbour's buffers at the ghost row that mirrors my row h-2 (r) / h-1 (s), or null
+    int rank, nranks;
+    unsigned long long xseq_base;
+    void *xunits_local;
+    void *xunits_peer[8];
+    int max_ctas;
 };
 
 // internal (non-ABI) entry points shared between translation units

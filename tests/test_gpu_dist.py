@@ -29,9 +29,11 @@ def _step_all(ranks):
 
 # variants of the cross-rank protocol inside the CG kernel (pano_sm100.cuh): halo flags (default) with static or dynamic tile
 # lists, halo tiles first with the flags raised early, and the fenced root exchange the flags replaced
-@pytest.mark.parametrize("dynamic,halo_first,xflags", [(0, 0, 1), (1, 0, 1), (0, 1, 1), (0, 0, 0), (1, 0, 0), (0, 1, 0)])
+# ... each with the two-reduction kernel (sr = 0, k_cg_stream) and with the single-reduction kernel (sr = 1, k_cg_sr: the default)
+@pytest.mark.parametrize("dynamic,halo_first,xflags,sr", [(0, 0, 1, 1), (1, 0, 1, 1), (0, 0, 0, 1), (1, 0, 0, 1),
+                                                          (0, 0, 1, 0), (1, 0, 1, 0), (0, 1, 1, 0), (0, 0, 0, 0), (1, 0, 0, 0), (0, 1, 0, 0)])
 @pytest.mark.parametrize("nranks,h,w", [(2, 256, 256), (4, 256, 128), (3, 250, 192)])
-def test_loopback_matches_single_gpu(nranks, h, w, dynamic, halo_first, xflags):
+def test_loopback_matches_single_gpu(nranks, h, w, dynamic, halo_first, xflags, sr):
     from tests import gpu_util as U
     from panopaea_b200 import dist, fluid
     k = 2
@@ -43,6 +45,7 @@ def test_loopback_matches_single_gpu(nranks, h, w, dynamic, halo_first, xflags):
         r.ctx.set_option("cg_dynamic", dynamic)      # 1: tiles claimed from a counter (by default only above 24 tiles per CTA)
         r.ctx.set_option("cg_halo_first", halo_first)
         r.ctx.set_option("cg_xflags", xflags)
+        r.ctx.set_option("cg_single_reduction", sr)
     for step in range(6):
         want = single.step()
         infos = _step_all(ranks)
@@ -119,3 +122,25 @@ def test_backtrace_longer_than_ghost_zone_is_reported():
         except P.PanoError:
             errs += 1
     assert errs >= 1
+
+
+@pytest.mark.parametrize("sr", [1, 0])
+def test_dist_solve_repeats_the_last_solve(sr):
+    """pano_dist_solve (BASELINE configs[4], the Poisson solve alone): again on the right-hand side of the last step, from a
+    zero guess (pcg.rs:32) -- the same bits as the solve inside the step."""
+    from panopaea_b200 import dist
+    k = 2
+    prm = dict(timestep=0.05, threshold=0.1, max_iterations=100, inflow=(5 * k, 20 * k, 54 * k, 64 * k), inflow_density=1.0,
+               inflow_vy=20.0, obstacle=(70 * k, 80 * k, 50 * k, 70 * k))
+    ranks = _make_ranks(2, 256, 256, prm)
+    for r in ranks:
+        r.ctx.set_option("cg_single_reduction", sr)
+    for _ in range(3):
+        infos = _step_all(ranks)
+    p0 = dist.gather_local(ranks, dist.PRESSURE)
+    for _ in range(2):
+        for r in ranks:
+            r.solve()
+        again = [r.sync() for r in ranks]
+        assert again == infos
+        assert np.array_equal(dist.gather_local(ranks, dist.PRESSURE), p0)
