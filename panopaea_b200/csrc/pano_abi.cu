@@ -123,6 +123,7 @@ int pano_ctx_destroy(pano_ctx *ctx) {
     cudaFree(ctx->d_tparts);
     cudaFree(ctx->d_sr_scratch);
     cudaFree(ctx->d_claim);
+    cudaFree(ctx->d_adv_claim);
     cudaFreeHost(ctx->h_cg);
     for (cudaEvent_t e : ctx->phase_events) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->marks) cudaEventDestroy(e);

@@ -1,0 +1,320 @@
+// pano_advect_tma.cu -- K1, fourth generation: the fused advection (advect + both loops of advect_mac,
+// examples/dec_fluid.rs:59-60, 173-291) as a persistent, warp-specialised, TMA-staged kernel (one CTA per SM).
+//
+// k_advect_march3 (pano_fused.cu) gathers through L1/L2 and is bound by the latency of those gathers (ncu, 4096^2:
+// DRAM 47 %, long-scoreboard stalls 7.7 per issue, no waste: 0.95 x the algorithmic bytes).  Here the loads are decoupled
+// from the arithmetic:
+//   * a producer lane claims 32 x 64-cell tiles from a counter and streams, per tile, the (32+4) x (64+4) boxes of q and vy
+//     and the box of vx into a 3-stage shared-memory ring with cp.async.bulk.tensor (TMA, mbarrier completion).  vx rows
+//     are w+1 doubles long -- an odd multiple of 8 bytes, which no tensor map accepts as a stride -- so vx is described as
+//     h/2 "super-rows" of 2(w+1) doubles and fetched as two boxes per tile: its even rows, and its odd rows one column to
+//     the left (TMA box starts must be 16-byte aligned: measured, scripts/probe/tma_probe.cu)
+//   * 16 consumer warps compute from shared memory: a thread marches down 4 rows of one column carrying the eight
+//     velocity samples around its cell in registers; the twelve gathers of a row are shared-memory loads
+//   * a backtrace that leaves the box (more than two cells: |v| dt >= 2) falls back to global memory for that cell; tiles
+//     within one tile of the domain border, where the reference's index / coordinate clamps bite, and the x = w / y = h
+//     strips run the marching body on global memory (pano_advect_body.cuh)
+// Arithmetic is pano_cell_math.h's in every path: bit-identical to the reference (tests/test_gpu_fused.py).
+// HBM traffic: 48 B per cell (halo re-reads hit the 126 MB L2: neighbouring tiles are in flight together).
+#include "pano_advect_body.cuh"
+#include "pano_sm100.cuh"
+
+using namespace pano_sm100;
+using pano_adv::V32;
+using pano_adv::V32W;
+
+namespace {
+
+constexpr int TH = 32, TW = 64;                 // tile (cells)
+constexpr int kG = 2;                           // halo: every gather of a cell whose backtrace is shorter than 2 cells stays inside
+constexpr int QW = TW + 2 * kG, QH = TH + 2 * kG;   // 68 x 36: q and vy boxes
+constexpr int XW = QW + 2, XH = QH / 2;         // 70 x 18: each of the two vx boxes (even rows; odd rows shifted one column left)
+constexpr int kQBytes = QH * QW * 8;            // 19584 (a multiple of 128)
+constexpr int kXBytes = XH * XW * 8;            // 10080
+constexpr int kXSlot = 10112;                   // rounded up to a multiple of 128
+constexpr int kXOdd = kXSlot / 8 + 1;           // offset (doubles) from an even-row element to the element one row down: odd box + its column shift
+constexpr int kStageBytes = 2 * kQBytes + 2 * kXSlot;   // 59392
+constexpr int kStages = 3;
+constexpr int kConsumerWarps = 16, kConsumers = 32 * kConsumerWarps;
+constexpr int kThreads = kConsumers + 32;       // + one producer warp
+constexpr int kRows = TH / (kConsumerWarps / 2);   // 4 rows per thread; a warp covers 32 columns
+constexpr int kTailBytes = 1024;
+constexpr int kSmemBytes = kStages * kStageBytes + kTailBytes;   // 179200
+
+struct AdvArgs {
+    CUtensorMap m_q, m_vy, m_vx;  // m_vx: the super-row view (2(w+1) wide, rows/2 high)
+    double *q_dst, *vy_dst, *vx_dst;              // all pointers are the (virtual) addresses of GLOBAL row 0
+    const double *q_src, *vy_src, *vx_src;
+    int h, w;                     // the whole grid (walls, clamps)
+    double dt;
+    int ya, yb;                   // cell rows produced here (0, h on one GPU; a slab otherwise)
+    int ylo;                      // global row held by row 0 of the stored source arrays (0 on one GPU)
+    int whi_q, whi_vy;            // slab: stored rows are [ylo, whi_q) for q and vx, [ylo, whi_vy) for vy
+    unsigned int *err;            // slab: raised (= 2) when a gather leaves the stored rows
+    int tiles_x, tiles_y;
+    unsigned int *claim;          // two tile counters, used alternately by successive launches
+    int parity;
+    int dynamic;
+};
+
+struct Tail {
+    uint64_t full[kStages], empty[kStages];
+    int tile[kStages];
+};
+
+__device__ __forceinline__ bool tile_interior(const AdvArgs &a, int ty0, int tx0) {
+    // no clamp of the reference can bite within two cells of the tile, and the tile is complete
+    return tx0 >= TW && tx0 + 2 * TW <= a.w && ty0 >= TH && ty0 + 2 * TH <= a.h && ty0 + TH <= a.yb;
+}
+
+// advect_mac's gather coordinates without the index clamps (the caller checks that the corner lies inside the staged box,
+// which lies inside the grid): same bits as pano::mac_coord_fast there
+struct MacCoordI {
+    int x0, y0;
+    double s, t;
+    unsigned bad;
+};
+__device__ __forceinline__ MacCoordI mac_coord_open(double relx, double rely) {
+    MacCoordI c;
+    const double rx = pano::clamp_lo0(relx), ry = pano::clamp_lo0(rely);
+    const pano::FloorNN fx = pano::floor_nonneg(rx), fy = pano::floor_nonneg(ry);
+    c.bad = (fx.hi ^ pano::kFloorHi) | (fy.hi ^ pano::kFloorHi);
+    c.x0 = (int)fx.i; c.y0 = (int)fy.i;
+    c.s = rx - fx.f; c.t = ry - fy.f;
+    return c;
+}
+
+// one cell whose backtrace left the staged boxes: the full forms on global memory
+template <class A>
+__device__ __noinline__ void cell_from_global(double *q_dst, double *vy_dst, double *vx_dst, A q, A vy, A vx, int h, int w, int y, int x,
+                                              pano::CellCoord cq, double rxx, double rxy, double ryx, double ryy) {
+    q_dst[y * w + x] = pano::advect_gather_at(cq, q);
+    const pano::MacCoord cx = pano::mac_coord_fast(rxx, rxy, h, w + 1), cy = pano::mac_coord_fast(ryx, ryy, h + 1, w);
+    vx_dst[y * (w + 1) + x] = cx.bad ? pano_adv::mac_gather_far(rxx, rxy, h, w + 1, vx) : pano::mac_gather_at(cx, vx);
+    vy_dst[y * w + x] = cy.bad ? pano_adv::mac_gather_far(ryx, ryy, h + 1, w, vy) : pano::mac_gather_at(cy, vy);
+}
+
+// Interior tile: column x = tx0 + lx, rows ty0 + ly0 .. + kRows - 1 (ly0 a multiple of 4), everything from shared memory.
+//   Q, VY: boxes with origin (ty0 - 2, tx0 - 2), pitch QW.   VX: even rows of the same box at VX[(r >> 1) * XW + c],
+//   odd rows at VX[kXOdd + (r >> 1) * XW + c]  (r, c box-relative).
+template <class A>
+__device__ __forceinline__ void advect_tile(const AdvArgs &a, const double *__restrict__ Q, const double *__restrict__ VY,
+                                            const double *__restrict__ VX, const A &gq, const A &gvy, const A &gvx, int ty0, int tx0,
+                                            int ly0, int lx) {
+    const int h = a.h, w = a.w;
+    const int x = tx0 + lx, ys = ty0 + ly0;
+    const int bx0 = tx0 - kG, by0 = ty0 - kG;
+    const int c0 = lx + kG, r0 = ly0 + kG;                     // box column / first box row (even) of this thread
+    const double ndt = -a.dt, xd = (double)x, xh = xd + 0.5;
+    const double wlim = (double)w - 1.00001, hlim = (double)h - 1.00001;
+    double yd = (double)ys;
+    const double *pvy = VY + r0 * QW + c0;
+    const double *pvx = VX + (r0 >> 1) * XW + c0;              // vx(ys, x): even box row
+    double C = pvy[0], E = pvy[-1];
+    double G = pvx[kXOdd - XW], H = pvx[kXOdd - XW + 1];       // vx(ys - 1, .): the odd row above
+    double *qo = a.q_dst + ys * w + x, *vyo = a.vy_dst + ys * w + x, *vxo = a.vx_dst + ys * (w + 1) + x;
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+        const int y = ys + k;
+        const double yh = yd + 0.5;
+        // vx(y, x), vx(y, x+1): rows alternate between the even and the odd box; vy(y+1, x), vy(y+1, x-1)
+        const double *px = pvx + (k >> 1) * XW + ((k & 1) ? kXOdd : 0);
+        const double A_ = px[0], B = px[1];
+        const double D = pvy[(k + 1) * QW], F = pvy[(k + 1) * QW - 1];
+        const double vvy = (C + D + E + F) / 4.0;               // dec_fluid.rs:220-225 with xc = x, xm = x - 1
+        const double vvx = (A_ + B + G + H) / 4.0;              // :257-263 with yc = y, ym = y - 1
+        const pano::CellCoord cq = pano::advect_coord_fast(xh, yh, wlim, hlim, ndt, (A_ + B) / 2.0, (C + D) / 2.0);
+        double rxx, rxy, ryx, ryy;
+        pano::mac_x_rel(xd, yh, ndt, A_, vvy, rxx, rxy);
+        pano::mac_y_rel(xh, yd, ndt, vvx, C, ryx, ryy);
+        const MacCoordI cx = mac_coord_open(rxx, rxy), cy = mac_coord_open(ryx, ryy);
+        // box-relative corners; a corner at (u, v) needs u + 1 and v + 1 as well
+        const unsigned qx = (unsigned)(cq.ix - bx0), qy = (unsigned)(cq.iy - by0);
+        const unsigned xx = (unsigned)(cx.x0 - bx0), xy = (unsigned)(cx.y0 - by0);
+        const unsigned yx = (unsigned)(cy.x0 - bx0), yy = (unsigned)(cy.y0 - by0);
+        const bool inside = (cx.bad | cy.bad) == 0u && qx <= (unsigned)(QW - 2) && xx <= (unsigned)(QW - 2) && yx <= (unsigned)(QW - 2) &&
+                            qy <= (unsigned)(QH - 2) && xy <= (unsigned)(QH - 2) && yy <= (unsigned)(QH - 2);
+        if (inside) {
+            // one straight-line block: all twelve gathers in flight together
+            const double *gq_ = Q + qy * QW + qx;
+            const double *gy_ = VY + yy * QW + yx;
+            const unsigned par = xy & 1u;
+            const double *gx0 = VX + (xy >> 1) * XW + xx + par * kXOdd;                  // row y0
+            const double *gx1 = VX + (xy >> 1) * XW + xx + kXOdd - par * (kXOdd - XW);   // row y0 + 1
+            const double q00 = gq_[0], q01 = gq_[1], q10 = gq_[QW], q11 = gq_[QW + 1];
+            const double x00 = gx0[0], x01 = gx0[1], x10 = gx1[0], x11 = gx1[1];
+            const double y00 = gy_[0], y01 = gy_[1], y10 = gy_[QW], y11 = gy_[QW + 1];
+            qo[k * w] = pano::bilinear(q00, q01, q10, q11, cq.u, cq.v);
+            vxo[k * (w + 1)] = pano::bilinear(x00, x01, x10, x11, cx.s, cx.t);
+            vyo[k * w] = pano::bilinear(y00, y01, y10, y11, cy.s, cy.t);
+        } else {
+            cell_from_global<A>(a.q_dst, a.vy_dst, a.vx_dst, gq, gvy, gvx, h, w, y, x, cq, rxx, rxy, ryx, ryy);
+        }
+        C = D; E = F; G = A_; H = B;
+        yd += 1.0;
+    }
+}
+
+template <bool kSlab>
+__global__ void __launch_bounds__(kThreads, 1) k_advect_tma(const __grid_constant__ AdvArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    Tail *tl = reinterpret_cast<Tail *>(smem + kStages * kStageBytes);
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int G = gridDim.x;
+    const int ntiles = a.tiles_x * a.tiles_y;
+    // no bounded wait here can expire unless the device is broken; the flag exists so that one does not hang a box
+    __shared__ unsigned int s_err;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&tl->full[s], 1);
+            mbar_init(&tl->empty[s], kConsumerWarps);
+        }
+        s_err = 0;
+        fence_mbar_init();
+    }
+    __syncthreads();
+    volatile unsigned int *err = &s_err;
+
+    if (wid == kConsumerWarps) {
+        // ============================================================ producer warp (one lane)
+        if (lane != 0) return;
+        tma_prefetch_desc(&a.m_q);
+        tma_prefetch_desc(&a.m_vy);
+        tma_prefetch_desc(&a.m_vx);
+        if (blockIdx.x == 0) a.claim[a.parity ^ 1] = 0u;        // the NEXT launch's counter (this one was zeroed by the previous launch)
+        unsigned n = 0;
+        for (int jj = 0;; ++jj) {
+            int t;
+            if (a.dynamic) t = (int)atomicAdd(&a.claim[a.parity], 1u);
+            else t = blockIdx.x + jj * G;
+            const int st = n % kStages;
+            if (!mbar_wait(&tl->empty[st], ((n / kStages) & 1) ^ 1, err)) return;
+            if (t >= ntiles) {                                  // end marker
+                tl->tile[st] = -1;
+                mbar_arrive(&tl->full[st]);
+                return;
+            }
+            tl->tile[st] = t;
+            const int tx0 = (t % a.tiles_x) * TW, ty0 = a.ya + (t / a.tiles_x) * TH;
+            if (tile_interior(a, ty0, tx0)) {
+                unsigned char *base = smem + st * kStageBytes;
+                uint64_t *bar = &tl->full[st];
+                mbar_arrive_expect_tx(bar, 2 * kQBytes + 2 * kXBytes);
+                const int by = ty0 - kG - a.ylo;                // box row in the stored arrays (even)
+                tma_load_2d(base, &a.m_q, bar, tx0 - kG, by);
+                tma_load_2d(base + kQBytes, &a.m_vy, bar, tx0 - kG, by);
+                tma_load_2d(base + 2 * kQBytes, &a.m_vx, bar, tx0 - kG, by >> 1);                       // even rows
+                tma_load_2d(base + 2 * kQBytes + kXSlot, &a.m_vx, bar, a.w + 1 + tx0 - kG - 1, by >> 1);   // odd rows, one column to the left
+            } else {
+                mbar_arrive(&tl->full[st]);                     // border tile: the consumers read global memory
+            }
+            ++n;
+        }
+    }
+
+    // ================================================================ consumer warps
+    using Acc = typename std::conditional<kSlab, V32W, V32<double>>::type;
+    Acc gq, gvy, gvx;
+    if constexpr (kSlab) {
+        gq = V32W{a.q_src, a.w, a.ylo, a.whi_q, a.err};
+        gvy = V32W{a.vy_src, a.w, a.ylo, a.whi_vy, a.err};
+        gvx = V32W{a.vx_src, a.w + 1, a.ylo, a.whi_q, a.err};
+    } else {
+        gq = V32<double>{a.q_src, a.w};
+        gvy = V32<double>{a.vy_src, a.w};
+        gvx = V32<double>{a.vx_src, a.w + 1};
+    }
+    const int lx = (wid & 1) * 32 + lane, ly0 = (wid >> 1) * kRows;
+    for (unsigned n = 0;; ++n) {
+        const int st = n % kStages;
+        if (!mbar_wait(&tl->full[st], (n / kStages) & 1, err)) return;
+        int t = 0;
+        if (lane == 0) t = *(const volatile int *)&tl->tile[st];
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t < 0) break;
+        const int tx0 = (t % a.tiles_x) * TW, ty0 = a.ya + (t / a.tiles_x) * TH;
+        if (tile_interior(a, ty0, tx0)) {
+            const double *Q = reinterpret_cast<const double *>(smem + st * kStageBytes);
+            advect_tile<Acc>(a, Q, Q + kQBytes / 8, Q + 2 * (kQBytes / 8), gq, gvy, gvx, ty0, tx0, ly0, lx);
+        } else {
+            const int x = tx0 + lx, ys = ty0 + ly0;
+            if (x < a.w && ys < a.yb)
+                pano_adv::advect_march3_body<true, kRows>(a.q_dst, a.vy_dst, a.vx_dst, gq, gvy, gvx, a.h, a.w, a.dt, x, ys, a.yb);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tl->empty[st]);
+    }
+    // the strips the cell tiles do not cover: column x = w (vx only) and, where this launch owns it, face row y = h (vy only)
+    const int ncol = a.yb - a.ya, nrow = a.yb == a.h ? a.w : 0;
+    for (int i = blockIdx.x * kConsumers + tid; i < ncol + nrow; i += G * kConsumers) {
+        if (i < ncol) pano_adv::advect_march3_body<true, 1>(a.q_dst, a.vy_dst, a.vx_dst, gq, gvy, gvx, a.h, a.w, a.dt, a.w, a.ya + i, a.ya + i + 1);
+        else pano_adv::advect_march3_body<true, 1>(a.q_dst, a.vy_dst, a.vx_dst, gq, gvy, gvx, a.h, a.w, a.dt, i - ncol, a.h, a.h + 1);
+    }
+}
+
+}  // namespace
+
+int pano_preload_advect_tma() {
+    cudaFuncAttributes fa;
+    PANO_CUDA(cudaFuncGetAttributes(&fa, k_advect_tma<false>));
+    PANO_CUDA(cudaFuncSetAttribute(k_advect_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    PANO_CUDA(cudaFuncGetAttributes(&fa, k_advect_tma<true>));
+    PANO_CUDA(cudaFuncSetAttribute(k_advect_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    return PANO_OK;
+}
+
+// Even sizes (the vx super-rows pair rows; TMA rows are 16-byte aligned), 16-byte aligned arrays, 32-bit indices, and a
+// grid large enough for interior tiles to exist.  rows_* = rows stored from global row ylo on.
+bool pano_advect_tma_supported(size_t h, size_t w, int ya, int ylo, size_t rows_q, const void *q, const void *vy, const void *vx) {
+    if (h % 2 || w % 2 || rows_q % 2 || ((ya - ylo) % 2) != 0) return false;
+    if (h < 4 * TH || w < 4 * TW) return false;
+    if ((h + 1) * (w + 1) >= ((size_t)1 << 31)) return false;
+    const void *ps[] = {q, vy, vx};
+    for (const void *p : ps)
+        if (((uintptr_t)p & 15u) != 0) return false;
+    return true;
+}
+
+// Sources are self-advected (src == vel).  Pointers are virtual global-row-0 addresses; *_stored point at stored row 0
+// (= global row ylo).  err: slab error word or null (one GPU: every row is stored).
+int pano_advect_tma_launch(pano_ctx *ctx, double *q_dst, double *vy_dst, double *vx_dst, const double *q_src, const double *vy_src,
+                           const double *vx_src, size_t h, size_t w, double dt, int ya, int yb, int ylo, size_t rows_q, size_t rows_vy,
+                           unsigned int *err) {
+    static_assert(sizeof(Tail) <= kTailBytes, "Tail does not fit");
+    static_assert(kQBytes % 128 == 0 && kXSlot % 128 == 0 && kXSlot >= kXBytes, "stage layout");
+    PANO_CUDA(cudaFuncSetAttribute(k_advect_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    PANO_CUDA(cudaFuncSetAttribute(k_advect_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    AdvArgs a;
+    memset(&a, 0, sizeof(a));
+    const double *q_st = q_src + (ptrdiff_t)ylo * (ptrdiff_t)w, *vy_st = vy_src + (ptrdiff_t)ylo * (ptrdiff_t)w,
+                 *vx_st = vx_src + (ptrdiff_t)ylo * (ptrdiff_t)(w + 1);
+    PANO_TRY(pano_make_tensor_map_2d(&a.m_q, q_st, 8, w, rows_q, (uint64_t)w * 8, QW, QH));
+    PANO_TRY(pano_make_tensor_map_2d(&a.m_vy, vy_st, 8, w, rows_vy, (uint64_t)w * 8, QW, QH));
+    PANO_TRY(pano_make_tensor_map_2d(&a.m_vx, vx_st, 8, 2 * (w + 1), rows_q / 2, (uint64_t)(w + 1) * 16, XW, XH));
+    a.q_dst = q_dst; a.vy_dst = vy_dst; a.vx_dst = vx_dst;
+    a.q_src = q_src; a.vy_src = vy_src; a.vx_src = vx_src;
+    a.h = (int)h; a.w = (int)w; a.dt = dt;
+    a.ya = ya; a.yb = yb; a.ylo = ylo;
+    a.whi_q = ylo + (int)rows_q; a.whi_vy = ylo + (int)rows_vy;
+    if (a.whi_q > (int)h) a.whi_q = (int)h;                    // rows beyond the grid are storage, not data
+    if (a.whi_vy > (int)h + 1) a.whi_vy = (int)h + 1;
+    a.err = err;
+    a.tiles_x = ((int)w + TW - 1) / TW;
+    a.tiles_y = (yb - ya + TH - 1) / TH;
+    if (!ctx->d_adv_claim) {
+        PANO_CUDA(cudaMalloc((void **)&ctx->d_adv_claim, 2 * sizeof(unsigned int)));
+        PANO_CUDA(cudaMemsetAsync(ctx->d_adv_claim, 0, 2 * sizeof(unsigned int), ctx->stream));
+    }
+    a.claim = ctx->d_adv_claim;
+    a.parity = (int)(ctx->adv_epoch++ & 1u);
+    a.dynamic = pano_option(ctx, "advect_dynamic", 1) != 0;
+    int G = ctx->num_sms;
+    const int64_t cap = pano_option(ctx, "advect_ctas", 0);
+    if (cap > 0 && cap < G) G = (int)cap;
+    const int ntiles = a.tiles_x * a.tiles_y;
+    if (G > ntiles) G = ntiles;
+    if (err) k_advect_tma<true><<<G, kThreads, kSmemBytes, ctx->stream>>>(a);
+    else k_advect_tma<false><<<G, kThreads, kSmemBytes, ctx->stream>>>(a);
+    return pano_after_launch(ctx, "advect_tma");
+}

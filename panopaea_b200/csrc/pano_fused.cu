@@ -4,8 +4,15 @@
 //   K5 laplacian_apply examples/dec_fluid.rs:100-119 (stand-alone form of the CG operator)
 //   K8 project         examples/dec_fluid.rs:124-141 (hodge_2 -> d0_dual -> scaled_add -> walls)
 // All are HBM-bound; see DESIGN.md for bytes per cell.
+#include "pano_advect_body.cuh"
 #include "pano_cell_math.h"
 #include "pano_internal.cuh"
+
+bool pano_advect_tma_supported(size_t h, size_t w, int ya, int ylo, size_t rows_q, const void *q, const void *vy, const void *vx);
+int pano_advect_tma_launch(pano_ctx *ctx, double *q_dst, double *vy_dst, double *vx_dst, const double *q_src, const double *vy_src,
+                           const double *vx_src, size_t h, size_t w, double dt, int ya, int yb, int ylo, size_t rows_q, size_t rows_vy,
+                           unsigned int *err);
+int pano_preload_advect_tma();
 
 namespace {
 
@@ -84,12 +91,7 @@ k_advect_slab(double *q_dst, double *vy_dst, double *vx_dst, const double *q_src
 // advected quantities.  Here a thread owns one column and marches down kRows rows: the eight velocity samples
 // around (y, x) are carried in registers (4 new loads per row), indices are 32-bit, clamps are fmin/fmax.
 // Arithmetic is pano_cell_math.h's, so results stay bit-identical.  (Self-advection only: src == vel.)
-template <class T>
-struct V32 {   // row-major array addressed with 32-bit indices (the host checks that every index fits)
-    const T *p;
-    int pitch;
-    __device__ __forceinline__ T operator()(int y, int x) const { return p[y * pitch + x]; }
-};
+using pano_adv::V32;
 
 constexpr int kAdvRows = 4;   // rows per thread; a 256-thread block covers 32 columns x 32 rows
 
@@ -141,75 +143,7 @@ k_advect_march(T *__restrict__ q_dst, T *__restrict__ vy_dst, T *__restrict__ vx
 
 // ------------------------------------------------------------------ K1, third generation (f64)
 // k_advect_march is issue-bound at ~370 instructions per cell (ncu: 63 % issue-active, DRAM 42 % of the copy peak).
-// Same marching scheme, but (a) the exact fast forms of pano_cell_math.h (floor by a round-down add, one clamp per
-// axis instead of three, no 64-bit conversions), (b) positions carried as doubles and advanced by +1.0 (exact),
-// (c) blocks that touch no domain border skip every border select (kEdge = false).
-__device__ __noinline__ double mac_gather_far(double relx, double rely, int H, int W, const double *p) {   // > 2^32 cells away: never in practice
-    return pano::mac_gather<double>(relx, rely, H, W, V32<double>{p, W});
-}
-
-template <bool kEdge, int kRows>
-__device__ __forceinline__ void advect_march3_body(double *__restrict__ q_dst, double *__restrict__ vy_dst, double *__restrict__ vx_dst,
-                                                   const double *__restrict__ q_src, const double *__restrict__ vy_src,
-                                                   const double *__restrict__ vx_src, int h, int w, double dt, int x, int ys) {
-    const V32<double> q{q_src, w}, vy{vy_src, w}, vx{vx_src, w + 1};
-    const bool xin = !kEdge || x < w, xpos = !kEdge || x > 0;
-    const double ndt = -dt, xd = (double)x, xh = xd + 0.5;
-    const double wlim = (double)w - 1.00001, hlim = (double)h - 1.00001;
-    double yd = (double)ys;
-    double C = xin ? vy(ys, x) : 0.0, E = xpos ? vy(ys, x - 1) : 0.0;
-    double G = 0.0, H = 0.0;
-    if (!kEdge || ys > 0) {
-        G = vx(ys - 1, x);
-        H = xin ? vx(ys - 1, x + 1) : 0.0;
-    }
-#pragma unroll
-    for (int k = 0; k < kRows; ++k) {
-        const int y = ys + k;
-        if (kEdge && y > h) break;
-        const bool yin = !kEdge || y < h;
-        const double yh = yd + 0.5;
-        double A = 0.0, B = 0.0, D = 0.0, F = 0.0;
-        if (yin) {
-            A = vx(y, x);
-            if (xin) { B = vx(y, x + 1); D = vy(y + 1, x); }
-            if (xpos) F = vy(y + 1, x - 1);
-        }
-        // the three backtraced positions of this row: advect (dec_fluid.rs:180-183), advect_mac x (:220-225) and y (:257-263)
-        double vvy, vvx;
-        if (kEdge) {
-            const bool ypos = y > 0;
-            const double t0 = xin ? C : E, t1 = xin ? D : F, t2 = xpos ? E : C, t3 = xpos ? F : D;
-            vvy = (t0 + t1 + t2 + t3) / 4.0;
-            const double u0 = yin ? A : G, u1 = yin ? B : H, u2 = ypos ? G : A, u3 = ypos ? H : B;
-            vvx = (u0 + u1 + u2 + u3) / 4.0;
-        } else {
-            vvy = (C + D + E + F) / 4.0;
-            vvx = (A + B + G + H) / 4.0;
-        }
-        const pano::CellCoord cq = pano::advect_coord_fast(xh, yh, wlim, hlim, ndt, (A + B) / 2.0, (C + D) / 2.0);
-        double rxx, rxy, ryx, ryy;
-        pano::mac_x_rel(xd, yh, ndt, A, vvy, rxx, rxy);
-        pano::mac_y_rel(xh, yd, ndt, vvx, C, ryx, ryy);
-        const pano::MacCoord cx = pano::mac_coord_fast(rxx, rxy, h, w + 1), cy = pano::mac_coord_fast(ryx, ryy, h + 1, w);
-        if ((cx.bad | cy.bad) == 0u) {
-            // one straight-line block: all twelve gathers can be in flight together
-            const double vq = (yin && xin) ? pano::advect_gather_at(cq, q) : 0.0;
-            const double vxn = yin ? pano::mac_gather_at(cx, vx) : 0.0;
-            const double vyn = xin ? pano::mac_gather_at(cy, vy) : 0.0;
-            if (yin && xin) q_dst[y * w + x] = vq;
-            if (yin) vx_dst[y * (w + 1) + x] = vxn;
-            if (xin) vy_dst[y * w + x] = vyn;
-        } else {                                             // a backtrace beyond 2^32 cells: the general form
-            if (yin && xin) q_dst[y * w + x] = pano::advect_gather_at(cq, q);
-            if (yin) vx_dst[y * (w + 1) + x] = mac_gather_far(rxx, rxy, h, w + 1, vx_src);
-            if (xin) vy_dst[y * w + x] = mac_gather_far(ryx, ryy, h + 1, w, vy_src);
-        }
-        C = D; E = F; G = A; H = B;
-        yd += 1.0;
-    }
-}
-
+// Same marching scheme with the exact fast forms: pano_advect_body.cuh.
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -246,10 +180,10 @@ k_advect_march3(double *__restrict__ q_dst, double *__restrict__ vy_dst, double 
                 else { prefetch_l1(a); prefetch_l1(b); prefetch_l1(c); }
             }
         }
-        advect_march3_body<false, kRows>(q_dst, vy_dst, vx_dst, q_src, vy_src, vx_src, h, w, dt, x, ys);
+        pano_adv::advect_march3_body<false, kRows>(q_dst, vy_dst, vx_dst, V32<double>{q_src, w}, V32<double>{vy_src, w}, V32<double>{vx_src, w + 1}, h, w, dt, x, ys, h + 1);
     } else {
         if (x > w || ys > h) return;
-        advect_march3_body<true, kRows>(q_dst, vy_dst, vx_dst, q_src, vy_src, vx_src, h, w, dt, x, ys);
+        pano_adv::advect_march3_body<true, kRows>(q_dst, vy_dst, vx_dst, V32<double>{q_src, w}, V32<double>{vy_src, w}, V32<double>{vx_src, w + 1}, h, w, dt, x, ys, h + 1);
     }
 }
 
@@ -425,10 +359,20 @@ int pano_advect_launch(pano_ctx *ctx, int dtype, void *q_dst, void *vel_dst, con
                        const void *vel, size_t h, size_t w, double dt) {
     const bool sc = q_dst != nullptr, mac = vel_dst != nullptr;
     const size_t off1 = w * (h + 1);
+    // "advect_kernel": 0 auto, 1 k_advect (any shape / dtype, separate advect / advect_mac), 2 k_advect_march, 3 k_advect_march3,
+    // 4 k_advect_tma (pano_advect_tma.cu; f64, even sizes).  auto: the TMA kernel once the grid gives every SM a few tiles
+    // (4 x 148 tiles of 32 x 64 cells, ~1.2 Mcell), the marching kernel below that.
+    const int64_t ak = pano_option(ctx, "advect_kernel", 0);
+    if (sc && mac && mac_src == vel && dtype == PANO_F64 && (ak == 0 || ak == 4) &&
+        pano_advect_tma_supported(h, w, 0, 0, h, q_src, vel, (const double *)vel + off1) &&
+        (ak == 4 || ((h + 31) / 32) * ((w + 63) / 64) >= (size_t)4 * ctx->num_sms)) {
+        return pano_advect_tma_launch(ctx, (double *)q_dst, (double *)vel_dst, (double *)vel_dst + off1, (const double *)q_src,
+                                      (const double *)vel, (const double *)vel + off1, h, w, dt, 0, (int)h, 0, h, h + 1, nullptr);
+    }
     // the marching kernel: both outputs, self-advection, 32-bit indices
-    if (sc && mac && mac_src == vel && (h + 1) * (w + 1) < ((size_t)1 << 31) && pano_option(ctx, "advect_kernel", 0) != 1) {
+    if (sc && mac && mac_src == vel && (h + 1) * (w + 1) < ((size_t)1 << 31) && ak != 1) {
         dim3 gm((unsigned)((w + 1 + 31) / 32), (unsigned)((h + 1 + 8 * kAdvRows - 1) / (8 * kAdvRows)));
-        if (dtype == PANO_F64 && pano_option(ctx, "advect_kernel", 0) != 2) {
+        if (dtype == PANO_F64 && ak != 2) {
             const int pf = (int)pano_option(ctx, "advect_prefetch", 1), mb = (int)pano_option(ctx, "advect_minblocks", 4);
             const int rows = (int)pano_option(ctx, "advect_rows", 4);
             if (rows != 2 && rows != 4 && rows != 8)   // the launch grid is sized from it; only these are instantiated
@@ -533,6 +477,7 @@ int pano_project_launch(pano_ctx *ctx, int dtype, void *vel, const void *p, size
 int pano_preload_fused() {
     cudaFuncAttributes fa;
     PANO_CUDA(cudaFuncGetAttributes(&fa, k_advect_slab));
+    PANO_TRY(pano_preload_advect_tma());
     PANO_CUDA(cudaFuncGetAttributes(&fa, k_neg_divergence<double>));
     PANO_CUDA(cudaFuncGetAttributes(&fa, k_project<double>));
     return PANO_OK;
@@ -542,6 +487,14 @@ int pano_preload_fused() {
 // the virtual address of global row 0 of its array
 int pano_advect_slab_launch(pano_ctx *ctx, double *q_dst, double *vy_dst, double *vx_dst, const double *q_src, const double *vy_src,
                             const double *vx_src, size_t h, size_t w, double dt, int ya, int yb, int wlo, int whi, unsigned int *err) {
+    // the stored rows are [ylo, whi) (+1 for vy) with ylo = ya - ghost, possibly negative on the first rank (wlo is clipped to 0)
+    const int ylo = ya - (whi - yb);
+    const size_t rows_q = (size_t)(whi - ylo);
+    const int64_t ak = pano_option(ctx, "advect_kernel", 0);
+    if ((ak == 0 || ak == 4) && pano_advect_tma_supported(h, w, ya, ylo, rows_q, q_src + (ptrdiff_t)ylo * (ptrdiff_t)w,
+                                                          vy_src + (ptrdiff_t)ylo * (ptrdiff_t)w, vx_src + (ptrdiff_t)ylo * (ptrdiff_t)(w + 1)) &&
+        (ak == 4 || (size_t)((yb - ya + 31) / 32) * ((w + 63) / 64) >= (size_t)2 * ctx->num_sms))
+        return pano_advect_tma_launch(ctx, q_dst, vy_dst, vx_dst, q_src, vy_src, vx_src, h, w, dt, ya, yb, ylo, rows_q, rows_q + 1, err);
     dim3 g = grid2d(yb - ya + 1, (int)w + 1);
     k_advect_slab<<<g, kThreads, 0, ctx->stream>>>(q_dst, vy_dst, vx_dst, q_src, vy_src, vx_src, (int)h, (int)w, dt, ya, yb, wlo, whi, err);
     return pano_after_launch(ctx, "advect_slab");

@@ -87,6 +87,8 @@ struct pano_ctx {
     void *d_tparts = nullptr;        // per-(tile, warp) reduction units of the dynamically scheduled streaming CG kernel
     size_t tparts_cap = 0;           // in 16-byte units
     unsigned long long *d_claim = nullptr;   // 4 tile-claim counters (one per phase in flight)
+    unsigned int *d_adv_claim = nullptr;     // two tile counters of the TMA advection kernel, used alternately
+    unsigned long long adv_epoch = 0;
     void *d_units = nullptr;         // publish+poll all-reduce units of the persistent kernels
     void *d_inbox = nullptr;         // per-CTA inboxes of the push all-reduce (pano_sm100.cuh), kPanoInboxBytes
     unsigned long long launch_epoch = 0;

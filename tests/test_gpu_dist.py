@@ -144,3 +144,33 @@ def test_dist_solve_repeats_the_last_solve(sr):
         again = [r.sync() for r in ranks]
         assert again == infos
         assert np.array_equal(dist.gather_local(ranks, dist.PRESSURE), p0)
+
+
+@pytest.mark.parametrize("nranks,h,w", [(2, 512, 512), (3, 768, 384)])
+def test_loopback_tma_advection(nranks, h, w):
+    """The slabs on the TMA-staged advection kernel (pano_advect_tma.cu; forced: the auto choice needs bigger slabs): tensor maps
+    over the stored rows of the window, ghost rows as tile halos, vx super-rows paired relative to the window."""
+    from tests import gpu_util as U
+    from panopaea_b200 import dist, fluid
+    k = h // 128
+    kx = w // 128
+    prm = dict(timestep=0.05, threshold=0.1, max_iterations=40, inflow=(5 * k, 20 * k, 54 * kx, 64 * kx), inflow_density=1.0,
+               inflow_vy=20.0, obstacle=(70 * k, 80 * k, 50 * kx, 70 * kx))
+    single = fluid.DecFluid(h=h, w=w, ctx=U.ctx(), **prm)
+    ranks = _make_ranks(nranks, h, w, prm)
+    for r in ranks:
+        r.ctx.set_option("advect_kernel", 4)
+    for step in range(5):
+        want = single.step()
+        infos = _step_all(ranks)
+        assert abs(infos[0]["iterations"] - want["iterations"]) <= 1
+        d = dist.gather_local(ranks, dist.DENSITY)
+        if step == 0:
+            assert np.array_equal(d, single.density.to_host())
+            assert infos[0]["rhs_max"] == want["rhs_max"]
+        assert np.abs(d - single.density.to_host()).max() <= 1e-9
+        if infos[0]["iterations"] != want["iterations"]:
+            break
+        vy, vx = single.vel.split()
+        assert np.abs(dist.gather_local(ranks, dist.VY) - vy).max() <= 1e-8 * max(1.0, np.abs(vy).max())
+        assert np.abs(dist.gather_local(ranks, dist.VX) - vx).max() <= 1e-8 * max(1.0, np.abs(vx).max())

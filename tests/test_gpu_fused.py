@@ -34,6 +34,75 @@ def test_advect_bit_exact(oracle, h, w, vmax):
     assert np.array_equal(dq2.to_host(), want_q) and np.array_equal(dv2.view_linear(), want_v)
 
 
+# The TMA-staged persistent advection kernel (pano_advect_tma.cu), forced with advect_kernel=4 on grids small enough for the
+# oracle: vmax 30 -> backtraces below 2 cells (every gather from shared memory), 60 -> 3 cells (many cells fall back to global
+# memory), 1e4 / 1e300 -> every cell falls back / the > 2^32-cell path; non-multiples of the tile (ragged tiles), the minimum size.
+TMA_CASES = [(128, 256, 30.0), (256, 256, 30.0), (256, 256, 60.0), (130, 258, 30.0), (514, 390, 39.9), (514, 390, 200.0),
+             (256, 512, 1e4), (128, 256, 1e300), (1024, 1024, 30.0), (1024, 1024, 45.0), (2048, 2048, 35.0)]
+
+
+@pytest.mark.parametrize("dynamic", [1, 0])
+@pytest.mark.parametrize("h,w,vmax", TMA_CASES)
+def test_advect_tma_bit_exact(oracle, h, w, vmax, dynamic):
+    from tests import gpu_util as U
+    from panopaea_b200 import fluid
+    if dynamic == 0 and h * w > 300000:
+        pytest.skip("static tile lists: small cases only")
+    grid = U.grid(h, w)
+    q, vel = U.rand_inputs(h, w, vmax, seed=h + w)
+    Q, V = U.s2(grid, q), U.s1(grid, vel)
+    oracle.set_threading(oracle.ALL_PARALLEL)
+    try:
+        want_q, want_v = oracle.advect(h, w, q, 0.05, vel), oracle.advect_mac(h, w, vel, 0.05, vel)
+    finally:
+        oracle.set_threading(oracle.SERIAL)
+    U.ctx().set_option("advect_kernel", 4)
+    U.ctx().set_option("advect_dynamic", dynamic)
+    try:
+        for rep in range(3):                                  # successive launches alternate between the two tile counters
+            dq, dv = grid.new_simplex_2(), grid.new_simplex_1()
+            dq.fill(-7.0)
+            dv.fill(-7.0)
+            n0 = U.ctx().launch_count()
+            fluid.advect_all(dq, dv, Q, V, 0.05)
+            assert np.array_equal(dq.to_host(), want_q), rep
+            assert np.array_equal(dv.view_linear(), want_v), rep
+    finally:
+        U.ctx().set_option("advect_kernel", 0)
+        U.ctx().set_option("advect_dynamic", 1)
+
+
+def test_advect_tma_smooth_flow_and_auto_choice(oracle):
+    """A smooth flow (the regime of the smoke plume: neighbouring cells trace back to neighbouring cells) on a grid where the
+    auto choice is the TMA kernel, and the same answer from the marching kernel."""
+    from tests import gpu_util as U
+    from panopaea_b200 import fluid
+    h, w = 1536, 2048
+    grid = U.grid(h, w)
+    yy, xx = np.mgrid[0:h + 1, 0:w + 1]
+    vy = 30.0 * np.sin(xx[:, :w] / 37.0) * np.cos(yy[:, :w] / 53.0)
+    vx = 30.0 * np.cos(xx[:h, :] / 41.0 + 1.0) * np.sin(yy[:h, :] / 29.0)
+    vel = oracle.join(vy, vx)
+    q = np.sin(xx[:h, :w] / 11.0) + np.cos(yy[:h, :w] / 7.0)
+    Q, V = U.s2(grid, q), U.s1(grid, vel)
+    out = []
+    for kernel in (0, 3):
+        U.ctx().set_option("advect_kernel", kernel)
+        try:
+            dq, dv = grid.new_simplex_2(), grid.new_simplex_1()
+            fluid.advect_all(dq, dv, Q, V, 0.05)
+            out.append((dq.to_host(), dv.view_linear().copy()))
+        finally:
+            U.ctx().set_option("advect_kernel", 0)
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    oracle.set_threading(oracle.ALL_PARALLEL)
+    try:
+        assert np.array_equal(out[0][0], oracle.advect(h, w, q, 0.05, vel))
+        assert np.array_equal(out[0][1], oracle.advect_mac(h, w, vel, 0.05, vel))
+    finally:
+        oracle.set_threading(oracle.SERIAL)
+
+
 def test_advect_mac_distinct_source(oracle):
     """advect_mac(dst, src, dt, vel) with src != vel (the signature allows it; the example passes vel twice)."""
     from tests import gpu_util as U
