@@ -78,6 +78,7 @@ struct SrArgs {
     int gy0, gh;                  // global row of the first owned row; global grid height (walls)
     double *up_r[2], *up_s[2];    // upper neighbour's arrays at the row that mirrors MY row 0 (its first ghost row below its slab), or null
     double *dn_r[2], *dn_s[2];    // lower neighbour's arrays at the row that mirrors MY row h-2 (r) / h-1 (s), or null
+    double *dn_x;                 // lower neighbour's x at the row that mirrors MY row h-1 (its projection reads it as p[y-1]), or null
     XRank xr;
 };
 
@@ -263,6 +264,7 @@ __device__ __forceinline__ void tile_sr(const SrArgs &a, const double *R, const 
                 }
                 *reinterpret_cast<double2 *>(a.p + gi) = pn;
                 *reinterpret_cast<double2 *>(a.x + gi) = xn;
+                if (a.dn_x && ly2 == a.h - 1) *reinterpret_cast<double2 *>(a.dn_x + gx) = xn;   // every pass; the last one counts
                 const double c0 = rn[1][1], c1 = rn[1][2];
                 acc_g = acc_g + c0 * c0;
                 acc_g = acc_g + c1 * c1;
@@ -512,7 +514,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_sr(const __grid_constant__ S
     const size_t ncell = (size_t)a.h * a.w, base = (size_t)a.row0 * a.w;
     const size_t stride = (size_t)G * kConsumers, i0 = base + (size_t)blockIdx.x * kConsumers + tid;
     if (early) {
-        for (size_t i = i0; i < base + ncell; i += stride) a.x[i] = 0.0;
+        // x = 0 (pcg.rs:32) -- including the ghost row above, which the upper neighbour (same decision) would have mirrored
+        const size_t first = (a.up_r[0] != nullptr && a.row0 > 0) ? base - (size_t)a.w : base;
+        for (size_t i = first + (size_t)blockIdx.x * kConsumers + tid; i < base + ncell; i += stride) a.x[i] = 0.0;
     } else {
         const double *r_fin = a.r[(it + 1) & 1];
         const bool copy_r = r_fin != a.r[0];
@@ -580,6 +584,7 @@ int pano_cg_sr_launch(pano_ctx *ctx, double *x, const double *b, double *r, doub
             a.up_r[i] = slab->up_r[i]; a.up_s[i] = slab->up_s[i];
             a.dn_r[i] = slab->dn_r[i]; a.dn_s[i] = slab->dn_s[i];
         }
+        a.dn_x = slab->dn_x;
         a.xr.rank = slab->rank; a.xr.nranks = slab->nranks;
         a.xr.seq_base = slab->xseq_base;
         a.xr.local = (ReduceUnit *)slab->xunits_local;

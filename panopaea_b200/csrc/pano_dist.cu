@@ -23,7 +23,7 @@
 using namespace pano_sm100;
 
 int pano_advect_slab_launch(pano_ctx *ctx, double *q_dst, double *vy_dst, double *vx_dst, const double *q_src, const double *vy_src,
-                            const double *vx_src, size_t h, size_t w, double dt, int ya, int yb, int wlo, int whi, unsigned int *err);
+                            const double *vx_src, size_t h, size_t w, double dt, int ya, int yb, int ylo, size_t rows_q, unsigned int *err);
 int pano_neg_divergence_slab_launch(pano_ctx *ctx, double *b, const double *vy, const double *vx, size_t h, size_t w, pano_rect obstacle,
                                     int ya, int yb);
 int pano_project_slab_launch(pano_ctx *ctx, double *vy, double *vx, const double *p, size_t h, size_t w, double dt, int ya, int yb);
@@ -32,14 +32,15 @@ int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, 
 
 int pano_cg_sr_launch(pano_ctx *ctx, double *x, const double *b, double *r, double *p, double *s0, double *r1, double *s1, size_t h,
                       size_t w, int max_iterations, double threshold, double timestep, RectI m, const PanoCgSrSlab *slab);
+int pano_preload_cg_sr();
 
 int pano_preload_fused();
 int pano_preload_cg_stream();
-int pano_preload_cg_sr();
 
 namespace {
 
-constexpr int kGhost = 8;          // ghost rows per side; the backtrace reach dt*max|v| + 2 must fit (checked on device)
+constexpr int kGhost = 12;         // ghost rows per side; the backtrace reach dt*max|v| + 2 (+ kExtend in the fused-halo step) must fit (checked on device)
+constexpr int kExtend = 4;         // fused-halo step: rows beyond the slab that a rank advects itself instead of receiving them (even: vx rows pair up)
 constexpr int kThreads = 256;
 enum { EX_ADV = 0, EX_VY = 1, EX_B = 2, EX_P = 3, EX_COUNT = 4 };
 // F_S0 is the search direction (p of the single-reduction kernel), F_S1 / F_S2 its s = A p buffers, F_R / F_R1 the residual's
@@ -216,7 +217,7 @@ int fill_owned(pano_dist *d, int f, pano_rect r, double value) {
 bool use_single_reduction(pano_dist *d) { return pano_option(d->ctx, "cg_single_reduction", 1) != 0; }
 
 // The persistent CG kernel on this rank's slab, right-hand side in array fB; x lands in F_P.
-int launch_cg(pano_dist *d, int fB) {
+int launch_cg(pano_dist *d, int fB, bool mirror_x) {
     pano_ctx *ctx = d->ctx;
     const Layout &L = d->L;
     const pano_step_params &p = d->prm;
@@ -249,6 +250,8 @@ int launch_cg(pano_dist *d, int fB) {
                 s.dn_r[i] = peer_row(d, d->rank + 1, Ldn, fr[i], (ptrdiff_t)L.y1 - 2);
                 s.dn_s[i] = peer_row(d, d->rank + 1, Ldn, fs[i], (ptrdiff_t)L.y1 - 1);
             }
+            // my last row of x = the p[y-1] its projection reads for its first face row (fused-halo step: no exchange of p)
+            if (mirror_x) s.dn_x = peer_row(d, d->rank + 1, Ldn, F_P, (ptrdiff_t)L.y1 - 1);
         }
         for (int r = 0; r < d->nranks; ++r) {
             const Layout Lr = r == d->rank ? L : make_layout(H, W, r, d->nranks);
@@ -484,6 +487,9 @@ int pano_dist_step(pano_dist *d) {
         fprintf(stderr, "[pano_dist rank %d] %-12s +%.3f ms\n", d->rank, what, (ts.tv_sec - ts0.tv_sec) * 1e3 + (ts.tv_nsec - ts0.tv_nsec) * 1e-6);
     };
 
+    const bool fused_halos = use_single_reduction(d) && pano_option(ctx, "dist_fused_halos", 1) != 0;
+    const int ylo = ya - kGhost;                     // first stored row of every array (storage, not data, where negative)
+    const size_t rows_q = L.hl + 2 * kGhost;
     PANO_TRY(pano_phase_mark(ctx, 0));
     // inflow  (dec_fluid.rs:48-57): the part of the rectangle this rank owns
     PANO_TRY(fill_owned(d, fD, p.inflow, p.inflow_density));
@@ -495,10 +501,32 @@ int pano_dist_step(pano_dist *d) {
     }
     mark("ex_adv");
     PANO_TRY(pano_phase_mark(ctx, 1));
+    const int fB = fD;                               // b reuses the old density buffer, as `temp` does in the reference
+    if (fused_halos) {
+        // ONE exchange per step.  Every rank advects kExtend rows beyond its slab from the ghost rows it has just received
+        // (same inputs, same code as their owner: the same bits), so the new vy face row y1, the two ghost rows of b the
+        // solver's halo recomputation reads, ... are all local; the solver itself mirrors its last row of x into the lower
+        // neighbour's ghost row, which is the p[y0-1] of that neighbour's projection.
+        const int A = ya - kExtend > 0 ? ya - kExtend : 0, B = yb + kExtend < (int)H ? yb + kExtend : (int)H;
+        PANO_TRY(pano_advect_slab_launch(ctx, virt(d, fDn), virt(d, fVYn), virt(d, fVXn), virt(d, fD), virt(d, fVY), virt(d, fVX), H, W,
+                                         p.timestep, A, B, ylo, rows_q, err));
+        mark("advect");
+        PANO_TRY(pano_phase_mark(ctx, 2));
+        const int A2 = ya - 2 > 0 ? ya - 2 : 0, B2 = yb + 2 < (int)H ? yb + 2 : (int)H;
+        PANO_TRY(pano_neg_divergence_slab_launch(ctx, virt(d, fB), virt(d, fVYn), virt(d, fVXn), H, W, p.obstacle, A2, B2));
+        PANO_TRY(pano_phase_mark(ctx, 3));
+        PANO_TRY(launch_cg(d, fB, true));
+        mark("cg");
+        PANO_TRY(pano_phase_mark(ctx, 4));
+        PANO_TRY(pano_project_slab_launch(ctx, virt(d, fVYn), virt(d, fVXn), virt(d, F_P), H, W, p.timestep, ya, yb));
+        PANO_TRY(pano_phase_mark(ctx, 5));
+        mark("project");
+        d->cur = nxt;
+        return PANO_OK;
+    }
     // advect + advect_mac on the owned rows, into the other ping-pong buffers  (:59-63)
-    const int wlo = ya - kGhost > 0 ? ya - kGhost : 0, whi = yb + kGhost;
     PANO_TRY(pano_advect_slab_launch(ctx, virt(d, fDn), virt(d, fVYn), virt(d, fVXn), virt(d, fD), virt(d, fVY), virt(d, fVX), H, W,
-                                     p.timestep, ya, yb, wlo, whi, err));
+                                     p.timestep, ya, yb, ylo, rows_q, err));
     mark("advect");
     // the face row y1 of the new vy belongs to the lower neighbour
     {
@@ -506,8 +534,7 @@ int pano_dist_step(pano_dist *d) {
         PANO_TRY(exchange(d, EX_VY, 1, fields, 1));
     }
     PANO_TRY(pano_phase_mark(ctx, 2));
-    // b = -div  (:69-83); b reuses the old density buffer, as `temp` does in the reference
-    const int fB = fD;
+    // b = -div  (:69-83)
     PANO_TRY(pano_neg_divergence_slab_launch(ctx, virt(d, fB), virt(d, fVYn), virt(d, fVXn), H, W, p.obstacle, ya, yb));
     {
         const int fields[1] = {fB};
@@ -516,7 +543,7 @@ int pano_dist_step(pano_dist *d) {
     mark("ex_b");
     PANO_TRY(pano_phase_mark(ctx, 3));
     // pressure solve  (:91-119): streaming CG on the slab, halo rows and reductions over NVLink from inside the kernel
-    PANO_TRY(launch_cg(d, fB));
+    PANO_TRY(launch_cg(d, fB, false));
     mark("cg");
     PANO_TRY(pano_phase_mark(ctx, 4));
     // p[y0 - 1] lives on the upper neighbour
@@ -538,7 +565,7 @@ int pano_dist_solve(pano_dist *d) {
     if (!d->connected) PANO_FAIL(PANO_ERR_COMM, "pano_dist_solve: call pano_dist_connect first");
     if (d->step_no == 0) PANO_FAIL(PANO_ERR_INVALID, "pano_dist_solve: no step has produced a right-hand side yet");
     PANO_TRY(pano_activate(d->ctx));
-    return launch_cg(d, (d->cur ^ 1) ? F_D1 : F_D0);
+    return launch_cg(d, (d->cur ^ 1) ? F_D1 : F_D0, true);
 }
 
 // wait for the enqueued steps; info (nullable) describes the last solve

@@ -187,24 +187,45 @@ k_advect_march3(double *__restrict__ q_dst, double *__restrict__ vy_dst, double 
     }
 }
 
+// The marching kernel on a slab: cell rows [ya, yb) (face rows up to yf), sources windowed (rows [wlo, whi), +1 for vy).
+__global__ void __launch_bounds__(kThreads, 4)
+k_advect_march3_slab(double *__restrict__ q_dst, double *__restrict__ vy_dst, double *__restrict__ vx_dst, const double *__restrict__ q_src,
+                     const double *__restrict__ vy_src, const double *__restrict__ vx_src, int h, int w, double dt, int ya, int yb, int wlo,
+                     int whi, unsigned int *err) {
+    using pano_adv::V32W;
+    const int yf = yb == h ? h + 1 : yb;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ys = ya + (blockIdx.y * 8 + (threadIdx.x >> 5)) * kAdvRows;
+    const int bx0 = blockIdx.x * 32, by0 = ya + blockIdx.y * 8 * kAdvRows;
+    const V32W q{q_src, w, wlo, whi > h ? h : whi, err}, vy{vy_src, w, wlo, whi + 1 > h + 1 ? h + 1 : whi + 1, err},
+        vx{vx_src, w + 1, wlo, whi > h ? h : whi, err};
+    if (bx0 >= 1 && bx0 + 31 <= w - 1 && by0 >= 1 && by0 + 8 * kAdvRows - 1 <= h - 1 && by0 + 8 * kAdvRows <= yb) {
+        pano_adv::advect_march3_body<false, kAdvRows>(q_dst, vy_dst, vx_dst, q, vy, vx, h, w, dt, x, ys, yf);
+    } else {
+        if (x > w || ys >= yf) return;
+        pano_adv::advect_march3_body<true, kAdvRows>(q_dst, vy_dst, vx_dst, q, vy, vx, h, w, dt, x, ys, yf);
+    }
+}
+
 // ------------------------------------------------------------------ K3, second generation (no reductions: the
 // solver computes max|b| and b.b itself): one column x kDivRows rows per thread, vy carried down in a register
 constexpr int kDivRows = 8;
 template <class T>
 __global__ void __launch_bounds__(kThreads)
-k_neg_divergence_march(T *__restrict__ b, const T *__restrict__ vy, const T *__restrict__ vx, int h, int w, RectI m) {
+k_neg_divergence_march(T *__restrict__ b, const T *__restrict__ vy, const T *__restrict__ vx, int h, int w, RectI m, int ya, int yb) {
+    // cell rows [ya, yb) (the whole grid on one GPU; a slab, whose pointers are virtual row-0 addresses, otherwise)
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int ys = (blockIdx.y * 8 + (threadIdx.x >> 5)) * kDivRows;
-    if (x >= w || ys >= h) return;
+    const int ys = ya + (blockIdx.y * 8 + (threadIdx.x >> 5)) * kDivRows;
+    if (x >= w || ys >= yb) return;
     // block-uniform test: does this 32 x 64 block touch the obstacle's edges?
-    const int bx0 = blockIdx.x * 32, by0 = blockIdx.y * 8 * kDivRows;
+    const int bx0 = blockIdx.x * 32, by0 = ya + blockIdx.y * 8 * kDivRows;
     const bool masked = m.y1 > m.y0 && m.x1 > m.x0 && by0 < m.y1 && by0 + 8 * kDivRows + 1 > m.y0 && bx0 < m.x1 && bx0 + 33 > m.x0;
     T vy0 = vy[ys * w + x];
     if (masked && in_rect(m, ys, x)) vy0 = (T)0;
 #pragma unroll
     for (int k = 0; k < kDivRows; ++k) {
         const int y = ys + k;
-        if (y >= h) break;
+        if (y >= yb) break;
         T vy1 = vy[(y + 1) * w + x], vx0 = vx[y * (w + 1) + x], vx1 = vx[y * (w + 1) + x + 1];
         if (masked) {
             if (in_rect(m, y + 1, x)) vy1 = (T)0;
@@ -306,16 +327,18 @@ k_project(T *__restrict__ vy, T *__restrict__ vx, const T *__restrict__ p, int h
 constexpr int kProjRows = 8;
 template <class T>
 __global__ void __launch_bounds__(kThreads)
-k_project_march(T *__restrict__ vy, T *__restrict__ vx, const T *__restrict__ p, int h, int w, T dt) {
+k_project_march(T *__restrict__ vy, T *__restrict__ vx, const T *__restrict__ p, int h, int w, T dt, int ya, int yb) {
+    // vx rows [ya, yb) and vy face rows [ya, yf): the face row y belongs to the slab that owns cell row y, face row h to the last one
+    const int yf = yb == h ? h + 1 : yb;
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int ys = (blockIdx.y * 8 + (threadIdx.x >> 5)) * kProjRows;
-    if (x > w || ys > h) return;
+    const int ys = ya + (blockIdx.y * 8 + (threadIdx.x >> 5)) * kProjRows;
+    if (x > w || ys >= yf) return;
     const bool xin = x < w;
     T pn = (xin && ys > 0) ? p[(ys - 1) * w + x] : (T)0;     // p[y-1, x]
 #pragma unroll
     for (int k = 0; k < kProjRows; ++k) {
         const int y = ys + k;
-        if (y > h) break;
+        if (y >= yf) break;
         const T c = (y < h && xin) ? p[y * w + x] : (T)0;
         if (xin) {   // vy[y, x]
             const int i = y * w + x;
@@ -434,9 +457,9 @@ int pano_neg_divergence_launch(pano_ctx *ctx, int dtype, void *b, const void *ve
     if (!want_scalars && (h + 1) * (w + 1) < ((size_t)1 << 31)) {
         dim3 gm((unsigned)((w + 31) / 32), (unsigned)((h + 8 * kDivRows - 1) / (8 * kDivRows)));
         if (dtype == PANO_F64)
-            k_neg_divergence_march<double><<<gm, kThreads, 0, ctx->stream>>>((double *)b, (const double *)vel, (const double *)vel + off, (int)h, (int)w, m);
+            k_neg_divergence_march<double><<<gm, kThreads, 0, ctx->stream>>>((double *)b, (const double *)vel, (const double *)vel + off, (int)h, (int)w, m, 0, (int)h);
         else
-            k_neg_divergence_march<float><<<gm, kThreads, 0, ctx->stream>>>((float *)b, (const float *)vel, (const float *)vel + off, (int)h, (int)w, m);
+            k_neg_divergence_march<float><<<gm, kThreads, 0, ctx->stream>>>((float *)b, (const float *)vel, (const float *)vel + off, (int)h, (int)w, m, 0, (int)h);
         return pano_after_launch(ctx, "neg_divergence_march");
     }
     dim3 g = grid2d((int)h, (int)w);
@@ -459,9 +482,9 @@ int pano_project_launch(pano_ctx *ctx, int dtype, void *vel, const void *p, size
     if ((h + 1) * (w + 1) < ((size_t)1 << 31) && pano_option(ctx, "project_kernel", 0) != 1) {
         dim3 gm((unsigned)((w + 1 + 31) / 32), (unsigned)((h + 1 + 8 * kProjRows - 1) / (8 * kProjRows)));
         if (dtype == PANO_F64)
-            k_project_march<double><<<gm, kThreads, 0, ctx->stream>>>((double *)vel, (double *)vel + off, (const double *)p, (int)h, (int)w, dt);
+            k_project_march<double><<<gm, kThreads, 0, ctx->stream>>>((double *)vel, (double *)vel + off, (const double *)p, (int)h, (int)w, dt, 0, (int)h);
         else
-            k_project_march<float><<<gm, kThreads, 0, ctx->stream>>>((float *)vel, (float *)vel + off, (const float *)p, (int)h, (int)w, (float)dt);
+            k_project_march<float><<<gm, kThreads, 0, ctx->stream>>>((float *)vel, (float *)vel + off, (const float *)p, (int)h, (int)w, (float)dt, 0, (int)h);
         return pano_after_launch(ctx, "project_march");
     }
     dim3 g = grid2d((int)h + 1, (int)w + 1);
@@ -477,24 +500,31 @@ int pano_project_launch(pano_ctx *ctx, int dtype, void *vel, const void *p, size
 int pano_preload_fused() {
     cudaFuncAttributes fa;
     PANO_CUDA(cudaFuncGetAttributes(&fa, k_advect_slab));
+    PANO_CUDA(cudaFuncGetAttributes(&fa, k_advect_march3_slab));
     PANO_TRY(pano_preload_advect_tma());
     PANO_CUDA(cudaFuncGetAttributes(&fa, k_neg_divergence<double>));
     PANO_CUDA(cudaFuncGetAttributes(&fa, k_project<double>));
+    PANO_CUDA(cudaFuncGetAttributes(&fa, k_neg_divergence_march<double>));
+    PANO_CUDA(cudaFuncGetAttributes(&fa, k_project_march<double>));
     return PANO_OK;
 }
 
 // ---- slab forms used by the multi-GPU step (pano_dist.cu): f64, rows [ya, yb) of an h x w grid, every pointer is
 // the virtual address of global row 0 of its array
+// Stored rows of the sources: [ylo, ylo + rows_q) for q and vx, one more for vy (ylo < 0 on the first rank: storage, not data).
 int pano_advect_slab_launch(pano_ctx *ctx, double *q_dst, double *vy_dst, double *vx_dst, const double *q_src, const double *vy_src,
-                            const double *vx_src, size_t h, size_t w, double dt, int ya, int yb, int wlo, int whi, unsigned int *err) {
-    // the stored rows are [ylo, whi) (+1 for vy) with ylo = ya - ghost, possibly negative on the first rank (wlo is clipped to 0)
-    const int ylo = ya - (whi - yb);
-    const size_t rows_q = (size_t)(whi - ylo);
+                            const double *vx_src, size_t h, size_t w, double dt, int ya, int yb, int ylo, size_t rows_q, unsigned int *err) {
     const int64_t ak = pano_option(ctx, "advect_kernel", 0);
     if ((ak == 0 || ak == 4) && pano_advect_tma_supported(h, w, ya, ylo, rows_q, q_src + (ptrdiff_t)ylo * (ptrdiff_t)w,
                                                           vy_src + (ptrdiff_t)ylo * (ptrdiff_t)w, vx_src + (ptrdiff_t)ylo * (ptrdiff_t)(w + 1)) &&
         (ak == 4 || (size_t)((yb - ya + 31) / 32) * ((w + 63) / 64) >= (size_t)2 * ctx->num_sms))
         return pano_advect_tma_launch(ctx, q_dst, vy_dst, vx_dst, q_src, vy_src, vx_src, h, w, dt, ya, yb, ylo, rows_q, rows_q + 1, err);
+    const int wlo = ylo > 0 ? ylo : 0, whi = ylo + (int)rows_q;
+    if (ak != 1 && (h + 1) * (w + 1) < ((size_t)1 << 31)) {
+        dim3 gm((unsigned)((w + 1 + 31) / 32), (unsigned)((yb - ya + 1 + 8 * kAdvRows - 1) / (8 * kAdvRows)));
+        k_advect_march3_slab<<<gm, kThreads, 0, ctx->stream>>>(q_dst, vy_dst, vx_dst, q_src, vy_src, vx_src, (int)h, (int)w, dt, ya, yb, wlo, whi, err);
+        return pano_after_launch(ctx, "advect_march3(slab)");
+    }
     dim3 g = grid2d(yb - ya + 1, (int)w + 1);
     k_advect_slab<<<g, kThreads, 0, ctx->stream>>>(q_dst, vy_dst, vx_dst, q_src, vy_src, vx_src, (int)h, (int)w, dt, ya, yb, wlo, whi, err);
     return pano_after_launch(ctx, "advect_slab");
@@ -502,13 +532,23 @@ int pano_advect_slab_launch(pano_ctx *ctx, double *q_dst, double *vy_dst, double
 
 int pano_neg_divergence_slab_launch(pano_ctx *ctx, double *b, const double *vy, const double *vx, size_t h, size_t w, pano_rect obstacle,
                                     int ya, int yb) {
-    dim3 g = grid2d(yb - ya, (int)w);
     RectI m = pano_clip_rect(obstacle, h + 1, w + 1);
+    if ((h + 1) * (w + 1) < ((size_t)1 << 31) && pano_option(ctx, "slab_kernels", 0) == 0) {
+        dim3 gm((unsigned)((w + 31) / 32), (unsigned)((yb - ya + 8 * kDivRows - 1) / (8 * kDivRows)));
+        k_neg_divergence_march<double><<<gm, kThreads, 0, ctx->stream>>>(b, vy, vx, (int)h, (int)w, m, ya, yb);
+        return pano_after_launch(ctx, "neg_divergence_march(slab)");
+    }
+    dim3 g = grid2d(yb - ya, (int)w);
     k_neg_divergence<double><<<g, kThreads, 0, ctx->stream>>>(b, vy, vx, (int)h, (int)w, m, ya, yb, nullptr, nullptr);
     return pano_after_launch(ctx, "neg_divergence_slab");
 }
 
 int pano_project_slab_launch(pano_ctx *ctx, double *vy, double *vx, const double *p, size_t h, size_t w, double dt, int ya, int yb) {
+    if ((h + 1) * (w + 1) < ((size_t)1 << 31) && pano_option(ctx, "slab_kernels", 0) == 0) {
+        dim3 gm((unsigned)((w + 1 + 31) / 32), (unsigned)((yb - ya + 1 + 8 * kProjRows - 1) / (8 * kProjRows)));
+        k_project_march<double><<<gm, kThreads, 0, ctx->stream>>>(vy, vx, p, (int)h, (int)w, dt, ya, yb);
+        return pano_after_launch(ctx, "project_march(slab)");
+    }
     dim3 g = grid2d(yb - ya + 1, (int)w + 1);
     k_project<double><<<g, kThreads, 0, ctx->stream>>>(vy, vx, p, (int)h, (int)w, dt, ya, yb);
     return pano_after_launch(ctx, "project_slab");

@@ -146,6 +146,7 @@ struct PanoCgSrSlab {
     int row0, rows_total, gy0, gh;
     double *up_r[2], *up_s[2];    // upper neighbour's r / s buffers at the ghost row that mirrors my row 0, or null
     double *dn_r[2], *dn_s[2];    // lower neighbour's buffers at the ghost row that mirrors my row h-2 (r) / h-1 (s), or null
+    double *dn_x;                 // lower neighbour's x at the ghost row that mirrors my row h-1, or null (then p is exchanged outside)
     int rank, nranks;
     unsigned long long xseq_base;
     void *xunits_local;
