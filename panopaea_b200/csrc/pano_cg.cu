@@ -308,6 +308,10 @@ bool pano_cg_resident2_supported(pano_ctx *ctx, size_t h, size_t w);
 int pano_cg_resident2_launch(pano_ctx *ctx, double *x, const double *b, double *r, double *s0, size_t h, size_t w,
                              int max_iterations, double threshold, double timestep, RectI m);
 
+bool pano_cg_resident_sr_supported(pano_ctx *ctx, size_t h, size_t w);
+int pano_cg_resident_sr_launch(pano_ctx *ctx, double *x, const double *b, double *r, double *s0, size_t h, size_t w,
+                               int max_iterations, double threshold, double timestep, RectI m);
+
 bool pano_cg_cluster_supported(pano_ctx *ctx, size_t h, size_t w);
 int pano_cg_cluster_launch(pano_ctx *ctx, double *x, const double *b, double *r, double *s0, size_t h, size_t w, int max_iterations,
                            double threshold, double timestep, RectI m);
@@ -342,7 +346,7 @@ int pano_cg_solve_raw(pano_ctx *ctx, int dtype, void *x, const void *b, void *r,
     // kernel choice: "cg_kernel" 0 = auto, 1 = generic (any shape / dtype), 2 = TMA streaming (f64, even width),
     // 3 = SM-resident (f64, grids that fit on chip), 4 = first-generation SM-resident kernel (run-time tile geometry),
     // 5 = one thread-block cluster (f64, grids up to ~40 k cells), 6 = TMA streaming with ONE reduction per iteration
-    // (pano_cg_sr.cu; f64, even width).
+    // (pano_cg_sr.cu; f64, even width), 7 = SM-resident with ONE reduction per iteration (pano_cg_resident_sr.cu).
     // auto: cluster if it fits, else resident if it fits, else streaming (the single-reduction form when option
     // "cg_single_reduction" is 1, the default), else generic.
     const int64_t want = pano_option(ctx, "cg_kernel", 0);
@@ -350,24 +354,29 @@ int pano_cg_solve_raw(pano_ctx *ctx, int dtype, void *x, const void *b, void *r,
     const bool resident_ok = dtype == PANO_F64 && pano_cg_resident_supported(ctx, h, w);
     const bool resident2_ok = dtype == PANO_F64 && pano_cg_resident2_supported(ctx, h, w);
     const bool cluster_ok = dtype == PANO_F64 && pano_cg_cluster_supported(ctx, h, w);
+    const bool resident_sr_ok = dtype == PANO_F64 && pano_cg_resident_sr_supported(ctx, h, w);
+    const bool single = pano_option(ctx, "cg_single_reduction", 1) != 0;
     if (want == 5 && !cluster_ok)
         PANO_FAIL(PANO_ERR_INVALID, "cg_kernel=5 (cluster) needs an f64 grid of at most 8 x 5120 cells and width <= 1024 (%zux%zu given)", h, w);
     if (want == 6 && !stream_ok)
         PANO_FAIL(PANO_ERR_INVALID, "cg_kernel=6 (single-reduction TMA streaming) needs f64 fields with an even width (%zux%zu given)", h, w);
     if (want == 2 && !stream_ok)
         PANO_FAIL(PANO_ERR_INVALID, "cg_kernel=2 (TMA streaming) needs f64 fields with an even width (%zux%zu given)", h, w);
-    if ((want == 3 && !resident2_ok) || (want == 4 && !resident_ok))
+    if ((want == 3 && !resident2_ok) || (want == 4 && !resident_ok) || (want == 7 && !resident_sr_ok))
         PANO_FAIL(PANO_ERR_INVALID, "cg_kernel=%d (SM-resident) needs an f64 grid that fits on chip (%zux%zu given)", (int)want, h, w);
     if (cluster_ok && (want == 0 || want == 5)) {
         PANO_TRY(pano_cg_cluster_launch(ctx, (double *)x, (const double *)b, (double *)r, (double *)s0, h, w, max_iterations, threshold,
                                         timestep, m));
+    } else if (resident_sr_ok && (want == 7 || (want == 0 && single))) {
+        PANO_TRY(pano_cg_resident_sr_launch(ctx, (double *)x, (const double *)b, (double *)r, (double *)s0, h, w, max_iterations,
+                                            threshold, timestep, m));
     } else if (resident2_ok && (want == 0 || want == 3)) {
         PANO_TRY(pano_cg_resident2_launch(ctx, (double *)x, (const double *)b, (double *)r, (double *)s0, h, w, max_iterations,
                                           threshold, timestep, m));
     } else if (resident_ok && (want == 0 || want == 4)) {
         PANO_TRY(pano_cg_resident_launch(ctx, (double *)x, (const double *)b, (double *)r, (double *)s0, h, w, max_iterations,
                                          threshold, timestep, m));
-    } else if (stream_ok && (want == 6 || (want == 0 && pano_option(ctx, "cg_single_reduction", 1) != 0))) {
+    } else if (stream_ok && (want == 6 || (want == 0 && single))) {
         // the second r and s buffers live in a scratch area the context keeps (two h x w arrays, 256-byte aligned)
         const size_t per = (h * w + 31) & ~(size_t)31;
         if (ctx->sr_scratch_cap < 2 * per) {

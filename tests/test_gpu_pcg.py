@@ -21,6 +21,7 @@ VARIANTS = {"generic": dict(_BASE, cg_kernel=1), "generic_ldcg": dict(_BASE, cg_
             "sr": dict(_BASE, cg_kernel=6, cg_dynamic=0),                    # ONE reduction per iteration (Chronopoulos-Gear), pano_cg_sr.cu
             "sr_dyn": dict(_BASE, cg_kernel=6, cg_dynamic=1),
             "sr_dyn_batch": dict(_BASE, cg_kernel=6, cg_dynamic=1, cg_batch=3),
+            "resident_sr": dict(_BASE, cg_kernel=7),                         # SM-resident, ONE reduction per iteration (pano_cg_resident_sr.cu)
             "resident": dict(_BASE, cg_kernel=3),                            # grid all-reduce above 32 CTAs: root protocol
             "resident_push": dict(_BASE, cg_kernel=3, cg_push=1),            # ... per-CTA inboxes instead (measured slower, kept as an option)
             "resident_v1": dict(_BASE, cg_kernel=4), "cluster": dict(_BASE, cg_kernel=5)}
@@ -121,7 +122,7 @@ def test_kernel_variants_agree(oracle, h, w):
     b = U.consistent_rhs(oracle, h, w, obstacle, seed=11)
     out = {}
     try:
-        names = ("generic", "stream", "stream_dyn", "stream_dyn_batch", "sr", "sr_dyn", "sr_dyn_batch", "resident", "resident_v1") + (("cluster",) if _cluster_fits(h, w) else ())
+        names = ("generic", "stream", "stream_dyn", "stream_dyn_batch", "sr", "sr_dyn", "sr_dyn_batch", "resident_sr", "resident", "resident_v1") + (("cluster",) if _cluster_fits(h, w) else ())
         for name in names:
             _set_variant(name)
             out[name] = _solve(grid, b, 100, 0.1, 0.05, obstacle)
@@ -136,7 +137,7 @@ def test_kernel_variants_agree(oracle, h, w):
                 assert np.allclose(u, v, rtol=0, atol=1e-8 * max(1.0, np.abs(u).max())), other
 
 
-@pytest.mark.parametrize("variant", ["generic", "stream", "stream_dyn", "sr", "sr_dyn", "resident", "resident_v1", "cluster"])
+@pytest.mark.parametrize("variant", ["generic", "stream", "stream_dyn", "sr", "sr_dyn", "resident_sr", "resident", "resident_v1", "cluster"])
 def test_early_out_leaves_scratch_untouched(oracle, variant):
     """pcg.rs:35-38: max|b| < threshold -> x = 0 and nothing else is written."""
     from tests import gpu_util as U
@@ -154,7 +155,7 @@ def test_early_out_leaves_scratch_untouched(oracle, variant):
     assert np.all(r == 123.0) and np.all(s == 123.0)
 
 
-@pytest.mark.parametrize("variant", ["generic", "stream", "stream_dyn", "sr", "sr_dyn", "resident", "resident_v1", "cluster"])
+@pytest.mark.parametrize("variant", ["generic", "stream", "stream_dyn", "sr", "sr_dyn", "resident_sr", "resident", "resident_v1", "cluster"])
 @pytest.mark.parametrize("max_it", [1, 2, 3, 7])
 def test_exhausted_iterations_match_reference_state(oracle, max_it, variant):
     """When the loop runs out (pcg.rs:48), the reference has still updated `search` (pcg.rs:72-77)."""
@@ -245,7 +246,7 @@ def test_deterministic(oracle):
     assert all(np.array_equal(u, v) for u, v in zip(a[1:], c[1:]))
 
 
-@pytest.mark.parametrize("variant", ["stream", "stream_dyn", "stream_dyn_batch", "sr", "sr_dyn", "sr_dyn_batch", "resident", "resident_push", "resident_v1"])
+@pytest.mark.parametrize("variant", ["stream", "stream_dyn", "stream_dyn_batch", "sr", "sr_dyn", "sr_dyn_batch", "resident_sr", "resident", "resident_push", "resident_v1"])
 def test_large_grid_capped_solve(oracle, variant):
     """1024^2 (BASELINE configs[1] size): the cap of 100 iterations is hit, as SURVEY.md 6 observes
     for N >= 512; compare the full iterate with the oracle after a fixed 100 iterations."""
