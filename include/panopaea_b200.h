@@ -122,11 +122,20 @@ PANO_API int pano_ctx_step_times(pano_ctx *ctx, double ms_out[PANO_STEP_PHASES],
 PANO_API int pano_ctx_cg_profile(pano_ctx *ctx, int64_t cycles_out[8]);
 /* Same option, streaming kernel: cycles every CTA spent in its P1 tile loop ([0, G)) and P2 tile loop ([G, 2G)), G = CTAs. */
 PANO_API int pano_ctx_cg_profile_ctas(pano_ctx *ctx, int64_t *cycles_out, int n);
-/* tuning knobs: "cg_kernel" 0 auto / 1 generic / 2 TMA streaming / 3 SM-resident / 4 SM-resident v1 / 5 one cluster, "cg_ldcg" 0/1,
- * "cg_zigzag" 0/1, "cg_blocks_per_sm" n, "cg_profile" 0/1, "step_timing" 0/1; streaming kernel: "cg_dynamic" -1 auto (from 24
+/* tuning knobs: "cg_kernel" 0 auto / 1 generic / 2 TMA streaming (two reductions per iteration, as pcg.rs is written) /
+ * 3 SM-resident / 4 SM-resident v1 / 5 one cluster / 6 TMA streaming with ONE reduction per iteration (Chronopoulos-Gear
+ * arrangement of the same iteration) / 7 SM-resident with one reduction; "cg_single_reduction" 1 (default: auto prefers
+ * kernels 7 and 6 over 3 and 2, also on the slabs of pano_dist) / 0; "cg_ldcg" 0/1,
+ * "cg_zigzag" 0/1, "cg_blocks_per_sm" n, "cg_profile" 0/1, "step_timing" 0/1; streaming kernels: "cg_dynamic" -1 auto (from 24
  * tiles per CTA) / 0 fixed tile lists / 1 claimed tiles, "cg_batch" n (claim unit, 0 auto), "cg_fence" bit 0 fence.acq_rel
  * instead of fence.sc, bit 1 system scope only in CTAs that stored into a peer; multi-GPU: "cg_xflags" 1 halo flags (default) /
- * 0 fenced root exchange, "cg_halo_first" 0/1; SM-resident kernel: "cg_push" 0 root all-reduce (default) / 1 per-CTA inboxes.
+ * 0 fenced root exchange, "cg_halo_first" 0/1, "dist_fused_halos" 1 (default with the single-reduction solver: ONE ghost-row
+ * exchange per step, everything else recomputed locally or mirrored from inside the solver) / 0 four exchanges, "slab_kernels"
+ * 0 marching kernels on the slabs (default) / 1 first-generation kernels; SM-resident kernel: "cg_push" 0 root all-reduce
+ * (default) / 1 per-CTA inboxes; advection: "advect_kernel" 0 auto / 1 k_advect / 2 k_advect_march / 3 k_advect_march3 /
+ * 4 k_advect_tma (TMA-staged persistent kernel; f64, even sizes, at least 128 x 256), "advect_dynamic" 1 tiles claimed from a
+ * counter (default) / 0 round-robin, "advect_ctas" n (cap on the persistent grid), "advect_rows" 2/4/8, "advect_prefetch" 0..3,
+ * "advect_minblocks" 3..5 (marching kernel).
  * A key that was not set with this call is looked up in the environment as PANO_OPT_<key> before its default applies. */
 PANO_API int pano_ctx_set_option(pano_ctx *ctx, const char *key, int64_t value);
 PANO_API int pano_ctx_get_option(pano_ctx *ctx, const char *key, int64_t *value);

@@ -70,6 +70,7 @@ struct SrArgs {
     int zigzag;
     int fence_mode;
     int dynamic;
+    int halo_mid;                 // slab with neighbours: the first and last tile row sit in the MIDDLE of the tile order (see tile_at)
     unsigned long long *claim;    // 4 claim counters, used round-robin by the passes (zeroed at launch)
     ReduceUnit *tparts;           // [3 values][nbatch * kConsumerWarps] per-(batch, warp) partials, {value, pass tag}
     int batch_len, nbatch_long, nbatch;
@@ -101,25 +102,28 @@ __device__ __forceinline__ int slot_word(const int *p) {   // read by lane 0 (th
     return __shfl_sync(0xffffffffu, v, 0);
 }
 
-__device__ __forceinline__ double consumer_sum(double v, double *wsum) {
-    v = warp_sum(v);
+// deterministic block reduction of {sum, sum, max} among the 256 consumer threads (one pair of barriers for the three values);
+// results in every consumer thread
+__device__ __forceinline__ void consumer_reduce3(double &v0, double &v1, double &v2, double (*wsum)[kConsumerWarps]) {
+    v0 = warp_sum(v0);
+    v1 = warp_sum(v1);
+    v2 = warp_max(v2);
     consumer_sync();
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+    if ((threadIdx.x & 31) == 0) {
+        const int wd = threadIdx.x >> 5;
+        wsum[0][wd] = v0;
+        wsum[1][wd] = v1;
+        wsum[2][wd] = v2;
+    }
     consumer_sync();
-    double t = 0;
+    double t0 = 0, t1 = 0, t2 = 0;
 #pragma unroll
-    for (int i = 0; i < kConsumerWarps; ++i) t += wsum[i];
-    return t;
-}
-__device__ __forceinline__ double consumer_max(double v, double *wsum) {
-    v = warp_max(v);
-    consumer_sync();
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
-    consumer_sync();
-    double t = 0;
-#pragma unroll
-    for (int i = 0; i < kConsumerWarps; ++i) t = wsum[i] > t ? wsum[i] : t;
-    return t;
+    for (int i = 0; i < kConsumerWarps; ++i) {
+        t0 += wsum[0][i];
+        t1 += wsum[1][i];
+        t2 = wsum[2][i] > t2 ? wsum[2][i] : t2;
+    }
+    v0 = t0; v1 = t1; v2 = t2;
 }
 
 struct Open4 { bool n, s, w, e; };
@@ -282,6 +286,23 @@ __device__ __forceinline__ void tile_sr(const SrArgs &a, const double *R, const 
     }
 }
 
+// Position in the (un-reversed) tile order -> tile.  Plain: row-major.  halo_mid (slab of a multi-GPU grid, >= 4 tile rows): tile
+// rows in the order 1 .. mid, 0, Ty-1, mid+1 .. Ty-2 -- the two tile rows whose cells are mirrored into the neighbours' memory are
+// done in the middle of a pass in EITHER direction (odd passes walk the order backwards for L2 reuse), so a CTA can fence at
+// system scope and raise its halo flags long before the pass ends (when it first gets a tile behind them), instead of putting
+// 3 us of MEMBAR.SYS and the flags' NVLink latency on the critical path of every reduction.
+__device__ __forceinline__ int tile_at(const SrArgs &a, int pos) {
+    if (!a.halo_mid) return pos;
+    const int q = pos / a.tiles_x, c = pos - q * a.tiles_x, mid = (a.tiles_y - 2) / 2;
+    const int row = q < mid ? q + 1 : (q == mid ? 0 : (q == mid + 1 ? a.tiles_y - 1 : q - 1));
+    return row * a.tiles_x + c;
+}
+// is tile t behind the halo rows in the direction of this pass?
+__device__ __forceinline__ bool behind_halo(const SrArgs &a, int t, bool reversed) {
+    const int row = t / a.tiles_x, mid = (a.tiles_y - 2) / 2;
+    return reversed ? (row >= 1 && row <= mid) : (row > mid && row < a.tiles_y - 1);
+}
+
 // all open: every cell of the tile AND of its one-cell ring is an interior cell away from the walls and the obstacle
 __device__ __forceinline__ bool tile_is_fast(const SrArgs &a, int ty0, int tx0) {
     const int g0 = a.gy0 + ty0;
@@ -349,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_sr(const __grid_constant__ S
                     if (jj >= n_my) return false;
                     const int j = ((k & 1) && a.zigzag) ? n_my - 1 - jj : jj;
                     ++jj;
-                    t = blockIdx.x + j * G;
+                    t = tile_at(a, blockIdx.x + j * G);
                     closes = -1;
                     return true;
                 }
@@ -362,7 +383,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_sr(const __grid_constant__ S
                     else { b_next = a.nbatch_long * a.batch_len + (b_idx - a.nbatch_long); b_end = b_next + 1; }
                 }
                 const int pos = b_next++;
-                t = ((k & 1) && a.zigzag) ? ntiles - 1 - pos : pos;
+                t = tile_at(a, ((k & 1) && a.zigzag) ? ntiles - 1 - pos : pos);
                 closes = b_next == b_end ? b_idx : -1;
                 return true;
             };
@@ -413,6 +434,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_sr(const __grid_constant__ S
         const unsigned long long tag = a.seq_base + (unsigned long long)k + 1;
         double *r_dst = a.r[(it + 1) & 1], *s_dst = a.s[it & 1];
         double *r_up = a.up_r[(it + 1) & 1], *r_dn = a.dn_r[(it + 1) & 1], *s_up = a.up_s[it & 1], *s_dn = a.dn_s[it & 1];
+        const bool reversed = (k & 1) && a.zigzag;
+        bool flags_pending = a.halo_mid != 0, flags_sent = false;
         for (;; ++n) {
             const int st = n % kStages;
             if (!mbar_wait(&tl->full[st], (n / kStages) & 1, err)) return;
@@ -424,6 +447,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_sr(const __grid_constant__ S
                 break;
             }
             const int tx0 = (t % a.tiles_x) * TW, ty0 = (t / a.tiles_x) * TH;
+            if (flags_pending && behind_halo(a, t, reversed)) {
+                // this CTA's halo tiles of the pass are behind it (tiles are claimed in increasing order): vouch for them now
+                consumer_sync();                   // every consumer warp's halo-row stores happen-before thread 0's fence
+                if (tid == 0) {
+                    fence_sys((a.fence_mode & kFenceLight) != 0);
+                    send_halo_flags(&a.xr, (unsigned long long)k);
+                }
+                flags_pending = false;
+                flags_sent = true;
+                remote = false;
+            }
             const double *R = reinterpret_cast<const double *>(smem + st * kStageBytes);
             const double *S = reinterpret_cast<const double *>(smem + st * kStageBytes + kRSlot);
             const double *Pb = reinterpret_cast<const double *>(smem + st * kStageBytes + kRSlot + kSSlot);
@@ -470,12 +504,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_sr(const __grid_constant__ S
                 acc_max = v > acc_max ? v : acc_max;
             }
         }
-        const double v0 = consumer_sum(acc_g, tl->wsum[0]);
-        const double v1 = consumer_sum(acc_d, tl->wsum[1]);
-        const double v2 = consumer_max(acc_max, tl->wsum[2]);
+        double v0 = acc_g, v1 = acc_d, v2 = acc_max;
+        consumer_reduce3(v0, v1, v2, tl->wsum);
         if (!grid_allreduce_units(a.units, a.seq_base + (unsigned long long)k, (unsigned long long)k, 3, v0, v1, v2, 0x4u, tl->vals, tl->out,
-                                  &tl->ok, &a.ctl->error, /*fenced=*/true, [] { consumer_sync(); }, red, &a.xr, NoWork(), nullptr, a.fence_mode,
-                                  remote, false)) {
+                                  &tl->ok, &a.ctl->error, /*fenced=*/true, [] { consumer_sync(); }, red, &a.xr, NoWork(), nullptr,
+                                  a.halo_mid ? (a.fence_mode | kFenceSysIfRemote) : a.fence_mode, remote, flags_sent)) {
             if (tid == 0) { tl->cont = 0; mbar_arrive(&tl->go); }
             return;
         }
@@ -618,6 +651,7 @@ int pano_cg_sr_launch(pano_ctx *ctx, double *x, const double *b, double *r, doub
     const int64_t dyn_opt = pano_option(ctx, "cg_dynamic", -1);
     const bool dynamic = dyn_opt > 0 || (dyn_opt < 0 && ntiles >= 24 * G);
     a.dynamic = dynamic ? 1 : 0;
+    a.halo_mid = (slab && slab->nranks > 1 && a.xr.hflags != nullptr && a.tiles_y >= 4 && pano_option(ctx, "cg_halo_mid", 0) != 0) ? 1 : 0;
     if (dynamic) {
         int bl = (int)pano_option(ctx, "cg_batch", 0);
         if (bl <= 0) bl = ntiles / (6 * G);

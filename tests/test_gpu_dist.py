@@ -177,3 +177,29 @@ def test_loopback_tma_advection(nranks, h, w):
         vy, vx = single.vel.split()
         assert np.abs(dist.gather_local(ranks, dist.VY) - vy).max() <= 1e-8 * max(1.0, np.abs(vy).max())
         assert np.abs(dist.gather_local(ranks, dist.VX) - vx).max() <= 1e-8 * max(1.0, np.abs(vx).max())
+
+
+@pytest.mark.parametrize("dynamic", [0, 1])
+@pytest.mark.parametrize("nranks,h,w", [(2, 256, 256), (3, 480, 192)])
+def test_loopback_halo_tiles_mid_pass(nranks, h, w, dynamic):
+    """cg_halo_mid = 1: the tile rows mirrored into the neighbours sit in the middle of every pass and the halo flags go out right
+    behind them (pano_cg_sr.cu: tile_at).  Tile order and flag timing change, the results must not: bit-identical to the default."""
+    from panopaea_b200 import dist
+    k = 2
+    prm = dict(timestep=0.05, threshold=0.1, max_iterations=60, inflow=(5 * k, 20 * k, 27 * k, 32 * k), inflow_density=1.0,
+               inflow_vy=20.0, obstacle=(70 * k, 80 * k, 25 * k, 35 * k))
+    out = []
+    for mid in (0, 1):
+        ranks = _make_ranks(nranks, h, w, prm)
+        for r in ranks:
+            r.ctx.set_option("cg_dynamic", dynamic)
+            r.ctx.set_option("cg_halo_mid", mid)
+        infos = None
+        for _ in range(4):
+            infos = _step_all(ranks)
+        out.append((infos, [dist.gather_local(ranks, f) for f in (dist.DENSITY, dist.VY, dist.VX, dist.PRESSURE)]))
+        for r in ranks:
+            r.close()
+    assert out[0][0] == out[1][0]
+    for a, b in zip(out[0][1], out[1][1]):
+        assert np.array_equal(a, b)
