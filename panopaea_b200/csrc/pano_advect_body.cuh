@@ -44,9 +44,9 @@ __device__ __noinline__ double mac_gather_far(double relx, double rely, int H, i
 // pano_cell_math.h (floor by a round-down add, one clamp per axis instead of three, no 64-bit conversions), positions
 // carried as doubles and advanced by +1.0 (exact).  kEdge = false: the caller guarantees 1 <= x <= w-1 and
 // 1 <= ys, ys+kRows-1 <= h-1, so every border select disappears.  kEdge = true: rows from yend on are skipped.
-template <bool kEdge, int kRows, class A>
+template <bool kEdge, int kRows, class A, class AX>
 __device__ __forceinline__ void advect_march3_body(double *__restrict__ q_dst, double *__restrict__ vy_dst, double *__restrict__ vx_dst,
-                                                   const A &q, const A &vy, const A &vx, int h, int w, double dt, int x, int ys, int yend) {
+                                                   const A &q, const A &vy, const AX &vx, int h, int w, double dt, int x, int ys, int yend) {
     const bool xin = !kEdge || x < w, xpos = !kEdge || x > 0;
     const double ndt = -dt, xd = (double)x, xh = xd + 0.5;
     const double wlim = (double)w - 1.00001, hlim = (double)h - 1.00001;

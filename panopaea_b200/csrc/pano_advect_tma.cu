@@ -12,8 +12,9 @@
 //   * 16 consumer warps compute from shared memory: a thread marches down 4 rows of one column carrying the eight
 //     velocity samples around its cell in registers; the twelve gathers of a row are shared-memory loads
 //   * a backtrace that leaves the box (more than two cells: |v| dt >= 2) falls back to global memory for that cell; tiles
-//     within one tile of the domain border, where the reference's index / coordinate clamps bite, and the x = w / y = h
-//     strips run the marching body on global memory (pano_advect_body.cuh)
+//     within one tile of the domain border, where the reference's index / coordinate clamps bite, run the marching body
+//     with its clamps on the same staged boxes (first version: on global memory -- 4.6 % of the tiles took 17 % of the
+//     kernel's stall samples, all long-scoreboard); the x = w / y = h strips run it on global memory (pano_advect_body.cuh)
 // Arithmetic is pano_cell_math.h's in every path: bit-identical to the reference (tests/test_gpu_fused.py).
 // HBM traffic: 48 B per cell (halo re-reads hit the 126 MB L2: neighbouring tiles are in flight together).
 #include "pano_advect_body.cuh"
@@ -69,6 +70,9 @@ __device__ __forceinline__ bool tile_interior(const AdvArgs &a, int ty0, int tx0
 
 // advect_mac's gather coordinates without the index clamps (the caller checks that the corner lies inside the staged box,
 // which lies inside the grid): same bits as pano::mac_coord_fast there
+// A negative coordinate makes floor_nonneg's guard word differ (v + 2^52 drops below 2^52), so it shows up in `bad` like a
+// coordinate beyond 2^32 does, and the cell takes the full forms; for v >= 0 max(v, 0) = v and the weight v - floor(v) is the
+// reference's (pano_cell_math.h).
 struct MacCoordI {
     int x0, y0;
     double s, t;
@@ -76,13 +80,39 @@ struct MacCoordI {
 };
 __device__ __forceinline__ MacCoordI mac_coord_open(double relx, double rely) {
     MacCoordI c;
-    const double rx = pano::clamp_lo0(relx), ry = pano::clamp_lo0(rely);
-    const pano::FloorNN fx = pano::floor_nonneg(rx), fy = pano::floor_nonneg(ry);
+    const pano::FloorNN fx = pano::floor_nonneg(relx), fy = pano::floor_nonneg(rely);
     c.bad = (fx.hi ^ pano::kFloorHi) | (fy.hi ^ pano::kFloorHi);
     c.x0 = (int)fx.i; c.y0 = (int)fy.i;
-    c.s = rx - fx.f; c.t = ry - fy.f;
+    c.s = relx - fx.f; c.t = rely - fy.f;
     return c;
 }
+
+// Border tiles: the marching body with the reference's clamps, reading the staged boxes where the (clamped, hence in-grid)
+// index falls inside them and global memory otherwise.  Out-of-grid parts of a box are zero-filled by TMA and never addressed.
+template <class A>
+struct BoxQ {      // q or vy: box origin (by0, bx0), QH x QW; rows from `rh` on lie beyond the STORED rows of a slab (zero-filled
+    const double *sm;   // like out-of-grid ones, but a long backtrace may address them: the global accessor then reports it)
+    int by0, bx0;
+    unsigned rh;
+    A g;
+    __device__ __forceinline__ double operator()(int y, int x) const {
+        const unsigned ry = (unsigned)(y - by0), rx = (unsigned)(x - bx0);
+        if (ry < rh && rx < (unsigned)QW) return sm[ry * QW + rx];
+        return g(y, x);
+    }
+};
+template <class A>
+struct BoxX {      // vx: even rows at [(r >> 1) * XW + c], odd rows at [kXOdd + (r >> 1) * XW + c]
+    const double *sm;
+    int by0, bx0;
+    unsigned rh;
+    A g;
+    __device__ __forceinline__ double operator()(int y, int x) const {
+        const unsigned ry = (unsigned)(y - by0), rx = (unsigned)(x - bx0);
+        if (ry < rh && rx < (unsigned)QW) return sm[(ry >> 1) * XW + rx + (ry & 1u) * kXOdd];
+        return g(y, x);
+    }
+};
 
 // one cell whose backtrace left the staged boxes: the full forms on global memory
 template <class A>
@@ -123,17 +153,21 @@ __device__ __forceinline__ void advect_tile(const AdvArgs &a, const double *__re
         const double D = pvy[(k + 1) * QW], F = pvy[(k + 1) * QW - 1];
         const double vvy = (C + D + E + F) / 4.0;               // dec_fluid.rs:220-225 with xc = x, xm = x - 1
         const double vvx = (A_ + B + G + H) / 4.0;              // :257-263 with yc = y, ym = y - 1
-        const pano::CellCoord cq = pano::advect_coord_fast(xh, yh, wlim, hlim, ndt, (A_ + B) / 2.0, (C + D) / 2.0);
+        // advect's coordinates (dec_fluid.rs:184-192): inside the box, which lies >= 62 cells inside the grid, the clamps
+        // max(., 0) and min(., w - 1.00001) are identities, so they are skipped here and the box test below stands in for them
+        const double ucx = (A_ + B) / 2.0, ucy = (C + D) / 2.0;
+        const double pqx = (xh + ndt * ucx) - 0.5, pqy = (yh + ndt * ucy) - 0.5;
+        const MacCoordI cq = mac_coord_open(pqx, pqy);
         double rxx, rxy, ryx, ryy;
         pano::mac_x_rel(xd, yh, ndt, A_, vvy, rxx, rxy);
         pano::mac_y_rel(xh, yd, ndt, vvx, C, ryx, ryy);
         const MacCoordI cx = mac_coord_open(rxx, rxy), cy = mac_coord_open(ryx, ryy);
         // box-relative corners; a corner at (u, v) needs u + 1 and v + 1 as well
-        const unsigned qx = (unsigned)(cq.ix - bx0), qy = (unsigned)(cq.iy - by0);
+        const unsigned qx = (unsigned)(cq.x0 - bx0), qy = (unsigned)(cq.y0 - by0);
         const unsigned xx = (unsigned)(cx.x0 - bx0), xy = (unsigned)(cx.y0 - by0);
         const unsigned yx = (unsigned)(cy.x0 - bx0), yy = (unsigned)(cy.y0 - by0);
-        const bool inside = (cx.bad | cy.bad) == 0u && qx <= (unsigned)(QW - 2) && xx <= (unsigned)(QW - 2) && yx <= (unsigned)(QW - 2) &&
-                            qy <= (unsigned)(QH - 2) && xy <= (unsigned)(QH - 2) && yy <= (unsigned)(QH - 2);
+        const unsigned mx = max(max(qx, xx), yx), my = max(max(qy, xy), yy);
+        const bool inside = (cq.bad | cx.bad | cy.bad) == 0u && mx <= (unsigned)(QW - 2) && my <= (unsigned)(QH - 2);
         if (inside) {
             // one straight-line block: all twelve gathers in flight together
             const double *gq_ = Q + qy * QW + qx;
@@ -144,15 +178,21 @@ __device__ __forceinline__ void advect_tile(const AdvArgs &a, const double *__re
             const double q00 = gq_[0], q01 = gq_[1], q10 = gq_[QW], q11 = gq_[QW + 1];
             const double x00 = gx0[0], x01 = gx0[1], x10 = gx1[0], x11 = gx1[1];
             const double y00 = gy_[0], y01 = gy_[1], y10 = gy_[QW], y11 = gy_[QW + 1];
-            qo[k * w] = pano::bilinear(q00, q01, q10, q11, cq.u, cq.v);
+            qo[k * w] = pano::bilinear(q00, q01, q10, q11, cq.s, cq.t);
             vxo[k * (w + 1)] = pano::bilinear(x00, x01, x10, x11, cx.s, cx.t);
             vyo[k * w] = pano::bilinear(y00, y01, y10, y11, cy.s, cy.t);
         } else {
-            cell_from_global<A>(a.q_dst, a.vy_dst, a.vx_dst, gq, gvy, gvx, h, w, y, x, cq, rxx, rxy, ryx, ryy);
+            const pano::CellCoord cqf = pano::advect_coord_fast(xh, yh, wlim, hlim, ndt, ucx, ucy);
+            cell_from_global<A>(a.q_dst, a.vy_dst, a.vx_dst, gq, gvy, gvx, h, w, y, x, cqf, rxx, rxy, ryx, ryy);
         }
         C = D; E = F; G = A_; H = B;
         yd += 1.0;
     }
+}
+
+template <class AQ, class AX>
+__device__ __noinline__ void advect_edge_tile(const AdvArgs &a, const AQ &q, const AQ &vy, const AX &vx, int x, int ys) {
+    pano_adv::advect_march3_body<true, kRows>(a.q_dst, a.vy_dst, a.vx_dst, q, vy, vx, a.h, a.w, a.dt, x, ys, a.yb);
 }
 
 template <bool kSlab>
@@ -197,17 +237,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_advect_tma(const __grid_constan
             }
             tl->tile[st] = t;
             const int tx0 = (t % a.tiles_x) * TW, ty0 = a.ya + (t / a.tiles_x) * TH;
-            if (tile_interior(a, ty0, tx0)) {
+            {   // border tiles are staged as well: TMA zero-fills what lies outside the stored arrays, the clamped indices never go there
                 unsigned char *base = smem + st * kStageBytes;
                 uint64_t *bar = &tl->full[st];
                 mbar_arrive_expect_tx(bar, 2 * kQBytes + 2 * kXBytes);
-                const int by = ty0 - kG - a.ylo;                // box row in the stored arrays (even)
+                const int by = ty0 - kG - a.ylo;                // box row in the stored arrays (even; -2 in the first tile row of the grid)
                 tma_load_2d(base, &a.m_q, bar, tx0 - kG, by);
                 tma_load_2d(base + kQBytes, &a.m_vy, bar, tx0 - kG, by);
                 tma_load_2d(base + 2 * kQBytes, &a.m_vx, bar, tx0 - kG, by >> 1);                       // even rows
                 tma_load_2d(base + 2 * kQBytes + kXSlot, &a.m_vx, bar, a.w + 1 + tx0 - kG - 1, by >> 1);   // odd rows, one column to the left
-            } else {
-                mbar_arrive(&tl->full[st]);                     // border tile: the consumers read global memory
             }
             ++n;
         }
@@ -239,8 +277,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_advect_tma(const __grid_constan
             advect_tile<Acc>(a, Q, Q + kQBytes / 8, Q + 2 * (kQBytes / 8), gq, gvy, gvx, ty0, tx0, ly0, lx);
         } else {
             const int x = tx0 + lx, ys = ty0 + ly0;
-            if (x < a.w && ys < a.yb)
-                pano_adv::advect_march3_body<true, kRows>(a.q_dst, a.vy_dst, a.vx_dst, gq, gvy, gvx, a.h, a.w, a.dt, x, ys, a.yb);
+            if (x < a.w && ys < a.yb) {
+                const double *Q = reinterpret_cast<const double *>(smem + st * kStageBytes);
+                const int by0 = ty0 - kG;
+                const unsigned rhq = kSlab ? (unsigned)min(QH, a.whi_q - by0) : (unsigned)QH;
+                const unsigned rhvy = kSlab ? (unsigned)min(QH, a.whi_vy - by0) : (unsigned)QH;
+                const BoxQ<Acc> bq{Q, by0, tx0 - kG, rhq, gq}, bvy{Q + kQBytes / 8, by0, tx0 - kG, rhvy, gvy};
+                const BoxX<Acc> bvx{Q + 2 * (kQBytes / 8), by0, tx0 - kG, rhq, gvx};
+                advect_edge_tile(a, bq, bvy, bvx, x, ys);
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&tl->empty[st]);

@@ -70,6 +70,7 @@ struct SrArgs {
     int zigzag;
     int fence_mode;
     int dynamic;
+    int sm_exchange;              // 1: tile_sr_sm (r_(i+1) exchanged through shared memory), 0: tile_sr (recomputed per thread)
     int halo_mid;                 // slab with neighbours: the first and last tile row sit in the MIDDLE of the tile order (see tile_at)
     unsigned long long *claim;    // 4 claim counters, used round-robin by the passes (zeroed at launch)
     ReduceUnit *tparts;           // [3 values][nbatch * kConsumerWarps] per-(batch, warp) partials, {value, pass tag}
@@ -286,6 +287,150 @@ __device__ __forceinline__ void tile_sr(const SrArgs &a, const double *R, const 
     }
 }
 
+// The same pass with the new residual exchanged through SHARED MEMORY instead of being recomputed four columns wide in every
+// thread (tile_sr evaluates 24 first-stage cells for 8 cells it owns; ncu: 6.2 G warp instructions per solve at 4096^2 against
+// 5.7 G for the two-reduction kernel, both latency-bound at 27 % issue utilisation, so time follows the instruction count):
+//   phase A  every thread evaluates the first stage (w_i, s_i, r_(i+1)) on its 8 own cells, 192 threads one cell of the tile's
+//            ring each; r_(i+1) goes to global memory (own cells) and, for all of them, into the staged s box IN PLACE -- the
+//            thread that read s_(i-1) of a cell is the one that overwrites it
+//   barrier  among the 256 consumers
+//   phase B  second stage (w_(i+1) = A r_(i+1), dots, p, x) with the neighbours' r_(i+1) from shared memory
+// The stage is handed back after a fence.proxy.async.shared::cta (generic writes, then TMA writes, to the same shared memory).
+template <bool kFast, int kMode>
+__device__ __forceinline__ void tile_sr_sm(const SrArgs &a, const double *R, double *S, const double *Pb, const double *Xb,
+                                           double *r_dst, double *s_dst, double *r_up, double *r_dn, double *s_up, double *s_dn,
+                                           int ty0, int tx0, double alpha, double beta, double &acc_g, double &acc_d, double &acc_max) {
+    static_assert(kMode == 1 || kMode == 2, "the opening pass has no first stage");
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int col = 2 * lane, row0 = wid * kRows;
+    const int gx = tx0 + col;
+    const double nalpha = -alpha;
+    // first stage at one cell: box indices of r (two-cell halo) and s (one-cell halo) of tile cell (ty, tx)
+    auto first_stage = [&](int ty, int tx, bool open_all, double &s_out) -> double {
+        const double *pr = R + (ty + 2) * BW + tx + kHX;
+        const double c = pr[0], n = pr[-BW], so = pr[BW], we = pr[-1], ea = pr[1];
+        double wv;
+        if (open_all) {
+            wv = pano::laplacian_cell<double>(c, n, so, we, ea, true, true, true, true, a.dt);
+        } else {
+            const Open4 o = open_edges(a, a.gy0 + ty0 + ty, tx0 + tx);
+            wv = pano::laplacian_cell<double>(c, n, so, we, ea, o.n, o.s, o.w, o.e, a.dt);
+        }
+        s_out = kMode == 2 ? wv + beta * S[(ty + 1) * BW + tx + kHX] : wv;
+        return c + nalpha * s_out;                                             // pcg.rs:56
+    };
+    // ---- phase A, own cells: rows row0 .. row0+3, columns col, col+1 (vertical register window over the r box)
+    {
+        const double *pr = R + (row0 + 2) * BW + col + kHX;
+        double2 up = *reinterpret_cast<const double2 *>(pr - BW), c = *reinterpret_cast<const double2 *>(pr);
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) {
+            const double2 dn = *reinterpret_cast<const double2 *>(pr + (k + 1) * BW);
+            const double wv = pr[k * BW - 1], ev = pr[k * BW + 2];
+            const int ly = ty0 + row0 + k, gy = a.gy0 + ly;
+            double z0, z1;
+            if (kFast) {
+                z0 = pano::laplacian_cell<double>(c.x, up.x, dn.x, wv, c.y, true, true, true, true, a.dt);
+                z1 = pano::laplacian_cell<double>(c.y, up.y, dn.y, c.x, ev, true, true, true, true, a.dt);
+            } else {
+                const Open4 o0 = open_edges(a, gy, gx), o1 = open_edges(a, gy, gx + 1);
+                z0 = pano::laplacian_cell<double>(c.x, up.x, dn.x, wv, c.y, o0.n, o0.s, o0.w, o0.e, a.dt);
+                z1 = pano::laplacian_cell<double>(c.y, up.y, dn.y, c.x, ev, o1.n, o1.s, o1.w, o1.e, a.dt);
+            }
+            double2 *ps = reinterpret_cast<double2 *>(S + (row0 + k + 1) * BW + col + kHX);
+            double2 sv;
+            if (kMode == 2) {
+                const double2 so = *ps;
+                sv.x = z0 + beta * so.x;
+                sv.y = z1 + beta * so.y;
+            } else {
+                sv = make_double2(z0, z1);
+            }
+            double2 rv;
+            rv.x = c.x + nalpha * sv.x;                                        // pcg.rs:56
+            rv.y = c.y + nalpha * sv.y;
+            *ps = rv;                                                          // r_(i+1) replaces s_(i-1) in the staged box
+            if (kFast || (ly < a.h && gx < a.w)) {
+                const size_t gi = (size_t)(a.row0 + ly) * a.w + gx;
+                *reinterpret_cast<double2 *>(s_dst + gi) = sv;
+                *reinterpret_cast<double2 *>(r_dst + gi) = rv;
+                // halo rows go straight into the neighbours' HBM (NVLink): two rows of r, one of s
+                if (r_up && ly < 2) *reinterpret_cast<double2 *>(r_up + (size_t)ly * a.w + gx) = rv;
+                if (r_dn && ly >= a.h - 2) *reinterpret_cast<double2 *>(r_dn + (size_t)(ly - (a.h - 2)) * a.w + gx) = rv;
+                if (s_up && ly == 0) *reinterpret_cast<double2 *>(s_up + gx) = sv;
+                if (s_dn && ly == a.h - 1) *reinterpret_cast<double2 *>(s_dn + gx) = sv;
+            }
+            up = c;
+            c = dn;
+        }
+    }
+    // ---- phase A, the ring: row -1 (threads 0..63), row TH (64..127), column -1 (128..159), column TW (160..191)
+    if (tid < 2 * TW + 2 * TH) {
+        int ty, tx;
+        if (tid < TW) { ty = -1; tx = tid; }
+        else if (tid < 2 * TW) { ty = TH; tx = tid - TW; }
+        else if (tid < 2 * TW + TH) { ty = tid - 2 * TW; tx = -1; }
+        else { ty = tid - 2 * TW - TH; tx = TW; }
+        double s_unused;
+        const double rv = first_stage(ty, tx, kFast, s_unused);
+        S[(ty + 1) * BW + tx + kHX] = rv;
+    }
+    consumer_sync();
+    // ---- phase B: w_(i+1) = A r_(i+1) from the shared r_(i+1), the dots, p and x on the own cells
+    {
+        const double *pn = S + (row0 + 1) * BW + col + kHX;
+        const double *pr = R + (row0 + 2) * BW + col + kHX;
+        double2 up = *reinterpret_cast<const double2 *>(pn - BW), c = *reinterpret_cast<const double2 *>(pn);
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) {
+            const double2 dn = *reinterpret_cast<const double2 *>(pn + (k + 1) * BW);
+            const double wv = pn[k * BW - 1], ev = pn[k * BW + 2];
+            const int ly = ty0 + row0 + k, gy = a.gy0 + ly;
+            double z0, z1;
+            bool valid = true;
+            if (kFast) {
+                z0 = pano::laplacian_cell<double>(c.x, up.x, dn.x, wv, c.y, true, true, true, true, a.dt);
+                z1 = pano::laplacian_cell<double>(c.y, up.y, dn.y, c.x, ev, true, true, true, true, a.dt);
+            } else {
+                valid = ly < a.h && gx < a.w;
+                const Open4 o0 = open_edges(a, gy, gx), o1 = open_edges(a, gy, gx + 1);
+                z0 = pano::laplacian_cell<double>(c.x, up.x, dn.x, wv, c.y, o0.n, o0.s, o0.w, o0.e, a.dt);
+                z1 = pano::laplacian_cell<double>(c.y, up.y, dn.y, c.x, ev, o1.n, o1.s, o1.w, o1.e, a.dt);
+            }
+            if (valid) {
+                const size_t gi = (size_t)(a.row0 + ly) * a.w + gx;
+                const int ti = (row0 + k) * TW + col;
+                const double2 ro = *reinterpret_cast<const double2 *>(pr + k * BW);   // r_i
+                double2 pv, xv;
+                if (kMode == 1) {
+                    pv = ro;                                                   // p_0 = r_0 (pcg.rs:40-42)
+                    xv = make_double2(alpha * ro.x, alpha * ro.y);             // x_1 = 0 + alpha_0 p_0
+                } else {
+                    const double2 po = *reinterpret_cast<const double2 *>(Pb + ti), xo = *reinterpret_cast<const double2 *>(Xb + ti);
+                    pv.x = ro.x + beta * po.x;                                 // pcg.rs:72-77
+                    pv.y = ro.y + beta * po.y;
+                    xv.x = xo.x + alpha * pv.x;                                // pcg.rs:55
+                    xv.y = xo.y + alpha * pv.y;
+                }
+                *reinterpret_cast<double2 *>(a.p + gi) = pv;
+                *reinterpret_cast<double2 *>(a.x + gi) = xv;
+                if (a.dn_x && ly == a.h - 1) *reinterpret_cast<double2 *>(a.dn_x + gx) = xv;   // every pass; the last one counts
+                acc_g = acc_g + c.x * c.x;
+                acc_g = acc_g + c.y * c.y;
+                acc_d = acc_d + z0 * c.x;
+                acc_d = acc_d + z1 * c.y;
+                const double a0 = c.x < 0 ? -c.x : c.x, a1 = c.y < 0 ? -c.y : c.y;
+                acc_max = a0 > acc_max ? a0 : acc_max;
+                acc_max = a1 > acc_max ? a1 : acc_max;
+            }
+            up = c;
+            c = dn;
+        }
+    }
+    // generic-proxy writes to the stage, then (once the slot is handed back) TMA writes to it
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 // Position in the (un-reversed) tile order -> tile.  Plain: row-major.  halo_mid (slab of a multi-GPU grid, >= 4 tile rows): tile
 // rows in the order 1 .. mid, 0, Ty-1, mid+1 .. Ty-2 -- the two tile rows whose cells are mirrored into the neighbours' memory are
 // done in the middle of a pass in EITHER direction (odd passes walk the order backwards for L2 reuse), so a CTA can fence at
@@ -459,7 +604,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_sr(const __grid_constant__ S
                 remote = false;
             }
             const double *R = reinterpret_cast<const double *>(smem + st * kStageBytes);
-            const double *S = reinterpret_cast<const double *>(smem + st * kStageBytes + kRSlot);
+            double *S = reinterpret_cast<double *>(smem + st * kStageBytes + kRSlot);
             const double *Pb = reinterpret_cast<const double *>(smem + st * kStageBytes + kRSlot + kSSlot);
             const double *Xb = Pb + TH * TW;
             const bool fast = tile_is_fast(a, ty0, tx0);
@@ -468,7 +613,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_sr(const __grid_constant__ S
                 else tile_sr<false, 0>(a, R, S, Pb, Xb, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ty0, tx0, 0.0, 0.0, acc_g, acc_d, acc_max);
             } else {
                 remote = remote || tile_stores_remote(a, ty0);
-                if (k == 1) {
+                if (a.sm_exchange) {
+                    if (k == 1) {
+                        if (fast) tile_sr_sm<true, 1>(a, R, S, Pb, Xb, r_dst, s_dst, r_up, r_dn, s_up, s_dn, ty0, tx0, alpha, 0.0, acc_g, acc_d, acc_max);
+                        else tile_sr_sm<false, 1>(a, R, S, Pb, Xb, r_dst, s_dst, r_up, r_dn, s_up, s_dn, ty0, tx0, alpha, 0.0, acc_g, acc_d, acc_max);
+                    } else {
+                        if (fast) tile_sr_sm<true, 2>(a, R, S, Pb, Xb, r_dst, s_dst, r_up, r_dn, s_up, s_dn, ty0, tx0, alpha, beta, acc_g, acc_d, acc_max);
+                        else tile_sr_sm<false, 2>(a, R, S, Pb, Xb, r_dst, s_dst, r_up, r_dn, s_up, s_dn, ty0, tx0, alpha, beta, acc_g, acc_d, acc_max);
+                    }
+                } else if (k == 1) {
                     if (fast) tile_sr<true, 1>(a, R, S, Pb, Xb, r_dst, s_dst, r_up, r_dn, s_up, s_dn, ty0, tx0, alpha, 0.0, acc_g, acc_d, acc_max);
                     else tile_sr<false, 1>(a, R, S, Pb, Xb, r_dst, s_dst, r_up, r_dn, s_up, s_dn, ty0, tx0, alpha, 0.0, acc_g, acc_d, acc_max);
                 } else {
@@ -651,6 +804,7 @@ int pano_cg_sr_launch(pano_ctx *ctx, double *x, const double *b, double *r, doub
     const int64_t dyn_opt = pano_option(ctx, "cg_dynamic", -1);
     const bool dynamic = dyn_opt > 0 || (dyn_opt < 0 && ntiles >= 24 * G);
     a.dynamic = dynamic ? 1 : 0;
+    a.sm_exchange = pano_option(ctx, "cg_sr_exchange", 1) != 0 ? 1 : 0;
     a.halo_mid = (slab && slab->nranks > 1 && a.xr.hflags != nullptr && a.tiles_y >= 4 && pano_option(ctx, "cg_halo_mid", 0) != 0) ? 1 : 0;
     if (dynamic) {
         int bl = (int)pano_option(ctx, "cg_batch", 0);
