@@ -127,10 +127,14 @@ __device__ __noinline__ void cell_from_global(double *q_dst, double *vy_dst, dou
 // Interior tile: column x = tx0 + lx, rows ty0 + ly0 .. + kRows - 1 (ly0 a multiple of 4), everything from shared memory.
 //   Q, VY: boxes with origin (ty0 - 2, tx0 - 2), pitch QW.   VX: even rows of the same box at VX[(r >> 1) * XW + c],
 //   odd rows at VX[kXOdd + (r >> 1) * XW + c]  (r, c box-relative).
-template <class A>
+// kBorder: the same path for the threads of a BORDER tile whose four cells are at least one cell away from every wall (no
+// border select in the velocity averages); a cell then also checks that its gathers stay two cells inside the grid, where no
+// clamp of the reference bites, and within the box rows that hold stored data (`rows_ok`, slabs); otherwise it takes the
+// full forms on global memory like a cell whose backtrace leaves the box.
+template <bool kBorder, class A>
 __device__ __forceinline__ void advect_tile(const AdvArgs &a, const double *__restrict__ Q, const double *__restrict__ VY,
                                             const double *__restrict__ VX, const A &gq, const A &gvy, const A &gvx, int ty0, int tx0,
-                                            int ly0, int lx) {
+                                            int ly0, int lx, unsigned rows_ok) {
     const int h = a.h, w = a.w;
     const int x = tx0 + lx, ys = ty0 + ly0;
     const int bx0 = tx0 - kG, by0 = ty0 - kG;
@@ -167,7 +171,9 @@ __device__ __forceinline__ void advect_tile(const AdvArgs &a, const double *__re
         const unsigned xx = (unsigned)(cx.x0 - bx0), xy = (unsigned)(cx.y0 - by0);
         const unsigned yx = (unsigned)(cy.x0 - bx0), yy = (unsigned)(cy.y0 - by0);
         const unsigned mx = max(max(qx, xx), yx), my = max(max(qy, xy), yy);
-        const bool inside = (cq.bad | cx.bad | cy.bad) == 0u && mx <= (unsigned)(QW - 2) && my <= (unsigned)(QH - 2);
+        bool inside = (cq.bad | cx.bad | cy.bad) == 0u && mx <= (unsigned)(QW - 2) && my <= (kBorder ? rows_ok : (unsigned)(QH - 2));
+        if (kBorder)   // corners at most (h-3, w-3): x0 + 1 <= w - 2 and y0 + 1 <= h - 2 in every array, and advect's min(., w - 1.00001) is idle
+            inside = inside && max(max(cq.x0, cx.x0), cy.x0) <= w - 3 && max(max(cq.y0, cx.y0), cy.y0) <= h - 3;
         if (inside) {
             // one straight-line block: all twelve gathers in flight together
             const double *gq_ = Q + qy * QW + qx;
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_advect_tma(const __grid_constan
         const int tx0 = (t % a.tiles_x) * TW, ty0 = a.ya + (t / a.tiles_x) * TH;
         if (tile_interior(a, ty0, tx0)) {
             const double *Q = reinterpret_cast<const double *>(smem + st * kStageBytes);
-            advect_tile<Acc>(a, Q, Q + kQBytes / 8, Q + 2 * (kQBytes / 8), gq, gvy, gvx, ty0, tx0, ly0, lx);
+            advect_tile<false, Acc>(a, Q, Q + kQBytes / 8, Q + 2 * (kQBytes / 8), gq, gvy, gvx, ty0, tx0, ly0, lx, 0u);
         } else {
             const int x = tx0 + lx, ys = ty0 + ly0;
             if (x < a.w && ys < a.yb) {
@@ -282,9 +288,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_advect_tma(const __grid_constan
                 const int by0 = ty0 - kG;
                 const unsigned rhq = kSlab ? (unsigned)min(QH, a.whi_q - by0) : (unsigned)QH;
                 const unsigned rhvy = kSlab ? (unsigned)min(QH, a.whi_vy - by0) : (unsigned)QH;
-                const BoxQ<Acc> bq{Q, by0, tx0 - kG, rhq, gq}, bvy{Q + kQBytes / 8, by0, tx0 - kG, rhvy, gvy};
-                const BoxX<Acc> bvx{Q + 2 * (kQBytes / 8), by0, tx0 - kG, rhq, gvx};
-                advect_edge_tile(a, bq, bvy, bvx, x, ys);
+                const int ylast = min(a.h, a.yb) - 1;             // last row this launch produces
+                if (x >= 1 && x <= a.w - 1 && ys >= 1 && ys + kRows - 1 <= min(a.h - 1, ylast)) {
+                    // away from the walls: the shared-memory path; rows_ok = last box row a gather corner may use
+                    advect_tile<true, Acc>(a, Q, Q + kQBytes / 8, Q + 2 * (kQBytes / 8), gq, gvy, gvx, ty0, tx0, ly0, lx, rhq - 2u);
+                } else {
+                    const BoxQ<Acc> bq{Q, by0, tx0 - kG, rhq, gq}, bvy{Q + kQBytes / 8, by0, tx0 - kG, rhvy, gvy};
+                    const BoxX<Acc> bvx{Q + 2 * (kQBytes / 8), by0, tx0 - kG, rhq, gvx};
+                    advect_edge_tile(a, bq, bvy, bvx, x, ys);
+                }
             }
         }
         __syncwarp();
