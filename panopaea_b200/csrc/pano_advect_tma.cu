@@ -115,13 +115,34 @@ struct BoxX {      // vx: even rows at [(r >> 1) * XW + c], odd rows at [kXOdd +
 };
 
 // one cell whose backtrace left the staged boxes: the full forms on global memory
-template <class A>
-__device__ __noinline__ void cell_from_global(double *q_dst, double *vy_dst, double *vx_dst, A q, A vy, A vx, int h, int w, int y, int x,
-                                              pano::CellCoord cq, double rxx, double rxy, double ryx, double ryy) {
-    q_dst[y * w + x] = pano::advect_gather_at(cq, q);
+// the global-memory accessors of a launch (slab: windowed, a gather beyond the stored rows raises the error word)
+template <bool kSlab>
+struct GlobalAcc {
+    using Acc = typename std::conditional<kSlab, V32W, V32<double>>::type;
+    Acc q, vy, vx;
+    __device__ __forceinline__ explicit GlobalAcc(const AdvArgs &a) {
+        if constexpr (kSlab) {
+            q = V32W{a.q_src, a.w, a.ylo, a.whi_q, a.err};
+            vy = V32W{a.vy_src, a.w, a.ylo, a.whi_vy, a.err};
+            vx = V32W{a.vx_src, a.w + 1, a.ylo, a.whi_q, a.err};
+        } else {
+            q = V32<double>{a.q_src, a.w};
+            vy = V32<double>{a.vy_src, a.w};
+            vx = V32<double>{a.vx_src, a.w + 1};
+        }
+    }
+};
+
+template <bool kSlab>
+__device__ __noinline__ void cell_from_global(const AdvArgs &a, int y, int x, double ucx, double ucy, double rxx, double rxy, double ryx,
+                                              double ryy) {
+    const GlobalAcc<kSlab> g(a);
+    const int h = a.h, w = a.w;
+    const pano::CellCoord cq = pano::advect_coord_fast((double)x + 0.5, (double)y + 0.5, (double)w - 1.00001, (double)h - 1.00001, -a.dt, ucx, ucy);
+    a.q_dst[y * w + x] = pano::advect_gather_at(cq, g.q);
     const pano::MacCoord cx = pano::mac_coord_fast(rxx, rxy, h, w + 1), cy = pano::mac_coord_fast(ryx, ryy, h + 1, w);
-    vx_dst[y * (w + 1) + x] = cx.bad ? pano_adv::mac_gather_far(rxx, rxy, h, w + 1, vx) : pano::mac_gather_at(cx, vx);
-    vy_dst[y * w + x] = cy.bad ? pano_adv::mac_gather_far(ryx, ryy, h + 1, w, vy) : pano::mac_gather_at(cy, vy);
+    a.vx_dst[y * (w + 1) + x] = cx.bad ? pano_adv::mac_gather_far(rxx, rxy, h, w + 1, g.vx) : pano::mac_gather_at(cx, g.vx);
+    a.vy_dst[y * w + x] = cy.bad ? pano_adv::mac_gather_far(ryx, ryy, h + 1, w, g.vy) : pano::mac_gather_at(cy, g.vy);
 }
 
 // Interior tile: column x = tx0 + lx, rows ty0 + ly0 .. + kRows - 1 (ly0 a multiple of 4), everything from shared memory.
@@ -131,16 +152,14 @@ __device__ __noinline__ void cell_from_global(double *q_dst, double *vy_dst, dou
 // border select in the velocity averages); a cell then also checks that its gathers stay two cells inside the grid, where no
 // clamp of the reference bites, and within the box rows that hold stored data (`rows_ok`, slabs); otherwise it takes the
 // full forms on global memory like a cell whose backtrace leaves the box.
-template <bool kBorder, class A>
+template <bool kBorder, bool kSlab>
 __device__ __forceinline__ void advect_tile(const AdvArgs &a, const double *__restrict__ Q, const double *__restrict__ VY,
-                                            const double *__restrict__ VX, const A &gq, const A &gvy, const A &gvx, int ty0, int tx0,
-                                            int ly0, int lx, unsigned rows_ok) {
+                                            const double *__restrict__ VX, int ty0, int tx0, int ly0, int lx, unsigned rows_ok) {
     const int h = a.h, w = a.w;
     const int x = tx0 + lx, ys = ty0 + ly0;
     const int bx0 = tx0 - kG, by0 = ty0 - kG;
     const int c0 = lx + kG, r0 = ly0 + kG;                     // box column / first box row (even) of this thread
     const double ndt = -a.dt, xd = (double)x, xh = xd + 0.5;
-    const double wlim = (double)w - 1.00001, hlim = (double)h - 1.00001;
     double yd = (double)ys;
     const double *pvy = VY + r0 * QW + c0;
     const double *pvx = VX + (r0 >> 1) * XW + c0;              // vx(ys, x): even box row
@@ -188,8 +207,7 @@ __device__ __forceinline__ void advect_tile(const AdvArgs &a, const double *__re
             vxo[k * (w + 1)] = pano::bilinear(x00, x01, x10, x11, cx.s, cx.t);
             vyo[k * w] = pano::bilinear(y00, y01, y10, y11, cy.s, cy.t);
         } else {
-            const pano::CellCoord cqf = pano::advect_coord_fast(xh, yh, wlim, hlim, ndt, ucx, ucy);
-            cell_from_global<A>(a.q_dst, a.vy_dst, a.vx_dst, gq, gvy, gvx, h, w, y, x, cqf, rxx, rxy, ryx, ryy);
+            cell_from_global<kSlab>(a, y, x, ucx, ucy, rxx, rxy, ryx, ryy);
         }
         C = D; E = F; G = A_; H = B;
         yd += 1.0;
@@ -258,17 +276,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_advect_tma(const __grid_constan
     }
 
     // ================================================================ consumer warps
-    using Acc = typename std::conditional<kSlab, V32W, V32<double>>::type;
-    Acc gq, gvy, gvx;
-    if constexpr (kSlab) {
-        gq = V32W{a.q_src, a.w, a.ylo, a.whi_q, a.err};
-        gvy = V32W{a.vy_src, a.w, a.ylo, a.whi_vy, a.err};
-        gvx = V32W{a.vx_src, a.w + 1, a.ylo, a.whi_q, a.err};
-    } else {
-        gq = V32<double>{a.q_src, a.w};
-        gvy = V32<double>{a.vy_src, a.w};
-        gvx = V32<double>{a.vx_src, a.w + 1};
-    }
+    using Acc = typename GlobalAcc<kSlab>::Acc;
+    const GlobalAcc<kSlab> ga(a);
+    const Acc &gq = ga.q, &gvy = ga.vy, &gvx = ga.vx;
     const int lx = (wid & 1) * 32 + lane, ly0 = (wid >> 1) * kRows;
     for (unsigned n = 0;; ++n) {
         const int st = n % kStages;
@@ -280,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_advect_tma(const __grid_constan
         const int tx0 = (t % a.tiles_x) * TW, ty0 = a.ya + (t / a.tiles_x) * TH;
         if (tile_interior(a, ty0, tx0)) {
             const double *Q = reinterpret_cast<const double *>(smem + st * kStageBytes);
-            advect_tile<false, Acc>(a, Q, Q + kQBytes / 8, Q + 2 * (kQBytes / 8), gq, gvy, gvx, ty0, tx0, ly0, lx, 0u);
+            advect_tile<false, kSlab>(a, Q, Q + kQBytes / 8, Q + 2 * (kQBytes / 8), ty0, tx0, ly0, lx, 0u);
         } else {
             const int x = tx0 + lx, ys = ty0 + ly0;
             if (x < a.w && ys < a.yb) {
@@ -291,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_advect_tma(const __grid_constan
                 const int ylast = min(a.h, a.yb) - 1;             // last row this launch produces
                 if (x >= 1 && x <= a.w - 1 && ys >= 1 && ys + kRows - 1 <= min(a.h - 1, ylast)) {
                     // away from the walls: the shared-memory path; rows_ok = last box row a gather corner may use
-                    advect_tile<true, Acc>(a, Q, Q + kQBytes / 8, Q + 2 * (kQBytes / 8), gq, gvy, gvx, ty0, tx0, ly0, lx, rhq - 2u);
+                    advect_tile<true, kSlab>(a, Q, Q + kQBytes / 8, Q + 2 * (kQBytes / 8), ty0, tx0, ly0, lx, rhq - 2u);
                 } else {
                     const BoxQ<Acc> bq{Q, by0, tx0 - kG, rhq, gq}, bvy{Q + kQBytes / 8, by0, tx0 - kG, rhvy, gvy};
                     const BoxX<Acc> bvx{Q + 2 * (kQBytes / 8), by0, tx0 - kG, rhq, gvx};
