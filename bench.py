@@ -52,7 +52,6 @@ BYTES_CG_ITER_FUSED, BYTES_CG_INIT_FUSED = 64, 8
 NOMINAL_GBS = 8000.0
 DEFAULT_GRID = 8192            # BASELINE configs[2]: the grid every N steps
 POISSON_GRID = 16384           # BASELINE configs[4] (2-D branch)
-SINGLE_REDUCTION_DEFAULT = {"single": 1, "multi": 1}   # the library's default of option cg_single_reduction (csrc/pano_cg.cu, pano_dist.cu)
 PARITY_TOL = 1e-8              # N > 1 fields against the one-GPU run of the same steps (relative to max|field|)
 
 
@@ -367,12 +366,14 @@ class _Slab:
 def cg_kernel_name(n, world, cells_per_gpu, opts):
     """The kernel the library's auto choice lands on (csrc/pano_cg.cu, pano_dist.cu), given the options of this run."""
     o = dict(kv.split("=") for kv in opts)
-    single = int(o.get("cg_single_reduction", SINGLE_REDUCTION_DEFAULT.get("multi" if world > 1 else "single", 1))) != 0
+    sr = int(o.get("cg_single_reduction", -1))       # -1 auto: single-reduction kernels on chip and on slabs, two-reduction streaming on one GPU
     if world == 1 and n <= 1024 and -(-n // 8) * n <= 5120:
         return "k_cg_cluster"                      # one thread-block cluster (csrc/pano_cg_cluster.cu): grids up to ~40 k cells
     if world == 1 and cells_per_gpu <= 1_200_000:
-        return "k_cg_resident_sr" if single else "k_cg_resident2"
-    return "k_cg_sr" if single else "k_cg_stream"
+        return "k_cg_resident_sr" if sr != 0 else "k_cg_resident2"
+    if world > 1:
+        return "k_cg_sr" if sr != 0 else "k_cg_stream"
+    return "k_cg_sr" if sr > 0 else "k_cg_stream"
 
 
 def timed_laps(ctx, work, K, flush=None):

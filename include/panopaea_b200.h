@@ -124,8 +124,8 @@ PANO_API int pano_ctx_cg_profile(pano_ctx *ctx, int64_t cycles_out[8]);
 PANO_API int pano_ctx_cg_profile_ctas(pano_ctx *ctx, int64_t *cycles_out, int n);
 /* tuning knobs: "cg_kernel" 0 auto / 1 generic / 2 TMA streaming (two reductions per iteration, as pcg.rs is written) /
  * 3 SM-resident / 4 SM-resident v1 / 5 one cluster / 6 TMA streaming with ONE reduction per iteration (Chronopoulos-Gear
- * arrangement of the same iteration) / 7 SM-resident with one reduction; "cg_single_reduction" 1 (default: auto prefers
- * kernels 7 and 6 over 3 and 2, also on the slabs of pano_dist) / 0; "cg_ldcg" 0/1,
+ * arrangement of the same iteration) / 7 SM-resident with one reduction; "cg_single_reduction" -1 (default: kernel 7 on chip, kernel 6 on the slabs
+ * of pano_dist, kernel 2 on one GPU's large grids, each where it measured fastest) / 1 (7 and 6 everywhere) / 0 (3 and 2); "cg_ldcg" 0/1,
  * "cg_zigzag" 0/1, "cg_blocks_per_sm" n, "cg_profile" 0/1, "step_timing" 0/1; streaming kernels: "cg_dynamic" -1 auto (from 24
  * tiles per CTA) / 0 fixed tile lists / 1 claimed tiles, "cg_batch" n (claim unit, 0 auto), "cg_fence" bit 0 fence.acq_rel
  * instead of fence.sc, bit 1 system scope only in CTAs that stored into a peer; multi-GPU: "cg_xflags" 1 halo flags (default) /

@@ -122,6 +122,7 @@ int pano_ctx_destroy(pano_ctx *ctx) {
     cudaFree(ctx->d_mail);
     cudaFree(ctx->d_tparts);
     cudaFree(ctx->d_sr_scratch);
+    cudaFree(ctx->d_sr_order);
     cudaFree(ctx->d_claim);
     cudaFree(ctx->d_adv_claim);
     cudaFreeHost(ctx->h_cg);

@@ -355,7 +355,12 @@ int pano_cg_solve_raw(pano_ctx *ctx, int dtype, void *x, const void *b, void *r,
     const bool resident2_ok = dtype == PANO_F64 && pano_cg_resident2_supported(ctx, h, w);
     const bool cluster_ok = dtype == PANO_F64 && pano_cg_cluster_supported(ctx, h, w);
     const bool resident_sr_ok = dtype == PANO_F64 && pano_cg_resident_sr_supported(ctx, h, w);
-    const bool single = pano_option(ctx, "cg_single_reduction", 1) != 0;
+    // "cg_single_reduction": -1 auto (default), 0, 1.  Measured on B200 (profiles/r02_*): the single-reduction arrangement wins where
+    // the reductions are a large share of an iteration -- on chip (1024^2: 1142 vs 980 Mcell-steps/s) and on the slabs of a
+    // multi-GPU grid (pano_dist.cu) -- and is 1.5-4 % behind the two-reduction kernel on one GPU's large grids (it prefetches half of a
+    // phase's boxes across its reductions, which a pass that rewrites all four vectors cannot).
+    const int64_t sr_opt = pano_option(ctx, "cg_single_reduction", -1);
+    const bool single = sr_opt > 0, single_auto = sr_opt < 0;
     if (want == 5 && !cluster_ok)
         PANO_FAIL(PANO_ERR_INVALID, "cg_kernel=5 (cluster) needs an f64 grid of at most 8 x 5120 cells and width <= 1024 (%zux%zu given)", h, w);
     if (want == 6 && !stream_ok)
@@ -367,7 +372,7 @@ int pano_cg_solve_raw(pano_ctx *ctx, int dtype, void *x, const void *b, void *r,
     if (cluster_ok && (want == 0 || want == 5)) {
         PANO_TRY(pano_cg_cluster_launch(ctx, (double *)x, (const double *)b, (double *)r, (double *)s0, h, w, max_iterations, threshold,
                                         timestep, m));
-    } else if (resident_sr_ok && (want == 7 || (want == 0 && single))) {
+    } else if (resident_sr_ok && (want == 7 || (want == 0 && (single || single_auto)))) {
         PANO_TRY(pano_cg_resident_sr_launch(ctx, (double *)x, (const double *)b, (double *)r, (double *)s0, h, w, max_iterations,
                                             threshold, timestep, m));
     } else if (resident2_ok && (want == 0 || want == 3)) {

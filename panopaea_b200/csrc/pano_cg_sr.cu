@@ -71,7 +71,9 @@ struct SrArgs {
     int fence_mode;
     int dynamic;
     int sm_exchange;              // 1: tile_sr_sm (r_(i+1) exchanged through shared memory), 0: tile_sr (recomputed per thread)
-    int halo_mid;                 // slab with neighbours: the first and last tile row sit in the MIDDLE of the tile order (see tile_at)
+    const int *order;             // tile order: position -> tile (see build_tile_order), or null: row-major
+    int slow_lo, slow_hi;         // the positions [slow_lo, slow_hi) hold the select-path tiles and the slab-edge tile rows
+    int halo_mid;                 // slab with neighbours: the halo flags go out as soon as a CTA is past those positions
     unsigned long long *claim;    // 4 claim counters, used round-robin by the passes (zeroed at launch)
     ReduceUnit *tparts;           // [3 values][nbatch * kConsumerWarps] per-(batch, warp) partials, {value, pass tag}
     int batch_len, nbatch_long, nbatch;
@@ -82,6 +84,9 @@ struct SrArgs {
     double *dn_r[2], *dn_s[2];    // lower neighbour's arrays at the row that mirrors MY row h-2 (r) / h-1 (s), or null
     double *dn_x;                 // lower neighbour's x at the row that mirrors MY row h-1 (its projection reads it as p[y-1]), or null
     XRank xr;
+    long long *dbg;               // optional per-section clock64 totals of CTA 0 (option "cg_profile"): 0 wait for the pass's first tile,
+                                  // 1 tile loop, 2 batch-unit poll, 3 CTA reduction, 4 grid (+ cross-GPU) all-reduce
+    long long *dbg_cta;           // optional [2][gridDim.x]: per-CTA totals of sections 0 and 1
 };
 
 struct Tail {                     // small shared-memory area behind the stage ring
@@ -92,6 +97,7 @@ struct Tail {                     // small shared-memory area behind the stage r
     int cont;                     // 1: producer continues with the next pass, 0: stop
     int tile[kStages];            // the tile staged in each ring slot, -1 = no more tiles in this pass
     int batch[kStages];           // its batch index if the tile is the LAST of its batch, else -1
+    int behind[kStages];          // 1: the tile lies behind the slow / halo positions of the order in this pass's direction
     int ok;
 };
 
@@ -431,32 +437,29 @@ __device__ __forceinline__ void tile_sr_sm(const SrArgs &a, const double *R, dou
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// Position in the (un-reversed) tile order -> tile.  Plain: row-major.  halo_mid (slab of a multi-GPU grid, >= 4 tile rows): tile
-// rows in the order 1 .. mid, 0, Ty-1, mid+1 .. Ty-2 -- the two tile rows whose cells are mirrored into the neighbours' memory are
-// done in the middle of a pass in EITHER direction (odd passes walk the order backwards for L2 reuse), so a CTA can fence at
-// system scope and raise its halo flags long before the pass ends (when it first gets a tile behind them), instead of putting
-// 3 us of MEMBAR.SYS and the flags' NVLink latency on the critical path of every reduction.
-__device__ __forceinline__ int tile_at(const SrArgs &a, int pos) {
-    if (!a.halo_mid) return pos;
-    const int q = pos / a.tiles_x, c = pos - q * a.tiles_x, mid = (a.tiles_y - 2) / 2;
-    const int row = q < mid ? q + 1 : (q == mid ? 0 : (q == mid + 1 ? a.tiles_y - 1 : q - 1));
-    return row * a.tiles_x + c;
-}
-// is tile t behind the halo rows in the direction of this pass?
-__device__ __forceinline__ bool behind_halo(const SrArgs &a, int t, bool reversed) {
-    const int row = t / a.tiles_x, mid = (a.tiles_y - 2) / 2;
-    return reversed ? (row >= 1 && row <= mid) : (row > mid && row < a.tiles_y - 1);
-}
+// Position in the (un-reversed) tile order -> tile.  The order (build_tile_order, host) is: an eighth of the all-open tiles in
+// row-major order; then the bulk of them with every tile that takes the select path (walls, obstacle, ragged edge) and the first
+// and last tile row of a slab that has neighbours spread evenly in between; then the last eighth of the all-open tiles.  Odd passes
+// walk it backwards (L2 reuse), so in EITHER direction a pass ends with all-open tiles.  Two reasons:
+//   * select-path tiles are 2-3x slower; with row-major order one wall row ends every pass and every reduction waited ~10 us for
+//     the CTAs that drew its tiles (option cg_profile: tile loops balanced to 2 %, yet 11.8 us in the all-reduce section per pass
+//     on a 1024 x 8192 slab)
+//   * on a slab of a multi-GPU grid the first and last tile row are mirrored into the neighbours' memory: a CTA can fence at system
+//     scope and raise its halo flags as soon as it is past them, long before the pass ends, instead of putting 3 us of MEMBAR.SYS
+//     and the flags' NVLink latency on the critical path of every reduction (halo_mid).
+__device__ __forceinline__ int tile_at(const SrArgs &a, int pos) { return a.order ? __ldg(a.order + pos) : pos; }
 
 // all open: every cell of the tile AND of its one-cell ring is an interior cell away from the walls and the obstacle
-__device__ __forceinline__ bool tile_is_fast(const SrArgs &a, int ty0, int tx0) {
-    const int g0 = a.gy0 + ty0;
-    if (ty0 + TH > a.h) return false;                                            // ragged tile at the end of the slab
-    if (g0 < 2 || g0 + TH > a.gh - 2 || tx0 < 2 || tx0 + TW > a.w - 2) return false;
-    if (a.m.y1 > a.m.y0 && a.m.x1 > a.m.x0 && g0 - 1 < a.m.y1 && g0 + TH + 1 > a.m.y0 - 1 && tx0 - 1 < a.m.x1 && tx0 + TW + 1 > a.m.x0 - 1)
+__host__ __device__ __forceinline__ bool tile_is_fast_hd(int h, int w, int gy0, int gh, const RectI &m, int ty0, int tx0) {
+    const int g0 = gy0 + ty0;
+    if (ty0 + TH > h) return false;                                              // ragged tile at the end of the slab
+    if (g0 < 2 || g0 + TH > gh - 2 || tx0 < 2 || tx0 + TW > w - 2) return false;
+    if (m.y1 > m.y0 && m.x1 > m.x0 && g0 - 1 < m.y1 && g0 + TH + 1 > m.y0 - 1 && tx0 - 1 < m.x1 && tx0 + TW + 1 > m.x0 - 1)
         return false;
     return true;
 }
+__device__ __forceinline__ bool tile_is_fast(const SrArgs &a, int ty0, int tx0) { return tile_is_fast_hd(a.h, a.w, a.gy0, a.gh, a.m, ty0, tx0); }
+static bool tile_is_fast_host(const SrArgs &a, int ty0, int tx0) { return tile_is_fast_hd(a.h, a.w, a.gy0, a.gh, a.m, ty0, tx0); }
 __device__ __forceinline__ bool tile_stores_remote(const SrArgs &a, int ty0) {
     return (ty0 == 0 && a.up_r[0] != nullptr) || (ty0 + TH >= a.h - 1 && a.dn_r[0] != nullptr);
 }
@@ -499,23 +502,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_sr(const __grid_constant__ S
         const unsigned long long M = (unsigned long long)a.nbatch + (unsigned long long)G;   // claims per pass (dynamic)
         bool stop = false;
         for (int k = 0; k <= a.max_iter && !stop; ++k) {
-            // everything a pass reads was written by the previous pass, possibly by other CTAs: wait for its reduction
-            if (k != 0) {
-                if (!mbar_wait(&tl->go, ngo & 1, err)) return;
-                ++ngo;
-                stop = !*(volatile int *)&tl->cont;
-                fence_proxy_async();
-                if (stop) return;
-            }
             const int it = k - 1;                                      // iteration of this pass (-1: the opening pass)
             bool exhausted = false;
             int b_idx = -1, b_next = 0, b_end = 0, jj = 0;
+            bool behind = false;      // set by next_tile: is the tile behind the slow / halo positions in this pass's direction?
             auto next_tile = [&](int &t, int &closes) -> bool {
                 if (!dyn) {
                     if (jj >= n_my) return false;
                     const int j = ((k & 1) && a.zigzag) ? n_my - 1 - jj : jj;
                     ++jj;
-                    t = tile_at(a, blockIdx.x + j * G);
+                    const int q = blockIdx.x + j * G;
+                    t = tile_at(a, q);
+                    behind = ((k & 1) && a.zigzag) ? q < a.slow_lo : q >= a.slow_hi;
                     closes = -1;
                     return true;
                 }
@@ -528,17 +526,39 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_sr(const __grid_constant__ S
                     else { b_next = a.nbatch_long * a.batch_len + (b_idx - a.nbatch_long); b_end = b_next + 1; }
                 }
                 const int pos = b_next++;
-                t = tile_at(a, ((k & 1) && a.zigzag) ? ntiles - 1 - pos : pos);
+                const int q = ((k & 1) && a.zigzag) ? ntiles - 1 - pos : pos;
+                t = tile_at(a, q);
+                behind = ((k & 1) && a.zigzag) ? q < a.slow_lo : q >= a.slow_hi;
                 closes = b_next == b_end ? b_idx : -1;
                 return true;
             };
-            for (;;) {
+            // the first tile is claimed (an atomic round trip through L2) while the previous pass is still being reduced ...
+            int t_first = -1, closes_first = -1;
+            bool have = next_tile(t_first, closes_first);
+            const bool behind_first = behind;
+            // ... but everything a pass READS was written by the previous pass, possibly by other CTAs: wait for its reduction
+            if (k != 0) {
+                if (!mbar_wait(&tl->go, ngo & 1, err)) return;
+                ++ngo;
+                stop = !*(volatile int *)&tl->cont;
+                fence_proxy_async();
+                if (stop) return;
+            }
+            for (bool first = true;; first = false) {
                 int t, closes;
-                if (!next_tile(t, closes)) break;
+                if (first) {
+                    if (!have) break;
+                    t = t_first;
+                    closes = closes_first;
+                    behind = behind_first;
+                } else if (!next_tile(t, closes)) {
+                    break;
+                }
                 const int st = n % kStages;
                 if (!mbar_wait(&tl->empty[st], ((n / kStages) & 1) ^ 1, err)) return;
                 tl->tile[st] = t;
                 tl->batch[st] = closes;
+                tl->behind[st] = behind ? 1 : 0;
                 const int tx0 = (t % a.tiles_x) * TW, ty0 = (t / a.tiles_x) * TH;
                 unsigned char *base = smem + st * kStageBytes;
                 uint64_t *bar = &tl->full[st];
@@ -572,18 +592,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_sr(const __grid_constant__ S
     bool converged = false, early = false;
     double red[3];
 
+    const bool prof = a.dbg != nullptr && tid == 0;
+    long long tprev = prof ? clock64() : 0;
+    auto stamp = [&](int slot) {
+        if (prof) {
+            const long long t = clock64();
+            if (blockIdx.x == 0) a.dbg[slot] += t - tprev;
+            if (slot < 2) a.dbg_cta[slot * gridDim.x + blockIdx.x] += t - tprev;
+            tprev = t;
+        }
+    };
     for (int k = 0; k <= a.max_iter; ++k) {
         it = k - 1;
+        bool first_tile = true;
         double acc_g = 0, acc_d = 0, acc_max = 0;
         bool remote = false;      // uniform over the CTA: every consumer warp walks the same tiles
         const unsigned long long tag = a.seq_base + (unsigned long long)k + 1;
         double *r_dst = a.r[(it + 1) & 1], *s_dst = a.s[it & 1];
         double *r_up = a.up_r[(it + 1) & 1], *r_dn = a.dn_r[(it + 1) & 1], *s_up = a.up_s[it & 1], *s_dn = a.dn_s[it & 1];
-        const bool reversed = (k & 1) && a.zigzag;
         bool flags_pending = a.halo_mid != 0, flags_sent = false;
         for (;; ++n) {
             const int st = n % kStages;
             if (!mbar_wait(&tl->full[st], (n / kStages) & 1, err)) return;
+            if (first_tile) { stamp(0); first_tile = false; }
             const int t = slot_word(&tl->tile[st]);
             if (t < 0) {                                    // end-of-pass marker: hand the slot back and leave
                 __syncwarp();
@@ -592,7 +623,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_sr(const __grid_constant__ S
                 break;
             }
             const int tx0 = (t % a.tiles_x) * TW, ty0 = (t / a.tiles_x) * TH;
-            if (flags_pending && behind_halo(a, t, reversed)) {
+            if (flags_pending && slot_word(&tl->behind[st]) != 0) {
                 // this CTA's halo tiles of the pass are behind it (tiles are claimed in increasing order): vouch for them now
                 consumer_sync();                   // every consumer warp's halo-row stores happen-before thread 0's fence
                 if (tid == 0) {
@@ -643,28 +674,35 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_sr(const __grid_constant__ S
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&tl->empty[st]);
         }
+        stamp(1);
         if (dyn) {   // the units of this CTA's FIXED batch range, whoever computed them, in a fixed order
             const size_t plane = (size_t)a.nbatch * kConsumerWarps;
             const int c0 = (int)((long long)blockIdx.x * a.nbatch / G), c1 = (int)((long long)(blockIdx.x + 1) * a.nbatch / G);
             const ReduceUnit *base = a.tparts + (size_t)c0 * kConsumerWarps;
             for (int e = tid; e < (c1 - c0) * kConsumerWarps; e += kConsumers) {
-                double v;
-                unit_poll(base + e, tag, v, err);
-                acc_g = acc_g + v;
-                unit_poll(base + plane + e, tag, v, err);
-                acc_d = acc_d + v;
-                unit_poll(base + 2 * plane + e, tag, v, err);
-                acc_max = v > acc_max ? v : acc_max;
+                const ReduceUnit *us[3] = {base + e, base + plane + e, base + 2 * plane + e};
+                double v[3] = {0.0, 0.0, 0.0};
+                unit_poll_n(us, 3, tag, v, err);             // the three values' units in flight together
+                acc_g = acc_g + v[0];
+                acc_d = acc_d + v[1];
+                acc_max = v[2] > acc_max ? v[2] : acc_max;
             }
         }
+        stamp(2);
         double v0 = acc_g, v1 = acc_d, v2 = acc_max;
         consumer_reduce3(v0, v1, v2, tl->wsum);
+        stamp(3);
+        if (prof) {   // diagnostic: how long does the fence that the all-reduce starts with take on its own?
+            fence_gpu(false);
+            stamp(5);
+        }
         if (!grid_allreduce_units(a.units, a.seq_base + (unsigned long long)k, (unsigned long long)k, 3, v0, v1, v2, 0x4u, tl->vals, tl->out,
                                   &tl->ok, &a.ctl->error, /*fenced=*/true, [] { consumer_sync(); }, red, &a.xr, NoWork(), nullptr,
                                   a.halo_mid ? (a.fence_mode | kFenceSysIfRemote) : a.fence_mode, remote, flags_sent)) {
             if (tid == 0) { tl->cont = 0; mbar_arrive(&tl->go); }
             return;
         }
+        stamp(4);
         const double gamma_new = red[0], delta = red[1];
         rmax = red[2];
         if (k == 0) {
@@ -725,6 +763,55 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_sr(const __grid_constant__ S
 
 }  // namespace
 
+// The tile order of tile_at: cached in the context (it depends only on the geometry), rebuilt and uploaded when that changes.
+static int build_tile_order(pano_ctx *ctx, SrArgs &a, bool has_up, bool has_dn) {
+    const int ntiles = a.tiles_x * a.tiles_y;
+    const long long key[10] = {a.h, a.w, a.gy0, a.gh, a.m.y0, a.m.y1, a.m.x0, a.m.x1, has_up ? 1 : 0, has_dn ? 1 : 0};
+    if (ctx->sr_order_n != ntiles || memcmp(ctx->sr_order_key, key, sizeof(key)) != 0) {
+        std::vector<int> fast, slow;
+        for (int t = 0; t < ntiles; ++t) {
+            const int ty = t / a.tiles_x, ty0 = ty * TH, tx0 = (t % a.tiles_x) * TW;
+            const bool edge_row = (ty == 0 && has_up) || (ty == a.tiles_y - 1 && has_dn);
+            (tile_is_fast_host(a, ty0, tx0) && !edge_row ? fast : slow).push_back(t);
+        }
+        // head and tail: an eighth of the all-open tiles each; in between the rest of them with the slow tiles spread evenly (all
+        // slow tiles at once would leave HBM idle while every SM computes: measured, 8192^2 2.6 % slower than spread out)
+        std::vector<int> order;
+        order.reserve((size_t)ntiles);
+        const size_t head = fast.size() / 8, mid_fast = fast.size() - 2 * head, mid = mid_fast + slow.size();
+        order.insert(order.end(), fast.begin(), fast.begin() + head);
+        size_t fi = head, si = 0;
+        for (size_t i = 0; i < mid; ++i) {
+            const bool take_slow = slow.size() && ((i + 1) * slow.size() / mid > i * slow.size() / mid);
+            if (take_slow && si < slow.size()) order.push_back(slow[si++]);
+            else if (fi < head + mid_fast) order.push_back(fast[fi++]);
+            else order.push_back(slow[si++]);
+        }
+        order.insert(order.end(), fast.begin() + head + mid_fast, fast.end());
+        const size_t half = head, nslow_span = mid;
+        if ((size_t)ntiles > ctx->sr_order_cap) {
+            if (ctx->d_sr_order) {
+                PANO_CUDA(cudaStreamSynchronize(ctx->stream));
+                PANO_CUDA(cudaFree(ctx->d_sr_order));
+                ctx->d_sr_order = nullptr;
+                ctx->sr_order_cap = 0;
+            }
+            PANO_CUDA(cudaMalloc((void **)&ctx->d_sr_order, (size_t)ntiles * sizeof(int)));
+            ctx->sr_order_cap = (size_t)ntiles;
+        }
+        // pageable host memory: the copy is staged before the call returns
+        PANO_CUDA(cudaMemcpyAsync(ctx->d_sr_order, order.data(), (size_t)ntiles * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        memcpy(ctx->sr_order_key, key, sizeof(key));
+        ctx->sr_order_n = ntiles;
+        ctx->sr_order_lo = (int)half;
+        ctx->sr_order_hi = (int)(half + nslow_span);
+    }
+    a.order = ctx->d_sr_order;
+    a.slow_lo = ctx->sr_order_lo;
+    a.slow_hi = ctx->sr_order_hi;
+    return PANO_OK;
+}
+
 int pano_preload_cg_sr() {
     cudaFuncAttributes fa;
     PANO_CUDA(cudaFuncGetAttributes(&fa, k_cg_sr));
@@ -761,6 +848,9 @@ int pano_cg_sr_launch(pano_ctx *ctx, double *x, const double *b, double *r, doub
     a.ctl = ctx->d_cg;
     a.zigzag = pano_option(ctx, "cg_zigzag", 1) != 0;
     a.fence_mode = (int)pano_option(ctx, "cg_fence", 0);
+    a.dbg = pano_option(ctx, "cg_profile", 0) ? ctx->d_cg->prof : nullptr;
+    a.dbg_cta = reinterpret_cast<long long *>(ctx->d_partials);   // >= 12288 doubles (pano_ctx_create); zeroed below when profiling
+    if (a.dbg) PANO_CUDA(cudaMemsetAsync(ctx->d_partials, 0, 2 * kMaxCtas * sizeof(long long), ctx->stream));
     a.row0 = 0; a.gy0 = 0; a.gh = (int)h;
     a.xr.rank = 0; a.xr.nranks = 1;
     int max_ctas = 0;
@@ -805,7 +895,13 @@ int pano_cg_sr_launch(pano_ctx *ctx, double *x, const double *b, double *r, doub
     const bool dynamic = dyn_opt > 0 || (dyn_opt < 0 && ntiles >= 24 * G);
     a.dynamic = dynamic ? 1 : 0;
     a.sm_exchange = pano_option(ctx, "cg_sr_exchange", 1) != 0 ? 1 : 0;
-    a.halo_mid = (slab && slab->nranks > 1 && a.xr.hflags != nullptr && a.tiles_y >= 4 && pano_option(ctx, "cg_halo_mid", 0) != 0) ? 1 : 0;
+    a.order = nullptr;
+    a.slow_lo = a.slow_hi = 0;
+    if (pano_option(ctx, "cg_order_mid", 1) != 0) {
+        const bool multi = slab && slab->nranks > 1;
+        PANO_TRY(build_tile_order(ctx, a, multi && slab->rank > 0, multi && slab->rank + 1 < slab->nranks));
+    }
+    a.halo_mid = (a.order && slab && slab->nranks > 1 && a.xr.hflags != nullptr && pano_option(ctx, "cg_halo_mid", 1) != 0) ? 1 : 0;
     if (dynamic) {
         int bl = (int)pano_option(ctx, "cg_batch", 0);
         if (bl <= 0) bl = ntiles / (6 * G);

@@ -213,8 +213,8 @@ int fill_owned(pano_dist *d, int f, pano_rect r, double value) {
 }
 
 
-// option "cg_single_reduction" (default 1; must agree on all ranks): the Chronopoulos-Gear kernel of pano_cg_sr.cu
-bool use_single_reduction(pano_dist *d) { return pano_option(d->ctx, "cg_single_reduction", 1) != 0; }
+// option "cg_single_reduction" (-1 auto = on for slabs, 0, 1; must agree on all ranks): the Chronopoulos-Gear kernel of pano_cg_sr.cu
+bool use_single_reduction(pano_dist *d) { return pano_option(d->ctx, "cg_single_reduction", -1) != 0; }   // -1 auto: yes on slabs
 
 // The persistent CG kernel on this rank's slab, right-hand side in array fB; x lands in F_P.
 int launch_cg(pano_dist *d, int fB, bool mirror_x) {

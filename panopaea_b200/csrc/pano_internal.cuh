@@ -84,6 +84,10 @@ struct pano_ctx {
     size_t mail_cap = 0;             // in doubles
     double *d_sr_scratch = nullptr;  // two more h x w arrays of the single-reduction CG kernel (second r and s buffers)
     size_t sr_scratch_cap = 0;       // in doubles
+    int *d_sr_order = nullptr;       // tile order of the single-reduction CG kernel (pano_cg_sr.cu: build_tile_order)
+    size_t sr_order_cap = 0;
+    long long sr_order_key[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int sr_order_n = 0, sr_order_lo = 0, sr_order_hi = 0;
     void *d_tparts = nullptr;        // per-(tile, warp) reduction units of the dynamically scheduled streaming CG kernel
     size_t tparts_cap = 0;           // in 16-byte units
     unsigned long long *d_claim = nullptr;   // 4 tile-claim counters (one per phase in flight)

@@ -98,6 +98,28 @@ __device__ __forceinline__ bool unit_poll(const ReduceUnit *u, unsigned long lon
     }
 }
 
+// up to three units polled CONCURRENTLY (their loads are in flight together: one L2 round trip instead of three; the reductions
+// of the single-reduction CG kernels carry three values).  u[k] must be valid for k < n.
+__device__ __forceinline__ bool unit_poll_n(const ReduceUnit *const *u, int n, unsigned long long seq, double *v, volatile unsigned int *err) {
+    long long spins = 0;
+    unsigned pending = (1u << n) - 1u;
+    for (;;) {
+        double t[3];
+        unsigned long long got[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (k < n && ((pending >> k) & 1u)) unit_load(u[k], t[k], got[k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (k < n && ((pending >> k) & 1u) && got[k] == seq) { v[k] = t[k]; pending &= ~(1u << k); }
+        if (pending == 0u) return true;
+        if (++spins > kSpinLimit || ((spins & 0x3ff) == 0 && *err)) {
+            atomicCAS((unsigned int *)err, 0u, 1u);
+            return false;
+        }
+    }
+}
+
 // the same poll with ld.acquire.sys: the poller synchronises with a releasing writer on another GPU without paying a
 // system-scope fence afterwards (SASS: LD + CCTL.IVALL; MEMBAR.SYS costs ~3.1 us on a B200 NVLink system)
 __device__ __forceinline__ bool unit_poll_acquire_sys(const ReduceUnit *u, unsigned long long seq, volatile unsigned int *err) {
@@ -270,12 +292,10 @@ __device__ __forceinline__ bool grid_allreduce_units(ReduceUnit *units, unsigned
     const bool root_mode = G > 32 || multi;
     if (!root_mode || blockIdx.x == 0) {
         if (tid < G) {
-            bool ok = true;
-            for (int k = 0; k < nvals && ok; ++k) {
-                double v;
-                ok = unit_poll(bank + k * kMaxCtas + tid, seq, v, err);
-                vals[k][tid] = v;
-            }
+            const ReduceUnit *us[3] = {bank + tid, bank + kMaxCtas + tid, bank + 2 * kMaxCtas + tid};
+            double v[3] = {0.0, 0.0, 0.0};
+            const bool ok = unit_poll_n(us, nvals, seq, v, err);   // the values' units in flight together
+            for (int k = 0; k < nvals; ++k) vals[k][tid] = v[k];
             if (fenced) fence_gpu(light);
             if (!ok) *ok_sh = 0;
         }

@@ -3,7 +3,7 @@
 set -u
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
-for opts in "cg_single_reduction=0 dist_fused_halos=0 slab_kernels=1 advect_kernel=1" "cg_single_reduction=0 dist_fused_halos=0" "cg_single_reduction=1 dist_fused_halos=0" "cg_single_reduction=1 dist_fused_halos=1" "cg_single_reduction=1 dist_fused_halos=1 cg_dynamic=0"; do
+for opts in "cg_single_reduction=0 dist_fused_halos=0" "cg_single_reduction=1" "cg_single_reduction=1 cg_halo_mid=0" "cg_single_reduction=1 cg_order_mid=0" "cg_single_reduction=1 cg_fence=1"; do
   timeout 300 $TR scripts/time_slab.py 2048 8192 $opts 2>&1 | grep -E "^rank|Error|error" | tee -a gpurun_out/r2_2gpu_slab.txt
 done
 timeout 300 python scripts/time_slab.py 1024 8192 cg_single_reduction=0 2>&1 | grep -E "^rank|rror" | tee -a gpurun_out/r2_2gpu_slab.txt

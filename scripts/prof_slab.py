@@ -37,7 +37,7 @@ if world > 1:
     sync = lambda: (D.sync(), dist_t.barrier())
     info = lambda: (D.step(), D.sync())[1]
 else:
-    ctx.set_option("cg_kernel", int(opts.get("cg_kernel", 2)))
+    ctx.set_option("cg_kernel", int(opts.get("cg_kernel", 6 if int(opts.get("cg_single_reduction", 1)) else 2)))
     sim = fluid.DecFluid(h=h, w=w, ctx=ctx, **prm)
     step = lambda: sim.step(want_info=False)
     sync = ctx.sync
@@ -61,12 +61,20 @@ arr = (C.c_int64 * (2 * G))()
 _lib.check(L.pano_ctx_cg_profile_ctas(ctx.handle, arr, 2 * G))
 ctx.set_option("cg_profile", 0)
 its = max(1, inf["applies"])
-us = [v / its / 1965.0 for v in out[:4]]
 a = np.array(arr[:], dtype=np.float64).reshape(2, G) / its / 1965.0
-line = (f"rank {rank}/{world} grid {h}x{w} opts {opts}: step {ms:.3f} ms; applies {its}; per iteration (CTA 0): P1 tiles {us[0]:.1f} us, "
-        f"reduce1 {us[1]:.1f}, P2 tiles {us[2]:.1f}, reduce2 {us[3]:.1f}, sum {sum(us):.1f} us; "
-        f"tile loops over CTAs: P1 min/med/max {a[0].min():.1f}/{np.median(a[0]):.1f}/{a[0].max():.1f}, "
-        f"P2 {a[1].min():.1f}/{np.median(a[1]):.1f}/{a[1].max():.1f}")
+if int(opts.get("cg_single_reduction", 1)) != 0 and (world > 1 or int(opts.get("cg_kernel", 6)) == 6):
+    # k_cg_sr: 0 wait for the pass's first tile, 1 tile loop, 2 batch-unit poll, 3 CTA reduction, 4 grid (+ cross-GPU) all-reduce
+    us = [v / its / 1965.0 for v in out[:6]]
+    line = (f"rank {rank}/{world} grid {h}x{w} opts {opts}: step {ms:.3f} ms; passes {its}+1; per pass (CTA 0): first-tile wait {us[0]:.1f} us, "
+            f"tile loop {us[1]:.1f}, unit poll {us[2]:.1f}, CTA reduce {us[3]:.1f}, thread-0 fence {us[5]:.1f}, all-reduce {us[4]:.1f}, sum {sum(us):.1f} us; "
+            f"over CTAs: first-tile wait min/med/max {a[0].min():.1f}/{np.median(a[0]):.1f}/{a[0].max():.1f}, "
+            f"tile loop {a[1].min():.1f}/{np.median(a[1]):.1f}/{a[1].max():.1f}")
+else:
+    us = [v / its / 1965.0 for v in out[:4]]
+    line = (f"rank {rank}/{world} grid {h}x{w} opts {opts}: step {ms:.3f} ms; applies {its}; per iteration (CTA 0): P1 tiles {us[0]:.1f} us, "
+            f"reduce1 {us[1]:.1f}, P2 tiles {us[2]:.1f}, reduce2 {us[3]:.1f}, sum {sum(us):.1f} us; "
+            f"tile loops over CTAs: P1 min/med/max {a[0].min():.1f}/{np.median(a[0]):.1f}/{a[0].max():.1f}, "
+            f"P2 {a[1].min():.1f}/{np.median(a[1]):.1f}/{a[1].max():.1f}")
 if world > 1:
     lines = [None] * world
     dist_t.all_gather_object(lines, line)
