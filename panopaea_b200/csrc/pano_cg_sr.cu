@@ -74,6 +74,7 @@ struct SrArgs {
     const int *order;             // tile order: position -> tile (see build_tile_order), or null: row-major
     int slow_lo, slow_hi;         // the positions [slow_lo, slow_hi) hold the select-path tiles and the slab-edge tile rows
     int halo_mid;                 // slab with neighbours: the halo flags go out as soon as a CTA is past those positions
+    int early_load;               // slab with neighbours: the first tiles of a pass are loaded on the GPU's "local done" (pano_sm100.cuh)
     unsigned long long *claim;    // 4 claim counters, used round-robin by the passes (zeroed at launch)
     ReduceUnit *tparts;           // [3 values][nbatch * kConsumerWarps] per-(batch, warp) partials, {value, pass tag}
     int batch_len, nbatch_long, nbatch;
@@ -506,6 +507,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_sr(const __grid_constant__ S
             bool exhausted = false;
             int b_idx = -1, b_next = 0, b_end = 0, jj = 0;
             bool behind = false;      // set by next_tile: is the tile behind the slow / halo positions in this pass's direction?
+            bool safe = false;        // ... and: does it lie outside them (an all-open tile that reads no other GPU's rows)?
             auto next_tile = [&](int &t, int &closes) -> bool {
                 if (!dyn) {
                     if (jj >= n_my) return false;
@@ -514,6 +516,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_sr(const __grid_constant__ S
                     const int q = blockIdx.x + j * G;
                     t = tile_at(a, q);
                     behind = ((k & 1) && a.zigzag) ? q < a.slow_lo : q >= a.slow_hi;
+                    safe = q < a.slow_lo || q >= a.slow_hi;
                     closes = -1;
                     return true;
                 }
@@ -529,36 +532,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_sr(const __grid_constant__ S
                 const int q = ((k & 1) && a.zigzag) ? ntiles - 1 - pos : pos;
                 t = tile_at(a, q);
                 behind = ((k & 1) && a.zigzag) ? q < a.slow_lo : q >= a.slow_hi;
+                safe = q < a.slow_lo || q >= a.slow_hi;
                 closes = b_next == b_end ? b_idx : -1;
                 return true;
             };
-            // the first tile is claimed (an atomic round trip through L2) while the previous pass is still being reduced ...
-            int t_first = -1, closes_first = -1;
-            bool have = next_tile(t_first, closes_first);
-            const bool behind_first = behind;
-            // ... but everything a pass READS was written by the previous pass, possibly by other CTAs: wait for its reduction
-            if (k != 0) {
-                if (!mbar_wait(&tl->go, ngo & 1, err)) return;
-                ++ngo;
-                stop = !*(volatile int *)&tl->cont;
-                fence_proxy_async();
-                if (stop) return;
-            }
-            for (bool first = true;; first = false) {
-                int t, closes;
-                if (first) {
-                    if (!have) break;
-                    t = t_first;
-                    closes = closes_first;
-                    behind = behind_first;
-                } else if (!next_tile(t, closes)) {
-                    break;
-                }
+            auto issue = [&](int t, int closes, bool bh) -> bool {
                 const int st = n % kStages;
-                if (!mbar_wait(&tl->empty[st], ((n / kStages) & 1) ^ 1, err)) return;
+                if (!mbar_wait(&tl->empty[st], ((n / kStages) & 1) ^ 1, err)) return false;
                 tl->tile[st] = t;
                 tl->batch[st] = closes;
-                tl->behind[st] = behind ? 1 : 0;
+                tl->behind[st] = bh ? 1 : 0;
                 const int tx0 = (t % a.tiles_x) * TW, ty0 = (t / a.tiles_x) * TH;
                 unsigned char *base = smem + st * kStageBytes;
                 uint64_t *bar = &tl->full[st];
@@ -573,6 +556,51 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_sr(const __grid_constant__ S
                     tma_load_2d(base + kRSlot + kSSlot + kIntBoxBytes, &a.m_x, bar, tx0, a.row0 + ty0);
                 }
                 ++n;
+                return true;
+            };
+            // The first tiles are claimed (atomic round trips through L2) while the previous pass is still being reduced ...
+            int pre_t[kStages], pre_c[kStages], npre = 0, nissued = 0;
+            bool pre_b[kStages], pre_s[kStages];
+            const int want_pre = (k != 0 && a.early_load) ? kStages : 1;
+            while (npre < want_pre) {
+                int t, closes;
+                if (!next_tile(t, closes)) break;
+                pre_t[npre] = t; pre_c[npre] = closes; pre_b[npre] = behind; pre_s[npre] = safe;
+                ++npre;
+            }
+            // ... but everything a pass READS was written by the previous pass, possibly by other CTAs: wait for its reduction.
+            if (k != 0) {
+                const unsigned n0 = n;
+                if (a.early_load && npre > 0 && pre_s[0]) {
+                    // Slab of a multi-GPU grid: tiles that read no other GPU's rows may be loaded as soon as THIS GPU has finished the
+                    // previous pass ("local done", published by the root while the totals are still crossing NVLink)
+                    const unsigned long long nprev = (unsigned long long)(k - 1);
+                    const ReduceUnit *done = a.units + (nprev & 1) * kUnitsPerBank + 3 * kMaxCtas + 3;
+                    double dummy;
+                    if (!unit_poll(done, a.seq_base + nprev, dummy, err)) return;
+                    fence_gpu(false);
+                    fence_proxy_async();
+                    while (nissued < npre && pre_s[nissued]) {
+                        if (!issue(pre_t[nissued], pre_c[nissued], pre_b[nissued])) return;
+                        ++nissued;
+                    }
+                }
+                if (!mbar_wait(&tl->go, ngo & 1, err)) return;
+                ++ngo;
+                stop = !*(volatile int *)&tl->cont;
+                fence_proxy_async();
+                if (stop) {                                             // let the early loads land before the CTA leaves
+                    for (unsigned m = n0; m < n; ++m)
+                        if (!mbar_wait(&tl->full[m % kStages], (m / kStages) & 1, err)) return;
+                    return;
+                }
+            }
+            for (; nissued < npre; ++nissued)
+                if (!issue(pre_t[nissued], pre_c[nissued], pre_b[nissued])) return;
+            for (;;) {
+                int t, closes;
+                if (!next_tile(t, closes)) break;
+                if (!issue(t, closes, behind)) return;
             }
             // end-of-pass marker for the consumers: an empty slot
             if (!mbar_wait(&tl->empty[n % kStages], ((n / kStages) & 1) ^ 1, err)) return;
@@ -902,6 +930,7 @@ int pano_cg_sr_launch(pano_ctx *ctx, double *x, const double *b, double *r, doub
         PANO_TRY(build_tile_order(ctx, a, multi && slab->rank > 0, multi && slab->rank + 1 < slab->nranks));
     }
     a.halo_mid = (a.order && slab && slab->nranks > 1 && a.xr.hflags != nullptr && pano_option(ctx, "cg_halo_mid", 1) != 0) ? 1 : 0;
+    a.early_load = (a.order && slab && slab->nranks > 1 && a.xr.hflags != nullptr && pano_option(ctx, "cg_early_load", 1) != 0) ? 1 : 0;
     if (dynamic) {
         int bl = (int)pano_option(ctx, "cg_batch", 0);
         if (bl <= 0) bl = ntiles / (6 * G);

@@ -300,6 +300,12 @@ __device__ __forceinline__ bool grid_allreduce_units(ReduceUnit *units, unsigned
             if (!ok) *ok_sh = 0;
         }
         sync();
+        if (multi && xr->hflags && tid == 32 * 7) {
+            // "local done": every CTA of THIS GPU has published (hence fenced) its part of the ending pass.  The producers of
+            // k_cg_sr start streaming the tiles that do not touch another GPU's rows on this, while the totals still travel.
+            fence_gpu(light);
+            unit_store(result + 3, 0.0, seq);
+        }
         if (wid < nvals) {
             const bool is_max = (max_mask >> wid) & 1u;
             double r = is_max ? warp_fixed_max(vals[wid], G, lane) : warp_fixed_sum(vals[wid], G, lane);
