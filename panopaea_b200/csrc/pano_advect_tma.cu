@@ -26,21 +26,25 @@ using pano_adv::V32W;
 
 namespace {
 
-constexpr int TH = 32, TW = 64;                 // tile (cells)
+#ifndef PANO_ADV_WARPS
+#define PANO_ADV_WARPS 16                       // consumer warps (measured at 4096^2: 16 -> 157 us, 18 -> 168 us with 36-row tiles; 20 leave 80 registers: spills)
+#endif
+constexpr int kConsumerWarps = PANO_ADV_WARPS, kConsumers = 32 * kConsumerWarps;
+constexpr int TH = 2 * kConsumerWarps, TW = 64; // tile (cells): a warp covers 32 columns x 4 rows
 constexpr int kG = 2;                           // halo: every gather of a cell whose backtrace is shorter than 2 cells stays inside
 constexpr int QW = TW + 2 * kG, QH = TH + 2 * kG;   // 68 x 36: q and vy boxes
 constexpr int XW = QW + 2, XH = QH / 2;         // 70 x 18: each of the two vx boxes (even rows; odd rows shifted one column left)
 constexpr int kQBytes = QH * QW * 8;            // 19584 (a multiple of 128)
 constexpr int kXBytes = XH * XW * 8;            // 10080
-constexpr int kXSlot = 10112;                   // rounded up to a multiple of 128
+constexpr int kXSlot = (kXBytes + 127) / 128 * 128;   // rounded up to a multiple of 128
 constexpr int kXOdd = kXSlot / 8 + 1;           // offset (doubles) from an even-row element to the element one row down: odd box + its column shift
 constexpr int kStageBytes = 2 * kQBytes + 2 * kXSlot;   // 59392
 constexpr int kStages = 3;
-constexpr int kConsumerWarps = 16, kConsumers = 32 * kConsumerWarps;
 constexpr int kThreads = kConsumers + 32;       // + one producer warp
-constexpr int kRows = TH / (kConsumerWarps / 2);   // 4 rows per thread; a warp covers 32 columns
+constexpr int kRows = TH / (kConsumerWarps / 2);   // 4 rows per thread
 constexpr int kTailBytes = 1024;
 constexpr int kSmemBytes = kStages * kStageBytes + kTailBytes;   // 179200
+static_assert(kQBytes % 128 == 0 && kRows == 4 && TH % 2 == 0 && kSmemBytes <= 232448, "stage layout");
 
 struct AdvArgs {
     CUtensorMap m_q, m_vy, m_vx;  // m_vx: the super-row view (2(w+1) wide, rows/2 high)
@@ -335,7 +339,7 @@ int pano_preload_advect_tma() {
 // grid large enough for interior tiles to exist.  rows_* = rows stored from global row ylo on.
 bool pano_advect_tma_supported(size_t h, size_t w, int ya, int ylo, size_t rows_q, const void *q, const void *vy, const void *vx) {
     if (h % 2 || w % 2 || rows_q % 2 || ((ya - ylo) % 2) != 0) return false;
-    if (h < 4 * TH || w < 4 * TW) return false;
+    if (h < 64 || w < 128) return false;   // smaller grids: every tile is a border tile (correct, but the marching kernel is the better fit)
     if ((h + 1) * (w + 1) >= ((size_t)1 << 31)) return false;
     const void *ps[] = {q, vy, vx};
     for (const void *p : ps)

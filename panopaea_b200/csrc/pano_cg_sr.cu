@@ -71,7 +71,7 @@ struct SrArgs {
     int fence_mode;
     int dynamic;
     int sm_exchange;              // 1: tile_sr_sm (r_(i+1) exchanged through shared memory), 0: tile_sr (recomputed per thread)
-    const int *order;             // tile order: position -> tile (see build_tile_order), or null: row-major
+    const int *order;             // tile order: position -> tile (see pano_cg_tile_order), or null: row-major
     int slow_lo, slow_hi;         // the positions [slow_lo, slow_hi) hold the select-path tiles and the slab-edge tile rows
     int halo_mid;                 // slab with neighbours: the halo flags go out as soon as a CTA is past those positions
     int early_load;               // slab with neighbours: the first tiles of a pass are loaded on the GPU's "local done" (pano_sm100.cuh)
@@ -438,7 +438,7 @@ __device__ __forceinline__ void tile_sr_sm(const SrArgs &a, const double *R, dou
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// Position in the (un-reversed) tile order -> tile.  The order (build_tile_order, host) is: an eighth of the all-open tiles in
+// Position in the (un-reversed) tile order -> tile.  The order (pano_cg_tile_order, host) is: an eighth of the all-open tiles in
 // row-major order; then the bulk of them with every tile that takes the select path (walls, obstacle, ragged edge) and the first
 // and last tile row of a slab that has neighbours spread evenly in between; then the last eighth of the all-open tiles.  Odd passes
 // walk it backwards (L2 reuse), so in EITHER direction a pass ends with all-open tiles.  Two reasons:
@@ -460,7 +460,7 @@ __host__ __device__ __forceinline__ bool tile_is_fast_hd(int h, int w, int gy0, 
     return true;
 }
 __device__ __forceinline__ bool tile_is_fast(const SrArgs &a, int ty0, int tx0) { return tile_is_fast_hd(a.h, a.w, a.gy0, a.gh, a.m, ty0, tx0); }
-static bool tile_is_fast_host(const SrArgs &a, int ty0, int tx0) { return tile_is_fast_hd(a.h, a.w, a.gy0, a.gh, a.m, ty0, tx0); }
+
 __device__ __forceinline__ bool tile_stores_remote(const SrArgs &a, int ty0) {
     return (ty0 == 0 && a.up_r[0] != nullptr) || (ty0 + TH >= a.h - 1 && a.dn_r[0] != nullptr);
 }
@@ -792,15 +792,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_sr(const __grid_constant__ S
 }  // namespace
 
 // The tile order of tile_at: cached in the context (it depends only on the geometry), rebuilt and uploaded when that changes.
-static int build_tile_order(pano_ctx *ctx, SrArgs &a, bool has_up, bool has_dn) {
-    const int ntiles = a.tiles_x * a.tiles_y;
-    const long long key[10] = {a.h, a.w, a.gy0, a.gh, a.m.y0, a.m.y1, a.m.x0, a.m.x1, has_up ? 1 : 0, has_dn ? 1 : 0};
+// margin: cells around a tile that must be all-open for its branch-free path (2 here, 1 in k_cg_stream, which shares the order).
+int pano_cg_tile_order(pano_ctx *ctx, int h, int w, int gy0, int gh, RectI m, int tiles_x, int tiles_y, int th, int tw, int margin,
+                       bool has_up, bool has_dn, const int **order_out, int *lo_out, int *hi_out) {
+    const int ntiles = tiles_x * tiles_y;
+    const long long key[12] = {h, w, gy0, gh, m.y0, m.y1, m.x0, m.x1, has_up ? 1 : 0, has_dn ? 1 : 0, margin, (long long)th * 65536 + tw};
     if (ctx->sr_order_n != ntiles || memcmp(ctx->sr_order_key, key, sizeof(key)) != 0) {
+        auto all_open = [&](int ty0, int tx0) {
+            const int g0 = gy0 + ty0;
+            if (ty0 + th > h) return false;                                      // ragged tile at the end of the slab
+            if (g0 < margin || g0 + th > gh - margin || tx0 < margin || tx0 + tw > w - margin) return false;
+            if (m.y1 > m.y0 && m.x1 > m.x0 && g0 - (margin - 1) < m.y1 && g0 + th + (margin - 1) > m.y0 - 1 && tx0 - (margin - 1) < m.x1 &&
+                tx0 + tw + (margin - 1) > m.x0 - 1)
+                return false;
+            return true;
+        };
         std::vector<int> fast, slow;
         for (int t = 0; t < ntiles; ++t) {
-            const int ty = t / a.tiles_x, ty0 = ty * TH, tx0 = (t % a.tiles_x) * TW;
-            const bool edge_row = (ty == 0 && has_up) || (ty == a.tiles_y - 1 && has_dn);
-            (tile_is_fast_host(a, ty0, tx0) && !edge_row ? fast : slow).push_back(t);
+            const int ty = t / tiles_x, ty0 = ty * th, tx0 = (t % tiles_x) * tw;
+            const bool edge_row = (ty == 0 && has_up) || (ty == tiles_y - 1 && has_dn);
+            (all_open(ty0, tx0) && !edge_row ? fast : slow).push_back(t);
         }
         // head and tail: an eighth of the all-open tiles each; in between the rest of them with the slow tiles spread evenly (all
         // slow tiles at once would leave HBM idle while every SM computes: measured, 8192^2 2.6 % slower than spread out)
@@ -816,7 +827,6 @@ static int build_tile_order(pano_ctx *ctx, SrArgs &a, bool has_up, bool has_dn) 
             else order.push_back(slow[si++]);
         }
         order.insert(order.end(), fast.begin() + head + mid_fast, fast.end());
-        const size_t half = head, nslow_span = mid;
         if ((size_t)ntiles > ctx->sr_order_cap) {
             if (ctx->d_sr_order) {
                 PANO_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -831,12 +841,12 @@ static int build_tile_order(pano_ctx *ctx, SrArgs &a, bool has_up, bool has_dn) 
         PANO_CUDA(cudaMemcpyAsync(ctx->d_sr_order, order.data(), (size_t)ntiles * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         memcpy(ctx->sr_order_key, key, sizeof(key));
         ctx->sr_order_n = ntiles;
-        ctx->sr_order_lo = (int)half;
-        ctx->sr_order_hi = (int)(half + nslow_span);
+        ctx->sr_order_lo = (int)head;
+        ctx->sr_order_hi = (int)(head + mid);
     }
-    a.order = ctx->d_sr_order;
-    a.slow_lo = ctx->sr_order_lo;
-    a.slow_hi = ctx->sr_order_hi;
+    *order_out = ctx->d_sr_order;
+    *lo_out = ctx->sr_order_lo;
+    *hi_out = ctx->sr_order_hi;
     return PANO_OK;
 }
 
@@ -927,7 +937,8 @@ int pano_cg_sr_launch(pano_ctx *ctx, double *x, const double *b, double *r, doub
     a.slow_lo = a.slow_hi = 0;
     if (pano_option(ctx, "cg_order_mid", 1) != 0) {
         const bool multi = slab && slab->nranks > 1;
-        PANO_TRY(build_tile_order(ctx, a, multi && slab->rank > 0, multi && slab->rank + 1 < slab->nranks));
+        PANO_TRY(pano_cg_tile_order(ctx, a.h, a.w, a.gy0, a.gh, a.m, a.tiles_x, a.tiles_y, TH, TW, 2, multi && slab->rank > 0,
+                                    multi && slab->rank + 1 < slab->nranks, &a.order, &a.slow_lo, &a.slow_hi));
     }
     a.halo_mid = (a.order && slab && slab->nranks > 1 && a.xr.hflags != nullptr && pano_option(ctx, "cg_halo_mid", 1) != 0) ? 1 : 0;
     a.early_load = (a.order && slab && slab->nranks > 1 && a.xr.hflags != nullptr && pano_option(ctx, "cg_early_load", 1) != 0) ? 1 : 0;

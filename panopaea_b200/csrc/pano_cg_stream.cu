@@ -61,6 +61,7 @@ struct StreamArgs {
     unsigned long long seq_base;
     PanoCgControl *ctl;
     int zigzag;
+    const int *order;             // tile order: position -> tile (pano_cg_sr.cu: pano_cg_tile_order), or null: row-major
     int halo_first;               // slab with neighbours: halo tile rows first in every phase (see slot_tile)
     int fence_mode;               // kFenceLight | kFenceSysIfRemote (pano_sm100.cuh), option "cg_fence"
     // ---- dynamic tile scheduling (k_cg_stream<true>)
@@ -307,6 +308,7 @@ __device__ __forceinline__ int slot_tile(const StreamArgs &a, int phase, int jj,
         j = jj < nh ? jj : n_my - 1 - (jj - nh);
     }
     const int q = blockIdx.x + j * G;
+    if (!halo_first && a.order) return __ldg(a.order + q);
     if (!halo_first || a.tiles_y <= 2) return q;
     if (q < a.tiles_x) return q;                                              // first tile row
     if (q < 2 * a.tiles_x) return ntiles - 2 * a.tiles_x + q;                 // last tile row
@@ -411,6 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg_stream(const __grid_constant
                         }
                         const int pos = b_next++;
                         t = (phase == 1 && a.zigzag) ? ntiles - 1 - pos : pos;
+                        if (a.order) t = __ldg(a.order + t);
                         closes = b_next == b_end ? b_idx : -1;
                         return true;
                     };
@@ -771,6 +774,9 @@ int pano_make_tensor_map_2d(CUtensorMap *map, const void *base, size_t elem_byte
     return PANO_OK;
 }
 
+int pano_cg_tile_order(pano_ctx *ctx, int h, int w, int gy0, int gh, RectI m, int tiles_x, int tiles_y, int th, int tw, int margin,
+                       bool has_up, bool has_dn, const int **order_out, int *lo_out, int *hi_out);
+
 int pano_preload_cg_stream() {
     cudaFuncAttributes fa;
     PANO_CUDA(cudaFuncGetAttributes(&fa, k_cg_stream<false>));
@@ -818,6 +824,7 @@ int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, 
     if (a.dbg) PANO_CUDA(cudaMemsetAsync(ctx->d_partials, 0, 2 * kMaxCtas * sizeof(long long), ctx->stream));
     a.zigzag = pano_option(ctx, "cg_zigzag", 1) != 0;
     a.fence_mode = (int)pano_option(ctx, "cg_fence", 0);
+    a.order = nullptr;
     a.row0 = 0; a.gy0 = 0; a.gh = (int)h;
     a.xr.rank = 0; a.xr.nranks = 1;
     int max_ctas = 0;
@@ -846,6 +853,13 @@ int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, 
         }
         max_ctas = slab->max_ctas;
         a.halo_first = (slab->nranks > 1 && pano_option(ctx, "cg_halo_first", 0) != 0) ? 1 : 0;
+    }
+    if (pano_option(ctx, "cg_order_mid", 1) != 0 && !a.halo_first) {
+        // select-path tiles (walls, obstacle) away from both ends of the tile order: see pano_cg_sr.cu, tile_at
+        const bool multi = slab && slab->nranks > 1;
+        int lo, hi;
+        PANO_TRY(pano_cg_tile_order(ctx, a.h, a.w, a.gy0, a.gh, a.m, a.tiles_x, a.tiles_y, TH, TW, 1, multi && slab->rank > 0,
+                                    multi && slab->rank + 1 < slab->nranks, &a.order, &lo, &hi));
     }
     static_assert(kUnitsTotal * sizeof(ReduceUnit) <= 4096 * 16, "d_units (allocated in pano_ctx_create) is too small");
     a.units = (ReduceUnit *)ctx->d_units;

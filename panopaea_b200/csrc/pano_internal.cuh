@@ -86,7 +86,7 @@ struct pano_ctx {
     size_t sr_scratch_cap = 0;       // in doubles
     int *d_sr_order = nullptr;       // tile order of the single-reduction CG kernel (pano_cg_sr.cu: build_tile_order)
     size_t sr_order_cap = 0;
-    long long sr_order_key[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long sr_order_key[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     int sr_order_n = 0, sr_order_lo = 0, sr_order_hi = 0;
     void *d_tparts = nullptr;        // per-(tile, warp) reduction units of the dynamically scheduled streaming CG kernel
     size_t tparts_cap = 0;           // in 16-byte units
@@ -167,6 +167,7 @@ void pano_mg_free_all(pano_ctx *ctx);
 int pano_pcg_precond_raw(pano_ctx *ctx, int precond, pano_field *x, const pano_field *b, int max_iterations, double threshold,
                          pano_field *residual, pano_field *auxiliary, pano_field *search, double dt, pano_rect ob, pano_pcg_info *info);
 int pano_norm_max_raw(pano_ctx *ctx, int dtype, const void *a, size_t n, double *out);   // max|a[k]| (synchronises)
+struct RectI;
 int pano_cg_control_reset(pano_ctx *ctx);          // before a CG launch: clear the control block, keep the sticky error word
 int pano_check_device_error(pano_ctx *ctx, const char *where);   // after a stream sync that copied d_cg into h_cg
 int pano_phase_mark(pano_ctx *ctx, int phase);     // record event #phase of the current step (no-op unless step_timing)
