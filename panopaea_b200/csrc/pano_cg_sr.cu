@@ -935,7 +935,9 @@ int pano_cg_sr_launch(pano_ctx *ctx, double *x, const double *b, double *r, doub
     a.sm_exchange = pano_option(ctx, "cg_sr_exchange", 1) != 0 ? 1 : 0;
     a.order = nullptr;
     a.slow_lo = a.slow_hi = 0;
-    if (pano_option(ctx, "cg_order_mid", 1) != 0) {
+    const int64_t om = pano_option(ctx, "cg_order_mid", -1);      // -1 auto (up to 96 tiles per CTA, see pano_cg_stream.cu), 0 off, 1 on
+    const bool multi_gpu = slab && slab->nranks > 1;
+    if (om > 0 || (om < 0 && (multi_gpu || (long long)a.tiles_x * a.tiles_y <= 96LL * ctx->num_sms))) {
         const bool multi = slab && slab->nranks > 1;
         PANO_TRY(pano_cg_tile_order(ctx, a.h, a.w, a.gy0, a.gh, a.m, a.tiles_x, a.tiles_y, TH, TW, 2, multi && slab->rank > 0,
                                     multi && slab->rank + 1 < slab->nranks, &a.order, &a.slow_lo, &a.slow_hi));

@@ -854,7 +854,10 @@ int pano_cg_stream_launch(pano_ctx *ctx, double *x, const double *b, double *r, 
         max_ctas = slab->max_ctas;
         a.halo_first = (slab->nranks > 1 && pano_option(ctx, "cg_halo_first", 0) != 0) ? 1 : 0;
     }
-    if (pano_option(ctx, "cg_order_mid", 1) != 0 && !a.halo_first) {
+    // "cg_order_mid": -1 auto, 0 off, 1 on.  Measured (two-reduction kernel, one GPU): 4096^2 (55 tiles per CTA) 17.70 -> 17.49 ms per
+    // solve, 8192^2 (221) 67.01 -> 67.62: the shorter a pass, the more the slow tiles at its end cost; auto = up to 96 tiles per CTA.
+    const int64_t om = pano_option(ctx, "cg_order_mid", -1);
+    if ((om > 0 || (om < 0 && (long long)a.tiles_x * a.tiles_y <= 96LL * ctx->num_sms)) && !a.halo_first) {
         // select-path tiles (walls, obstacle) away from both ends of the tile order: see pano_cg_sr.cu, tile_at
         const bool multi = slab && slab->nranks > 1;
         int lo, hi;
