@@ -13,8 +13,8 @@ timeout 600 $NCU -k regex:k_cg -s 4 -c 1 -o gpurun_out/prof/r02_cg_1024 $B --gri
 timeout 600 $NCU -k regex:k_cg -s 4 -c 1 -o gpurun_out/prof/r02_cg_128 $B --grid 128 --warmup 3 > gpurun_out/prof/ncu_128.log 2>&1; echo "128 rc=$?"
 # the per-GPU slab of 8192^2 on 8 GPUs (1024 x 8192), through pano_dist with one rank: slab forms of all four kernels (step 12 of time_slab.py)
 timeout 900 $NCU -k regex:'k_advect|k_neg_divergence|k_project|k_cg' -s 44 -c 4 -o gpurun_out/prof/r02_slab_1024x8192 python scripts/time_slab.py 1024 8192 > gpurun_out/prof/ncu_slab.log 2>&1; echo "slab rc=$?"
-# the two-reduction streaming kernel for comparison (4096^2)
-timeout 900 $NCU -k regex:k_cg -s 4 -c 1 -o gpurun_out/prof/r02_cg_stream2_4096 $B --grid 4096 --warmup 3 --opt cg_single_reduction=0 > gpurun_out/prof/ncu_4096_two.log 2>&1; echo "4096 two-reduction rc=$?"
+# the single-reduction streaming kernel on one GPU's 4096^2 for comparison (the auto choice there is the two-reduction kernel)
+timeout 900 $NCU -k regex:k_cg -s 4 -c 1 -o gpurun_out/prof/r02_cg_sr_4096 $B --grid 4096 --warmup 3 --opt cg_single_reduction=1 > gpurun_out/prof/ncu_4096_sr.log 2>&1; echo "4096 single-reduction rc=$?"
 for r in gpurun_out/prof/*.ncu-rep; do
   python scripts/ncu_summary.py $r > ${r%.ncu-rep}_ncu.txt 2>&1
 done
