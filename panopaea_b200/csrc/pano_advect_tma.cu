@@ -29,8 +29,12 @@ namespace {
 #ifndef PANO_ADV_WARPS
 #define PANO_ADV_WARPS 16                       // consumer warps (measured at 4096^2: 16 -> 157 us, 18 -> 168 us with 36-row tiles; 20 leave 80 registers: spills)
 #endif
+#ifndef PANO_ADV_TW
+#define PANO_ADV_TW 64                          // tile width (cells): 64 -> 32-row tiles; 128 -> 16-row tiles with rows twice as long measured 166 vs 157 us at 4096^2
+#endif
 constexpr int kConsumerWarps = PANO_ADV_WARPS, kConsumers = 32 * kConsumerWarps;
-constexpr int TH = 2 * kConsumerWarps, TW = 64; // tile (cells): a warp covers 32 columns x 4 rows
+constexpr int TW = PANO_ADV_TW, kColGroups = TW / 32;          // a warp covers 32 columns x 4 rows
+constexpr int TH = 4 * (kConsumerWarps / kColGroups);          // tile (cells)
 constexpr int kG = 2;                           // halo: every gather of a cell whose backtrace is shorter than 2 cells stays inside
 constexpr int QW = TW + 2 * kG, QH = TH + 2 * kG;   // 68 x 36: q and vy boxes
 constexpr int XW = QW + 2, XH = QH / 2;         // 70 x 18: each of the two vx boxes (even rows; odd rows shifted one column left)
@@ -41,7 +45,7 @@ constexpr int kXOdd = kXSlot / 8 + 1;           // offset (doubles) from an even
 constexpr int kStageBytes = 2 * kQBytes + 2 * kXSlot;   // 59392
 constexpr int kStages = 3;
 constexpr int kThreads = kConsumers + 32;       // + one producer warp
-constexpr int kRows = TH / (kConsumerWarps / 2);   // 4 rows per thread
+constexpr int kRows = TH / (kConsumerWarps / kColGroups);   // 4 rows per thread
 constexpr int kTailBytes = 1024;
 constexpr int kSmemBytes = kStages * kStageBytes + kTailBytes;   // 179200
 static_assert(kQBytes % 128 == 0 && kRows == 4 && TH % 2 == 0 && kSmemBytes <= 232448, "stage layout");
@@ -283,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_advect_tma(const __grid_constan
     using Acc = typename GlobalAcc<kSlab>::Acc;
     const GlobalAcc<kSlab> ga(a);
     const Acc &gq = ga.q, &gvy = ga.vy, &gvx = ga.vx;
-    const int lx = (wid & 1) * 32 + lane, ly0 = (wid >> 1) * kRows;
+    const int lx = (wid % kColGroups) * 32 + lane, ly0 = (wid / kColGroups) * kRows;
     for (unsigned n = 0;; ++n) {
         const int st = n % kStages;
         if (!mbar_wait(&tl->full[st], (n / kStages) & 1, err)) return;
