@@ -64,6 +64,7 @@ struct AdvArgs {
     unsigned int *claim;          // two tile counters, used alternately by successive launches
     int parity;
     int dynamic;
+    int border_first;             // claim order: border tiles first (tile_at)
 };
 
 struct Tail {
@@ -227,6 +228,24 @@ __device__ __noinline__ void advect_edge_tile(const AdvArgs &a, const AQ &q, con
     pano_adv::advect_march3_body<true, kRows>(a.q_dst, a.vy_dst, a.vx_dst, q, vy, vx, a.h, a.w, a.dt, x, ys, a.yb);
 }
 
+// Position in the claim order -> tile.  Border tiles first (first and last tile row, then the first and last tile of every other
+// row), interior tiles after them in row-major order: border tiles take the select path and cost 2-3x an interior tile; in plain
+// row-major order the last tile ROW of the grid -- all border tiles -- ends the kernel and the SMs that drew them finish long
+// after the others (the kernel's fixed cost, measured from a + b x cells over grid sizes, was ~30 us).
+__device__ __forceinline__ int tile_at(const AdvArgs &a, int p) {
+    const int nx = a.tiles_x, ny = a.tiles_y;
+    if (nx < 3 || ny < 3) return p;
+    if (p < nx) return p;                                            // first tile row
+    if (p < 2 * nx) return (ny - 1) * nx + (p - nx);                 // last tile row
+    const int nb = 2 * nx + 2 * (ny - 2);
+    if (p < nb) {
+        const int q = p - 2 * nx;
+        return (1 + (q >> 1)) * nx + ((q & 1) ? nx - 1 : 0);         // first / last tile of rows 1 .. ny-2
+    }
+    const int q = p - nb;
+    return (1 + q / (nx - 2)) * nx + 1 + q % (nx - 2);               // the interior
+}
+
 template <bool kSlab>
 __global__ void __launch_bounds__(kThreads, 1) k_advect_tma(const __grid_constant__ AdvArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -260,6 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_advect_tma(const __grid_constan
             int t;
             if (a.dynamic) t = (int)atomicAdd(&a.claim[a.parity], 1u);
             else t = blockIdx.x + jj * G;
+            if (t < ntiles && a.border_first) t = tile_at(a, t);
             const int st = n % kStages;
             if (!mbar_wait(&tl->empty[st], ((n / kStages) & 1) ^ 1, err)) return;
             if (t >= ntiles) {                                  // end marker
@@ -288,6 +308,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_advect_tma(const __grid_constan
     const GlobalAcc<kSlab> ga(a);
     const Acc &gq = ga.q, &gvy = ga.vy, &gvx = ga.vx;
     const int lx = (wid % kColGroups) * 32 + lane, ly0 = (wid / kColGroups) * kRows;
+    // First, while the first boxes are in flight: the strips the cell tiles do not cover -- column x = w (vx only) and, where this launch owns it, face row y = h (vy only)
+    const int ncol = a.yb - a.ya, nrow = a.yb == a.h ? a.w : 0;
+    for (int i = blockIdx.x * kConsumers + tid; i < ncol + nrow; i += G * kConsumers) {
+        if (i < ncol) pano_adv::advect_march3_body<true, 1>(a.q_dst, a.vy_dst, a.vx_dst, gq, gvy, gvx, a.h, a.w, a.dt, a.w, a.ya + i, a.ya + i + 1);
+        else pano_adv::advect_march3_body<true, 1>(a.q_dst, a.vy_dst, a.vx_dst, gq, gvy, gvx, a.h, a.w, a.dt, i - ncol, a.h, a.h + 1);
+    }
     for (unsigned n = 0;; ++n) {
         const int st = n % kStages;
         if (!mbar_wait(&tl->full[st], (n / kStages) & 1, err)) return;
@@ -319,12 +345,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_advect_tma(const __grid_constan
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&tl->empty[st]);
-    }
-    // the strips the cell tiles do not cover: column x = w (vx only) and, where this launch owns it, face row y = h (vy only)
-    const int ncol = a.yb - a.ya, nrow = a.yb == a.h ? a.w : 0;
-    for (int i = blockIdx.x * kConsumers + tid; i < ncol + nrow; i += G * kConsumers) {
-        if (i < ncol) pano_adv::advect_march3_body<true, 1>(a.q_dst, a.vy_dst, a.vx_dst, gq, gvy, gvx, a.h, a.w, a.dt, a.w, a.ya + i, a.ya + i + 1);
-        else pano_adv::advect_march3_body<true, 1>(a.q_dst, a.vy_dst, a.vx_dst, gq, gvy, gvx, a.h, a.w, a.dt, i - ncol, a.h, a.h + 1);
     }
 }
 
@@ -384,6 +404,7 @@ int pano_advect_tma_launch(pano_ctx *ctx, double *q_dst, double *vy_dst, double 
     a.claim = ctx->d_adv_claim;
     a.parity = (int)(ctx->adv_epoch++ & 1u);
     a.dynamic = pano_option(ctx, "advect_dynamic", 1) != 0;
+    a.border_first = pano_option(ctx, "advect_border_first", 1) != 0;
     int G = ctx->num_sms;
     const int64_t cap = pano_option(ctx, "advect_ctas", 0);
     if (cap > 0 && cap < G) G = (int)cap;
