@@ -404,6 +404,10 @@ def kernel_table(phase_ms, phase_steps, cells, iters, peak, traffic, grid_key):
             row.update({"algorithmic_bytes": b, "algorithmic_gbs": gbs, "frac_of_measured_peak": gbs / peak, "frac_of_8000": gbs / NOMINAL_GBS})
             if nm == "cg":
                 row["survey_88_byte_model_gbs"] = cells * (BYTES_CG_INIT + BYTES_CG_ITER * iters) / (ms * 1e-3) / 1e9
+            us = traffic.get(f"{nm}_{grid_key}_ncu_us")
+            if us:                                 # the kernel's own duration under ncu (no launch gap), from the committed capture
+                row.update({"ncu_us": us, "algorithmic_gbs_on_ncu_duration": b / (us * 1e-6) / 1e9,
+                            "frac_of_8000_on_ncu_duration": b / (us * 1e-6) / 1e9 / NOMINAL_GBS})
             t = traffic.get(f"{nm}_{grid_key}")
             row["ncu_dram_bytes"] = t
             if t:
