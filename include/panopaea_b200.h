@@ -285,6 +285,56 @@ PANO_API int pano_dist_step(pano_dist *d);
 PANO_API int pano_dist_solve(pano_dist *d);
 PANO_API int pano_dist_sync(pano_dist *d, pano_pcg_info *info);
 
+/* --------------------------------------------------------------------- Grid3d
+ * SURVEY.md 8(f) rank 4.  The reference holds two 3-D items and nothing else: the struct
+ * `Grid3d { dim: (z, y, x) }` (panopaea/src/domain/grid.rs:17-20, no methods) and the free function
+ * `trilinear` (panopaea/src/math/interp.rs:23-36, never called).  The family below is the dec_fluid loop body
+ * (examples/dec_fluid.rs:46-141) carried to three dimensions by the same rules, one rule per 2-D line; there is
+ * no reference code to match, so DESIGN.md 5c IS the definition (restated by oracle/pano_oracle3.inc and,
+ * independently, by oracle/np_oracle3.py).  f64 only.
+ *   PANO_CELL3 (d,h,w): cell-centred scalar, row-major (z,y,x), x contiguous            -- Simplex2's role
+ *   PANO_FACE3 (d,h,w): ONE flat buffer, vz (d+1,h,w), then vy (d,h+1,w), then vx (d,h,w+1) -- Simplex1's role
+ * Handles are pano_field: upload/download/fill/assign/swap/scaled_add/scale/xpby/dot/norm_max above work on the
+ * flat view unchanged; the 2-D operators reject them with PANO_ERR_SHAPE. */
+enum { PANO_CELL3 = 3, PANO_FACE3 = 4 };
+enum { PANO_COMP_VZ = 3 };
+/* half-open index box [z0,z1) x [y0,y1) x [x0,x1) */
+typedef struct pano_box { int64_t z0, z1, y0, y1, x0, x1; } pano_box;
+typedef struct pano_step3_params {
+    double timestep;          /* 0.05 */
+    double threshold;         /* 0.1  */
+    int32_t max_iterations;   /* 100  */
+    int32_t precond;          /* PANO_PRECOND_IDENTITY only */
+    pano_box inflow;          /* density = inflow_density, vy = inflow_vy on the box before advection */
+    double inflow_density;
+    double inflow_vy;
+    pano_box obstacle;        /* faces vz/vy/vx with index in the box are closed in b and in A (not in the projection) */
+} pano_step3_params;
+PANO_API int pano_field3_new(pano_ctx *ctx, int kind, size_t d, size_t h, size_t w, pano_field **out);
+PANO_API int pano_field3_num_elem(int kind, size_t d, size_t h, size_t w, size_t *n);
+PANO_API int pano_field3_dim(const pano_field *f, size_t *d, size_t *h, size_t *w);
+/* comp: PANO_COMP_ALL (a cell field, or the same (z,y,x) in all three face arrays) / VZ / VY / VX */
+PANO_API int pano_field3_fill_box(pano_field *f, int comp, pano_box box, double value);
+/* math::trilinear (interp.rs:23-36) evaluated on the host with the library's own expression (argument order kept) */
+PANO_API double pano_trilinear(double a000, double a001, double a010, double a011, double a100, double a101,
+                               double a110, double a111, double s, double t, double u);
+/* advect / advect_mac / both in one pass, as the 2-D entry points above */
+PANO_API int pano_advect3(pano_field *dst, const pano_field *src, double timestep, const pano_field *vel);
+PANO_API int pano_advect3_mac(pano_field *dst, const pano_field *src, double timestep, const pano_field *vel);
+PANO_API int pano_advect3_all(pano_field *q_dst, pano_field *vel_dst, const pano_field *q_src, const pano_field *vel,
+                              double timestep);
+PANO_API int pano_neg_divergence3(pano_field *b, const pano_field *vel, pano_box obstacle, double *rhs_max);
+/* the 7-point Laplacian: z = A(s), walls and obstacle faces closed */
+PANO_API int pano_laplacian3_apply(pano_field *z, const pano_field *s, double timestep, pano_box obstacle);
+PANO_API int pano_project3(pano_field *vel, const pano_field *pressure, double timestep);
+/* pcg.rs:14-82 with the 7-point closure, ONE persistent kernel; arguments as pano_pcg_solve */
+PANO_API int pano_pcg3_solve(int precond, pano_field *x, const pano_field *b, int32_t max_iterations, double threshold,
+                             pano_field *residual, pano_field *auxiliary, pano_field *search, double timestep,
+                             pano_box obstacle, pano_pcg_info *info);
+PANO_API int pano_fluid3_step(const pano_step3_params *params, pano_field *density, pano_field *vel, pano_field *pressure,
+                              pano_field *temp, pano_field *vel_temp, pano_field *residual, pano_field *auxiliary,
+                              pano_field *search, pano_pcg_info *info);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,7 @@ EXPORT void orc_set_num_threads(int n) { (void)n; }
 #undef FLOOR
 
 #include "pano_oracle_mg.inc"
+#include "pano_oracle3.inc"   /* Grid3d specification (f64), uses the f64 body above */
 
 #define REAL float
 #define FN(x) x##_f32

@@ -23,7 +23,7 @@ SERIAL, REFERENCE_FAITHFUL, ALL_PARALLEL = 0, 1, 2
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("pano_oracle.c", "pano_oracle_body.inc", "pano_oracle_mg.inc", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("pano_oracle.c", "pano_oracle_body.inc", "pano_oracle_mg.inc", "pano_oracle3.inc", "Makefile")]
     stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-s"] + (["-B"] if force else []), check=True)
@@ -66,6 +66,11 @@ def lib():
             getattr(_lib, f"orc_state_field_{sfx}").restype = C.c_void_p
             getattr(_lib, f"orc_num_elem_1_{sfx}").restype = C.c_size_t
         _lib.orc_mg_new.restype = C.c_void_p
+        _lib.orc_trilinear.restype = C.c_double
+        _lib.orc_trilinear.argtypes = [C.c_double] * 11
+        _lib.orc3_num_faces.restype = C.c_size_t
+        _lib.orc3_state_new.restype = C.c_void_p
+        _lib.orc3_state_field.restype = C.c_void_p
         _lib.orc_mg_level_wy.restype = C.c_void_p
         _lib.orc_mg_level_wx.restype = C.c_void_p
     return _lib

@@ -42,6 +42,15 @@ class StepParams(C.Structure):
                 ("inflow", Rect), ("inflow_density", C.c_double), ("inflow_vy", C.c_double), ("obstacle", Rect)]
 
 
+class Box(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in ("z0", "z1", "y0", "y1", "x0", "x1")]
+
+
+class Step3Params(C.Structure):
+    _fields_ = [("timestep", C.c_double), ("threshold", C.c_double), ("max_iterations", C.c_int32), ("precond", C.c_int32),
+                ("inflow", Box), ("inflow_density", C.c_double), ("inflow_vy", C.c_double), ("obstacle", Box)]
+
+
 _P = C.c_void_p
 _SIGS = {
     # name: (restype, argtypes)
@@ -118,6 +127,19 @@ _SIGS = {
     "pano_dist_step": (C.c_int, [_P]),
     "pano_dist_solve": (C.c_int, [_P]),
     "pano_dist_sync": (C.c_int, [_P, C.POINTER(PcgInfo)]),
+    "pano_field3_new": (C.c_int, [_P, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(_P)]),
+    "pano_field3_num_elem": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "pano_field3_dim": (C.c_int, [_P, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "pano_field3_fill_box": (C.c_int, [_P, C.c_int, Box, C.c_double]),
+    "pano_trilinear": (C.c_double, [C.c_double] * 11),
+    "pano_advect3": (C.c_int, [_P, _P, C.c_double, _P]),
+    "pano_advect3_mac": (C.c_int, [_P, _P, C.c_double, _P]),
+    "pano_advect3_all": (C.c_int, [_P, _P, _P, _P, C.c_double]),
+    "pano_neg_divergence3": (C.c_int, [_P, _P, Box, C.POINTER(C.c_double)]),
+    "pano_laplacian3_apply": (C.c_int, [_P, _P, C.c_double, Box]),
+    "pano_project3": (C.c_int, [_P, _P, C.c_double]),
+    "pano_pcg3_solve": (C.c_int, [C.c_int, _P, _P, C.c_int32, C.c_double, _P, _P, _P, C.c_double, Box, C.POINTER(PcgInfo)]),
+    "pano_fluid3_step": (C.c_int, [C.POINTER(Step3Params), _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(PcgInfo)]),
 }
 IPC_HANDLE_BYTES = 64
 

@@ -395,7 +395,7 @@ int pano_check_kind(const pano_field *f, int kind, const char *name) {
 
 int pano_check_same(const pano_field *a, const pano_field *b, const char *what) {
     if (a->ctx != b->ctx) PANO_FAIL(PANO_ERR_INVALID, "%s: fields belong to different contexts", what);
-    if (a->kind != b->kind || a->dtype != b->dtype || a->h != b->h || a->w != b->w)
+    if (a->kind != b->kind || a->dtype != b->dtype || a->h != b->h || a->w != b->w || a->dep != b->dep)
         PANO_FAIL(PANO_ERR_SHAPE, "%s: shape mismatch: Simplex%d %zux%zu dtype %d vs Simplex%d %zux%zu dtype %d", what,
                   a->kind, a->h, a->w, a->dtype, b->kind, b->h, b->w, b->dtype);
     return PANO_OK;
@@ -403,7 +403,7 @@ int pano_check_same(const pano_field *a, const pano_field *b, const char *what) 
 
 int pano_check_grid(const pano_field *a, const pano_field *b, const char *what) {
     if (a->ctx != b->ctx) PANO_FAIL(PANO_ERR_INVALID, "%s: fields belong to different contexts", what);
-    if (a->dtype != b->dtype || a->h != b->h || a->w != b->w)
+    if (a->dtype != b->dtype || a->h != b->h || a->w != b->w || a->dep != b->dep)
         PANO_FAIL(PANO_ERR_SHAPE, "%s: grid mismatch: %zux%zu dtype %d vs %zux%zu dtype %d", what, a->h, a->w, a->dtype,
                   b->h, b->w, b->dtype);
     return PANO_OK;

@@ -257,4 +257,150 @@ PANO_HD T neg_divergence_cell(T vy0, T vy1, T vx0, T vx1) {
     return -(-bottom + top - vx0 + vx1);
 }
 
+// ================================================================================= Grid3d
+// The reference has `trilinear` (panopaea/src/math/interp.rs:23-36) and the bare struct Grid3d (domain/grid.rs:17-20);
+// everything else below is dec_fluid.rs carried to (z, y, x) rule by rule -- the 2-D line each expression extends is cited.
+template <class T>
+PANO_HD T trilinear(T a000, T a001, T a010, T a011, T a100, T a101, T a110, T a111, T s, T t, T u) {
+    return linear(bilinear(a000, a001, a010, a011, s, t), bilinear(a100, a101, a110, a111, s, t), u);
+}
+
+// ---- advect in 3-D (dec_fluid.rs:173-211 + a z axis): Q(z, y, x) -> T; the averaged velocity is passed in
+template <class T, class Q>
+PANO_HD T advect3_cell_uv(int z, int y, int x, int d, int h, int w, T timestep, T ucx, T ucy, T ucz, const Q &q) {
+    const T ndt = -timestep;
+    const T ppx = ((T)x + (T)0.5) + ndt * ucx;
+    const T ppy = ((T)y + (T)0.5) + ndt * ucy;
+    const T ppz = ((T)z + (T)0.5) + ndt * ucz;
+    const T px = tmin(tmax(ppx - (T)0.5, (T)0), (T)w - (T)1.00001);
+    const T py = tmin(tmax(ppy - (T)0.5, (T)0), (T)h - (T)1.00001);
+    const T pz = tmin(tmax(ppz - (T)0.5, (T)0), (T)d - (T)1.00001);
+    const int ix = (int)tfloor(px), iy = (int)tfloor(py), iz = (int)tfloor(pz);
+    const T s = px - (T)ix, t = py - (T)iy, u = pz - (T)iz;
+    return trilinear(q(iz, iy, ix), q(iz, iy, ix + 1), q(iz, iy + 1, ix), q(iz, iy + 1, ix + 1), q(iz + 1, iy, ix),
+                     q(iz + 1, iy, ix + 1), q(iz + 1, iy + 1, ix), q(iz + 1, iy + 1, ix + 1), s, t, u);
+}
+
+// one axis of advect_mac's index-clamped gather (dec_fluid.rs:232-246), general form
+struct MacAxis {
+    int i0, i1;
+    double s;
+};
+PANO_HD MacAxis mac_axis(double rel, int N) {
+    const double fp = tmax(tfloor(rel), 0.0);
+    MacAxis a;
+    a.i0 = to_index_min(fp, N - 1);
+    a.i1 = a.i0 + 1 < N - 1 ? a.i0 + 1 : N - 1;
+    a.s = tmax(tmin(rel - fp, 1.0), 0.0);
+    return a;
+}
+// the same bits through the exact fast forms above; anything beyond 2^32 cells takes the general form
+PANO_HD MacAxis mac_axis_fast(double rel, int N) {
+    const double r = clamp_lo0(rel);
+    const FloorNN f = floor_nonneg(r);
+    if (f.hi != kFloorHi) return mac_axis(rel, N);
+    const unsigned nm = (unsigned)(N - 1);
+    MacAxis a;
+    const unsigned i0 = f.i < nm ? f.i : nm;
+    a.i0 = (int)i0;
+    a.i1 = (int)(i0 + 1u < nm ? i0 + 1u : nm);
+    a.s = r - f.f;
+    return a;
+}
+// index-clamped trilinear gather on a (D, H, W) array at the position (relx, rely, relz) relative to its samples
+template <bool kFast, class Q>
+PANO_HD double mac3_gather(double relx, double rely, double relz, int D, int H, int W, const Q &q) {
+    const MacAxis ax = kFast ? mac_axis_fast(relx, W) : mac_axis(relx, W);
+    const MacAxis ay = kFast ? mac_axis_fast(rely, H) : mac_axis(rely, H);
+    const MacAxis az = kFast ? mac_axis_fast(relz, D) : mac_axis(relz, D);
+    return trilinear(q(az.i0, ay.i0, ax.i0), q(az.i0, ay.i0, ax.i1), q(az.i0, ay.i1, ax.i0), q(az.i0, ay.i1, ax.i1),
+                     q(az.i1, ay.i0, ax.i0), q(az.i1, ay.i0, ax.i1), q(az.i1, ay.i1, ax.i0), q(az.i1, ay.i1, ax.i1), ax.s, ay.s, az.s);
+}
+// one axis of advect's coordinate-clamped gather, fast form: ch = coordinate + 0.5, lim = N - 1.00001
+struct CellAxis {
+    int i;
+    double f;
+};
+PANO_HD CellAxis advect_axis_fast(double ch, double lim, double ndt, double u) {
+    const double pp = ch + ndt * u;
+    const double p = clamp_hi(clamp_lo0(pp - 0.5), lim);
+    const FloorNN fl = floor_nonneg(p);
+    CellAxis a;
+    a.i = (int)fl.i;
+    a.f = p - fl.f;
+    return a;
+}
+template <class Q>
+PANO_HD double advect3_cell_fast(int z, int y, int x, int d, int h, int w, double timestep, double ucx, double ucy, double ucz,
+                                 const Q &q) {
+    const double ndt = -timestep;
+    const CellAxis ax = advect_axis_fast((double)x + 0.5, (double)w - 1.00001, ndt, ucx);
+    const CellAxis ay = advect_axis_fast((double)y + 0.5, (double)h - 1.00001, ndt, ucy);
+    const CellAxis az = advect_axis_fast((double)z + 0.5, (double)d - 1.00001, ndt, ucz);
+    return trilinear(q(az.i, ay.i, ax.i), q(az.i, ay.i, ax.i + 1), q(az.i, ay.i + 1, ax.i), q(az.i, ay.i + 1, ax.i + 1),
+                     q(az.i + 1, ay.i, ax.i), q(az.i + 1, ay.i, ax.i + 1), q(az.i + 1, ay.i + 1, ax.i), q(az.i + 1, ay.i + 1, ax.i + 1),
+                     ax.f, ay.f, az.f);
+}
+
+// ---- the 3-D advection of every quantity stored at one (z, y, x): VZ/VY/VX/Q are callables (z, y, x) -> double.
+// Velocity sampling extends dec_fluid.rs:222-228 / :259-265: the component's own value, and the four-sample mean of
+// each other component over the two faces either side along its axis and the two cells either side of this face.
+template <bool kFast, class Q, class VZ, class VY, class VX>
+PANO_HD double advect3_cell(int z, int y, int x, int d, int h, int w, double dt, const Q &q, const VZ &vz, const VY &vy, const VX &vx) {
+    const double ucx = (vx(z, y, x) + vx(z, y, x + 1)) / 2.0;       // :182-185
+    const double ucy = (vy(z, y, x) + vy(z, y + 1, x)) / 2.0;
+    const double ucz = (vz(z, y, x) + vz(z + 1, y, x)) / 2.0;
+    if (kFast) return advect3_cell_fast(z, y, x, d, h, w, dt, ucx, ucy, ucz, q);
+    return advect3_cell_uv<double>(z, y, x, d, h, w, dt, ucx, ucy, ucz, q);
+}
+template <bool kFast, class Q, class VZ, class VY, class VX>
+PANO_HD double advect3_mac_x(int z, int y, int x, int d, int h, int w, double dt, const Q &qx, const VZ &vz, const VY &vy, const VX &vx) {
+    const int xc = x < w - 1 ? x : w - 1, xm = x > 0 ? x - 1 : 0;   // (z, y, x) in (d, h, w+1), :218-253
+    const double ndt = -dt;
+    const double vvx = vx(z, y, x);
+    const double vvy = (vy(z, y, xc) + vy(z, y + 1, xc) + vy(z, y, xm) + vy(z, y + 1, xm)) / 4.0;
+    const double vvz = (vz(z, y, xc) + vz(z + 1, y, xc) + vz(z, y, xm) + vz(z + 1, y, xm)) / 4.0;
+    const double ppx = ((double)x + 0.0) + ndt * vvx, ppy = ((double)y + 0.5) + ndt * vvy, ppz = ((double)z + 0.5) + ndt * vvz;
+    return mac3_gather<kFast>(ppx - 0.0, ppy - 0.5, ppz - 0.5, d, h, w + 1, qx);
+}
+template <bool kFast, class Q, class VZ, class VY, class VX>
+PANO_HD double advect3_mac_y(int z, int y, int x, int d, int h, int w, double dt, const Q &qy, const VZ &vz, const VY &vy, const VX &vx) {
+    const int yc = y < h - 1 ? y : h - 1, ym = y > 0 ? y - 1 : 0;   // (z, y, x) in (d, h+1, w), :255-290
+    const double ndt = -dt;
+    const double vvx = (vx(z, yc, x) + vx(z, yc, x + 1) + vx(z, ym, x) + vx(z, ym, x + 1)) / 4.0;
+    const double vvy = vy(z, y, x);
+    const double vvz = (vz(z, yc, x) + vz(z + 1, yc, x) + vz(z, ym, x) + vz(z + 1, ym, x)) / 4.0;
+    const double ppx = ((double)x + 0.5) + ndt * vvx, ppy = ((double)y + 0.0) + ndt * vvy, ppz = ((double)z + 0.5) + ndt * vvz;
+    return mac3_gather<kFast>(ppx - 0.5, ppy - 0.0, ppz - 0.5, d, h + 1, w, qy);
+}
+template <bool kFast, class Q, class VZ, class VY, class VX>
+PANO_HD double advect3_mac_z(int z, int y, int x, int d, int h, int w, double dt, const Q &qz, const VZ &vz, const VY &vy, const VX &vx) {
+    const int zc = z < d - 1 ? z : d - 1, zm = z > 0 ? z - 1 : 0;   // (z, y, x) in (d+1, h, w)
+    const double ndt = -dt;
+    const double vvx = (vx(zc, y, x) + vx(zc, y, x + 1) + vx(zm, y, x) + vx(zm, y, x + 1)) / 4.0;
+    const double vvy = (vy(zc, y, x) + vy(zc, y + 1, x) + vy(zm, y, x) + vy(zm, y + 1, x)) / 4.0;
+    const double vvz = vz(z, y, x);
+    const double ppx = ((double)x + 0.5) + ndt * vvx, ppy = ((double)y + 0.5) + ndt * vvy, ppz = ((double)z + 0.0) + ndt * vvz;
+    return mac3_gather<kFast>(ppx - 0.5, ppy - 0.5, ppz - 0.0, d + 1, h, w, qz);
+}
+
+// ---- the 7-point closure at one cell (dec_fluid.rs:100-119 with a z pair in front): f / k = p at (z-1) / (z+1)
+//   e.vz[z] = p[z] - p[z-1], e.vz[z+1] = p[z+1] - p[z];  cell = -back + front - bottom + top - left + right;  * dt
+template <class T>
+PANO_HD T laplacian3_cell(T c, T f, T k, T n, T s, T w_, T e, bool oF, bool oK, bool oN, bool oS, bool oW, bool oE, T dt) {
+    const T front = oF ? (c - f) : (T)0;
+    const T back = oK ? (k - c) : (T)0;
+    const T top = oN ? (c - n) : (T)0;
+    const T bottom = oS ? (s - c) : (T)0;
+    const T left = oW ? (w_ - c) : (T)0;
+    const T right = oE ? (c - e) : (T)0;
+    return (-back + front - bottom + top - left + right) * dt;
+}
+// ---- -divergence (dec_fluid.rs:69-83): the hodge negates vz and vy, masked faces arrive as zero
+template <class T>
+PANO_HD T neg_divergence3_cell(T vz0, T vz1, T vy0, T vy1, T vx0, T vx1) {
+    const T front = -vz0, back = -vz1, top = -vy0, bottom = -vy1;
+    return -(-back + front - bottom + top - vx0 + vx1);
+}
+
 }  // namespace pano

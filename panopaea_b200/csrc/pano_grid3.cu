@@ -1,0 +1,679 @@
+// pano_grid3.cu -- Grid3d: the dec_fluid loop body on a (z, y, x) staggered grid.
+//
+// The reference has the bare struct Grid3d (panopaea/src/domain/grid.rs:17-20) and the unused `trilinear`
+// (panopaea/src/math/interp.rs:23-36); DESIGN.md 5c defines the rest as examples/dec_fluid.rs:46-141 with a z axis
+// added rule by rule (the test suite holds a plain-C and a numpy statement of it).  Per-cell arithmetic: pano_cell_math.h.
+//
+// Layout (as the 2-D containers, dec/grid.rs:37-62, 76): CELL3 = (d, h, w) row-major; FACE3 = one flat buffer,
+// vz (d+1, h, w) | vy (d, h+1, w) | vx (d, h, w+1).
+//
+// Kernels (all HBM-bound; algorithmic bytes per cell in f64):
+//   k3_advect        q, vz, vy, vx advected in ONE pass                      64 B   (4 reads + 4 writes)
+//   k3_neg_div       hodge -> box zero -> d2 -> negate fused, z-marching      32 B
+//   k3_cg            the WHOLE pcg.rs:14-82 loop, one persistent cooperative kernel, two phases per
+//                    iteration as pano_cg.cu, columns marching along z with s'[z-1], s'[z], s'[z+1] in
+//                    registers                                                64 B per iteration
+//   k3_project       gradient + axpy + walls fused, z-marching                56 B   (p, 3 faces read; 3 faces written)
+#include "pano_cell_math.h"
+#include "pano_gridsync.cuh"
+#include "pano_internal.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;   // 32 (x) x 8 (y)
+
+struct BoxI {
+    int z0, z1, y0, y1, x0, x1;
+};
+__device__ __forceinline__ bool in_box(const BoxI &b, int z, int y, int x) {
+    return z >= b.z0 && z < b.z1 && y >= b.y0 && y < b.y1 && x >= b.x0 && x < b.x1;
+}
+BoxI clip_box(pano_box r, size_t dmax, size_t hmax, size_t wmax) {
+    auto clip = [](int64_t v, size_t hi) -> int { return v < 0 ? 0 : (v > (int64_t)hi ? (int)hi : (int)v); };
+    BoxI o{clip(r.z0, dmax), clip(r.z1, dmax), clip(r.y0, hmax), clip(r.y1, hmax), clip(r.x0, wmax), clip(r.x1, wmax)};
+    if (o.z1 <= o.z0 || o.y1 <= o.y0 || o.x1 <= o.x0) o = BoxI{0, 0, 0, 0, 0, 0};
+    return o;
+}
+
+// (z, y, x) -> value on a (., H, W) array
+struct V3 {
+    const double *p;
+    int H, W;
+    __device__ __forceinline__ double operator()(int z, int y, int x) const { return __ldg(p + ((size_t)z * H + y) * W + x); }
+};
+
+// ------------------------------------------------------------------ fills
+__global__ void k3_fill_box(double *a, int H, int W, BoxI b, double v) {
+    const int nx = b.x1 - b.x0, ny = b.y1 - b.y0;
+    const size_t n = (size_t)(b.z1 - b.z0) * ny * nx;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = b.x0 + (int)(i % nx), y = b.y0 + (int)((i / nx) % ny), z = b.z0 + (int)(i / ((size_t)nx * ny));
+        a[((size_t)z * H + y) * W + x] = v;
+    }
+}
+
+// ------------------------------------------------------------------ advection: every quantity stored at (z, y, x), one pass
+// grid: x tiles of 32 over [0, w], y groups of 8 over [0, h], z over [0, d]
+template <bool kScalar, bool kMac>
+__global__ void __launch_bounds__(kThreads)
+k3_advect(double *__restrict__ q_dst, double *__restrict__ vz_dst, double *__restrict__ vy_dst, double *__restrict__ vx_dst,
+          const double *__restrict__ q_src, const double *__restrict__ mz_src, const double *__restrict__ my_src,
+          const double *__restrict__ mx_src, const double *__restrict__ vz_p, const double *__restrict__ vy_p,
+          const double *__restrict__ vx_p, int d, int h, int w, double dt) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), z = blockIdx.z;
+    if (x > w || y > h) return;
+    const V3 vz{vz_p, h, w}, vy{vy_p, h + 1, w}, vx{vx_p, h, w + 1};
+    const bool xin = x < w, yin = y < h, zin = z < d;
+    if (kScalar && xin && yin && zin)
+        q_dst[((size_t)z * h + y) * w + x] = pano::advect3_cell<true>(z, y, x, d, h, w, dt, V3{q_src, h, w}, vz, vy, vx);
+    if (kMac) {
+        if (yin && zin)
+            vx_dst[((size_t)z * h + y) * (w + 1) + x] = pano::advect3_mac_x<true>(z, y, x, d, h, w, dt, V3{mx_src, h, w + 1}, vz, vy, vx);
+        if (xin && zin)
+            vy_dst[((size_t)z * (h + 1) + y) * w + x] = pano::advect3_mac_y<true>(z, y, x, d, h, w, dt, V3{my_src, h + 1, w}, vz, vy, vx);
+        if (xin && yin)
+            vz_dst[((size_t)z * h + y) * w + x] = pano::advect3_mac_z<true>(z, y, x, d, h, w, dt, V3{mz_src, h, w}, vz, vy, vx);
+    }
+}
+
+// ------------------------------------------------------------------ -divergence: a column of kZ cells per thread, vz carried
+constexpr int kDivZ = 8;
+__global__ void __launch_bounds__(kThreads)
+k3_neg_div(double *__restrict__ b, const double *__restrict__ vz, const double *__restrict__ vy, const double *__restrict__ vx, int d,
+           int h, int w, BoxI m) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), zs = blockIdx.z * kDivZ;
+    if (x >= w || y >= h) return;
+    const size_t plane = (size_t)h * w;
+    double vz0 = in_box(m, zs, y, x) ? 0.0 : vz[zs * plane + (size_t)y * w + x];
+#pragma unroll
+    for (int k = 0; k < kDivZ; ++k) {
+        const int z = zs + k;
+        if (z >= d) break;
+        const bool here = in_box(m, z, y, x);
+        const double vz1 = in_box(m, z + 1, y, x) ? 0.0 : vz[(z + 1) * plane + (size_t)y * w + x];
+        const double vy0 = here ? 0.0 : vy[((size_t)z * (h + 1) + y) * w + x];
+        const double vy1 = in_box(m, z, y + 1, x) ? 0.0 : vy[((size_t)z * (h + 1) + y + 1) * w + x];
+        const double vx0 = here ? 0.0 : vx[((size_t)z * h + y) * (w + 1) + x];
+        const double vx1 = in_box(m, z, y, x + 1) ? 0.0 : vx[((size_t)z * h + y) * (w + 1) + x + 1];
+        b[z * plane + (size_t)y * w + x] = pano::neg_divergence3_cell<double>(vz0, vz1, vy0, vy1, vx0, vx1);
+        vz0 = vz1;
+    }
+}
+
+// ------------------------------------------------------------------ stand-alone 7-point closure
+__global__ void __launch_bounds__(kThreads)
+k3_laplacian(double *__restrict__ out, const double *__restrict__ p, int d, int h, int w, double dt, BoxI m) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), z = blockIdx.z;
+    if (x >= w || y >= h) return;
+    const size_t plane = (size_t)h * w, i = z * plane + (size_t)y * w + x;
+    const bool here = in_box(m, z, y, x);
+    const bool oF = z > 0 && !here, oK = z < d - 1 && !in_box(m, z + 1, y, x);
+    const bool oN = y > 0 && !here, oS = y < h - 1 && !in_box(m, z, y + 1, x);
+    const bool oW = x > 0 && !here, oE = x < w - 1 && !in_box(m, z, y, x + 1);
+    const double c = p[i];
+    const double f = oF ? p[i - plane] : 0.0, k = oK ? p[i + plane] : 0.0;
+    const double n = oN ? p[i - w] : 0.0, s = oS ? p[i + w] : 0.0;
+    const double l = oW ? p[i - 1] : 0.0, e = oE ? p[i + 1] : 0.0;
+    out[i] = pano::laplacian3_cell<double>(c, f, k, n, s, l, e, oF, oK, oN, oS, oW, oE, dt);
+}
+
+// ------------------------------------------------------------------ projection + walls: z-marching, p[z-1] carried
+constexpr int kProjZ = 8;
+__global__ void __launch_bounds__(kThreads)
+k3_project(double *__restrict__ vz, double *__restrict__ vy, double *__restrict__ vx, const double *__restrict__ p, int d, int h, int w,
+           double dt) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), zs = blockIdx.z * kProjZ;
+    if (x > w || y > h) return;
+    const bool xin = x < w, yin = y < h, cell = xin && yin;
+    const size_t plane = (size_t)h * w;
+    double pf = (cell && zs > 0) ? p[(zs - 1) * plane + (size_t)y * w + x] : 0.0;   // p[z-1, y, x]
+#pragma unroll
+    for (int k = 0; k < kProjZ; ++k) {
+        const int z = zs + k;
+        if (z > d) break;
+        const bool zin = z < d;
+        const double c = (cell && zin) ? p[z * plane + (size_t)y * w + x] : 0.0;
+        if (cell) {   // vz[z, y, x]
+            const size_t i = z * plane + (size_t)y * w + x;
+            if (z == 0 || z == d) vz[i] = 0.0;
+            else vz[i] = vz[i] + dt * (pf - c);
+        }
+        if (xin && zin) {   // vy[z, y, x], y in [0, h]
+            const size_t i = ((size_t)z * (h + 1) + y) * w + x;
+            if (y == 0 || y == h) vy[i] = 0.0;
+            else vy[i] = vy[i] + dt * (p[z * plane + (size_t)(y - 1) * w + x] - c);
+        }
+        if (yin && zin) {   // vx[z, y, x], x in [0, w]
+            const size_t i = ((size_t)z * h + y) * (w + 1) + x;
+            if (x == 0 || x == w) vx[i] = 0.0;
+            else vx[i] = vx[i] + dt * (p[z * plane + (size_t)y * w + x - 1] - c);
+        }
+        pf = c;
+    }
+}
+
+// ------------------------------------------------------------------ the solve (pcg.rs:14-82, 7-point closure)
+// Phases exactly as pano_cg.cu: P1 s' = r + beta s (folded search update; recomputed on the six neighbours from their OLD values,
+// hence s double-buffered), z = A s' evaluated and reduced against s' but never stored; P2 z recomputed from s', x += alpha s',
+// r -= alpha z, r.r and max|r| reduced.  64 B per cell and iteration.  A tile is 32 x 8 columns of `zc` cells; a thread walks its
+// column with s'[z-1], s'[z], s'[z+1] in registers, so along z every value is formed once per tile.
+struct Cg3Args {
+    double *x;
+    const double *b;
+    double *r, *s0, *s1;
+    int d, h, w;
+    double dt, threshold;
+    int max_iter;
+    BoxI m;
+    double *partials;   // 5 * G
+    PanoCgControl *ctl;
+    int tiles_x, tiles_y, tiles_z, zc;
+};
+
+__global__ void __launch_bounds__(kThreads) k3_cg(Cg3Args a) {
+    __shared__ double scratch[32];
+    __shared__ int s_flag;
+    const int G = gridDim.x;
+    const int d = a.d, h = a.h, w = a.w;
+    const size_t plane = (size_t)h * w;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int txy = a.tiles_x * a.tiles_y, ntiles = txy * a.tiles_z;
+    double *pA = a.partials, *pB = pA + G, *pC = pA + 2 * G, *pD = pA + 3 * G, *pE = pA + 4 * G;
+    unsigned long long nbar = 0;
+    double sigma = 0, alpha = 0, beta = 0, rmax = 0, bmax = 0;
+    int it = 0, applies = 0;
+    bool converged = false;
+    double *s_cur = a.s0, *s_old = a.s1;
+
+    for (it = 0; it < a.max_iter; ++it) {
+        const bool first = it == 0;
+        const double *r_src = first ? a.b : a.r;
+        // ---------------------------------------------------------------- P1
+        double acc_zs = 0, acc_bb = 0, acc_bmax = 0;
+        for (int t = blockIdx.x; t < ntiles; t += G) {
+            const int x = (t % a.tiles_x) * 32 + lx, y = ((t / a.tiles_x) % a.tiles_y) * 8 + ly, z0 = (t / txy) * a.zc;
+            if (x >= w || y >= h) continue;
+            const int z1 = z0 + a.zc < d ? z0 + a.zc : d;
+            size_t i = z0 * plane + (size_t)y * w + x;
+            auto sval = [&](size_t j) -> double { return first ? __ldcg(r_src + j) : __ldcg(r_src + j) + beta * __ldcg(s_old + j); };
+            double sm1 = z0 > 0 ? sval(i - plane) : 0.0, sc = sval(i);
+            for (int z = z0; z < z1; ++z, i += plane) {
+                const double sp1 = z + 1 < d ? sval(i + plane) : 0.0;
+                const bool here = in_box(a.m, z, y, x);
+                const bool oF = z > 0 && !here, oK = z < d - 1 && !in_box(a.m, z + 1, y, x);
+                const bool oN = y > 0 && !here, oS = y < h - 1 && !in_box(a.m, z, y + 1, x);
+                const bool oW = x > 0 && !here, oE = x < w - 1 && !in_box(a.m, z, y, x + 1);
+                const double n = oN ? sval(i - w) : 0.0, s = oS ? sval(i + w) : 0.0;
+                const double l = oW ? sval(i - 1) : 0.0, e = oE ? sval(i + 1) : 0.0;
+                if (first) {
+                    const double ab = sc < 0 ? -sc : sc;
+                    acc_bmax = ab > acc_bmax ? ab : acc_bmax;
+                    acc_bb = acc_bb + sc * sc;
+                } else {
+                    s_cur[i] = sc;
+                }
+                const double zv = pano::laplacian3_cell<double>(sc, sm1, sp1, n, s, l, e, oF, oK, oN, oS, oW, oE, a.dt);
+                acc_zs = acc_zs + zv * sc;
+                sm1 = sc;
+                sc = sp1;
+            }
+        }
+        {
+            const double v = block_sum(acc_zs, scratch);
+            if (threadIdx.x == 0) pA[blockIdx.x] = v;
+            if (first) {
+                const double v2 = block_sum(acc_bb, scratch), v3 = block_max(acc_bmax, scratch);
+                if (threadIdx.x == 0) {
+                    pB[blockIdx.x] = v2;
+                    pC[blockIdx.x] = v3;
+                }
+            }
+        }
+        if (!grid_barrier(a.ctl, (++nbar) * (unsigned long long)G, &s_flag)) return;
+        const double zs = sum_partials<double>(pA, G, scratch);
+        if (first) {
+            sigma = sum_partials<double>(pB, G, scratch);      // pcg.rs:46
+            bmax = max_partials<double>(pC, G, scratch);       // pcg.rs:35
+            rmax = bmax;
+            if (bmax < a.threshold) {                          // early out: x = 0, scratch untouched
+                const size_t n = plane * d;
+                for (size_t j = blockIdx.x * (size_t)kThreads + threadIdx.x; j < n; j += (size_t)G * kThreads) a.x[j] = 0.0;
+                if (blockIdx.x == 0 && threadIdx.x == 0) {
+                    a.ctl->iterations = -1;
+                    a.ctl->applies = 0;
+                    a.ctl->final_residual = bmax;
+                    a.ctl->rhs_max = bmax;
+                }
+                return;
+            }
+        }
+        ++applies;
+        alpha = sigma / zs;                                    // pcg.rs:53
+        const double nalpha = -alpha;
+        // ---------------------------------------------------------------- P2
+        double acc_rr = 0, acc_rmax = 0;
+        const double *s_rd = first ? a.b : s_cur;
+        for (int t = blockIdx.x; t < ntiles; t += G) {
+            const int x = (t % a.tiles_x) * 32 + lx, y = ((t / a.tiles_x) % a.tiles_y) * 8 + ly, z0 = (t / txy) * a.zc;
+            if (x >= w || y >= h) continue;
+            const int z1 = z0 + a.zc < d ? z0 + a.zc : d;
+            size_t i = z0 * plane + (size_t)y * w + x;
+            double sm1 = z0 > 0 ? __ldcg(s_rd + i - plane) : 0.0, sc = __ldcg(s_rd + i);
+            for (int z = z0; z < z1; ++z, i += plane) {
+                const double sp1 = z + 1 < d ? __ldcg(s_rd + i + plane) : 0.0;
+                const bool here = in_box(a.m, z, y, x);
+                const bool oF = z > 0 && !here, oK = z < d - 1 && !in_box(a.m, z + 1, y, x);
+                const bool oN = y > 0 && !here, oS = y < h - 1 && !in_box(a.m, z, y + 1, x);
+                const bool oW = x > 0 && !here, oE = x < w - 1 && !in_box(a.m, z, y, x + 1);
+                const double n = oN ? __ldcg(s_rd + i - w) : 0.0, s = oS ? __ldcg(s_rd + i + w) : 0.0;
+                const double l = oW ? __ldcg(s_rd + i - 1) : 0.0, e = oE ? __ldcg(s_rd + i + 1) : 0.0;
+                const double zv = pano::laplacian3_cell<double>(sc, sm1, sp1, n, s, l, e, oF, oK, oN, oS, oW, oE, a.dt);
+                if (first) a.s0[i] = sc;                       // pcg.rs:40-42: s = aux = r = b
+                const double xo = first ? 0.0 : __ldcg(a.x + i);
+                a.x[i] = xo + alpha * sc;                      // pcg.rs:55
+                const double rn = __ldcg(r_src + i) + nalpha * zv;   // pcg.rs:56
+                a.r[i] = rn;
+                const double ar = rn < 0 ? -rn : rn;
+                acc_rmax = ar > acc_rmax ? ar : acc_rmax;
+                acc_rr = acc_rr + rn * rn;
+                sm1 = sc;
+                sc = sp1;
+            }
+        }
+        {
+            const double v = block_sum(acc_rr, scratch), v2 = block_max(acc_rmax, scratch);
+            if (threadIdx.x == 0) {
+                pD[blockIdx.x] = v;
+                pE[blockIdx.x] = v2;
+            }
+        }
+        if (!grid_barrier(a.ctl, (++nbar) * (unsigned long long)G, &s_flag)) return;
+        const double rr = sum_partials<double>(pD, G, scratch);
+        rmax = max_partials<double>(pE, G, scratch);           // pcg.rs:58
+        if (rmax < a.threshold) {                              // pcg.rs:60-63
+            converged = true;
+            break;
+        }
+        beta = rr / sigma;                                     // pcg.rs:67-68
+        sigma = rr;                                            // pcg.rs:79
+        double *tmp = s_cur;
+        s_cur = s_old;
+        s_old = tmp;
+    }
+    // as pano_cg.cu: `search` must end up holding what the reference leaves in it (pcg.rs:72-77 runs once more when the loop runs out)
+    const double *s_fin = converged ? s_cur : s_old;
+    if (a.max_iter > 0 && (!converged || s_fin != a.s0)) {
+        const size_t n = plane * d;
+        for (size_t j = blockIdx.x * (size_t)kThreads + threadIdx.x; j < n; j += (size_t)G * kThreads) {
+            const double sv = __ldcg(s_fin + j);
+            a.s0[j] = converged ? sv : __ldcg(a.r + j) + beta * sv;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.ctl->iterations = converged ? it : a.max_iter;
+        a.ctl->applies = applies;
+        a.ctl->final_residual = rmax;
+        a.ctl->rhs_max = bmax;
+    }
+}
+
+// ---------------------------------------------------------------------------------- host side
+int check3(const pano_field *f, int kind, const char *name) {
+    PANO_TRY(pano_check_field(f, name));
+    if (f->kind != kind || f->dep == 0)
+        PANO_FAIL(PANO_ERR_SHAPE, "%s: expected a %s of a Grid3d, got kind %d", name, kind == PANO_CELL3 ? "cell field" : "face field", f->kind);
+    if (f->dtype != PANO_F64) PANO_FAIL(PANO_ERR_SHAPE, "%s: the Grid3d path is f64 only", name);
+    return PANO_OK;
+}
+int same_grid3(const pano_field *a, const pano_field *b, const char *what) {
+    if (a->ctx != b->ctx) PANO_FAIL(PANO_ERR_INVALID, "%s: fields belong to different contexts", what);
+    if (a->dep != b->dep || a->h != b->h || a->w != b->w)
+        PANO_FAIL(PANO_ERR_SHAPE, "%s: grid mismatch: %zux%zux%zu vs %zux%zux%zu", what, a->dep, a->h, a->w, b->dep, b->h, b->w);
+    return PANO_OK;
+}
+int check_box_within(const pano_box &r, size_t d, size_t h, size_t w, const char *what) {
+    if (r.z0 < 0 || r.y0 < 0 || r.x0 < 0 || r.z1 < r.z0 || r.y1 < r.y0 || r.x1 < r.x0) PANO_FAIL(PANO_ERR_INVALID, "%s: malformed box", what);
+    if (r.z1 > r.z0 && r.y1 > r.y0 && r.x1 > r.x0 && ((size_t)r.z1 > d || (size_t)r.y1 > h || (size_t)r.x1 > w))
+        PANO_FAIL(PANO_ERR_SHAPE, "%s: box exceeds the %zux%zux%zu grid (an index panic in Rust)", what, d, h, w);
+    return PANO_OK;
+}
+struct Face3 {
+    double *vz, *vy, *vx;
+};
+Face3 split3(const pano_field *f) {   // Simplex1::split (dec/grid.rs:48-61) with a third part in front
+    double *p = (double *)f->d;
+    const size_t nz = (f->dep + 1) * f->h * f->w, ny = f->dep * (f->h + 1) * f->w;
+    return Face3{p, p + nz, p + nz + ny};
+}
+dim3 grid3(size_t xs, size_t ys, size_t zs) { return dim3((unsigned)((xs + 31) / 32), (unsigned)((ys + 7) / 8), (unsigned)zs); }
+
+int advect3_launch(pano_ctx *ctx, bool scalar, bool mac, double *q_dst, pano_field *mac_dst, const double *q_src, const pano_field *mac_src,
+                   const pano_field *vel, double dt) {
+    const size_t d = vel->dep, h = vel->h, w = vel->w;
+    const Face3 v = split3(vel);
+    Face3 md{nullptr, nullptr, nullptr}, ms{nullptr, nullptr, nullptr};
+    if (mac) {
+        md = split3(mac_dst);
+        ms = split3(mac_src);
+    }
+    const dim3 g = grid3(w + 1, h + 1, d + 1);
+    if (g.y > 65535u || g.z > 65535u) PANO_FAIL(PANO_ERR_SHAPE, "Grid3d: %zux%zux%zu exceeds the launch grid", d, h, w);
+    if (scalar && mac)
+        k3_advect<true, true><<<g, kThreads, 0, ctx->stream>>>(q_dst, md.vz, md.vy, md.vx, q_src, ms.vz, ms.vy, ms.vx, v.vz, v.vy, v.vx, (int)d, (int)h, (int)w, dt);
+    else if (scalar)
+        k3_advect<true, false><<<g, kThreads, 0, ctx->stream>>>(q_dst, nullptr, nullptr, nullptr, q_src, nullptr, nullptr, nullptr, v.vz, v.vy, v.vx, (int)d, (int)h, (int)w, dt);
+    else
+        k3_advect<false, true><<<g, kThreads, 0, ctx->stream>>>(nullptr, md.vz, md.vy, md.vx, nullptr, ms.vz, ms.vy, ms.vx, v.vz, v.vy, v.vx, (int)d, (int)h, (int)w, dt);
+    return pano_after_launch(ctx, "k3_advect");
+}
+
+int neg_div3_launch(pano_ctx *ctx, double *b, const pano_field *vel, pano_box ob) {
+    const size_t d = vel->dep, h = vel->h, w = vel->w;
+    const Face3 v = split3(vel);
+    k3_neg_div<<<grid3(w, h, (d + kDivZ - 1) / kDivZ), kThreads, 0, ctx->stream>>>(b, v.vz, v.vy, v.vx, (int)d, (int)h, (int)w,
+                                                                                    clip_box(ob, d + 1, h + 1, w + 1));
+    return pano_after_launch(ctx, "k3_neg_div");
+}
+
+int project3_launch(pano_ctx *ctx, pano_field *vel, const double *p, double dt) {
+    const size_t d = vel->dep, h = vel->h, w = vel->w;
+    const Face3 v = split3(vel);
+    k3_project<<<grid3(w + 1, h + 1, (d + 1 + kProjZ - 1) / kProjZ), kThreads, 0, ctx->stream>>>(v.vz, v.vy, v.vx, p, (int)d, (int)h, (int)w, dt);
+    return pano_after_launch(ctx, "k3_project");
+}
+
+int cg3_solve_raw(pano_ctx *ctx, double *x, const double *b, double *r, double *s0, double *s1, size_t d, size_t h, size_t w,
+                  int max_iterations, double threshold, double dt, pano_box ob, pano_pcg_info *info) {
+    const size_t n = d * h * w;
+    if (max_iterations <= 0) {   // pcg.rs:32-46 with an empty loop, as pano_cg_solve_raw
+        double bmax = 0.0;
+        PANO_TRY(pano_norm_max_raw(ctx, PANO_F64, b, n, &bmax));
+        PANO_CUDA(cudaMemsetAsync(x, 0, n * 8, ctx->stream));
+        const bool early = bmax < threshold;
+        if (!early) {
+            PANO_CUDA(cudaMemcpyAsync(r, b, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            PANO_CUDA(cudaMemcpyAsync(s0, b, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        if (info) {
+            PANO_CUDA(cudaStreamSynchronize(ctx->stream));
+            *info = pano_pcg_info{early ? -1 : 0, 0, bmax, bmax};
+        }
+        return PANO_OK;
+    }
+    int per_sm = 0;
+    PANO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_cg, kThreads, 0));
+    if (per_sm < 1) PANO_FAIL(PANO_ERR_CUDA, "cg3: kernel does not fit on an SM");
+    const int64_t cap = pano_option(ctx, "cg_blocks_per_sm", 0);
+    if (cap > 0 && cap < per_sm) per_sm = (int)cap;
+    Cg3Args a{x, b, r, s0, s1, (int)d, (int)h, (int)w, dt, threshold, max_iterations, clip_box(ob, d + 1, h + 1, w + 1), nullptr, ctx->d_cg,
+              (int)((w + 31) / 32), (int)((h + 7) / 8), 0, 0};
+    // column length per tile: long columns re-read less (two extra planes per tile in P1), short ones balance the static
+    // round-robin better.  Pick the candidate with the best (useful planes / planes read) x (tiles / rounded-up tiles per CTA).
+    const int64_t want_zc = pano_option(ctx, "cg3_zc", 0);
+    int best_zc = 8;
+    double best = -1.0;
+    const int Gfull = ctx->num_sms * per_sm;
+    for (int zc : {8, 16, 32, 64}) {
+        if (want_zc > 0 && zc != want_zc) continue;
+        const long long tz = ((long long)d + zc - 1) / zc, nt = tz * a.tiles_x * a.tiles_y;
+        const long long G = nt < Gfull ? nt : Gfull, rounds = (nt + G - 1) / G;
+        const double eff = ((double)zc / (zc + 1.0)) * ((double)nt / (double)(rounds * G));   // +2 planes on r and s of 64 B -> ~ +1 plane in 8
+        if (eff > best) {
+            best = eff;
+            best_zc = zc;
+        }
+    }
+    a.zc = best_zc;
+    a.tiles_z = (int)((d + a.zc - 1) / a.zc);
+    const long long ntiles = (long long)a.tiles_x * a.tiles_y * a.tiles_z;
+    int G = Gfull;
+    if (G > ntiles) G = (int)ntiles;
+    if (G < 1) G = 1;
+    PANO_TRY(pano_ensure_partials(ctx, 5 * (size_t)G));
+    a.partials = ctx->d_partials;
+    PANO_TRY(pano_cg_control_reset(ctx));
+    void *kargs[] = {(void *)&a};
+    PANO_CUDA(cudaLaunchCooperativeKernel((const void *)k3_cg, dim3((unsigned)G), dim3(kThreads), kargs, 0, ctx->stream));
+    PANO_TRY(pano_after_launch(ctx, "k3_cg"));
+    if (info) {
+        PANO_CUDA(cudaMemcpyAsync(ctx->h_cg, ctx->d_cg, sizeof(PanoCgControl), cudaMemcpyDeviceToHost, ctx->stream));
+        PANO_CUDA(cudaStreamSynchronize(ctx->stream));
+        PANO_TRY(pano_check_device_error(ctx, "pano_pcg3_solve"));
+        *info = pano_pcg_info{ctx->h_cg->iterations, ctx->h_cg->applies, ctx->h_cg->final_residual, ctx->h_cg->rhs_max};
+    }
+    return PANO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pano_field3_num_elem(int kind, size_t d, size_t h, size_t w, size_t *n) {
+    if (!n) PANO_FAIL(PANO_ERR_INVALID, "pano_field3_num_elem: null out pointer");
+    if (kind == PANO_CELL3) *n = d * h * w;
+    else if (kind == PANO_FACE3) *n = (d + 1) * h * w + d * (h + 1) * w + d * h * (w + 1);
+    else PANO_FAIL(PANO_ERR_INVALID, "pano_field3_num_elem: bad kind %d", kind);
+    return PANO_OK;
+}
+
+int pano_field3_new(pano_ctx *ctx, int kind, size_t d, size_t h, size_t w, pano_field **out) {
+    if (!ctx || !out) PANO_FAIL(PANO_ERR_INVALID, "pano_field3_new: null argument");
+    *out = nullptr;
+    if (kind != PANO_CELL3 && kind != PANO_FACE3) PANO_FAIL(PANO_ERR_INVALID, "pano_field3_new: bad kind %d", kind);
+    if (d == 0 || h == 0 || w == 0) PANO_FAIL(PANO_ERR_SHAPE, "pano_field3_new: empty grid %zux%zux%zu", d, h, w);
+    if (d > 4096 || h > 65536 || w > 65536 || (d + 1) * (h + 1) * (w + 1) >= ((size_t)1 << 31))
+        PANO_FAIL(PANO_ERR_INVALID, "pano_field3_new: grid %zux%zux%zu exceeds 2^31 samples per array", d, h, w);
+    PANO_TRY(pano_activate(ctx));
+    pano_field *f = new pano_field();
+    f->ctx = ctx;
+    f->kind = kind;
+    f->dtype = PANO_F64;
+    f->dep = d;
+    f->h = h;
+    f->w = w;
+    pano_field3_num_elem(kind, d, h, w, &f->n);
+    const size_t bytes = f->n * 8;
+    cudaError_t e = cudaMalloc(&f->d, bytes + 256);
+    if (e == cudaSuccess) e = cudaMemsetAsync(f->d, 0, bytes + 256, ctx->stream);
+    if (e != cudaSuccess) {
+        if (f->d) cudaFree(f->d);
+        delete f;
+        PANO_FAIL(PANO_ERR_CUDA, "pano_field3_new: allocating %zu bytes -> %s", bytes, cudaGetErrorString(e));
+    }
+    *out = f;
+    return PANO_OK;
+}
+
+int pano_field3_dim(const pano_field *f, size_t *d, size_t *h, size_t *w) {
+    PANO_TRY(pano_check_field(f, "pano_field3_dim"));
+    if (f->dep == 0) PANO_FAIL(PANO_ERR_SHAPE, "pano_field3_dim: a 2-D field");
+    if (d) *d = f->dep;
+    if (h) *h = f->h;
+    if (w) *w = f->w;
+    return PANO_OK;
+}
+
+int pano_field3_fill_box(pano_field *f, int comp, pano_box box, double value) {
+    PANO_TRY(pano_check_field(f, "pano_field3_fill_box"));
+    if (f->dep == 0 || f->dtype != PANO_F64) PANO_FAIL(PANO_ERR_SHAPE, "pano_field3_fill_box: not a Grid3d field");
+    pano_ctx *ctx = f->ctx;
+    PANO_TRY(pano_activate(ctx));
+    struct Part { size_t off, D, H, W; };
+    Part parts[3];
+    int np = 0;
+    const size_t d = f->dep, h = f->h, w = f->w;
+    if (f->kind == PANO_CELL3) {
+        if (comp != PANO_COMP_ALL) PANO_FAIL(PANO_ERR_INVALID, "pano_field3_fill_box: component %d on a cell field", comp);
+        parts[np++] = Part{0, d, h, w};
+    } else {
+        const size_t nz = (d + 1) * h * w, ny = d * (h + 1) * w;
+        if (comp == PANO_COMP_ALL || comp == PANO_COMP_VZ) parts[np++] = Part{0, d + 1, h, w};
+        if (comp == PANO_COMP_ALL || comp == PANO_COMP_VY) parts[np++] = Part{nz, d, h + 1, w};
+        if (comp == PANO_COMP_ALL || comp == PANO_COMP_VX) parts[np++] = Part{nz + ny, d, h, w + 1};
+        if (np == 0) PANO_FAIL(PANO_ERR_INVALID, "pano_field3_fill_box: bad component %d", comp);
+    }
+    for (int i = 0; i < np; ++i) PANO_TRY(check_box_within(box, parts[i].D, parts[i].H, parts[i].W, "pano_field3_fill_box"));
+    if (box.z1 == box.z0 || box.y1 == box.y0 || box.x1 == box.x0) return PANO_OK;
+    const size_t cells = (size_t)(box.z1 - box.z0) * (size_t)(box.y1 - box.y0) * (size_t)(box.x1 - box.x0);
+    size_t g = (cells + kThreads - 1) / kThreads;
+    if (g > (size_t)ctx->num_sms * 8) g = (size_t)ctx->num_sms * 8;
+    const BoxI bi{(int)box.z0, (int)box.z1, (int)box.y0, (int)box.y1, (int)box.x0, (int)box.x1};
+    for (int i = 0; i < np; ++i) {
+        k3_fill_box<<<(unsigned)g, kThreads, 0, ctx->stream>>>((double *)f->d + parts[i].off, (int)parts[i].H, (int)parts[i].W, bi, value);
+        PANO_TRY(pano_after_launch(ctx, "pano_field3_fill_box"));
+    }
+    return PANO_OK;
+}
+
+double pano_trilinear(double a000, double a001, double a010, double a011, double a100, double a101, double a110, double a111, double s,
+                      double t, double u) {
+    return pano::trilinear<double>(a000, a001, a010, a011, a100, a101, a110, a111, s, t, u);
+}
+
+int pano_advect3(pano_field *dst, const pano_field *src, double timestep, const pano_field *vel) {
+    PANO_TRY(check3(dst, PANO_CELL3, "pano_advect3(dst)"));
+    PANO_TRY(check3(src, PANO_CELL3, "pano_advect3(src)"));
+    PANO_TRY(check3(vel, PANO_FACE3, "pano_advect3(vel)"));
+    PANO_TRY(same_grid3(dst, src, "pano_advect3"));
+    PANO_TRY(same_grid3(dst, vel, "pano_advect3"));
+    if (dst->d == src->d) PANO_FAIL(PANO_ERR_INVALID, "pano_advect3: dst aliases src");
+    PANO_TRY(pano_activate(dst->ctx));
+    return advect3_launch(dst->ctx, true, false, (double *)dst->d, nullptr, (const double *)src->d, nullptr, vel, timestep);
+}
+
+int pano_advect3_mac(pano_field *dst, const pano_field *src, double timestep, const pano_field *vel) {
+    PANO_TRY(check3(dst, PANO_FACE3, "pano_advect3_mac(dst)"));
+    PANO_TRY(check3(src, PANO_FACE3, "pano_advect3_mac(src)"));
+    PANO_TRY(check3(vel, PANO_FACE3, "pano_advect3_mac(vel)"));
+    PANO_TRY(same_grid3(dst, src, "pano_advect3_mac"));
+    PANO_TRY(same_grid3(dst, vel, "pano_advect3_mac"));
+    if (dst->d == src->d || dst->d == vel->d) PANO_FAIL(PANO_ERR_INVALID, "pano_advect3_mac: dst aliases src or vel");
+    PANO_TRY(pano_activate(dst->ctx));
+    return advect3_launch(dst->ctx, false, true, nullptr, dst, nullptr, src, vel, timestep);
+}
+
+int pano_advect3_all(pano_field *q_dst, pano_field *vel_dst, const pano_field *q_src, const pano_field *vel, double timestep) {
+    PANO_TRY(check3(q_dst, PANO_CELL3, "pano_advect3_all(q_dst)"));
+    PANO_TRY(check3(q_src, PANO_CELL3, "pano_advect3_all(q_src)"));
+    PANO_TRY(check3(vel_dst, PANO_FACE3, "pano_advect3_all(vel_dst)"));
+    PANO_TRY(check3(vel, PANO_FACE3, "pano_advect3_all(vel)"));
+    PANO_TRY(same_grid3(q_dst, q_src, "pano_advect3_all"));
+    PANO_TRY(same_grid3(q_dst, vel, "pano_advect3_all"));
+    PANO_TRY(same_grid3(q_dst, vel_dst, "pano_advect3_all"));
+    if (q_dst->d == q_src->d || vel_dst->d == vel->d) PANO_FAIL(PANO_ERR_INVALID, "pano_advect3_all: destination aliases source");
+    PANO_TRY(pano_activate(q_dst->ctx));
+    return advect3_launch(q_dst->ctx, true, true, (double *)q_dst->d, vel_dst, (const double *)q_src->d, vel, vel, timestep);
+}
+
+int pano_neg_divergence3(pano_field *b, const pano_field *vel, pano_box obstacle, double *rhs_max) {
+    PANO_TRY(check3(b, PANO_CELL3, "pano_neg_divergence3(b)"));
+    PANO_TRY(check3(vel, PANO_FACE3, "pano_neg_divergence3(vel)"));
+    PANO_TRY(same_grid3(b, vel, "pano_neg_divergence3"));
+    PANO_TRY(check_box_within(obstacle, b->dep, b->h, b->w, "pano_neg_divergence3(obstacle)"));
+    PANO_TRY(pano_activate(b->ctx));
+    PANO_TRY(neg_div3_launch(b->ctx, (double *)b->d, vel, obstacle));
+    if (rhs_max) return pano_norm_max_raw(b->ctx, PANO_F64, b->d, b->n, rhs_max);
+    return PANO_OK;
+}
+
+int pano_laplacian3_apply(pano_field *z, const pano_field *s, double timestep, pano_box obstacle) {
+    PANO_TRY(check3(z, PANO_CELL3, "pano_laplacian3_apply(z)"));
+    PANO_TRY(check3(s, PANO_CELL3, "pano_laplacian3_apply(s)"));
+    PANO_TRY(same_grid3(z, s, "pano_laplacian3_apply"));
+    if (z->d == s->d) PANO_FAIL(PANO_ERR_INVALID, "pano_laplacian3_apply: z aliases s");
+    PANO_TRY(check_box_within(obstacle, z->dep, z->h, z->w, "pano_laplacian3_apply(obstacle)"));
+    pano_ctx *ctx = z->ctx;
+    PANO_TRY(pano_activate(ctx));
+    const size_t d = z->dep, h = z->h, w = z->w;
+    k3_laplacian<<<grid3(w, h, d), kThreads, 0, ctx->stream>>>((double *)z->d, (const double *)s->d, (int)d, (int)h, (int)w, timestep,
+                                                                clip_box(obstacle, d + 1, h + 1, w + 1));
+    return pano_after_launch(ctx, "k3_laplacian");
+}
+
+int pano_project3(pano_field *vel, const pano_field *pressure, double timestep) {
+    PANO_TRY(check3(vel, PANO_FACE3, "pano_project3(vel)"));
+    PANO_TRY(check3(pressure, PANO_CELL3, "pano_project3(pressure)"));
+    PANO_TRY(same_grid3(vel, pressure, "pano_project3"));
+    PANO_TRY(pano_activate(vel->ctx));
+    return project3_launch(vel->ctx, vel, (const double *)pressure->d, timestep);
+}
+
+int pano_pcg3_solve(int precond, pano_field *x, const pano_field *b, int32_t max_iterations, double threshold, pano_field *residual,
+                    pano_field *auxiliary, pano_field *search, double timestep, pano_box obstacle, pano_pcg_info *info) {
+    if (precond != PANO_PRECOND_IDENTITY)
+        PANO_FAIL(PANO_ERR_UNIMPLEMENTED, "pano_pcg3_solve: only the identity preconditioner `()` (pcg.rs:8-12) exists on a Grid3d");
+    const pano_field *all[] = {x, b, residual, auxiliary, search};
+    const char *names[] = {"x", "b", "residual", "auxiliary", "search"};
+    for (int i = 0; i < 5; ++i) {
+        char nm[64];
+        snprintf(nm, sizeof(nm), "pano_pcg3_solve(%s)", names[i]);
+        PANO_TRY(check3(all[i], PANO_CELL3, nm));
+        PANO_TRY(same_grid3(all[0], all[i], "pano_pcg3_solve"));
+        for (int j = 0; j < i; ++j)
+            if (all[i]->d == all[j]->d) PANO_FAIL(PANO_ERR_INVALID, "pano_pcg3_solve: %s aliases %s", names[i], names[j]);
+    }
+    PANO_TRY(check_box_within(obstacle, x->dep, x->h, x->w, "pano_pcg3_solve(obstacle)"));
+    PANO_TRY(pano_activate(x->ctx));
+    return cg3_solve_raw(x->ctx, (double *)x->d, (const double *)b->d, (double *)residual->d, (double *)search->d, (double *)auxiliary->d,
+                         x->dep, x->h, x->w, max_iterations, threshold, timestep, obstacle, info);
+}
+
+int pano_fluid3_step(const pano_step3_params *params, pano_field *density, pano_field *vel, pano_field *pressure, pano_field *temp,
+                     pano_field *vel_temp, pano_field *residual, pano_field *auxiliary, pano_field *search, pano_pcg_info *info) {
+    if (!params) PANO_FAIL(PANO_ERR_INVALID, "pano_fluid3_step: null params");
+    const pano_field *c3[] = {density, pressure, temp, residual, auxiliary, search};
+    const char *n3[] = {"density", "pressure", "temp", "residual", "auxiliary", "search"};
+    for (int i = 0; i < 6; ++i) {
+        char nm[64];
+        snprintf(nm, sizeof(nm), "pano_fluid3_step(%s)", n3[i]);
+        PANO_TRY(check3(c3[i], PANO_CELL3, nm));
+        PANO_TRY(same_grid3(density, c3[i], "pano_fluid3_step"));
+        for (int j = 0; j < i; ++j)
+            if (c3[i]->d == c3[j]->d) PANO_FAIL(PANO_ERR_INVALID, "pano_fluid3_step: %s aliases %s", n3[i], n3[j]);
+    }
+    PANO_TRY(check3(vel, PANO_FACE3, "pano_fluid3_step(vel)"));
+    PANO_TRY(check3(vel_temp, PANO_FACE3, "pano_fluid3_step(vel_temp)"));
+    PANO_TRY(same_grid3(density, vel, "pano_fluid3_step"));
+    PANO_TRY(same_grid3(density, vel_temp, "pano_fluid3_step"));
+    if (vel->d == vel_temp->d) PANO_FAIL(PANO_ERR_INVALID, "pano_fluid3_step: vel aliases vel_temp");
+    if (params->precond != PANO_PRECOND_IDENTITY)
+        PANO_FAIL(PANO_ERR_UNIMPLEMENTED, "pano_fluid3_step: only the identity preconditioner exists on a Grid3d");
+    const size_t d = density->dep, h = density->h, w = density->w;
+    if (d < 2 || h < 2 || w < 2) PANO_FAIL(PANO_ERR_SHAPE, "pano_fluid3_step: grid %zux%zux%zu below 2x2x2", d, h, w);
+    PANO_TRY(check_box_within(params->inflow, d, h, w, "pano_fluid3_step(inflow)"));
+    PANO_TRY(check_box_within(params->obstacle, d, h, w, "pano_fluid3_step(obstacle)"));
+    pano_ctx *ctx = density->ctx;
+    PANO_TRY(pano_activate(ctx));
+    const double dt = params->timestep;
+    PANO_TRY(pano_phase_mark(ctx, 0));
+    PANO_TRY(pano_field3_fill_box(density, PANO_COMP_ALL, params->inflow, params->inflow_density));   // :48-57
+    PANO_TRY(pano_field3_fill_box(vel, PANO_COMP_VY, params->inflow, params->inflow_vy));
+    PANO_TRY(pano_phase_mark(ctx, 1));
+    PANO_TRY(advect3_launch(ctx, true, true, (double *)temp->d, vel_temp, (const double *)density->d, vel, vel, dt));   // :59-60
+    PANO_TRY(pano_field_swap(density, temp));                                                          // :62-63
+    PANO_TRY(pano_field_swap(vel, vel_temp));
+    PANO_TRY(pano_phase_mark(ctx, 2));
+    PANO_TRY(neg_div3_launch(ctx, (double *)temp->d, vel, params->obstacle));                           // :69-83
+    PANO_TRY(pano_phase_mark(ctx, 3));
+    PANO_TRY(cg3_solve_raw(ctx, (double *)pressure->d, (const double *)temp->d, (double *)residual->d, (double *)search->d,
+                           (double *)auxiliary->d, d, h, w, params->max_iterations, params->threshold, dt, params->obstacle, nullptr));
+    PANO_TRY(pano_phase_mark(ctx, 4));
+    PANO_TRY(project3_launch(ctx, vel, (const double *)pressure->d, dt));                               // :124-141
+    PANO_TRY(pano_phase_mark(ctx, 5));
+    if (info) {
+        if (params->max_iterations <= 0) {
+            PANO_CUDA(cudaStreamSynchronize(ctx->stream));
+            double bmax = 0.0;
+            PANO_TRY(pano_norm_max_raw(ctx, PANO_F64, temp->d, temp->n, &bmax));
+            *info = pano_pcg_info{bmax < params->threshold ? -1 : 0, 0, bmax, bmax};
+            return PANO_OK;
+        }
+        PANO_CUDA(cudaMemcpyAsync(ctx->h_cg, ctx->d_cg, sizeof(PanoCgControl), cudaMemcpyDeviceToHost, ctx->stream));
+        PANO_CUDA(cudaStreamSynchronize(ctx->stream));
+        PANO_TRY(pano_check_device_error(ctx, "pano_fluid3_step"));
+        *info = pano_pcg_info{ctx->h_cg->iterations, ctx->h_cg->applies, ctx->h_cg->final_residual, ctx->h_cg->rhs_max};
+    }
+    return PANO_OK;
+}
+
+}  // extern "C"

@@ -110,6 +110,7 @@ struct pano_field {
     pano_ctx *ctx = nullptr;
     int kind = 0, dtype = 0;
     size_t h = 0, w = 0, n = 0;
+    size_t dep = 0;   // depth of a Grid3d field (kinds PANO_CELL3 / PANO_FACE3), 0 on a Grid2d
     void *d = nullptr;
 };
 

@@ -226,6 +226,7 @@ int pano_field_fill(pano_field *f, double value) {
 
 int pano_field_fill_rect(pano_field *f, int comp, pano_rect rect, double value) {
     PANO_TRY(pano_check_field(f, "pano_field_fill_rect"));
+    if (f->dep != 0) PANO_FAIL(PANO_ERR_SHAPE, "pano_field_fill_rect: a Grid3d field (use pano_field3_fill_box)");
     pano_ctx *ctx = f->ctx;
     PANO_TRY(pano_activate(ctx));
     if (rect.y0 < 0 || rect.x0 < 0 || rect.y1 < rect.y0 || rect.x1 < rect.x0)

@@ -19,9 +19,12 @@ pub const PANO_F32: c_int = 1;
 pub const PANO_SIMPLEX0: c_int = 0;
 pub const PANO_SIMPLEX1: c_int = 1;
 pub const PANO_SIMPLEX2: c_int = 2;
+pub const PANO_CELL3: c_int = 3;
+pub const PANO_FACE3: c_int = 4;
 pub const PANO_COMP_ALL: c_int = 0;
 pub const PANO_COMP_VY: c_int = 1;
 pub const PANO_COMP_VX: c_int = 2;
+pub const PANO_COMP_VZ: c_int = 3;
 pub const PANO_PRECOND_IDENTITY: c_int = 0;
 pub const PANO_PRECOND_JACOBI: c_int = 1;
 pub const PANO_PRECOND_MULTIGRID: c_int = 2;
@@ -77,6 +80,32 @@ pub struct pano_step_params {
     pub inflow_density: f64,
     pub inflow_vy: f64,
     pub obstacle: pano_rect,
+}
+
+/// half-open index box `[z0,z1) x [y0,y1) x [x0,x1)` of a `Grid3d` (`panopaea/src/domain/grid.rs:17-20`)
+#[repr(C)]
+#[derive(Copy, Clone, Debug, Default, PartialEq, Eq)]
+pub struct pano_box {
+    pub z0: i64,
+    pub z1: i64,
+    pub y0: i64,
+    pub y1: i64,
+    pub x0: i64,
+    pub x1: i64,
+}
+
+/// `pano_step_params` on a `Grid3d`
+#[repr(C)]
+#[derive(Copy, Clone, Debug, PartialEq)]
+pub struct pano_step3_params {
+    pub timestep: f64,
+    pub threshold: f64,
+    pub max_iterations: i32,
+    pub precond: i32,
+    pub inflow: pano_box,
+    pub inflow_density: f64,
+    pub inflow_vy: f64,
+    pub obstacle: pano_box,
 }
 
 extern "C" {
@@ -178,6 +207,28 @@ extern "C" {
     pub fn pano_dist_step(d: *mut pano_dist) -> c_int;
     pub fn pano_dist_solve(d: *mut pano_dist) -> c_int;
     pub fn pano_dist_sync(d: *mut pano_dist, info: *mut pano_pcg_info) -> c_int;
+
+    // ------------------------------------------------------------------- Grid3d
+    pub fn pano_field3_new(ctx: *mut pano_ctx, kind: c_int, d: usize, h: usize, w: usize, out: *mut *mut pano_field) -> c_int;
+    pub fn pano_field3_num_elem(kind: c_int, d: usize, h: usize, w: usize, n: *mut usize) -> c_int;
+    pub fn pano_field3_dim(f: *const pano_field, d: *mut usize, h: *mut usize, w: *mut usize) -> c_int;
+    pub fn pano_field3_fill_box(f: *mut pano_field, comp: c_int, bx: pano_box, value: f64) -> c_int;
+    pub fn pano_trilinear(a000: f64, a001: f64, a010: f64, a011: f64, a100: f64, a101: f64, a110: f64, a111: f64, s: f64, t: f64,
+                          u: f64) -> f64;
+    pub fn pano_advect3(dst: *mut pano_field, src: *const pano_field, timestep: f64, vel: *const pano_field) -> c_int;
+    pub fn pano_advect3_mac(dst: *mut pano_field, src: *const pano_field, timestep: f64, vel: *const pano_field) -> c_int;
+    pub fn pano_advect3_all(q_dst: *mut pano_field, vel_dst: *mut pano_field, q_src: *const pano_field, vel: *const pano_field,
+                            timestep: f64) -> c_int;
+    pub fn pano_neg_divergence3(b: *mut pano_field, vel: *const pano_field, obstacle: pano_box, rhs_max: *mut f64) -> c_int;
+    pub fn pano_laplacian3_apply(z: *mut pano_field, s: *const pano_field, timestep: f64, obstacle: pano_box) -> c_int;
+    pub fn pano_project3(vel: *mut pano_field, pressure: *const pano_field, timestep: f64) -> c_int;
+    pub fn pano_pcg3_solve(precond: c_int, x: *mut pano_field, b: *const pano_field, max_iterations: i32, threshold: f64,
+                           residual: *mut pano_field, auxiliary: *mut pano_field, search: *mut pano_field, timestep: f64,
+                           obstacle: pano_box, info: *mut pano_pcg_info) -> c_int;
+    pub fn pano_fluid3_step(params: *const pano_step3_params, density: *mut pano_field, vel: *mut pano_field,
+                            pressure: *mut pano_field, temp: *mut pano_field, vel_temp: *mut pano_field,
+                            residual: *mut pano_field, auxiliary: *mut pano_field, search: *mut pano_field,
+                            info: *mut pano_pcg_info) -> c_int;
 }
 
 /// The reference panics on shape mismatches (`ndarray` `Zip`/`assign`) and on `unimplemented!()`; so does the shim.

@@ -94,3 +94,68 @@ void hc_laplacian_f32(int h, int w, float *z, const float *p, float dt, int y0, 
 void hc_neg_divergence_f64(int h, int w, double *b, const double *v, int y0, int y1, int x0, int x1) { neg_divergence<double>(h, w, b, v, RectI{y0, y1, x0, x1}); }
 void hc_neg_divergence_f32(int h, int w, float *b, const float *v, int y0, int y1, int x0, int x1) { neg_divergence<float>(h, w, b, v, RectI{y0, y1, x0, x1}); }
 }
+
+// ------------------------------------------------------------------ Grid3d forms
+struct H3 {
+    const double *p;
+    int H, W;
+    double operator()(int z, int y, int x) const { return p[((size_t)z * H + y) * W + x]; }
+};
+template <bool kFast>
+static void advect3_all(int d, int h, int w, double *qd, double *vd, const double *q, const double *src, const double *vel, double dt) {
+    const size_t nz = (size_t)(d + 1) * h * w, ny = (size_t)d * (h + 1) * w;
+    const H3 vz{vel, h, w}, vy{vel + nz, h + 1, w}, vx{vel + nz + ny, h, w + 1};
+    const H3 qz{src, h, w}, qy{src + nz, h + 1, w}, qx{src + nz + ny, h, w + 1};
+    for (int z = 0; z <= d; ++z)
+        for (int y = 0; y <= h; ++y)
+            for (int x = 0; x <= w; ++x) {
+                const bool xin = x < w, yin = y < h, zin = z < d;
+                if (xin && yin && zin) qd[((size_t)z * h + y) * w + x] = pano::advect3_cell<kFast>(z, y, x, d, h, w, dt, H3{q, h, w}, vz, vy, vx);
+                if (yin && zin) vd[nz + ny + ((size_t)z * h + y) * (w + 1) + x] = pano::advect3_mac_x<kFast>(z, y, x, d, h, w, dt, qx, vz, vy, vx);
+                if (xin && zin) vd[nz + ((size_t)z * (h + 1) + y) * w + x] = pano::advect3_mac_y<kFast>(z, y, x, d, h, w, dt, qy, vz, vy, vx);
+                if (xin && yin) vd[((size_t)z * h + y) * w + x] = pano::advect3_mac_z<kFast>(z, y, x, d, h, w, dt, qz, vz, vy, vx);
+            }
+}
+struct Box3 {
+    int z0, z1, y0, y1, x0, x1;
+    bool has(int z, int y, int x) const { return z >= z0 && z < z1 && y >= y0 && y < y1 && x >= x0 && x < x1; }
+};
+static void laplacian3(int d, int h, int w, double *out, const double *p, double dt, Box3 m) {
+    const size_t plane = (size_t)h * w;
+    for (int z = 0; z < d; ++z)
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                const size_t i = z * plane + (size_t)y * w + x;
+                const bool here = m.has(z, y, x);
+                const bool oF = z > 0 && !here, oK = z < d - 1 && !m.has(z + 1, y, x);
+                const bool oN = y > 0 && !here, oS = y < h - 1 && !m.has(z, y + 1, x);
+                const bool oW = x > 0 && !here, oE = x < w - 1 && !m.has(z, y, x + 1);
+                out[i] = pano::laplacian3_cell<double>(p[i], oF ? p[i - plane] : 0.0, oK ? p[i + plane] : 0.0, oN ? p[i - w] : 0.0,
+                                                       oS ? p[i + w] : 0.0, oW ? p[i - 1] : 0.0, oE ? p[i + 1] : 0.0, oF, oK, oN, oS, oW, oE, dt);
+            }
+}
+static void neg_divergence3(int d, int h, int w, double *b, const double *vel, Box3 m) {
+    const size_t nz = (size_t)(d + 1) * h * w, ny = (size_t)d * (h + 1) * w;
+    const H3 vz{vel, h, w}, vy{vel + nz, h + 1, w}, vx{vel + nz + ny, h, w + 1};
+    for (int z = 0; z < d; ++z)
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                const bool here = m.has(z, y, x);
+                b[((size_t)z * h + y) * w + x] = pano::neg_divergence3_cell<double>(
+                    here ? 0.0 : vz(z, y, x), m.has(z + 1, y, x) ? 0.0 : vz(z + 1, y, x), here ? 0.0 : vy(z, y, x),
+                    m.has(z, y + 1, x) ? 0.0 : vy(z, y + 1, x), here ? 0.0 : vx(z, y, x), m.has(z, y, x + 1) ? 0.0 : vx(z, y, x + 1));
+            }
+}
+
+extern "C" {
+void hc_advect3_all(int fast, int d, int h, int w, double *qd, double *vd, const double *q, const double *src, const double *vel, double dt) {
+    if (fast) advect3_all<true>(d, h, w, qd, vd, q, src, vel, dt);
+    else advect3_all<false>(d, h, w, qd, vd, q, src, vel, dt);
+}
+void hc_laplacian3(int d, int h, int w, double *out, const double *p, double dt, int z0, int z1, int y0, int y1, int x0, int x1) {
+    laplacian3(d, h, w, out, p, dt, Box3{z0, z1, y0, y1, x0, x1});
+}
+void hc_neg_divergence3(int d, int h, int w, double *b, const double *v, int z0, int z1, int y0, int y1, int x0, int x1) {
+    neg_divergence3(d, h, w, b, v, Box3{z0, z1, y0, y1, x0, x1});
+}
+}

@@ -77,3 +77,40 @@ def test_laplacian_and_divergence(hc, oracle, dtype, h, w):
         ey[y0:y1, x0:x1] = 0
         ex[y0:y1, x0:x1] = 0
         assert np.array_equal(b, -oracle.derivative_1_primal(h, w, e))
+
+
+# ------------------------------------------------------------------ Grid3d forms against oracle/pano_oracle3.inc
+CASES3 = [(2, 2, 2, 50.0), (3, 4, 5, 30.0), (9, 17, 12, 30.0), (16, 8, 33, 200.0), (6, 7, 5, 1e4), (5, 6, 7, 1e11), (4, 5, 6, 1e14), (3, 4, 5, 1e300),
+          (7, 6, 5, 1e-300)]
+
+
+@pytest.mark.parametrize("fast", [0, 1])
+@pytest.mark.parametrize("d,h,w,vmax", CASES3)
+def test_advect3_all(hc, fast, d, h, w, vmax):
+    from oracle import pano_oracle3 as O3
+    rng = np.random.default_rng(21)
+    q = rng.uniform(-1, 1, (d, h, w))
+    vel = rng.uniform(-vmax, vmax, O3.num_faces(d, h, w))
+    vel[::7] = 0.0
+    vel[3::11] *= 1e-3
+    src = rng.uniform(-2, 2, vel.size)
+    qd, vd = np.zeros_like(q), np.zeros_like(vel)
+    hc.hc_advect3_all(fast, d, h, w, _p(qd), _p(vd), _p(q), _p(src), _p(vel), C.c_double(0.05))
+    assert np.array_equal(qd, O3.advect(d, h, w, q, 0.05, vel))
+    assert np.array_equal(vd, O3.advect_mac(d, h, w, src, 0.05, vel))
+
+
+@pytest.mark.parametrize("d,h,w", [(2, 2, 2), (3, 4, 5), (8, 8, 8), (7, 12, 9)])
+def test_laplacian3_and_divergence3(hc, d, h, w):
+    from oracle import pano_oracle3 as O3
+    rng = np.random.default_rng(22)
+    p = rng.uniform(-3, 3, (d, h, w))
+    vel = rng.uniform(-5, 5, O3.num_faces(d, h, w))
+    for ob in [(0,) * 6, (d // 2, min(d, d // 2 + 2), h // 2, min(h, h // 2 + 2), w // 3, min(w, w // 3 + 3)), (0, 1, 0, 2, 0, 2),
+               (d - 1, d, h - 2, h, w - 1, w), (0, d, 0, h, 0, w)]:
+        out = np.zeros_like(p)
+        hc.hc_laplacian3(d, h, w, _p(out), _p(p), C.c_double(0.05), *ob)
+        assert np.array_equal(out, O3.laplacian_closure(d, h, w, p, 0.05, ob))
+        b = np.zeros_like(p)
+        hc.hc_neg_divergence3(d, h, w, _p(b), _p(vel), *ob)
+        assert np.array_equal(b, O3.neg_divergence(d, h, w, vel, ob))
