@@ -170,7 +170,16 @@ struct Cg3Args {
     int tiles_x, tiles_y, tiles_z, zc;
 };
 
-__global__ void __launch_bounds__(kThreads) k3_cg(Cg3Args a) {
+template <bool kCg>
+__device__ __forceinline__ double ld3(const double *p) {
+    if (kCg) return __ldcg(p);
+    return *p;
+}
+
+// kCg: every field load through L2 only (ld.global.cg); otherwise (default) plain loads, whose L1 lines the grid barrier's
+// gpu-scope fence invalidates (the contract of cooperative_groups::grid_group::sync()) -- the four lateral neighbours then hit L1.
+template <bool kCg>
+__global__ void __launch_bounds__(kThreads, 4) k3_cg(Cg3Args a) {
     __shared__ double scratch[32];
     __shared__ int s_flag;
     const int G = gridDim.x;
@@ -195,8 +204,9 @@ __global__ void __launch_bounds__(kThreads) k3_cg(Cg3Args a) {
             if (x >= w || y >= h) continue;
             const int z1 = z0 + a.zc < d ? z0 + a.zc : d;
             size_t i = z0 * plane + (size_t)y * w + x;
-            auto sval = [&](size_t j) -> double { return first ? __ldcg(r_src + j) : __ldcg(r_src + j) + beta * __ldcg(s_old + j); };
+            auto sval = [&](size_t j) -> double { return first ? ld3<kCg>(r_src + j) : ld3<kCg>(r_src + j) + beta * ld3<kCg>(s_old + j); };
             double sm1 = z0 > 0 ? sval(i - plane) : 0.0, sc = sval(i);
+#pragma unroll 2
             for (int z = z0; z < z1; ++z, i += plane) {
                 const double sp1 = z + 1 < d ? sval(i + plane) : 0.0;
                 const bool here = in_box(a.m, z, y, x);
@@ -258,20 +268,21 @@ __global__ void __launch_bounds__(kThreads) k3_cg(Cg3Args a) {
             if (x >= w || y >= h) continue;
             const int z1 = z0 + a.zc < d ? z0 + a.zc : d;
             size_t i = z0 * plane + (size_t)y * w + x;
-            double sm1 = z0 > 0 ? __ldcg(s_rd + i - plane) : 0.0, sc = __ldcg(s_rd + i);
+            double sm1 = z0 > 0 ? ld3<kCg>(s_rd + i - plane) : 0.0, sc = ld3<kCg>(s_rd + i);
+#pragma unroll 2
             for (int z = z0; z < z1; ++z, i += plane) {
-                const double sp1 = z + 1 < d ? __ldcg(s_rd + i + plane) : 0.0;
+                const double sp1 = z + 1 < d ? ld3<kCg>(s_rd + i + plane) : 0.0;
                 const bool here = in_box(a.m, z, y, x);
                 const bool oF = z > 0 && !here, oK = z < d - 1 && !in_box(a.m, z + 1, y, x);
                 const bool oN = y > 0 && !here, oS = y < h - 1 && !in_box(a.m, z, y + 1, x);
                 const bool oW = x > 0 && !here, oE = x < w - 1 && !in_box(a.m, z, y, x + 1);
-                const double n = oN ? __ldcg(s_rd + i - w) : 0.0, s = oS ? __ldcg(s_rd + i + w) : 0.0;
-                const double l = oW ? __ldcg(s_rd + i - 1) : 0.0, e = oE ? __ldcg(s_rd + i + 1) : 0.0;
+                const double n = oN ? ld3<kCg>(s_rd + i - w) : 0.0, s = oS ? ld3<kCg>(s_rd + i + w) : 0.0;
+                const double l = oW ? ld3<kCg>(s_rd + i - 1) : 0.0, e = oE ? ld3<kCg>(s_rd + i + 1) : 0.0;
                 const double zv = pano::laplacian3_cell<double>(sc, sm1, sp1, n, s, l, e, oF, oK, oN, oS, oW, oE, a.dt);
                 if (first) a.s0[i] = sc;                       // pcg.rs:40-42: s = aux = r = b
-                const double xo = first ? 0.0 : __ldcg(a.x + i);
+                const double xo = first ? 0.0 : ld3<kCg>(a.x + i);
                 a.x[i] = xo + alpha * sc;                      // pcg.rs:55
-                const double rn = __ldcg(r_src + i) + nalpha * zv;   // pcg.rs:56
+                const double rn = ld3<kCg>(r_src + i) + nalpha * zv;   // pcg.rs:56
                 a.r[i] = rn;
                 const double ar = rn < 0 ? -rn : rn;
                 acc_rmax = ar > acc_rmax ? ar : acc_rmax;
@@ -305,8 +316,324 @@ __global__ void __launch_bounds__(kThreads) k3_cg(Cg3Args a) {
     if (a.max_iter > 0 && (!converged || s_fin != a.s0)) {
         const size_t n = plane * d;
         for (size_t j = blockIdx.x * (size_t)kThreads + threadIdx.x; j < n; j += (size_t)G * kThreads) {
-            const double sv = __ldcg(s_fin + j);
-            a.s0[j] = converged ? sv : __ldcg(a.r + j) + beta * sv;
+            const double sv = ld3<kCg>(s_fin + j);
+            a.s0[j] = converged ? sv : ld3<kCg>(a.r + j) + beta * sv;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.ctl->iterations = converged ? it : a.max_iter;
+        a.ctl->applies = applies;
+        a.ctl->final_residual = rmax;
+        a.ctl->rhs_max = bmax;
+    }
+}
+
+// ------------------------------------------------------------------ the solve, second generation (even widths): plane tiles
+// staged in shared memory.  A CTA (512 threads) owns a 64 (x) x 16 (y) column bundle of `zc` planes; every thread owns 2 adjacent
+// columns of one row and walks along z with s'[z-1], s'[z], s'[z+1] of its two cells in registers.  The plane being evaluated lies
+// in shared memory WITH its one-cell ring (160 ring cells, one each for the first 160 threads, recomputed with the owner's
+// expression: the same bits), double-buffered, one barrier per plane: the four lateral neighbours come from shared memory or
+// from the thread's own registers, global memory is touched with coalesced 16-byte accesses only, and each value of r, s, x is
+// loaded once per tile (+ ring and two z planes: ~1.2x on the reads of r and s).  Loads run ONE PLANE AHEAD of their use: the raw
+// r, s of plane z+2 (and x, r of plane z+1 in the update phase) are requested before plane z is evaluated.  Tiles that no wall and
+// no obstacle face touches skip the open/closed flags altogether, tiles at a wall only compare coordinates (same expression, same bits).
+constexpr int kTileThreads = 512;
+constexpr int kTX = 64, kTY = 16;
+constexpr int kSW = kTX + 4;                  // row stride: interior from column 2 (pairs stay 16-byte aligned), ring in columns 1 and kTX + 2
+constexpr int kSPlane = (kTY + 2) * kSW;
+
+struct TileGeo {
+    int x0, y0, z0, z1;
+    int mode;   // 0: every face of every cell is open; 1: walls only; 2: obstacle faces too
+};
+__device__ __forceinline__ TileGeo tile_geo(const Cg3Args &a, int t) {
+    TileGeo g;
+    const int txy = a.tiles_x * a.tiles_y;
+    g.x0 = (t % a.tiles_x) * kTX;
+    g.y0 = ((t / a.tiles_x) % a.tiles_y) * kTY;
+    g.z0 = (t / txy) * a.zc;
+    g.z1 = g.z0 + a.zc < a.d ? g.z0 + a.zc : a.d;
+    const bool walls = g.x0 == 0 || g.x0 + kTX >= a.w || g.y0 == 0 || g.y0 + kTY >= a.h || g.z0 == 0 || g.z1 >= a.d;
+    // a cell is touched by the obstacle if one of its six faces has its index in the box: cells [b0 - 1, b1) per axis
+    const bool box = a.m.z1 > a.m.z0 && g.z0 < a.m.z1 && g.z1 > a.m.z0 - 1 && g.y0 < a.m.y1 && g.y0 + kTY > a.m.y0 - 1 && g.x0 < a.m.x1 &&
+                     g.x0 + kTX > a.m.x0 - 1;
+    g.mode = box ? 2 : walls ? 1 : 0;
+    return g;
+}
+
+struct Own3 {        // this thread's share of a plane tile
+    int xa, ya;      // cells (ya, xa) and (ya, xa + 1)
+    bool v;          // inside the grid
+    int so;          // shared-memory offset of (ya, xa)
+    size_t j;        // offset of (ya, xa) inside a plane
+    bool ring, ring_in;   // this thread also carries one ring cell; it lies inside the grid
+    int rso;         // its shared-memory offset
+    size_t rj;       // its offset inside a plane
+};
+__device__ __forceinline__ Own3 own_of(const Cg3Args &a, const TileGeo &g) {
+    Own3 o;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    o.xa = g.x0 + 2 * tx;
+    o.ya = g.y0 + ty;
+    o.v = o.xa < a.w && o.ya < a.h;
+    o.so = (ty + 1) * kSW + 2 + 2 * tx;
+    o.j = (size_t)o.ya * a.w + o.xa;
+    int gy = 0, gx = 0;
+    o.ring = tid < 2 * kTX + 2 * kTY;
+    o.rso = 0;
+    if (tid < kTX) { gy = g.y0 - 1; gx = g.x0 + tid; o.rso = 2 + tid; }
+    else if (tid < 2 * kTX) { gy = g.y0 + kTY; gx = g.x0 + tid - kTX; o.rso = (kTY + 1) * kSW + 2 + tid - kTX; }
+    else if (tid < 2 * kTX + kTY) { gy = g.y0 + tid - 2 * kTX; gx = g.x0 - 1; o.rso = (tid - 2 * kTX + 1) * kSW + 1; }
+    else if (o.ring) { gy = g.y0 + tid - 2 * kTX - kTY; gx = g.x0 + kTX; o.rso = (tid - 2 * kTX - kTY + 1) * kSW + kTX + 2; }
+    o.ring_in = o.ring && gy >= 0 && gy < a.h && gx >= 0 && gx < a.w;
+    o.rj = o.ring_in ? (size_t)gy * a.w + gx : 0;
+    return o;
+}
+
+__device__ __forceinline__ double2 ldv2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ void stv2(double *p, double x, double y) { *reinterpret_cast<double2 *>(p) = make_double2(x, y); }
+
+// z = A s' on the two cells of plane z; c = s'[z], f = s'[z-1], k = s'[z+1] in registers, the plane with its ring in `buf`
+template <int kMode>
+__device__ __forceinline__ double2 lap_pair(const Cg3Args &a, const Own3 &o, const double *buf, int z, double2 c, double2 f, double2 k) {
+    const double2 n = ldv2(buf + o.so - kSW), s = ldv2(buf + o.so + kSW);
+    const double l = buf[o.so - 1], e = buf[o.so + 2];
+    double2 out;
+    if (kMode == 0) {
+        out.x = pano::laplacian3_cell<double>(c.x, f.x, k.x, n.x, s.x, l, c.y, true, true, true, true, true, true, a.dt);
+        out.y = pano::laplacian3_cell<double>(c.y, f.y, k.y, n.y, s.y, c.x, e, true, true, true, true, true, true, a.dt);
+    } else {
+        const int y = o.ya, x = o.xa;
+        const bool zlo = z > 0, zhi = z < a.d - 1, ylo = y > 0, yhi = y < a.h - 1;
+        bool oF0 = zlo, oK0 = zhi, oN0 = ylo, oS0 = yhi, oW0 = x > 0, oE0 = true;            // x + 1 <= w - 1 (even width)
+        bool oF1 = zlo, oK1 = zhi, oN1 = ylo, oS1 = yhi, oW1 = true, oE1 = x + 1 < a.w - 1;
+        if (kMode == 2) {
+            const bool h0 = in_box(a.m, z, y, x), h1 = in_box(a.m, z, y, x + 1);
+            oF0 = oF0 && !h0; oN0 = oN0 && !h0; oW0 = oW0 && !h0;
+            oF1 = oF1 && !h1; oN1 = oN1 && !h1; oW1 = oW1 && !h1;
+            oK0 = oK0 && !in_box(a.m, z + 1, y, x); oS0 = oS0 && !in_box(a.m, z, y + 1, x); oE0 = oE0 && !h1;
+            oK1 = oK1 && !in_box(a.m, z + 1, y, x + 1); oS1 = oS1 && !in_box(a.m, z, y + 1, x + 1); oE1 = oE1 && !in_box(a.m, z, y, x + 2);
+        }
+        out.x = pano::laplacian3_cell<double>(c.x, f.x, k.x, n.x, s.x, l, c.y, oF0, oK0, oN0, oS0, oW0, oE0, a.dt);
+        out.y = pano::laplacian3_cell<double>(c.y, f.y, k.y, n.y, s.y, c.x, e, oF1, oK1, oN1, oS1, oW1, oE1, a.dt);
+    }
+    return out;
+}
+
+// raw r (and s) of this thread's pair and ring cell in the plane at offset `pz`; zeros outside the grid
+struct Raw3 {
+    double2 r, s;
+    double rr, rs;
+};
+__device__ __forceinline__ Raw3 load_raw(const Own3 &o, const double *r_src, const double *s_old, size_t pz, bool with_s, bool with_ring) {
+    Raw3 q;
+    q.r = q.s = make_double2(0.0, 0.0);
+    q.rr = q.rs = 0.0;
+    if (o.v) {
+        q.r = ldv2(r_src + pz + o.j);
+        if (with_s) q.s = ldv2(s_old + pz + o.j);
+    }
+    if (with_ring && o.ring_in) {
+        q.rr = r_src[pz + o.rj];
+        if (with_s) q.rs = s_old[pz + o.rj];
+    }
+    return q;
+}
+__device__ __forceinline__ double2 combine(const Raw3 &q, bool with_s, double beta) {   // s' = r + beta s (pcg.rs:75-77), or the value itself
+    if (!with_s) return q.r;
+    return make_double2(q.r.x + beta * q.s.x, q.r.y + beta * q.s.y);
+}
+__device__ __forceinline__ double combine_ring(const Raw3 &q, bool with_s, double beta) { return with_s ? q.rr + beta * q.rs : q.rr; }
+__device__ __forceinline__ void put_plane(const Own3 &o, double *buf, double2 c, double ringv) {
+    stv2(buf + o.so, c.x, c.y);
+    if (o.ring) buf[o.rso] = ringv;
+}
+
+struct Acc3 {
+    double zs, bb, bmax, rr, rmax;
+};
+
+// P1 (with_s: s' = r + beta s_old, stored to s_cur) / the opening pass (s' = b: max|b|, b.b)
+template <int kMode>
+__device__ __forceinline__ void p1_tile(const Cg3Args &a, const TileGeo &g, double *smem, const double *r_src, const double *s_old, double *s_cur,
+                                        bool first, double beta, Acc3 &acc) {
+    const Own3 o = own_of(a, g);
+    const bool ws = !first;
+    const size_t plane = (size_t)a.h * a.w;
+    size_t pz = (size_t)g.z0 * plane;
+    const Raw3 q0 = load_raw(o, r_src, s_old, g.z0 > 0 ? pz - plane : pz, ws, false);
+    const Raw3 q1 = load_raw(o, r_src, s_old, pz, ws, true);
+    Raw3 q2 = load_raw(o, r_src, s_old, g.z0 + 1 < a.d ? pz + plane : pz, ws, true);
+    double2 f = g.z0 > 0 ? combine(q0, ws, beta) : make_double2(0.0, 0.0);
+    double2 c = combine(q1, ws, beta);
+    put_plane(o, smem + (g.z0 & 1) * kSPlane, c, combine_ring(q1, ws, beta));
+    __syncthreads();
+    for (int z = g.z0; z < g.z1; ++z, pz += plane) {
+        const bool more = z + 1 < a.d;
+        const double2 k = more ? combine(q2, ws, beta) : make_double2(0.0, 0.0);
+        const double kring = combine_ring(q2, ws, beta);
+        if (z + 2 < a.d && z + 1 < g.z1) q2 = load_raw(o, r_src, s_old, pz + 2 * plane, ws, z + 2 < g.z1);   // one plane ahead of its use
+        const double2 zv = lap_pair<kMode>(a, o, smem + (z & 1) * kSPlane, z, c, f, k);
+        if (o.v) {
+            if (ws) stv2(s_cur + pz + o.j, c.x, c.y);
+            acc.zs = acc.zs + zv.x * c.x;
+            acc.zs = acc.zs + zv.y * c.y;
+            if (first) {   // max|b| and b.b (pcg.rs:35, 46)
+                const double a0 = c.x < 0 ? -c.x : c.x, a1 = c.y < 0 ? -c.y : c.y;
+                acc.bmax = a0 > acc.bmax ? a0 : acc.bmax;
+                acc.bmax = a1 > acc.bmax ? a1 : acc.bmax;
+                acc.bb = acc.bb + c.x * c.x;
+                acc.bb = acc.bb + c.y * c.y;
+            }
+        }
+        if (z + 1 < g.z1) put_plane(o, smem + ((z + 1) & 1) * kSPlane, k, kring);
+        __syncthreads();
+        f = c;
+        c = k;
+    }
+}
+
+// P2: z recomputed from s', x += alpha s', r -= alpha z, r.r and max|r|
+template <int kMode>
+__device__ __forceinline__ void p2_tile(const Cg3Args &a, const TileGeo &g, double *smem, const double *s_rd, const double *r_src, bool first,
+                                        double alpha, Acc3 &acc) {
+    const Own3 o = own_of(a, g);
+    const size_t plane = (size_t)a.h * a.w;
+    const double nalpha = -alpha;
+    size_t pz = (size_t)g.z0 * plane;
+    const Raw3 q0 = load_raw(o, s_rd, nullptr, g.z0 > 0 ? pz - plane : pz, false, false);
+    const Raw3 q1 = load_raw(o, s_rd, nullptr, pz, false, true);
+    Raw3 q2 = load_raw(o, s_rd, nullptr, g.z0 + 1 < a.d ? pz + plane : pz, false, true);
+    double2 xv = make_double2(0.0, 0.0), rv = xv;
+    if (o.v) {
+        if (!first) xv = ldv2(a.x + pz + o.j);
+        rv = ldv2(r_src + pz + o.j);
+    }
+    double2 f = g.z0 > 0 ? q0.r : make_double2(0.0, 0.0);
+    double2 c = q1.r;
+    put_plane(o, smem + (g.z0 & 1) * kSPlane, c, q1.rr);
+    __syncthreads();
+    for (int z = g.z0; z < g.z1; ++z, pz += plane) {
+        const bool more = z + 1 < a.d;
+        const double2 k = more ? q2.r : make_double2(0.0, 0.0);
+        const double kring = q2.rr;
+        double2 xn = make_double2(0.0, 0.0), rn = xn;
+        if (z + 1 < g.z1) {                       // next plane's x, r and the plane after's s': one plane ahead of their use
+            if (o.v) {
+                if (!first) xn = ldv2(a.x + pz + plane + o.j);
+                rn = ldv2(r_src + pz + plane + o.j);
+            }
+            if (z + 2 < a.d) q2 = load_raw(o, s_rd, nullptr, pz + 2 * plane, false, z + 2 < g.z1);
+        }
+        const double2 zv = lap_pair<kMode>(a, o, smem + (z & 1) * kSPlane, z, c, f, k);
+        if (o.v) {
+            if (first) stv2(a.s0 + pz + o.j, c.x, c.y);                       // pcg.rs:40-42: s = aux = r = b
+            stv2(a.x + pz + o.j, xv.x + alpha * c.x, xv.y + alpha * c.y);     // pcg.rs:55
+            const double r0 = rv.x + nalpha * zv.x, r1 = rv.y + nalpha * zv.y;   // pcg.rs:56
+            stv2(a.r + pz + o.j, r0, r1);
+            const double a0 = r0 < 0 ? -r0 : r0, a1 = r1 < 0 ? -r1 : r1;
+            acc.rmax = a0 > acc.rmax ? a0 : acc.rmax;
+            acc.rmax = a1 > acc.rmax ? a1 : acc.rmax;
+            acc.rr = acc.rr + r0 * r0;
+            acc.rr = acc.rr + r1 * r1;
+        }
+        if (z + 1 < g.z1) put_plane(o, smem + ((z + 1) & 1) * kSPlane, k, kring);
+        __syncthreads();
+        f = c;
+        c = k;
+        xv = xn;
+        rv = rn;
+    }
+}
+
+__global__ void __launch_bounds__(kTileThreads, 2) k3_cg_tile(Cg3Args a) {
+    __shared__ __align__(16) double smem[2 * kSPlane];
+    __shared__ double scratch[32];
+    __shared__ int s_flag;
+    const int G = gridDim.x;
+    const int ntiles = a.tiles_x * a.tiles_y * a.tiles_z;
+    double *pA = a.partials, *pB = pA + G, *pC = pA + 2 * G, *pD = pA + 3 * G, *pE = pA + 4 * G;
+    unsigned long long nbar = 0;
+    double sigma = 0, alpha = 0, beta = 0, rmax = 0, bmax = 0;
+    int it = 0, applies = 0;
+    bool converged = false;
+    double *s_cur = a.s0, *s_old = a.s1;
+    const size_t n = (size_t)a.d * a.h * a.w;
+
+    for (it = 0; it < a.max_iter; ++it) {
+        const bool first = it == 0;
+        const double *r_src = first ? a.b : a.r;
+        Acc3 acc{0.0, 0.0, 0.0, 0.0, 0.0};
+        // ---------------------------------------------------------------- P1
+        for (int t = blockIdx.x; t < ntiles; t += G) {
+            const TileGeo g = tile_geo(a, t);
+            if (g.mode == 0) p1_tile<0>(a, g, smem, r_src, s_old, s_cur, first, beta, acc);
+            else if (g.mode == 1) p1_tile<1>(a, g, smem, r_src, s_old, s_cur, first, beta, acc);
+            else p1_tile<2>(a, g, smem, r_src, s_old, s_cur, first, beta, acc);
+        }
+        {
+            const double v = block_sum(acc.zs, scratch);
+            if (threadIdx.x == 0) pA[blockIdx.x] = v;
+            if (first) {
+                const double v2 = block_sum(acc.bb, scratch), v3 = block_max(acc.bmax, scratch);
+                if (threadIdx.x == 0) {
+                    pB[blockIdx.x] = v2;
+                    pC[blockIdx.x] = v3;
+                }
+            }
+        }
+        if (!grid_barrier(a.ctl, (++nbar) * (unsigned long long)G, &s_flag)) return;
+        const double zs = sum_partials<double>(pA, G, scratch);
+        if (first) {
+            sigma = sum_partials<double>(pB, G, scratch);      // pcg.rs:46
+            bmax = max_partials<double>(pC, G, scratch);       // pcg.rs:35
+            rmax = bmax;
+            if (bmax < a.threshold) {                          // early out: x = 0, scratch untouched
+                for (size_t j = blockIdx.x * (size_t)kTileThreads + threadIdx.x; j < n; j += (size_t)G * kTileThreads) a.x[j] = 0.0;
+                if (blockIdx.x == 0 && threadIdx.x == 0) {
+                    a.ctl->iterations = -1;
+                    a.ctl->applies = 0;
+                    a.ctl->final_residual = bmax;
+                    a.ctl->rhs_max = bmax;
+                }
+                return;
+            }
+        }
+        ++applies;
+        alpha = sigma / zs;                                    // pcg.rs:53
+        // ---------------------------------------------------------------- P2
+        const double *s_rd = first ? a.b : s_cur;
+        for (int t = blockIdx.x; t < ntiles; t += G) {
+            const TileGeo g = tile_geo(a, t);
+            if (g.mode == 0) p2_tile<0>(a, g, smem, s_rd, r_src, first, alpha, acc);
+            else if (g.mode == 1) p2_tile<1>(a, g, smem, s_rd, r_src, first, alpha, acc);
+            else p2_tile<2>(a, g, smem, s_rd, r_src, first, alpha, acc);
+        }
+        {
+            const double v = block_sum(acc.rr, scratch), v2 = block_max(acc.rmax, scratch);
+            if (threadIdx.x == 0) {
+                pD[blockIdx.x] = v;
+                pE[blockIdx.x] = v2;
+            }
+        }
+        if (!grid_barrier(a.ctl, (++nbar) * (unsigned long long)G, &s_flag)) return;
+        const double rr = sum_partials<double>(pD, G, scratch);
+        rmax = max_partials<double>(pE, G, scratch);           // pcg.rs:58
+        if (rmax < a.threshold) {                              // pcg.rs:60-63
+            converged = true;
+            break;
+        }
+        beta = rr / sigma;                                     // pcg.rs:67-68
+        sigma = rr;                                            // pcg.rs:79
+        double *tmp = s_cur;
+        s_cur = s_old;
+        s_old = tmp;
+    }
+    const double *s_fin = converged ? s_cur : s_old;
+    if (a.max_iter > 0 && (!converged || s_fin != a.s0)) {     // what the reference leaves in `search` (pcg.rs:72-77), as k3_cg
+        for (size_t j = blockIdx.x * (size_t)kTileThreads + threadIdx.x; j < n; j += (size_t)G * kTileThreads) {
+            const double sv = s_fin[j];
+            a.s0[j] = converged ? sv : a.r[j] + beta * sv;
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -400,29 +727,39 @@ int cg3_solve_raw(pano_ctx *ctx, double *x, const double *b, double *r, double *
         }
         return PANO_OK;
     }
+    // "cg3_kernel": 0 auto (the shared-memory plane-tile kernel for even widths, else the column kernel) / 1 column kernel / 2 plane tiles
+    const int64_t want = pano_option(ctx, "cg3_kernel", 0);
+    const bool tile_ok = w % 2 == 0;
+    if (want == 2 && !tile_ok) PANO_FAIL(PANO_ERR_INVALID, "cg3_kernel=2 (plane tiles) needs an even width (%zu given)", w);
+    const bool tiled = tile_ok && want != 1;
     int per_sm = 0;
-    PANO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_cg, kThreads, 0));
+    const bool cg_loads = pano_option(ctx, "cg_ldcg", 0) != 0;
+    const void *fn = tiled ? (const void *)k3_cg_tile : cg_loads ? (const void *)k3_cg<true> : (const void *)k3_cg<false>;
+    const int nthreads = tiled ? kTileThreads : kThreads;
+    PANO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, nthreads, 0));
     if (per_sm < 1) PANO_FAIL(PANO_ERR_CUDA, "cg3: kernel does not fit on an SM");
     const int64_t cap = pano_option(ctx, "cg_blocks_per_sm", 0);
     if (cap > 0 && cap < per_sm) per_sm = (int)cap;
+    const int tw = tiled ? kTX : 32, th = tiled ? kTY : 8;
     Cg3Args a{x, b, r, s0, s1, (int)d, (int)h, (int)w, dt, threshold, max_iterations, clip_box(ob, d + 1, h + 1, w + 1), nullptr, ctx->d_cg,
-              (int)((w + 31) / 32), (int)((h + 7) / 8), 0, 0};
-    // column length per tile: long columns re-read less (two extra planes per tile in P1), short ones balance the static
-    // round-robin better.  Pick the candidate with the best (useful planes / planes read) x (tiles / rounded-up tiles per CTA).
+              (int)((w + tw - 1) / tw), (int)((h + th - 1) / th), 0, 0};
+    // column length per tile: long columns re-read less (two extra planes per tile), short ones balance the static round-robin
+    // better.  Pick the candidate with the best (useful planes / planes read) x (tiles / rounded-up tiles per CTA).
     const int64_t want_zc = pano_option(ctx, "cg3_zc", 0);
     int best_zc = 8;
     double best = -1.0;
     const int Gfull = ctx->num_sms * per_sm;
-    for (int zc : {8, 16, 32, 64}) {
+    for (int zc : {4, 6, 8, 10, 12, 16, 20, 24, 32, 48, 64}) {
         if (want_zc > 0 && zc != want_zc) continue;
         const long long tz = ((long long)d + zc - 1) / zc, nt = tz * a.tiles_x * a.tiles_y;
-        const long long G = nt < Gfull ? nt : Gfull, rounds = (nt + G - 1) / G;
-        const double eff = ((double)zc / (zc + 1.0)) * ((double)nt / (double)(rounds * G));   // +2 planes on r and s of 64 B -> ~ +1 plane in 8
+        const long long rounds = (nt + Gfull - 1) / Gfull;   // every SM slot should be busy in every round: the SMs share the HBM
+        const double eff = ((double)zc / (zc + 1.0)) * ((double)nt / (double)(rounds * Gfull));   // +2 planes on the reads: ~ +1 plane in all
         if (eff > best) {
             best = eff;
             best_zc = zc;
         }
     }
+    if (want_zc > 0 && best < 0) best_zc = (int)want_zc;
     a.zc = best_zc;
     a.tiles_z = (int)((d + a.zc - 1) / a.zc);
     const long long ntiles = (long long)a.tiles_x * a.tiles_y * a.tiles_z;
@@ -433,7 +770,7 @@ int cg3_solve_raw(pano_ctx *ctx, double *x, const double *b, double *r, double *
     a.partials = ctx->d_partials;
     PANO_TRY(pano_cg_control_reset(ctx));
     void *kargs[] = {(void *)&a};
-    PANO_CUDA(cudaLaunchCooperativeKernel((const void *)k3_cg, dim3((unsigned)G), dim3(kThreads), kargs, 0, ctx->stream));
+    PANO_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)G), dim3(nthreads), kargs, 0, ctx->stream));
     PANO_TRY(pano_after_launch(ctx, "k3_cg"));
     if (info) {
         PANO_CUDA(cudaMemcpyAsync(ctx->h_cg, ctx->d_cg, sizeof(PanoCgControl), cudaMemcpyDeviceToHost, ctx->stream));

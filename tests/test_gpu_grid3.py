@@ -70,15 +70,18 @@ def test_divergence_laplacian_projection_bit_exact(d, h, w):
     assert np.array_equal(fv.view_linear(), O3.project(d, h, w, vel, p, 0.05))
 
 
-@pytest.mark.parametrize("zc", [0, 8, 64])
-@pytest.mark.parametrize("d,h,w", [(3, 4, 5), (9, 17, 12), (16, 8, 33), (33, 31, 32), (64, 64, 64), (70, 40, 96)])
-def test_pcg3_matches_oracle(d, h, w, zc):
-    """pcg.rs:14-82 with the 7-point closure: iteration count within +-2 (north_star), x / r / s as the reference leaves them."""
+@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("zc", [0, 4, 64])
+@pytest.mark.parametrize("d,h,w", [(3, 4, 5), (9, 17, 12), (16, 8, 33), (33, 31, 32), (64, 64, 64), (70, 40, 96), (20, 50, 130), (5, 16, 64), (2, 2, 2)])
+def test_pcg3_matches_oracle(d, h, w, zc, kernel):
+    """pcg.rs:14-82 with the 7-point closure: iteration count within +-2 (north_star), x / r / s as the reference leaves them.
+    kernel 0: auto (shared-memory plane tiles for even widths, the column kernel otherwise); 1: the column kernel everywhere."""
     from oracle import np_oracle3 as NP3
     from oracle import pano_oracle3 as O3
     from panopaea_b200 import grid3
     from tests import gpu_util as U
     U.ctx().set_option("cg3_zc", zc)
+    U.ctx().set_option("cg3_kernel", kernel)
     try:
         g = _g3(d, h, w)
         ob = (d // 2, min(d, d // 2 + 2), h // 2, min(h, h // 2 + 2), w // 3, min(w, w // 3 + 3))
@@ -105,6 +108,7 @@ def test_pcg3_matches_oracle(d, h, w, zc):
                 assert np.abs(res - r.to_host()).max() <= 1e-9 * np.abs(b).max()
     finally:
         U.ctx().set_option("cg3_zc", 0)
+        U.ctx().set_option("cg3_kernel", 0)
 
 
 def test_pcg3_rejects_what_the_2d_entry_points_reject():
