@@ -661,6 +661,37 @@ def run_ours(args, rank, world, local_rank):
             js.close()
             del js
         del fl
+        # ---- Grid3d (the reference has no 3-D fluid path, so configs[3] is quoted on its 2-D branch above):
+        # the 256^3 smoke plume through pano_fluid3_step, per-kernel algorithmic rooflines
+        if not args.no_3d:
+            from panopaea_b200 import grid3
+            n3 = 256
+            s3 = grid3.DecFluid3(**grid3.smoke_params(n3), ctx=ctx)
+            for _ in range(20):
+                s3.step(want_info=False)
+            i3 = s3.step()
+            ctx.set_option("step_timing", 1)
+            ctx.step_times()
+            lp3 = timed_laps(ctx, lambda: s3.step(want_info=False), 10)
+            pm3, ps3 = ctx.step_times()
+            ctx.set_option("step_timing", 0)
+            i3b = s3.step()
+            c3 = n3 ** 3
+            b3 = {"advect_all": 64, "neg_divergence": 32, "cg": 8 + 64 * i3b["applies"], "project": 56}
+            k3 = {}
+            for nm, ms in zip(["inflow", "advect_all", "neg_divergence", "cg", "project"], pm3):
+                ms = ms / max(1, ps3)
+                row = {"ms": ms}
+                if nm in b3 and ms > 0:
+                    gbs = c3 * b3[nm] / (ms * 1e-3) / 1e9
+                    row.update({"algorithmic_bytes": c3 * b3[nm], "algorithmic_gbs": gbs, "frac_of_measured_peak": gbs / peak, "frac_of_8000": gbs / NOMINAL_GBS})
+                k3[nm] = row
+            extra["grid3d_256"] = {"value": c3 / (median(lp3) * 1e-3) / 1e6, "unit": UNIT, "median_ms_per_step": median(lp3), "steps": 10, "warmup": 21,
+                                   "grid": [n3, n3, n3], "cg_iterations_per_step": i3b["applies"], "cg_info_first_timed_step": i3, "kernels": k3,
+                                   "kernel": "k3_cg_tile (persistent 7-point CG: cp.async plane ring, dynamic tiles)",
+                                   "note": "3-D smoke plume, 7-point Laplacian, identity preconditioner, converging solves (threshold 0.1); parity "
+                                           "unpinned: the reference holds only the struct Grid3d and the unused trilinear (DESIGN.md 5c)"}
+            del s3
 
     # ---- configs[4]: the pressure Poisson solve alone at 16384^2 on these N GPUs and on rank 0 alone
     if multi and not args.no_poisson and not poisson:
@@ -759,6 +790,7 @@ def main():
     ap.add_argument("--no-mg", action="store_true", help="skip the multigrid-preconditioned step timing")
     ap.add_argument("--no-single", action="store_true", help="N > 1: skip the one-GPU run of the same grid (and the parity check against it)")
     ap.add_argument("--no-extra", action="store_true", help="N = 1: skip the 4096^2 / 1024^2 / 128^2 legs")
+    ap.add_argument("--no-3d", dest="no_3d", action="store_true", help="N = 1: skip the 256^3 Grid3d leg")
     ap.add_argument("--no-poisson", action="store_true", help="N > 1: skip the 16384^2 Poisson-only leg")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (e.g. cg_kernel=1)")
     args = ap.parse_args()

@@ -35,11 +35,11 @@ BoxI clip_box(pano_box r, size_t dmax, size_t hmax, size_t wmax) {
     return o;
 }
 
-// (z, y, x) -> value on a (., H, W) array
+// (z, y, x) -> value on a (., H, W) array (fewer than 2^31 samples: 32-bit index arithmetic)
 struct V3 {
     const double *p;
     int H, W;
-    __device__ __forceinline__ double operator()(int z, int y, int x) const { return __ldg(p + ((size_t)z * H + y) * W + x); }
+    __device__ __forceinline__ double operator()(int z, int y, int x) const { return __ldg(p + (unsigned)((z * H + y) * W + x)); }
 };
 
 // ------------------------------------------------------------------ fills
@@ -329,18 +329,30 @@ __global__ void __launch_bounds__(kThreads, 4) k3_cg(Cg3Args a) {
 }
 
 // ------------------------------------------------------------------ the solve, second generation (even widths): plane tiles
-// staged in shared memory.  A CTA (512 threads) owns a 64 (x) x 16 (y) column bundle of `zc` planes; every thread owns 2 adjacent
-// columns of one row and walks along z with s'[z-1], s'[z], s'[z+1] of its two cells in registers.  The plane being evaluated lies
-// in shared memory WITH its one-cell ring (160 ring cells, one each for the first 160 threads, recomputed with the owner's
-// expression: the same bits), double-buffered, one barrier per plane: the four lateral neighbours come from shared memory or
-// from the thread's own registers, global memory is touched with coalesced 16-byte accesses only, and each value of r, s, x is
-// loaded once per tile (+ ring and two z planes: ~1.2x on the reads of r and s).  Loads run ONE PLANE AHEAD of their use: the raw
-// r, s of plane z+2 (and x, r of plane z+1 in the update phase) are requested before plane z is evaluated.  Tiles that no wall and
-// no obstacle face touches skip the open/closed flags altogether, tiles at a wall only compare coordinates (same expression, same bits).
+// streamed through shared memory.  A CTA (512 threads) owns a 64 (x) x 16 (y) column bundle of `zc` planes at a time; every thread
+// owns 2 adjacent columns of one row and walks along z with s'[z-1], s'[z], s'[z+1] of its two cells in registers.
+//   * Planes arrive through a FOUR-STAGE cp.async ring (16-byte copies of the thread's own pair, 8-byte copies of one ring cell for
+//     the first 160 threads; zero-filled outside the grid): plane z+3 is requested while plane z is evaluated, no register holds
+//     data in flight, one __syncthreads per plane.
+//   * P1 turns the raw r, s of plane z+1 into s' = r + beta s IN PLACE (own pair + ring cell, the owner's expression: the same
+//     bits) one step before the plane is evaluated, so the four lateral neighbours are plain shared-memory reads (or the thread's
+//     own registers); P2 stages s' (with ring), x and r.
+//   * Tiles are claimed from a counter (first tile static); every tile leaves its own partial sums, and after the grid barrier every
+//     CTA adds the per-TILE partials in tile order: the scalars do not depend on which CTA ran which tile -- deterministic.
+//   * Tiles that no wall and no obstacle face touches skip the open/closed flags, tiles at a wall only compare coordinates.
 constexpr int kTileThreads = 512;
 constexpr int kTX = 64, kTY = 16;
 constexpr int kSW = kTX + 4;                  // row stride: interior from column 2 (pairs stay 16-byte aligned), ring in columns 1 and kTX + 2
-constexpr int kSPlane = (kTY + 2) * kSW;
+constexpr int kSPlane = (kTY + 2) * kSW;      // a plane with its ring
+constexpr int kStages = 4;
+constexpr int kStageDoubles = kSPlane + 2 * kTX * kTY;   // P2: s' (ring) | x | r;  P1: r (ring) | s (ring) = 2 kSPlane, smaller
+constexpr size_t kTileSmemBytes = (size_t)kStages * kStageDoubles * sizeof(double);
+static_assert(2 * kSPlane <= kStageDoubles, "P1 stage must fit");
+
+struct Cg3TileArgs {
+    Cg3Args c;
+    unsigned long long *claim;   // zero at launch
+};
 
 struct TileGeo {
     int x0, y0, z0, z1;
@@ -361,14 +373,14 @@ __device__ __forceinline__ TileGeo tile_geo(const Cg3Args &a, int t) {
     return g;
 }
 
-struct Own3 {        // this thread's share of a plane tile
+struct Own3 {        // this thread's share of a plane tile (offsets in elements; every array holds fewer than 2^31)
     int xa, ya;      // cells (ya, xa) and (ya, xa + 1)
     bool v;          // inside the grid
-    int so;          // shared-memory offset of (ya, xa)
-    size_t j;        // offset of (ya, xa) inside a plane
     bool ring, ring_in;   // this thread also carries one ring cell; it lies inside the grid
-    int rso;         // its shared-memory offset
-    size_t rj;       // its offset inside a plane
+    int so;          // shared-memory offset of (ya, xa) in a ringed plane
+    int xo;          // ... in an interior-only 16 x 64 plane
+    int rso;         // shared-memory offset of the ring cell
+    unsigned j, rj;  // offsets of (ya, xa) / the ring cell inside a plane of the grid
 };
 __device__ __forceinline__ Own3 own_of(const Cg3Args &a, const TileGeo &g) {
     Own3 o;
@@ -377,7 +389,8 @@ __device__ __forceinline__ Own3 own_of(const Cg3Args &a, const TileGeo &g) {
     o.ya = g.y0 + ty;
     o.v = o.xa < a.w && o.ya < a.h;
     o.so = (ty + 1) * kSW + 2 + 2 * tx;
-    o.j = (size_t)o.ya * a.w + o.xa;
+    o.xo = ty * kTX + 2 * tx;
+    o.j = o.v ? (unsigned)o.ya * (unsigned)a.w + (unsigned)o.xa : 0u;
     int gy = 0, gx = 0;
     o.ring = tid < 2 * kTX + 2 * kTY;
     o.rso = 0;
@@ -386,12 +399,24 @@ __device__ __forceinline__ Own3 own_of(const Cg3Args &a, const TileGeo &g) {
     else if (tid < 2 * kTX + kTY) { gy = g.y0 + tid - 2 * kTX; gx = g.x0 - 1; o.rso = (tid - 2 * kTX + 1) * kSW + 1; }
     else if (o.ring) { gy = g.y0 + tid - 2 * kTX - kTY; gx = g.x0 + kTX; o.rso = (tid - 2 * kTX - kTY + 1) * kSW + kTX + 2; }
     o.ring_in = o.ring && gy >= 0 && gy < a.h && gx >= 0 && gx < a.w;
-    o.rj = o.ring_in ? (size_t)gy * a.w + gx : 0;
+    o.rj = o.ring_in ? (unsigned)gy * (unsigned)a.w + (unsigned)gx : 0u;
     return o;
 }
 
 __device__ __forceinline__ double2 ldv2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ void stv2(double *p, double x, double y) { *reinterpret_cast<double2 *>(p) = make_double2(x, y); }
+// asynchronous global -> shared copies; `ok` false writes zeros (source size 0)
+__device__ __forceinline__ void cp16(double *smem_dst, const double *gsrc, bool ok) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), n = ok ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp8(double *smem_dst, const double *gsrc, bool ok) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), n = ok ? 8u : 0u;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // z = A s' on the two cells of plane z; c = s'[z], f = s'[z-1], k = s'[z+1] in registers, the plane with its ring in `buf`
 template <int kMode>
@@ -420,140 +445,155 @@ __device__ __forceinline__ double2 lap_pair(const Cg3Args &a, const Own3 &o, con
     return out;
 }
 
-// raw r (and s) of this thread's pair and ring cell in the plane at offset `pz`; zeros outside the grid
-struct Raw3 {
-    double2 r, s;
-    double rr, rs;
-};
-__device__ __forceinline__ Raw3 load_raw(const Own3 &o, const double *r_src, const double *s_old, size_t pz, bool with_s, bool with_ring) {
-    Raw3 q;
-    q.r = q.s = make_double2(0.0, 0.0);
-    q.rr = q.rs = 0.0;
-    if (o.v) {
-        q.r = ldv2(r_src + pz + o.j);
-        if (with_s) q.s = ldv2(s_old + pz + o.j);
+// request plane p of the tile's arrays into `st` (nothing for a plane outside [0, plast], plast = the last plane the tile reads;
+// the caller commits the group either way)
+__device__ __forceinline__ void issue_p1(const Cg3Args &a, const Own3 &o, double *st, int p, int plast, const double *r_src, const double *s_old,
+                                         bool ws) {
+    if (p < 0 || p > plast) return;
+    const unsigned pz = (unsigned)p * (unsigned)(a.h * a.w);
+    cp16(st + o.so, r_src + pz + o.j, o.v);
+    if (ws) cp16(st + kSPlane + o.so, s_old + pz + o.j, o.v);
+    if (o.ring) {
+        cp8(st + o.rso, r_src + pz + o.rj, o.ring_in);
+        if (ws) cp8(st + kSPlane + o.rso, s_old + pz + o.rj, o.ring_in);
     }
-    if (with_ring && o.ring_in) {
-        q.rr = r_src[pz + o.rj];
-        if (with_s) q.rs = s_old[pz + o.rj];
+}
+__device__ __forceinline__ void issue_p2(const Cg3Args &a, const Own3 &o, double *st, int p, int plast, const double *s_rd, const double *r_src,
+                                         bool first, bool with_xr) {
+    if (p < 0 || p > plast) return;
+    const unsigned pz = (unsigned)p * (unsigned)(a.h * a.w);
+    cp16(st + o.so, s_rd + pz + o.j, o.v);
+    if (o.ring) cp8(st + o.rso, s_rd + pz + o.rj, o.ring_in);
+    if (with_xr) {
+        if (!first) cp16(st + kSPlane + o.xo, a.x + pz + o.j, o.v);
+        cp16(st + kSPlane + kTX * kTY + o.xo, r_src + pz + o.j, o.v);
     }
-    return q;
 }
-__device__ __forceinline__ double2 combine(const Raw3 &q, bool with_s, double beta) {   // s' = r + beta s (pcg.rs:75-77), or the value itself
-    if (!with_s) return q.r;
-    return make_double2(q.r.x + beta * q.s.x, q.r.y + beta * q.s.y);
-}
-__device__ __forceinline__ double combine_ring(const Raw3 &q, bool with_s, double beta) { return with_s ? q.rr + beta * q.rs : q.rr; }
-__device__ __forceinline__ void put_plane(const Own3 &o, double *buf, double2 c, double ringv) {
-    stv2(buf + o.so, c.x, c.y);
-    if (o.ring) buf[o.rso] = ringv;
+// s' = r + beta s (pcg.rs:75-77) of the own pair and the ring cell of a landed plane, in place; returns the own pair
+__device__ __forceinline__ double2 transform_p1(const Own3 &o, double *st, bool ws, double beta) {
+    double2 rv = ldv2(st + o.so);
+    if (ws) {
+        const double2 sv = ldv2(st + kSPlane + o.so);
+        rv = make_double2(rv.x + beta * sv.x, rv.y + beta * sv.y);
+        stv2(st + o.so, rv.x, rv.y);
+        if (o.ring) st[o.rso] = st[o.rso] + beta * st[kSPlane + o.rso];
+    }
+    return rv;
 }
 
-struct Acc3 {
-    double zs, bb, bmax, rr, rmax;
-};
-
-// P1 (with_s: s' = r + beta s_old, stored to s_cur) / the opening pass (s' = b: max|b|, b.b)
+// P1 over one tile (ws: s' = r + beta s_old, stored to s_cur; else the opening pass on b: max|b| and b.b too).  out: zs, bb, bmax
 template <int kMode>
 __device__ __forceinline__ void p1_tile(const Cg3Args &a, const TileGeo &g, double *smem, const double *r_src, const double *s_old, double *s_cur,
-                                        bool first, double beta, Acc3 &acc) {
+                                        bool ws, double beta, double &zs, double &bb, double &bmax) {
     const Own3 o = own_of(a, g);
-    const bool ws = !first;
-    const size_t plane = (size_t)a.h * a.w;
-    size_t pz = (size_t)g.z0 * plane;
-    const Raw3 q0 = load_raw(o, r_src, s_old, g.z0 > 0 ? pz - plane : pz, ws, false);
-    const Raw3 q1 = load_raw(o, r_src, s_old, pz, ws, true);
-    Raw3 q2 = load_raw(o, r_src, s_old, g.z0 + 1 < a.d ? pz + plane : pz, ws, true);
-    double2 f = g.z0 > 0 ? combine(q0, ws, beta) : make_double2(0.0, 0.0);
-    double2 c = combine(q1, ws, beta);
-    put_plane(o, smem + (g.z0 & 1) * kSPlane, c, combine_ring(q1, ws, beta));
+    const unsigned plane = (unsigned)(a.h * a.w);
+    const int plast = g.z1 < a.d ? g.z1 : a.d - 1;
+    // planes z0-1 .. z0+2 into stages 0 .. 3; plane p lives in stage (p - z0 + 1) & 3
+#pragma unroll
+    for (int q = 0; q < kStages; ++q) {
+        issue_p1(a, o, smem + q * kStageDoubles, g.z0 - 1 + q, plast, r_src, s_old, ws);
+        cp_commit();
+    }
+    cp_wait<2>();
     __syncthreads();
+    double2 f = make_double2(0.0, 0.0);
+    if (g.z0 > 0) {
+        const double *st = smem;   // plane z0 - 1: only this thread's pair is ever needed, nothing is written back
+        f = ldv2(st + o.so);
+        if (ws) {
+            const double2 sv = ldv2(st + kSPlane + o.so);
+            f = make_double2(f.x + beta * sv.x, f.y + beta * sv.y);
+        }
+    }
+    double2 c = transform_p1(o, smem + kStageDoubles, ws, beta);
+    unsigned pz = (unsigned)g.z0 * plane;
     for (int z = g.z0; z < g.z1; ++z, pz += plane) {
-        const bool more = z + 1 < a.d;
-        const double2 k = more ? combine(q2, ws, beta) : make_double2(0.0, 0.0);
-        const double kring = combine_ring(q2, ws, beta);
-        if (z + 2 < a.d && z + 1 < g.z1) q2 = load_raw(o, r_src, s_old, pz + 2 * plane, ws, z + 2 < g.z1);   // one plane ahead of its use
-        const double2 zv = lap_pair<kMode>(a, o, smem + (z & 1) * kSPlane, z, c, f, k);
+        const int q = z - g.z0 + 1;                    // stage index of plane z (mod 4)
+        cp_wait<1>();                                  // plane z + 1 has landed (this thread's copies) ...
+        __syncthreads();                               // ... and everybody's; plane z is transformed; plane z - 1 is no longer read
+        issue_p1(a, o, smem + ((q + 3) & 3) * kStageDoubles, z + 3, plast, r_src, s_old, ws);   // into the stage of plane z - 1
+        cp_commit();
+        double2 k = make_double2(0.0, 0.0);
+        if (z + 1 < a.d) k = transform_p1(o, smem + ((q + 1) & 3) * kStageDoubles, ws, beta);
+        const double2 zv = lap_pair<kMode>(a, o, smem + (q & 3) * kStageDoubles, z, c, f, k);
         if (o.v) {
             if (ws) stv2(s_cur + pz + o.j, c.x, c.y);
-            acc.zs = acc.zs + zv.x * c.x;
-            acc.zs = acc.zs + zv.y * c.y;
-            if (first) {   // max|b| and b.b (pcg.rs:35, 46)
+            zs = zs + zv.x * c.x;
+            zs = zs + zv.y * c.y;
+            if (!ws) {   // max|b| and b.b (pcg.rs:35, 46)
                 const double a0 = c.x < 0 ? -c.x : c.x, a1 = c.y < 0 ? -c.y : c.y;
-                acc.bmax = a0 > acc.bmax ? a0 : acc.bmax;
-                acc.bmax = a1 > acc.bmax ? a1 : acc.bmax;
-                acc.bb = acc.bb + c.x * c.x;
-                acc.bb = acc.bb + c.y * c.y;
+                bmax = a0 > bmax ? a0 : bmax;
+                bmax = a1 > bmax ? a1 : bmax;
+                bb = bb + c.x * c.x;
+                bb = bb + c.y * c.y;
             }
         }
-        if (z + 1 < g.z1) put_plane(o, smem + ((z + 1) & 1) * kSPlane, k, kring);
-        __syncthreads();
         f = c;
         c = k;
     }
+    cp_wait<0>();
 }
 
-// P2: z recomputed from s', x += alpha s', r -= alpha z, r.r and max|r|
+// P2 over one tile: z recomputed from s', x += alpha s', r -= alpha z, r.r and max|r|
 template <int kMode>
 __device__ __forceinline__ void p2_tile(const Cg3Args &a, const TileGeo &g, double *smem, const double *s_rd, const double *r_src, bool first,
-                                        double alpha, Acc3 &acc) {
+                                        double alpha, double &rr, double &rmax) {
     const Own3 o = own_of(a, g);
-    const size_t plane = (size_t)a.h * a.w;
+    const unsigned plane = (unsigned)(a.h * a.w);
     const double nalpha = -alpha;
-    size_t pz = (size_t)g.z0 * plane;
-    const Raw3 q0 = load_raw(o, s_rd, nullptr, g.z0 > 0 ? pz - plane : pz, false, false);
-    const Raw3 q1 = load_raw(o, s_rd, nullptr, pz, false, true);
-    Raw3 q2 = load_raw(o, s_rd, nullptr, g.z0 + 1 < a.d ? pz + plane : pz, false, true);
-    double2 xv = make_double2(0.0, 0.0), rv = xv;
-    if (o.v) {
-        if (!first) xv = ldv2(a.x + pz + o.j);
-        rv = ldv2(r_src + pz + o.j);
+    const int plast = g.z1 < a.d ? g.z1 : a.d - 1;
+#pragma unroll
+    for (int q = 0; q < kStages; ++q) {
+        const int p = g.z0 - 1 + q;
+        issue_p2(a, o, smem + q * kStageDoubles, p, plast, s_rd, r_src, first, p >= g.z0 && p < g.z1);
+        cp_commit();
     }
-    double2 f = g.z0 > 0 ? q0.r : make_double2(0.0, 0.0);
-    double2 c = q1.r;
-    put_plane(o, smem + (g.z0 & 1) * kSPlane, c, q1.rr);
+    cp_wait<2>();
     __syncthreads();
+    double2 f = make_double2(0.0, 0.0);
+    if (g.z0 > 0) f = ldv2(smem + o.so);
+    double2 c = ldv2(smem + kStageDoubles + o.so);
+    unsigned pz = (unsigned)g.z0 * plane;
     for (int z = g.z0; z < g.z1; ++z, pz += plane) {
-        const bool more = z + 1 < a.d;
-        const double2 k = more ? q2.r : make_double2(0.0, 0.0);
-        const double kring = q2.rr;
-        double2 xn = make_double2(0.0, 0.0), rn = xn;
-        if (z + 1 < g.z1) {                       // next plane's x, r and the plane after's s': one plane ahead of their use
-            if (o.v) {
-                if (!first) xn = ldv2(a.x + pz + plane + o.j);
-                rn = ldv2(r_src + pz + plane + o.j);
-            }
-            if (z + 2 < a.d) q2 = load_raw(o, s_rd, nullptr, pz + 2 * plane, false, z + 2 < g.z1);
-        }
-        const double2 zv = lap_pair<kMode>(a, o, smem + (z & 1) * kSPlane, z, c, f, k);
+        const int q = z - g.z0 + 1;
+        cp_wait<1>();
+        __syncthreads();
+        issue_p2(a, o, smem + ((q + 3) & 3) * kStageDoubles, z + 3, plast, s_rd, r_src, first, z + 3 < g.z1);
+        cp_commit();
+        const double *st = smem + (q & 3) * kStageDoubles;
+        double2 k = make_double2(0.0, 0.0);
+        if (z + 1 < a.d) k = ldv2(smem + ((q + 1) & 3) * kStageDoubles + o.so);
+        const double2 zv = lap_pair<kMode>(a, o, st, z, c, f, k);
         if (o.v) {
+            double2 xv = make_double2(0.0, 0.0);
+            if (!first) xv = ldv2(st + kSPlane + o.xo);
+            const double2 rv = ldv2(st + kSPlane + kTX * kTY + o.xo);
             if (first) stv2(a.s0 + pz + o.j, c.x, c.y);                       // pcg.rs:40-42: s = aux = r = b
             stv2(a.x + pz + o.j, xv.x + alpha * c.x, xv.y + alpha * c.y);     // pcg.rs:55
             const double r0 = rv.x + nalpha * zv.x, r1 = rv.y + nalpha * zv.y;   // pcg.rs:56
             stv2(a.r + pz + o.j, r0, r1);
             const double a0 = r0 < 0 ? -r0 : r0, a1 = r1 < 0 ? -r1 : r1;
-            acc.rmax = a0 > acc.rmax ? a0 : acc.rmax;
-            acc.rmax = a1 > acc.rmax ? a1 : acc.rmax;
-            acc.rr = acc.rr + r0 * r0;
-            acc.rr = acc.rr + r1 * r1;
+            rmax = a0 > rmax ? a0 : rmax;
+            rmax = a1 > rmax ? a1 : rmax;
+            rr = rr + r0 * r0;
+            rr = rr + r1 * r1;
         }
-        if (z + 1 < g.z1) put_plane(o, smem + ((z + 1) & 1) * kSPlane, k, kring);
-        __syncthreads();
         f = c;
         c = k;
-        xv = xn;
-        rv = rn;
     }
+    cp_wait<0>();
 }
 
-__global__ void __launch_bounds__(kTileThreads, 2) k3_cg_tile(Cg3Args a) {
-    __shared__ __align__(16) double smem[2 * kSPlane];
+__global__ void __launch_bounds__(kTileThreads, 2) k3_cg_tile(Cg3TileArgs ta) {
+    extern __shared__ __align__(16) double smem[];
     __shared__ double scratch[32];
     __shared__ int s_flag;
+    __shared__ int s_next[2];
+    const Cg3Args &a = ta.c;
     const int G = gridDim.x;
-    const int ntiles = a.tiles_x * a.tiles_y * a.tiles_z;
-    double *pA = a.partials, *pB = pA + G, *pC = pA + 2 * G, *pD = pA + 3 * G, *pE = pA + 4 * G;
-    unsigned long long nbar = 0;
+    const int ntiles = a.tiles_x * a.tiles_y * a.tiles_z;   // >= G
+    double *pA = a.partials, *pB = pA + ntiles, *pC = pA + 2 * ntiles, *pD = pA + 3 * ntiles, *pE = pA + 4 * ntiles;   // per TILE
+    unsigned long long nbar = 0, phase = 0;
     double sigma = 0, alpha = 0, beta = 0, rmax = 0, bmax = 0;
     int it = 0, applies = 0;
     bool converged = false;
@@ -563,32 +603,38 @@ __global__ void __launch_bounds__(kTileThreads, 2) k3_cg_tile(Cg3Args a) {
     for (it = 0; it < a.max_iter; ++it) {
         const bool first = it == 0;
         const double *r_src = first ? a.b : a.r;
-        Acc3 acc{0.0, 0.0, 0.0, 0.0, 0.0};
         // ---------------------------------------------------------------- P1
-        for (int t = blockIdx.x; t < ntiles; t += G) {
-            const TileGeo g = tile_geo(a, t);
-            if (g.mode == 0) p1_tile<0>(a, g, smem, r_src, s_old, s_cur, first, beta, acc);
-            else if (g.mode == 1) p1_tile<1>(a, g, smem, r_src, s_old, s_cur, first, beta, acc);
-            else p1_tile<2>(a, g, smem, r_src, s_old, s_cur, first, beta, acc);
-        }
         {
-            const double v = block_sum(acc.zs, scratch);
-            if (threadIdx.x == 0) pA[blockIdx.x] = v;
-            if (first) {
-                const double v2 = block_sum(acc.bb, scratch), v3 = block_max(acc.bmax, scratch);
-                if (threadIdx.x == 0) {
-                    pB[blockIdx.x] = v2;
-                    pC[blockIdx.x] = v3;
+            const unsigned long long base = phase * (unsigned long long)ntiles;
+            int t = blockIdx.x;
+            for (int i = 0; t < ntiles; ++i) {
+                if (threadIdx.x == 0) s_next[i & 1] = G + (int)(atomicAdd(ta.claim, 1ULL) - base);   // claimed a tile ahead
+                const TileGeo g = tile_geo(a, t);
+                double zs = 0, bb = 0, bm = 0;
+                if (g.mode == 0) p1_tile<0>(a, g, smem, r_src, s_old, s_cur, !first, beta, zs, bb, bm);
+                else if (g.mode == 1) p1_tile<1>(a, g, smem, r_src, s_old, s_cur, !first, beta, zs, bb, bm);
+                else p1_tile<2>(a, g, smem, r_src, s_old, s_cur, !first, beta, zs, bb, bm);
+                const double v = block_sum(zs, scratch);     // (its barriers also fence the stages against the next tile's copies)
+                if (threadIdx.x == 0) pA[t] = v;
+                if (first) {
+                    const double v2 = block_sum(bb, scratch), v3 = block_max(bm, scratch);
+                    if (threadIdx.x == 0) {
+                        pB[t] = v2;
+                        pC[t] = v3;
+                    }
                 }
+                __syncthreads();
+                t = s_next[i & 1];
             }
+            ++phase;
         }
         if (!grid_barrier(a.ctl, (++nbar) * (unsigned long long)G, &s_flag)) return;
-        const double zs = sum_partials<double>(pA, G, scratch);
+        const double zs_all = sum_partials<double>(pA, ntiles, scratch);
         if (first) {
-            sigma = sum_partials<double>(pB, G, scratch);      // pcg.rs:46
-            bmax = max_partials<double>(pC, G, scratch);       // pcg.rs:35
+            sigma = sum_partials<double>(pB, ntiles, scratch);   // pcg.rs:46
+            bmax = max_partials<double>(pC, ntiles, scratch);    // pcg.rs:35
             rmax = bmax;
-            if (bmax < a.threshold) {                          // early out: x = 0, scratch untouched
+            if (bmax < a.threshold) {                            // early out: x = 0, scratch untouched
                 for (size_t j = blockIdx.x * (size_t)kTileThreads + threadIdx.x; j < n; j += (size_t)G * kTileThreads) a.x[j] = 0.0;
                 if (blockIdx.x == 0 && threadIdx.x == 0) {
                     a.ctl->iterations = -1;
@@ -600,37 +646,44 @@ __global__ void __launch_bounds__(kTileThreads, 2) k3_cg_tile(Cg3Args a) {
             }
         }
         ++applies;
-        alpha = sigma / zs;                                    // pcg.rs:53
+        alpha = sigma / zs_all;                                  // pcg.rs:53
         // ---------------------------------------------------------------- P2
-        const double *s_rd = first ? a.b : s_cur;
-        for (int t = blockIdx.x; t < ntiles; t += G) {
-            const TileGeo g = tile_geo(a, t);
-            if (g.mode == 0) p2_tile<0>(a, g, smem, s_rd, r_src, first, alpha, acc);
-            else if (g.mode == 1) p2_tile<1>(a, g, smem, s_rd, r_src, first, alpha, acc);
-            else p2_tile<2>(a, g, smem, s_rd, r_src, first, alpha, acc);
-        }
         {
-            const double v = block_sum(acc.rr, scratch), v2 = block_max(acc.rmax, scratch);
-            if (threadIdx.x == 0) {
-                pD[blockIdx.x] = v;
-                pE[blockIdx.x] = v2;
+            const double *s_rd = first ? a.b : s_cur;
+            const unsigned long long base = phase * (unsigned long long)ntiles;
+            int t = blockIdx.x;
+            for (int i = 0; t < ntiles; ++i) {
+                if (threadIdx.x == 0) s_next[i & 1] = G + (int)(atomicAdd(ta.claim, 1ULL) - base);
+                const TileGeo g = tile_geo(a, t);
+                double rr = 0, rm = 0;
+                if (g.mode == 0) p2_tile<0>(a, g, smem, s_rd, r_src, first, alpha, rr, rm);
+                else if (g.mode == 1) p2_tile<1>(a, g, smem, s_rd, r_src, first, alpha, rr, rm);
+                else p2_tile<2>(a, g, smem, s_rd, r_src, first, alpha, rr, rm);
+                const double v = block_sum(rr, scratch), v2 = block_max(rm, scratch);
+                if (threadIdx.x == 0) {
+                    pD[t] = v;
+                    pE[t] = v2;
+                }
+                __syncthreads();
+                t = s_next[i & 1];
             }
+            ++phase;
         }
         if (!grid_barrier(a.ctl, (++nbar) * (unsigned long long)G, &s_flag)) return;
-        const double rr = sum_partials<double>(pD, G, scratch);
-        rmax = max_partials<double>(pE, G, scratch);           // pcg.rs:58
-        if (rmax < a.threshold) {                              // pcg.rs:60-63
+        const double rr_all = sum_partials<double>(pD, ntiles, scratch);
+        rmax = max_partials<double>(pE, ntiles, scratch);        // pcg.rs:58
+        if (rmax < a.threshold) {                                // pcg.rs:60-63
             converged = true;
             break;
         }
-        beta = rr / sigma;                                     // pcg.rs:67-68
-        sigma = rr;                                            // pcg.rs:79
+        beta = rr_all / sigma;                                   // pcg.rs:67-68
+        sigma = rr_all;                                          // pcg.rs:79
         double *tmp = s_cur;
         s_cur = s_old;
         s_old = tmp;
     }
     const double *s_fin = converged ? s_cur : s_old;
-    if (a.max_iter > 0 && (!converged || s_fin != a.s0)) {     // what the reference leaves in `search` (pcg.rs:72-77), as k3_cg
+    if (a.max_iter > 0 && (!converged || s_fin != a.s0)) {       // what the reference leaves in `search` (pcg.rs:72-77), as k3_cg
         for (size_t j = blockIdx.x * (size_t)kTileThreads + threadIdx.x; j < n; j += (size_t)G * kTileThreads) {
             const double sv = s_fin[j];
             a.s0[j] = converged ? sv : a.r[j] + beta * sv;
@@ -736,41 +789,58 @@ int cg3_solve_raw(pano_ctx *ctx, double *x, const double *b, double *r, double *
     const bool cg_loads = pano_option(ctx, "cg_ldcg", 0) != 0;
     const void *fn = tiled ? (const void *)k3_cg_tile : cg_loads ? (const void *)k3_cg<true> : (const void *)k3_cg<false>;
     const int nthreads = tiled ? kTileThreads : kThreads;
-    PANO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, nthreads, 0));
+    const size_t dyn_smem = tiled ? kTileSmemBytes : 0;
+    if (tiled) PANO_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    PANO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, nthreads, dyn_smem));
     if (per_sm < 1) PANO_FAIL(PANO_ERR_CUDA, "cg3: kernel does not fit on an SM");
     const int64_t cap = pano_option(ctx, "cg_blocks_per_sm", 0);
     if (cap > 0 && cap < per_sm) per_sm = (int)cap;
     const int tw = tiled ? kTX : 32, th = tiled ? kTY : 8;
     Cg3Args a{x, b, r, s0, s1, (int)d, (int)h, (int)w, dt, threshold, max_iterations, clip_box(ob, d + 1, h + 1, w + 1), nullptr, ctx->d_cg,
               (int)((w + tw - 1) / tw), (int)((h + th - 1) / th), 0, 0};
-    // column length per tile: long columns re-read less (two extra planes per tile), short ones balance the static round-robin
-    // better.  Pick the candidate with the best (useful planes / planes read) x (tiles / rounded-up tiles per CTA).
     const int64_t want_zc = pano_option(ctx, "cg3_zc", 0);
-    int best_zc = 8;
-    double best = -1.0;
     const int Gfull = ctx->num_sms * per_sm;
-    for (int zc : {4, 6, 8, 10, 12, 16, 20, 24, 32, 48, 64}) {
-        if (want_zc > 0 && zc != want_zc) continue;
-        const long long tz = ((long long)d + zc - 1) / zc, nt = tz * a.tiles_x * a.tiles_y;
-        const long long rounds = (nt + Gfull - 1) / Gfull;   // every SM slot should be busy in every round: the SMs share the HBM
-        const double eff = ((double)zc / (zc + 1.0)) * ((double)nt / (double)(rounds * Gfull));   // +2 planes on the reads: ~ +1 plane in all
-        if (eff > best) {
-            best = eff;
-            best_zc = zc;
+    if (tiled) {
+        // tiles are claimed dynamically: long columns (two extra planes and one pipeline fill per tile) as long as every CTA still
+        // gets a few tiles to even out the tail.  256^3 on B200: zc 8 / 16 / 32 / 64 = 13.7 / 12.9 / 13.5 / 13.1 ms per 62-iteration solve
+        int zc = 32;
+        while (zc > 16 && ((long long)((d + zc - 1) / zc) * a.tiles_x * a.tiles_y) < 3LL * Gfull) zc /= 2;
+        while (zc > 4 && ((long long)((d + zc - 1) / zc) * a.tiles_x * a.tiles_y) < (long long)Gfull) zc /= 2;   // small grids: fill the GPU first
+        a.zc = want_zc > 0 ? (int)want_zc : zc;
+    } else {
+        // static round-robin: pick the column length with the best (useful planes / planes read) x (tiles / rounded-up tiles per CTA)
+        int best_zc = 8;
+        double best = -1.0;
+        for (int zc : {4, 6, 8, 10, 12, 16, 20, 24, 32, 48, 64}) {
+            if (want_zc > 0 && zc != want_zc) continue;
+            const long long tz = ((long long)d + zc - 1) / zc, nt = tz * a.tiles_x * a.tiles_y;
+            const long long rounds = (nt + Gfull - 1) / Gfull;   // every SM slot should be busy in every round: the SMs share the HBM
+            const double eff = ((double)zc / (zc + 1.0)) * ((double)nt / (double)(rounds * Gfull));
+            if (eff > best) {
+                best = eff;
+                best_zc = zc;
+            }
         }
+        a.zc = want_zc > 0 && best < 0 ? (int)want_zc : best_zc;
     }
-    if (want_zc > 0 && best < 0) best_zc = (int)want_zc;
-    a.zc = best_zc;
     a.tiles_z = (int)((d + a.zc - 1) / a.zc);
     const long long ntiles = (long long)a.tiles_x * a.tiles_y * a.tiles_z;
     int G = Gfull;
     if (G > ntiles) G = (int)ntiles;
     if (G < 1) G = 1;
-    PANO_TRY(pano_ensure_partials(ctx, 5 * (size_t)G));
+    PANO_TRY(pano_ensure_partials(ctx, 5 * (size_t)(tiled ? ntiles : G)));
     a.partials = ctx->d_partials;
     PANO_TRY(pano_cg_control_reset(ctx));
-    void *kargs[] = {(void *)&a};
-    PANO_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)G), dim3(nthreads), kargs, 0, ctx->stream));
+    if (tiled) {
+        if (!ctx->d_claim) PANO_CUDA(cudaMalloc((void **)&ctx->d_claim, 4 * sizeof(unsigned long long)));
+        PANO_CUDA(cudaMemsetAsync(ctx->d_claim, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        Cg3TileArgs ta{a, ctx->d_claim};
+        void *kargs[] = {(void *)&ta};
+        PANO_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)G), dim3(nthreads), kargs, dyn_smem, ctx->stream));
+    } else {
+        void *kargs[] = {(void *)&a};
+        PANO_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)G), dim3(nthreads), kargs, 0, ctx->stream));
+    }
     PANO_TRY(pano_after_launch(ctx, "k3_cg"));
     if (info) {
         PANO_CUDA(cudaMemcpyAsync(ctx->h_cg, ctx->d_cg, sizeof(PanoCgControl), cudaMemcpyDeviceToHost, ctx->stream));

@@ -1,8 +1,9 @@
 // dec_fluid.cpp -- examples/dec_fluid.rs, line for line, on top of host/panopaea.hpp.
-// Usage: dec_fluid [steps=100] [mode=composed|fused] [out.bin]
+// Usage: dec_fluid [steps=100] [mode=composed|fused|multigrid|grid3] [out.bin]
 //   composed: the reference's own call sequence (one device kernel per Manifold2d call, the generic
 //             precond_conjugate_gradient with the Laplacian as a closure)
 //   fused   : pano_fluid_step, one call per loop pass
+//   grid3   : the same loop on a 64^3 Grid3d (the library's 3-D addition; out.bin receives density, vel, pressure)
 // Prints "step i: Iterations k" like the reference prints "Iterations k" (pcg.rs:61), then a checksum.
 // The optional output file receives density (h*w), vel (flat Simplex1) and pressure as raw f64.
 #include <cstdio>
@@ -21,6 +22,19 @@ int main(int argc, char **argv) {
     const std::string mode = argc > 2 ? argv[2] : "composed";
     try {
         Context ctx(0);
+        if (mode == "grid3") {
+            domain::Grid3d g3(ctx, 64, 64, 64);
+            DecFluid3 sim(g3, pano_step3_params{0.05, 0.1, 100, PANO_PRECOND_IDENTITY, pano_box{27, 32, 2, 10, 27, 32}, 1.0, 20.0,
+                                                pano_box{25, 35, 35, 40, 25, 35}});
+            for (int i = 0; i < steps; ++i) printf("step %d: Iterations %ld\n", i, (long)sim.step().iterations);
+            if (argc > 3) {
+                FILE *f = fopen(argv[3], "wb");
+                if (!f) return 2;
+                for (const auto &v : {sim.density.to_host(), sim.vel.to_host(), sim.pressure.to_host()}) fwrite(v.data(), 8, v.size(), f);
+                fclose(f);
+            }
+            return 0;
+        }
         domain::Grid2d grid(ctx, {128, 128});                                   // :27
         auto vel = grid.new_simplex_1<double>();                                // :29
         auto pressure = grid.new_simplex_2<double>();

@@ -215,4 +215,71 @@ inline void advect_mac(dec::Simplex1<double> &dst, const dec::Simplex1<double> &
     check(pano_advect_mac(dst.handle(), src.handle(), timestep, vel.handle()));
 }
 
+// ---- Grid3d (panopaea/src/domain/grid.rs:17-20 is the bare struct; math/interp.rs:23-36 `trilinear`): the library's 3-D addition
+namespace domain {
+class Grid3d {
+  public:
+    Grid3d(const Context &ctx, size_t d, size_t h, size_t w) : ctx_(&ctx), d_(d), h_(h), w_(w) {}
+    size_t depth() const { return d_; }
+    size_t height() const { return h_; }
+    size_t width() const { return w_; }
+    const Context &context() const { return *ctx_; }
+
+  private:
+    const Context *ctx_;
+    size_t d_, h_, w_;
+};
+}  // namespace domain
+
+namespace math {
+inline double trilinear(double a000, double a001, double a010, double a011, double a100, double a101, double a110, double a111, double s,
+                        double t, double u) {
+    return pano_trilinear(a000, a001, a010, a011, a100, a101, a110, a111, s, t, u);
+}
+}  // namespace math
+
+namespace dec {
+template <int Kind>
+class Field3 {   // PANO_CELL3 / PANO_FACE3, f64
+  public:
+    explicit Field3(const domain::Grid3d &g) { check(pano_field3_new(g.context().handle(), Kind, g.depth(), g.height(), g.width(), &h_)); }
+    ~Field3() { pano_field_free(h_); }
+    Field3(const Field3 &) = delete;
+    Field3 &operator=(const Field3 &) = delete;
+    pano_field *handle() const { return h_; }
+    size_t len() const {
+        size_t n = 0;
+        check(pano_field_info(h_, nullptr, nullptr, nullptr, nullptr, &n));
+        return n;
+    }
+    void upload(const std::vector<double> &host) { check(pano_field_upload(h_, host.data(), host.size())); }
+    std::vector<double> to_host() const {
+        std::vector<double> out(len());
+        check(pano_field_download(h_, out.data(), out.size()));
+        return out;
+    }
+    void fill_box(pano_box box, double v, int comp = PANO_COMP_ALL) { check(pano_field3_fill_box(h_, comp, box, v)); }
+
+  private:
+    pano_field *h_ = nullptr;
+};
+using Cells3 = Field3<PANO_CELL3>;
+using Faces3 = Field3<PANO_FACE3>;
+}  // namespace dec
+
+// one pass of the dec_fluid loop body on a Grid3d
+struct DecFluid3 {
+    pano_step3_params params;
+    dec::Faces3 vel, vel_temp;
+    dec::Cells3 pressure, density, temp, auxiliary, residual, search;
+    DecFluid3(const domain::Grid3d &g, const pano_step3_params &p)
+        : params(p), vel(g), vel_temp(g), pressure(g), density(g), temp(g), auxiliary(g), residual(g), search(g) {}
+    pano_pcg_info step() {
+        pano_pcg_info info;
+        check(pano_fluid3_step(&params, density.handle(), vel.handle(), pressure.handle(), temp.handle(), vel_temp.handle(),
+                               residual.handle(), auxiliary.handle(), search.handle(), &info));
+        return info;
+    }
+};
+
 }  // namespace panopaea

@@ -28,3 +28,29 @@ impl Grid2d {
         &self.ctx
     }
 }
+
+/// `Grid3d { dim: (z, y, x) }` (`panopaea/src/domain/grid.rs:17-20`: the struct is all the reference has).  The dec_fluid loop
+/// body on it is an addition of the library (`pano_fluid3_step` and friends), reached through `ffi`.
+#[derive(Clone)]
+pub struct Grid3d {
+    dim: (usize, usize, usize), // (z, y, x)
+    ctx: Context,
+}
+
+impl Grid3d {
+    pub fn new(dim: (usize, usize, usize)) -> Self {
+        Grid3d { dim, ctx: Context::default_for_thread() }
+    }
+
+    pub fn with_context(dim: (usize, usize, usize), ctx: &Context) -> Self {
+        Grid3d { dim, ctx: ctx.clone() }
+    }
+
+    pub fn dim(&self) -> (usize, usize, usize) {
+        self.dim
+    }
+
+    pub fn context(&self) -> &Context {
+        &self.ctx
+    }
+}

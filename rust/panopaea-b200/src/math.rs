@@ -112,3 +112,10 @@ pub trait LinearViewReal<A: Real>: LinearView<Elem = A> {
 }
 
 impl<T, A: Real> LinearViewReal<A> for T where T: LinearView<Elem = A> {}
+
+/// `math::trilinear` (`panopaea/src/math/interp.rs:23-36`), argument order kept; evaluated by the library's own expression
+/// (the one its 3-D advection kernels use), so host and device agree bit for bit.
+#[allow(clippy::too_many_arguments)]
+pub fn trilinear(a000: f64, a001: f64, a010: f64, a011: f64, a100: f64, a101: f64, a110: f64, a111: f64, s: f64, t: f64, u: f64) -> f64 {
+    unsafe { ffi::pano_trilinear(a000, a001, a010, a011, a100, a101, a110, a111, s, t, u) }
+}
