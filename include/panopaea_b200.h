@@ -96,6 +96,8 @@ PANO_API int pano_device_count(int *count);
 /* ------------------------------------------------------------------ context */
 /* stream: a cudaStream_t to enqueue on, or NULL to create a private one. */
 PANO_API int pano_ctx_create(int device, void *stream, pano_ctx **out);
+/* Fields of the context that are still alive keep its device state alive: it is released with the last of them, so handles
+ * may be freed in any order. */
 PANO_API int pano_ctx_destroy(pano_ctx *ctx);
 PANO_API int pano_ctx_sync(pano_ctx *ctx);
 PANO_API int pano_ctx_stream(pano_ctx *ctx, void **stream);

@@ -107,12 +107,10 @@ static int ctx_init(pano_ctx *c, int device, const cudaDeviceProp &prop, void *s
     return PANO_OK;
 }
 
-int pano_ctx_destroy(pano_ctx *ctx) {
-    if (!ctx) return PANO_OK;
+// releases everything the context owns; no field handle refers to it any more
+static void ctx_finalize(pano_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    pano_workspace_free_all(ctx);
-    pano_mg_free_all(ctx);
     cudaFree(ctx->d_partials);
     cudaFree(ctx->d_scalars);
     cudaFreeHost(ctx->h_scalars);
@@ -133,6 +131,21 @@ int pano_ctx_destroy(pano_ctx *ctx) {
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+// Fields created on the context that are still alive keep its device state alive: the context goes away with the last of
+// them (hosts with garbage collection release handles in no particular order; nothing may dangle across the boundary).
+int pano_ctx_destroy(pano_ctx *ctx) {
+    if (!ctx || ctx->destroy_pending) return PANO_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    pano_workspace_free_all(ctx);
+    pano_mg_free_all(ctx);
+    if (ctx->live_fields > 0) {
+        ctx->destroy_pending = true;
+        return PANO_OK;
+    }
+    ctx_finalize(ctx);
     return PANO_OK;
 }
 
@@ -303,18 +316,21 @@ int pano_field_new(pano_ctx *ctx, int kind, int dtype, size_t h, size_t w, pano_
         delete f;
         PANO_FAIL(PANO_ERR_CUDA, "pano_field_new: cudaMemsetAsync -> %s", cudaGetErrorString(e));
     }
+    pano_ctx_field_born(ctx);
     *out = f;
     return PANO_OK;
 }
 
 int pano_field_free(pano_field *f) {
     if (!f) return PANO_OK;
-    if (f->ctx) {
-        cudaSetDevice(f->ctx->device);
-        cudaStreamSynchronize(f->ctx->stream);
+    pano_ctx *ctx = f->ctx;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
     }
     cudaFree(f->d);
     delete f;
+    if (ctx && --ctx->live_fields == 0 && ctx->destroy_pending) ctx_finalize(ctx);   // the context was waiting for this handle
     return PANO_OK;
 }
 
@@ -382,6 +398,8 @@ int pano_field_swap(pano_field *a, pano_field *b) {
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------ helpers
+void pano_ctx_field_born(pano_ctx *ctx) { ++ctx->live_fields; }
+
 int pano_check_field(const pano_field *f, const char *name) {
     if (!f || !f->ctx || !f->d) PANO_FAIL(PANO_ERR_INVALID, "%s: null or freed field handle", name);
     return PANO_OK;

@@ -209,21 +209,28 @@ k_advect_march3_slab(double *__restrict__ q_dst, double *__restrict__ vy_dst, do
 
 // ------------------------------------------------------------------ K3, second generation (no reductions: the
 // solver computes max|b| and b.b itself): one column x kDivRows rows per thread, vy carried down in a register
+// option "fused_wide": 0 / 8 / 16 (one GPU, f64).  Measured on B200 (4096^2 / 8192^2): -div 69.8 / 264 us -> 67.9 / 256 us with 8,
+// projection 126.5 / 488 -> 124.9 / 481 us; 16 rows is no better.  Default: 8 from 1024 columns on.
+constexpr int kFusedWideMinCols = 1024;
 constexpr int kDivRows = 8;
-template <class T>
+// kWide = 0: a block is 32 columns x (8 warps x kDivRows rows).  kWide = R > 0: a block is 256 CONSECUTIVE columns x R rows (every warp
+// 32 of them): 2 KB contiguous per row and array instead of 256 B, which the HBM pages like better.
+template <class T, int kWide>
 __global__ void __launch_bounds__(kThreads)
 k_neg_divergence_march(T *__restrict__ b, const T *__restrict__ vy, const T *__restrict__ vx, int h, int w, RectI m, int ya, int yb) {
     // cell rows [ya, yb) (the whole grid on one GPU; a slab, whose pointers are virtual row-0 addresses, otherwise)
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int ys = ya + (blockIdx.y * 8 + (threadIdx.x >> 5)) * kDivRows;
+    constexpr int kRows = kWide > 0 ? kWide : kDivRows;
+    const int x = kWide > 0 ? blockIdx.x * kThreads + threadIdx.x : blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ys = ya + (kWide > 0 ? blockIdx.y : blockIdx.y * 8 + (threadIdx.x >> 5)) * kRows;
     if (x >= w || ys >= yb) return;
-    // block-uniform test: does this 32 x 64 block touch the obstacle's edges?
-    const int bx0 = blockIdx.x * 32, by0 = ya + blockIdx.y * 8 * kDivRows;
-    const bool masked = m.y1 > m.y0 && m.x1 > m.x0 && by0 < m.y1 && by0 + 8 * kDivRows + 1 > m.y0 && bx0 < m.x1 && bx0 + 33 > m.x0;
+    // block-uniform test: does this block touch the obstacle's edges?
+    const int bw = kWide > 0 ? kThreads : 32, bh = kWide > 0 ? kRows : 8 * kRows;
+    const int bx0 = blockIdx.x * bw, by0 = ya + blockIdx.y * bh;
+    const bool masked = m.y1 > m.y0 && m.x1 > m.x0 && by0 < m.y1 && by0 + bh + 1 > m.y0 && bx0 < m.x1 && bx0 + bw + 1 > m.x0;
     T vy0 = vy[ys * w + x];
     if (masked && in_rect(m, ys, x)) vy0 = (T)0;
 #pragma unroll
-    for (int k = 0; k < kDivRows; ++k) {
+    for (int k = 0; k < kRows; ++k) {
         const int y = ys + k;
         if (y >= yb) break;
         T vy1 = vy[(y + 1) * w + x], vx0 = vx[y * (w + 1) + x], vx1 = vx[y * (w + 1) + x + 1];
@@ -325,18 +332,19 @@ k_project(T *__restrict__ vy, T *__restrict__ vx, const T *__restrict__ p, int h
 // K8, second generation: one column x kProjRows rows per thread, p carried down the column in a register (each p value is
 // loaded once for vy and once per neighbour column for vx instead of three times), 32-bit indices
 constexpr int kProjRows = 8;
-template <class T>
+template <class T, int kWide>   // kWide as k_neg_divergence_march
 __global__ void __launch_bounds__(kThreads)
 k_project_march(T *__restrict__ vy, T *__restrict__ vx, const T *__restrict__ p, int h, int w, T dt, int ya, int yb) {
     // vx rows [ya, yb) and vy face rows [ya, yf): the face row y belongs to the slab that owns cell row y, face row h to the last one
+    constexpr int kRows = kWide > 0 ? kWide : kProjRows;
     const int yf = yb == h ? h + 1 : yb;
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int ys = ya + (blockIdx.y * 8 + (threadIdx.x >> 5)) * kProjRows;
+    const int x = kWide > 0 ? blockIdx.x * kThreads + threadIdx.x : blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ys = ya + (kWide > 0 ? blockIdx.y : blockIdx.y * 8 + (threadIdx.x >> 5)) * kRows;
     if (x > w || ys >= yf) return;
     const bool xin = x < w;
     T pn = (xin && ys > 0) ? p[(ys - 1) * w + x] : (T)0;     // p[y-1, x]
 #pragma unroll
-    for (int k = 0; k < kProjRows; ++k) {
+    for (int k = 0; k < kRows; ++k) {
         const int y = ys + k;
         if (y >= yf) break;
         const T c = (y < h && xin) ? p[y * w + x] : (T)0;
@@ -455,11 +463,18 @@ int pano_neg_divergence_launch(pano_ctx *ctx, int dtype, void *b, const void *ve
     RectI m = pano_clip_rect(obstacle, h + 1, w + 1);
     const size_t off = w * (h + 1);
     if (!want_scalars && (h + 1) * (w + 1) < ((size_t)1 << 31)) {
+        const int64_t wide = dtype == PANO_F64 ? pano_option(ctx, "fused_wide", w >= (size_t)kFusedWideMinCols ? 8 : 0) : 0;
         dim3 gm((unsigned)((w + 31) / 32), (unsigned)((h + 8 * kDivRows - 1) / (8 * kDivRows)));
-        if (dtype == PANO_F64)
-            k_neg_divergence_march<double><<<gm, kThreads, 0, ctx->stream>>>((double *)b, (const double *)vel, (const double *)vel + off, (int)h, (int)w, m, 0, (int)h);
+        if (wide == 16) {
+            dim3 gw((unsigned)((w + kThreads - 1) / kThreads), (unsigned)((h + 15) / 16));
+            k_neg_divergence_march<double, 16><<<gw, kThreads, 0, ctx->stream>>>((double *)b, (const double *)vel, (const double *)vel + off, (int)h, (int)w, m, 0, (int)h);
+        } else if (wide == 8) {
+            dim3 gw((unsigned)((w + kThreads - 1) / kThreads), (unsigned)((h + 7) / 8));
+            k_neg_divergence_march<double, 8><<<gw, kThreads, 0, ctx->stream>>>((double *)b, (const double *)vel, (const double *)vel + off, (int)h, (int)w, m, 0, (int)h);
+        } else if (dtype == PANO_F64)
+            k_neg_divergence_march<double, 0><<<gm, kThreads, 0, ctx->stream>>>((double *)b, (const double *)vel, (const double *)vel + off, (int)h, (int)w, m, 0, (int)h);
         else
-            k_neg_divergence_march<float><<<gm, kThreads, 0, ctx->stream>>>((float *)b, (const float *)vel, (const float *)vel + off, (int)h, (int)w, m, 0, (int)h);
+            k_neg_divergence_march<float, 0><<<gm, kThreads, 0, ctx->stream>>>((float *)b, (const float *)vel, (const float *)vel + off, (int)h, (int)w, m, 0, (int)h);
         return pano_after_launch(ctx, "neg_divergence_march");
     }
     dim3 g = grid2d((int)h, (int)w);
@@ -480,11 +495,18 @@ int pano_neg_divergence_launch(pano_ctx *ctx, int dtype, void *b, const void *ve
 int pano_project_launch(pano_ctx *ctx, int dtype, void *vel, const void *p, size_t h, size_t w, double dt) {
     const size_t off = w * (h + 1);
     if ((h + 1) * (w + 1) < ((size_t)1 << 31) && pano_option(ctx, "project_kernel", 0) != 1) {
+        const int64_t wide = dtype == PANO_F64 ? pano_option(ctx, "fused_wide", w >= (size_t)kFusedWideMinCols ? 8 : 0) : 0;
         dim3 gm((unsigned)((w + 1 + 31) / 32), (unsigned)((h + 1 + 8 * kProjRows - 1) / (8 * kProjRows)));
-        if (dtype == PANO_F64)
-            k_project_march<double><<<gm, kThreads, 0, ctx->stream>>>((double *)vel, (double *)vel + off, (const double *)p, (int)h, (int)w, dt, 0, (int)h);
+        if (wide == 16) {
+            dim3 gw((unsigned)((w + 1 + kThreads - 1) / kThreads), (unsigned)((h + 1 + 15) / 16));
+            k_project_march<double, 16><<<gw, kThreads, 0, ctx->stream>>>((double *)vel, (double *)vel + off, (const double *)p, (int)h, (int)w, dt, 0, (int)h);
+        } else if (wide == 8) {
+            dim3 gw((unsigned)((w + 1 + kThreads - 1) / kThreads), (unsigned)((h + 1 + 7) / 8));
+            k_project_march<double, 8><<<gw, kThreads, 0, ctx->stream>>>((double *)vel, (double *)vel + off, (const double *)p, (int)h, (int)w, dt, 0, (int)h);
+        } else if (dtype == PANO_F64)
+            k_project_march<double, 0><<<gm, kThreads, 0, ctx->stream>>>((double *)vel, (double *)vel + off, (const double *)p, (int)h, (int)w, dt, 0, (int)h);
         else
-            k_project_march<float><<<gm, kThreads, 0, ctx->stream>>>((float *)vel, (float *)vel + off, (const float *)p, (int)h, (int)w, (float)dt, 0, (int)h);
+            k_project_march<float, 0><<<gm, kThreads, 0, ctx->stream>>>((float *)vel, (float *)vel + off, (const float *)p, (int)h, (int)w, (float)dt, 0, (int)h);
         return pano_after_launch(ctx, "project_march");
     }
     dim3 g = grid2d((int)h + 1, (int)w + 1);
@@ -504,8 +526,8 @@ int pano_preload_fused() {
     PANO_TRY(pano_preload_advect_tma());
     PANO_CUDA(cudaFuncGetAttributes(&fa, k_neg_divergence<double>));
     PANO_CUDA(cudaFuncGetAttributes(&fa, k_project<double>));
-    PANO_CUDA(cudaFuncGetAttributes(&fa, k_neg_divergence_march<double>));
-    PANO_CUDA(cudaFuncGetAttributes(&fa, k_project_march<double>));
+    PANO_CUDA(cudaFuncGetAttributes(&fa, (k_neg_divergence_march<double, 0>)));
+    PANO_CUDA(cudaFuncGetAttributes(&fa, (k_project_march<double, 0>)));
     return PANO_OK;
 }
 
@@ -535,7 +557,7 @@ int pano_neg_divergence_slab_launch(pano_ctx *ctx, double *b, const double *vy, 
     RectI m = pano_clip_rect(obstacle, h + 1, w + 1);
     if ((h + 1) * (w + 1) < ((size_t)1 << 31) && pano_option(ctx, "slab_kernels", 0) == 0) {
         dim3 gm((unsigned)((w + 31) / 32), (unsigned)((yb - ya + 8 * kDivRows - 1) / (8 * kDivRows)));
-        k_neg_divergence_march<double><<<gm, kThreads, 0, ctx->stream>>>(b, vy, vx, (int)h, (int)w, m, ya, yb);
+        k_neg_divergence_march<double, 0><<<gm, kThreads, 0, ctx->stream>>>(b, vy, vx, (int)h, (int)w, m, ya, yb);
         return pano_after_launch(ctx, "neg_divergence_march(slab)");
     }
     dim3 g = grid2d(yb - ya, (int)w);
@@ -546,7 +568,7 @@ int pano_neg_divergence_slab_launch(pano_ctx *ctx, double *b, const double *vy, 
 int pano_project_slab_launch(pano_ctx *ctx, double *vy, double *vx, const double *p, size_t h, size_t w, double dt, int ya, int yb) {
     if ((h + 1) * (w + 1) < ((size_t)1 << 31) && pano_option(ctx, "slab_kernels", 0) == 0) {
         dim3 gm((unsigned)((w + 1 + 31) / 32), (unsigned)((yb - ya + 1 + 8 * kProjRows - 1) / (8 * kProjRows)));
-        k_project_march<double><<<gm, kThreads, 0, ctx->stream>>>(vy, vx, p, (int)h, (int)w, dt, ya, yb);
+        k_project_march<double, 0><<<gm, kThreads, 0, ctx->stream>>>(vy, vx, p, (int)h, (int)w, dt, ya, yb);
         return pano_after_launch(ctx, "project_march(slab)");
     }
     dim3 g = grid2d(yb - ya + 1, (int)w + 1);

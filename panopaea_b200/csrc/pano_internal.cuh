@@ -104,6 +104,9 @@ struct pano_ctx {
     std::map<std::string, int64_t> options;
     std::map<std::pair<size_t, size_t>, PanoWorkspace *> workspaces;
     std::vector<pano_mg *> mg_cache;             // preconditioners built on this context (pano_mg_create)
+    // handles may be released in any order (garbage-collected hosts): fields keep the context alive
+    int64_t live_fields = 0;
+    bool destroy_pending = false;
 };
 
 struct pano_field {
@@ -123,6 +126,7 @@ inline size_t pano_num_elem(int kind, size_t h, size_t w) {
     }
 }
 
+void pano_ctx_field_born(pano_ctx *ctx);   // a field handle now refers to ctx
 int pano_check_field(const pano_field *f, const char *name);
 int pano_check_same(const pano_field *a, const pano_field *b, const char *what);
 int pano_check_kind(const pano_field *f, int kind, const char *name);

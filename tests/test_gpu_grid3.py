@@ -100,8 +100,10 @@ def test_pcg3_matches_oracle(d, h, w, zc, kernel):
             assert info["rhs_max"] == np.abs(b).max()
             if info["iterations"] == want.iterations:
                 assert info["applies"] == want.applies
-                assert _close(x.to_host(), want.x, 1e-6) and _close(r.to_host(), want.residual, 1e-6)
-                assert _close(s.to_host(), want.search, 1e-6)
+                floor = 1e-9 * np.abs(b).max()                  # a converged residual is rounding noise: compare against the scale of b there
+                assert _close(x.to_host(), want.x, 1e-6)
+                assert np.abs(r.to_host() - want.residual).max() <= max(1e-6 * np.abs(want.residual).max(), floor)
+                assert np.abs(s.to_host() - want.search).max() <= max(1e-6 * np.abs(want.search).max(), floor)
                 assert abs(info["final_residual"] - want.final_residual) <= 1e-6 * max(1.0, want.final_residual)
                 # the returned residual really is b - A x
                 res = b - O3.laplacian_closure(d, h, w, x.to_host(), 0.05, ob)
@@ -157,3 +159,22 @@ def test_step3_resynchronised(n):
         assert ref.field("density").max() > 0.5 and np.abs(ref.field("vel")).max() > 1.0
     finally:
         O.set_threading(O.SERIAL)
+
+
+def test_handles_may_be_released_in_any_order():
+    """pano_ctx_destroy with fields still alive: the context's device state lives until the last field goes (garbage-collected
+    hosts release handles in no particular order; nothing may dangle across the boundary)."""
+    import ctypes as C
+    from panopaea_b200 import _lib
+    L = _lib.load()
+    ctx = C.c_void_p()
+    assert L.pano_ctx_create(0, None, C.byref(ctx)) == 0
+    f2, f3 = C.c_void_p(), C.c_void_p()
+    assert L.pano_field_new(ctx, _lib.SIMPLEX2, _lib.F64, 64, 64, C.byref(f2)) == 0
+    assert L.pano_field3_new(ctx, 3, 8, 8, 8, C.byref(f3)) == 0
+    assert L.pano_ctx_destroy(ctx) == 0            # deferred: two fields alive
+    assert L.pano_field_fill(f2, 3.0) == 0         # the fields still work
+    out = C.c_double()
+    assert L.pano_field_norm_max(f2, C.byref(out)) == 0 and out.value == 3.0
+    assert L.pano_field_free(f2) == 0
+    assert L.pano_field_free(f3) == 0              # the last one takes the context with it
