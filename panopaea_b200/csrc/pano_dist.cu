@@ -158,7 +158,18 @@ inline ReduceUnit *flag_of(const pano_dist *d, int r, const Layout &Lr, int ex, 
 }
 
 // Push `nrows` boundary rows of each listed field to both neighbours and wait for theirs.
-int exchange(pano_dist *d, int ex, int nfields, const int *fields, int nrows) {
+// the second half of an exchange: a one-thread kernel that holds the stream until both neighbours' rows (flags) have arrived
+int exchange_wait(pano_dist *d, int ex) {
+    pano_ctx *ctx = d->ctx;
+    const Layout &L = d->L;
+    const bool has_up = d->rank > 0, has_dn = d->rank + 1 < d->nranks;
+    if (!has_up && !has_dn) return PANO_OK;
+    k_wait<<<1, 1, 0, ctx->stream>>>(has_up ? flag_of(d, d->rank, L, ex, 0) : nullptr, has_dn ? flag_of(d, d->rank, L, ex, 1) : nullptr,
+                                     d->step_no, reinterpret_cast<unsigned int *>(d->window + L.err));
+    return pano_after_launch(ctx, "dist_wait");
+}
+
+int exchange(pano_dist *d, int ex, int nfields, const int *fields, int nrows, bool wait_too = true) {
     pano_ctx *ctx = d->ctx;
     const Layout &L = d->L;
     const bool has_up = d->rank > 0, has_dn = d->rank + 1 < d->nranks;
@@ -194,9 +205,8 @@ int exchange(pano_dist *d, int ex, int nfields, const int *fields, int nrows) {
     if (blocks > 64) blocks = 64;
     k_push<<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(seg, flag_up, flag_dn, seq, d->d_counter);
     PANO_TRY(pano_after_launch(ctx, "dist_push"));
-    k_wait<<<1, 1, 0, ctx->stream>>>(has_up ? flag_of(d, d->rank, L, ex, 0) : nullptr, has_dn ? flag_of(d, d->rank, L, ex, 1) : nullptr,
-                                     seq, reinterpret_cast<unsigned int *>(d->window + L.err));
-    return pano_after_launch(ctx, "dist_wait");
+    if (!wait_too) return PANO_OK;
+    return exchange_wait(d, ex);
 }
 
 int fill_owned(pano_dist *d, int f, pano_rect r, double value) {
@@ -494,10 +504,15 @@ int pano_dist_step(pano_dist *d) {
     // inflow  (dec_fluid.rs:48-57): the part of the rectangle this rank owns
     PANO_TRY(fill_owned(d, fD, p.inflow, p.inflow_density));
     PANO_TRY(fill_owned(d, fVY, p.inflow, p.inflow_vy));
-    // ghost rows of everything the advection gathers from
+    // ghost rows of everything the advection gathers from.  Option "dist_overlap" = 1 (fused halos): the stream does not wait for
+    // the neighbours' rows here -- the rows at least kGhost away from both slab edges gather from owned rows only, so they are
+    // advected while the halos cross NVLink; the wait and the two edge strips follow.  Measured on 2 B200 (2048 x 8192 slabs,
+    // profiles/r02_dist_overlap_2gpu.txt): 10.778 ms per step against 10.762 without -- the exchange is ~5 us of transfer behind
+    // ~25 us of launches, and the two strip launches cost more than the wait they hide.  Default 0; kept and tested.
+    const bool overlap = fused_halos && pano_option(ctx, "dist_overlap", 0) != 0 && (yb - ya) > 4 * kGhost;
     {
         const int fields[3] = {fD, fVY, fVX};
-        PANO_TRY(exchange(d, EX_ADV, 3, fields, kGhost));
+        PANO_TRY(exchange(d, EX_ADV, 3, fields, kGhost, !overlap));
     }
     mark("ex_adv");
     PANO_TRY(pano_phase_mark(ctx, 1));
@@ -508,8 +523,26 @@ int pano_dist_step(pano_dist *d) {
         // solver's halo recomputation reads, ... are all local; the solver itself mirrors its last row of x into the lower
         // neighbour's ghost row, which is the p[y0-1] of that neighbour's projection.
         const int A = ya - kExtend > 0 ? ya - kExtend : 0, B = yb + kExtend < (int)H ? yb + kExtend : (int)H;
-        PANO_TRY(pano_advect_slab_launch(ctx, virt(d, fDn), virt(d, fVYn), virt(d, fVXn), virt(d, fD), virt(d, fVY), virt(d, fVX), H, W,
-                                         p.timestep, A, B, ylo, rows_q, err));
+        if (overlap) {
+            const bool has_up = d->rank > 0, has_dn = d->rank + 1 < d->nranks;
+            const int ia = has_up ? ya + kGhost : A, ib = has_dn ? yb - kGhost : B;
+            // the interior pass may only SEE rows this rank owns (the ghost rows are still in flight): a backtrace that leaves
+            // them raises the slab error word instead of reading stale rows (the edge strips bound the supported backtrace
+            // more tightly anyway: kGhost - kExtend - 2 rows)
+            const int wlo_i = has_up ? ya : ylo, whi_i = has_dn ? yb - 2 : ylo + (int)rows_q;
+            PANO_TRY(pano_advect_slab_launch(ctx, virt(d, fDn), virt(d, fVYn), virt(d, fVXn), virt(d, fD), virt(d, fVY), virt(d, fVX), H, W,
+                                             p.timestep, ia, ib, wlo_i, (size_t)(whi_i - wlo_i), err));
+            PANO_TRY(exchange_wait(d, EX_ADV));
+            if (ia > A)
+                PANO_TRY(pano_advect_slab_launch(ctx, virt(d, fDn), virt(d, fVYn), virt(d, fVXn), virt(d, fD), virt(d, fVY), virt(d, fVX), H, W,
+                                                 p.timestep, A, ia, ylo, rows_q, err));
+            if (ib < B)
+                PANO_TRY(pano_advect_slab_launch(ctx, virt(d, fDn), virt(d, fVYn), virt(d, fVXn), virt(d, fD), virt(d, fVY), virt(d, fVX), H, W,
+                                                 p.timestep, ib, B, ylo, rows_q, err));
+        } else {
+            PANO_TRY(pano_advect_slab_launch(ctx, virt(d, fDn), virt(d, fVYn), virt(d, fVXn), virt(d, fD), virt(d, fVY), virt(d, fVX), H, W,
+                                             p.timestep, A, B, ylo, rows_q, err));
+        }
         mark("advect");
         PANO_TRY(pano_phase_mark(ctx, 2));
         const int A2 = ya - 2 > 0 ? ya - 2 : 0, B2 = yb + 2 < (int)H ? yb + 2 : (int)H;

@@ -32,7 +32,8 @@ def _step_all(ranks):
 # ... each with the two-reduction kernel (sr = 0, k_cg_stream) and with the single-reduction kernel (sr = 1, k_cg_sr: the default)
 # sr = 2: the single-reduction kernel inside the fused-halo step (the default: ONE ghost-row exchange per step, the rest recomputed
 # or mirrored from inside the solver); sr = 1: the same kernel with the four exchanges of the two-reduction path
-@pytest.mark.parametrize("dynamic,halo_first,xflags,sr", [(0, 0, 1, 2), (1, 0, 1, 2), (0, 0, 0, 2), (1, 0, 0, 2), (0, 0, 1, 1), (1, 0, 0, 1),
+# sr = 3: sr = 2 with "dist_overlap": interior rows advected while the ghost rows are in flight, edge strips after the wait
+@pytest.mark.parametrize("dynamic,halo_first,xflags,sr", [(0, 0, 1, 2), (1, 0, 1, 2), (0, 0, 0, 2), (1, 0, 0, 2), (0, 0, 1, 3), (1, 0, 1, 3), (0, 0, 1, 1), (1, 0, 0, 1),
                                                           (0, 0, 1, 0), (1, 0, 1, 0), (0, 1, 1, 0), (0, 0, 0, 0), (1, 0, 0, 0), (0, 1, 0, 0)])
 @pytest.mark.parametrize("nranks,h,w", [(2, 256, 256), (4, 256, 128), (3, 250, 192)])
 def test_loopback_matches_single_gpu(nranks, h, w, dynamic, halo_first, xflags, sr):
@@ -48,7 +49,8 @@ def test_loopback_matches_single_gpu(nranks, h, w, dynamic, halo_first, xflags, 
         r.ctx.set_option("cg_halo_first", halo_first)
         r.ctx.set_option("cg_xflags", xflags)
         r.ctx.set_option("cg_single_reduction", 1 if sr else 0)
-        r.ctx.set_option("dist_fused_halos", 1 if sr == 2 else 0)
+        r.ctx.set_option("dist_fused_halos", 1 if sr >= 2 else 0)
+        r.ctx.set_option("dist_overlap", 1 if sr == 3 else 0)
     for step in range(6):
         want = single.step()
         infos = _step_all(ranks)
