@@ -343,6 +343,8 @@ __global__ void __launch_bounds__(kThreads, 4) k3_cg(Cg3Args a) {
 //   Measured and rejected (B200, 256^3 / 512^3 solves of 59 / 100 iterations, this kernel 12.9 / 129 ms): static equal shares of a
 //   plane stream whose cp.async ring never drains across tile changes -- 15.3 / 154 ms (the per-slot role dispatch costs more than
 //   the pipeline fills it removes); the same with column-major shares 17.1 / 174 ms (ring cells and z-neighbour planes then miss L2).
+//   Also rejected: a tile's last two request slots fetching the first two planes of the CTA's next tile (12.7 / 126 ms: the second
+//   CTA of the SM already covers a tile's pipeline fill).
 constexpr int kTileThreads = 512;
 constexpr int kTX = 64, kTY = 16;
 constexpr int kSW = kTX + 4;                  // row stride: interior from column 2 (pairs stay 16-byte aligned), ring in columns 1 and kTX + 2
