@@ -137,7 +137,10 @@ PANO_API int pano_ctx_cg_profile_ctas(pano_ctx *ctx, int64_t *cycles_out, int n)
  * (default) / 1 per-CTA inboxes; advection: "advect_kernel" 0 auto / 1 k_advect / 2 k_advect_march / 3 k_advect_march3 /
  * 4 k_advect_tma (TMA-staged persistent kernel; f64, even sizes, at least 128 x 256), "advect_dynamic" 1 tiles claimed from a
  * counter (default) / 0 round-robin, "advect_ctas" n (cap on the persistent grid), "advect_rows" 2/4/8, "advect_prefetch" 0..3,
- * "advect_minblocks" 3..5 (marching kernel).
+ * "advect_minblocks" 3..5 (marching kernel); "fused_wide" 0 / 8 / 16: -div and projection blocks of 256 consecutive columns x that
+ * many rows (default 8 from 1024 columns on, else the 32-column blocks); multi-GPU: "dist_overlap" 0 (default) / 1 interior rows
+ * advected while the ghost rows are in flight; Grid3d: "cg3_kernel" 0 auto (plane tiles through a cp.async ring for even widths,
+ * else the column kernel) / 1 column kernel / 2 plane tiles, "cg3_zc" planes per tile (0 auto).
  * A key that was not set with this call is looked up in the environment as PANO_OPT_<key> before its default applies. */
 PANO_API int pano_ctx_set_option(pano_ctx *ctx, const char *key, int64_t value);
 PANO_API int pano_ctx_get_option(pano_ctx *ctx, const char *key, int64_t *value);
