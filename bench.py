@@ -343,16 +343,11 @@ class _Slab:
             self.counts.append(count)
             _lib.check(L.pano_dist_download(D._h, which, self.bufs[which], None))
         self.h2d, self.d2h = sum(self.counts) * 8, sum(self.counts) * 8       # bytes of THIS rank
-        self.call = "pano_dist_upload x3 + pano_dist_step + pano_dist_sync + pano_dist_download x3 (pinned host rows of this rank: density, vy, vx)"
+        self.call = ("pano_dist_step_host (pinned host rows of this rank in and out, every step: density, vy, vx; the density comes "
+                     "back while the solver runs)")
 
     def e2e_step(self):
-        L, _lib, D, dist = self._lib.load(), self._lib, self.D, self.dist
-        for which in (dist.DENSITY, dist.VY, dist.VX):
-            _lib.check(L.pano_dist_upload(D._h, which, self.bufs[which]))
-        D.step()
-        D.sync()
-        for which in (dist.DENSITY, dist.VY, dist.VX):
-            _lib.check(L.pano_dist_download(D._h, which, self.bufs[which], None))
+        self.D.step_host(self.bufs[self.dist.DENSITY], self.bufs[self.dist.VY], self.bufs[self.dist.VX])
 
     def e2e_teardown(self):
         L = self._lib.load()

@@ -289,6 +289,10 @@ PANO_API int pano_dist_step(pano_dist *d);
  * last step: BASELINE configs[4], "pressure Poisson solve strong scaling".  Collective, asynchronous. */
 PANO_API int pano_dist_solve(pano_dist *d);
 PANO_API int pano_dist_sync(pano_dist *d, pano_pcg_info *info);
+/* The slab step for callers that keep their rows in HOST memory, as pano_fluid_step_host on one GPU: uploads this rank's rows of
+ * density, vy and vx (layout and row counts of pano_dist_upload; pinned buffers), steps, brings them back -- the density while the
+ * solver runs, the velocity after the projection -- and synchronises (pano_dist_sync).  Collective. */
+PANO_API int pano_dist_step_host(pano_dist *d, double *density_rows, double *vy_rows, double *vx_rows, pano_pcg_info *info);
 
 /* --------------------------------------------------------------------- Grid3d
  * SURVEY.md 8(f) rank 4.  The reference holds two 3-D items and nothing else: the struct

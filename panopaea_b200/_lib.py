@@ -127,6 +127,7 @@ _SIGS = {
     "pano_dist_step": (C.c_int, [_P]),
     "pano_dist_solve": (C.c_int, [_P]),
     "pano_dist_sync": (C.c_int, [_P, C.POINTER(PcgInfo)]),
+    "pano_dist_step_host": (C.c_int, [_P, _P, _P, _P, C.POINTER(PcgInfo)]),
     "pano_field3_new": (C.c_int, [_P, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(_P)]),
     "pano_field3_num_elem": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t)]),
     "pano_field3_dim": (C.c_int, [_P, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),

@@ -471,8 +471,15 @@ int pano_dist_download(pano_dist *d, int which, double *host_rows, size_t *rows)
     return PANO_OK;
 }
 
+// after_advect (nullable) runs once the new density is final, long before the solve ends: the host-buffer entry point starts the
+// density download on the copy stream there (as pano_fluid_step_host does on one GPU)
+typedef int (*DistStepHook)(pano_dist *d, void *user);
+static int dist_step_impl(pano_dist *d, DistStepHook after_advect, void *user);
+
 // One step, enqueued asynchronously on the context's stream (collective: every rank must call it).
-int pano_dist_step(pano_dist *d) {
+int pano_dist_step(pano_dist *d) { return dist_step_impl(d, nullptr, nullptr); }
+
+static int dist_step_impl(pano_dist *d, DistStepHook after_advect, void *user) {
     if (!d) PANO_FAIL(PANO_ERR_INVALID, "pano_dist_step: null handle");
     if (!d->connected) PANO_FAIL(PANO_ERR_COMM, "pano_dist_step: call pano_dist_connect first");
     pano_ctx *ctx = d->ctx;
@@ -544,6 +551,7 @@ int pano_dist_step(pano_dist *d) {
                                              p.timestep, A, B, ylo, rows_q, err));
         }
         mark("advect");
+        if (after_advect) PANO_TRY(after_advect(d, user));
         PANO_TRY(pano_phase_mark(ctx, 2));
         const int A2 = ya - 2 > 0 ? ya - 2 : 0, B2 = yb + 2 < (int)H ? yb + 2 : (int)H;
         PANO_TRY(pano_neg_divergence_slab_launch(ctx, virt(d, fB), virt(d, fVYn), virt(d, fVXn), H, W, p.obstacle, A2, B2));
@@ -561,6 +569,7 @@ int pano_dist_step(pano_dist *d) {
     PANO_TRY(pano_advect_slab_launch(ctx, virt(d, fDn), virt(d, fVYn), virt(d, fVXn), virt(d, fD), virt(d, fVY), virt(d, fVX), H, W,
                                      p.timestep, ya, yb, ylo, rows_q, err));
     mark("advect");
+    if (after_advect) PANO_TRY(after_advect(d, user));
     // the face row y1 of the new vy belongs to the lower neighbour
     {
         const int fields[1] = {fVYn};
@@ -602,6 +611,47 @@ int pano_dist_solve(pano_dist *d) {
 }
 
 // wait for the enqueued steps; info (nullable) describes the last solve
+struct DistHostCopy {
+    double *density_rows;
+};
+static int dist_start_density_download(pano_dist *d, void *user) {
+    // the advection has just written the NEXT density buffer; cur flips at the end of the step
+    pano_ctx *ctx = d->ctx;
+    const Layout &L = d->L;
+    const int f = (d->cur ^ 1) ? F_D1 : F_D0;
+    PANO_CUDA(cudaEventRecord(ctx->ev_advect, ctx->stream));
+    PANO_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_advect, 0));
+    PANO_CUDA(cudaMemcpyAsync(static_cast<DistHostCopy *>(user)->density_rows, peer_row(d, d->rank, L, f, (ptrdiff_t)L.y0),
+                              L.hl * L.pitch[f] * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    PANO_CUDA(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+    return PANO_OK;
+}
+
+int pano_dist_step_host(pano_dist *d, double *density_rows, double *vy_rows, double *vx_rows, pano_pcg_info *info) {
+    if (!d || !density_rows || !vy_rows || !vx_rows) PANO_FAIL(PANO_ERR_INVALID, "pano_dist_step_host: null argument");
+    pano_ctx *ctx = d->ctx;
+    PANO_TRY(pano_activate(ctx));
+    double *host[3] = {density_rows, vy_rows, vx_rows};
+    for (int which = 0; which < 3; ++which) {          // this rank's rows in, back to back on the step's stream
+        int f;
+        size_t g0, n;
+        PANO_TRY(dist_rows(d, which, &f, &g0, &n));
+        PANO_CUDA(cudaMemcpyAsync(peer_row(d, d->rank, d->L, f, (ptrdiff_t)g0), host[which], n * d->L.pitch[f] * sizeof(double),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    }
+    DistHostCopy hook{density_rows};
+    PANO_TRY(dist_step_impl(d, dist_start_density_download, &hook));     // the density goes home under the solve
+    PANO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+    for (int which = 1; which < 3; ++which) {          // the projected velocity follows the last kernel
+        int f;
+        size_t g0, n;
+        PANO_TRY(dist_rows(d, which, &f, &g0, &n));    // (cur has flipped: the new buffers)
+        PANO_CUDA(cudaMemcpyAsync(host[which], peer_row(d, d->rank, d->L, f, (ptrdiff_t)g0), n * d->L.pitch[f] * sizeof(double),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return pano_dist_sync(d, info);
+}
+
 int pano_dist_sync(pano_dist *d, pano_pcg_info *info) {
     if (!d) PANO_FAIL(PANO_ERR_INVALID, "pano_dist_sync: null handle");
     pano_ctx *ctx = d->ctx;

@@ -83,6 +83,13 @@ class DistFluid:
     def step(self):
         check(self._L.pano_dist_step(self._h))
 
+    def step_host(self, density_rows, vy_rows, vx_rows):
+        """pano_dist_step_host: this rank's rows (C pointers to pinned host buffers, layout of upload / download) in, one step, rows
+        out -- the density under the solve -- and the synchronisation; returns the solver info."""
+        info = PcgInfo()
+        check(self._L.pano_dist_step_host(self._h, density_rows, vy_rows, vx_rows, C.byref(info)))
+        return info.as_dict()
+
     def solve(self):
         """The pressure solve alone, on the right-hand side of the last step (collective, asynchronous)."""
         check(self._L.pano_dist_solve(self._h))

@@ -207,6 +207,8 @@ extern "C" {
     pub fn pano_dist_step(d: *mut pano_dist) -> c_int;
     pub fn pano_dist_solve(d: *mut pano_dist) -> c_int;
     pub fn pano_dist_sync(d: *mut pano_dist, info: *mut pano_pcg_info) -> c_int;
+    pub fn pano_dist_step_host(d: *mut pano_dist, density_rows: *mut f64, vy_rows: *mut f64, vx_rows: *mut f64,
+                               info: *mut pano_pcg_info) -> c_int;
 
     // ------------------------------------------------------------------- Grid3d
     pub fn pano_field3_new(ctx: *mut pano_ctx, kind: c_int, d: usize, h: usize, w: usize, out: *mut *mut pano_field) -> c_int;

@@ -206,3 +206,57 @@ def test_loopback_halo_tiles_mid_pass(nranks, h, w, dynamic):
     assert [i["iterations"] for i in out[0][0]] == [i["iterations"] for i in out[1][0]]
     for a, b in zip(out[0][1], out[1][1]):
         assert np.abs(a - b).max() <= 1e-9 * max(1.0, np.abs(a).max())
+
+
+def test_step_host_two_ranks_threads():
+    """pano_dist_step_host (host rows in, step, host rows out, synchronising): the call is collective, so the two loop-back ranks are
+    driven from two threads (ctypes releases the GIL).  Compared with pano_fluid_step_host on one GPU, which it mirrors."""
+    import ctypes as C
+    import threading
+    from tests import gpu_util as U
+    from panopaea_b200 import _lib, dist, fluid
+    h = w = 256
+    k = 2
+    prm = dict(timestep=0.05, threshold=0.1, max_iterations=100, inflow=(5 * k, 20 * k, 27 * k, 32 * k), inflow_density=1.0,
+               inflow_vy=20.0, obstacle=(70 * k, 80 * k, 25 * k, 35 * k))
+    L = _lib.load()
+    single = fluid.DecFluid(h=h, w=w, ctx=U.ctx(), **prm)
+    ranks = _make_ranks(2, h, w, prm)
+    bufs = []
+    for r in ranks:
+        mine = []
+        for which in (dist.DENSITY, dist.VY, dist.VX):
+            n = r._rows(which) * r._pitch(which)
+            p = C.c_void_p()
+            _lib.check(L.pano_host_alloc(n * 8, C.byref(p)))
+            a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(n,))
+            a[:] = 0.0
+            mine.append((p, a))
+        bufs.append(mine)
+    infos = [None, None]
+
+    def run(i):
+        infos[i] = ranks[i].step_host(*[p for p, _ in bufs[i]])
+
+    for step in range(4):
+        want = single.step()
+        ts = [threading.Thread(target=run, args=(i,)) for i in range(2)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join(timeout=120)
+        assert all(not t.is_alive() for t in ts)
+        assert infos[0] == infos[1] and abs(infos[0]["iterations"] - want["iterations"]) <= 1, (step, infos, want)
+        if infos[0]["iterations"] != want["iterations"]:
+            break
+        y0 = [r.y0 for r in ranks] + [h]
+        d = np.concatenate([bufs[i][0][1].reshape(-1, w) for i in range(2)])
+        vy = np.concatenate([bufs[i][1][1].reshape(-1, w) for i in range(2)])
+        vx = np.concatenate([bufs[i][2][1].reshape(-1, w + 1) for i in range(2)])
+        svy, svx = single.vel.split()
+        assert d.shape == (h, w) and vy.shape == (h + 1, w) and vx.shape == (h, w + 1), y0
+        assert np.abs(d - single.density.to_host()).max() <= 1e-9
+        assert np.abs(vy - svy).max() <= 1e-8 * max(1.0, np.abs(svy).max()) and np.abs(vx - svx).max() <= 1e-8 * max(1.0, np.abs(svx).max())
+    for mine in bufs:
+        for p, _ in mine:
+            L.pano_host_free(p)
