@@ -178,3 +178,34 @@ def test_handles_may_be_released_in_any_order():
     assert L.pano_field_norm_max(f2, C.byref(out)) == 0 and out.value == 3.0
     assert L.pano_field_free(f2) == 0
     assert L.pano_field_free(f3) == 0              # the last one takes the context with it
+
+
+def test_step3_256_vs_oracle():
+    """The bench size of the Grid3d leg (256^3) against the all-parallel checker on identical inputs: the device runs a developed
+    plume (10 free steps), its state is handed to the checker, and both advance it by one step -- advection and -div bit-exact,
+    iteration count within +-2, pressure / velocity within 1e-5 relative (the bars of north_star)."""
+    from oracle import pano_oracle as O
+    from oracle import pano_oracle3 as O3
+    from panopaea_b200 import grid3
+    from tests import gpu_util as U
+    n = 256
+    sim = grid3.DecFluid3(**grid3.smoke_params(n), ctx=U.ctx())
+    for _ in range(10):
+        sim.step(want_info=False)
+    ref = O3.FluidState3(**O3.smoke_params(n))
+    ref.field("density")[...] = sim.density.to_host()
+    ref.field("vel")[...] = sim.vel.view_linear()
+    assert np.abs(ref.field("vel")).max() > 5.0 and ref.field("density").max() > 0.5        # a developed plume, not a zero field
+    O.set_threading(O.ALL_PARALLEL)
+    try:
+        g, o = sim.step(), ref.step(want_rhs=True)
+    finally:
+        O.set_threading(O.SERIAL)
+    assert abs(g["iterations"] - o["iterations"]) <= 2, (g, o)
+    assert g["rhs_max"] == np.abs(o["rhs"]).max()
+    assert np.array_equal(sim.density.to_host(), ref.field("density"))
+    if g["iterations"] == o["iterations"]:
+        assert _close(sim.pressure.to_host(), ref.field("pressure"), 1e-5)
+        assert _close(sim.vel.view_linear(), ref.field("vel"), 1e-5)
+        assert g["final_residual"] == pytest.approx(o["final_residual"], rel=1e-5)
+    ref.close()
