@@ -17,6 +17,7 @@
 #include "pano_cell_math.h"
 #include "pano_gridsync.cuh"
 #include "pano_internal.cuh"
+#include "pano_sm100.cuh"
 
 namespace {
 
@@ -329,35 +330,56 @@ __global__ void __launch_bounds__(kThreads, 4) k3_cg(Cg3Args a) {
 }
 
 // ------------------------------------------------------------------ the solve, second generation (even widths): plane tiles
-// streamed through shared memory.  A CTA (512 threads) owns a 64 (x) x 16 (y) column bundle of `zc` planes at a time; every thread
-// owns 2 adjacent columns of one row and walks along z with s'[z-1], s'[z], s'[z+1] of its two cells in registers.
-//   * Planes arrive through a FOUR-STAGE cp.async ring (16-byte copies of the thread's own pair, 8-byte copies of one ring cell for
-//     the first 160 threads; zero-filled outside the grid): plane z+3 is requested while plane z is evaluated, no register holds
-//     data in flight, one __syncthreads per plane.
-//   * P1 turns the raw r, s of plane z+1 into s' = r + beta s IN PLACE (own pair + ring cell, the owner's expression: the same
-//     bits) one step before the plane is evaluated, so the four lateral neighbours are plain shared-memory reads (or the thread's
-//     own registers); P2 stages s' (with ring), x and r.
-//   * Tiles are claimed from a counter (first tile static); every tile leaves its own partial sums, and after the grid barrier every
-//     CTA adds the per-TILE partials in tile order: the scalars do not depend on which CTA ran which tile -- deterministic.
+// streamed through shared memory by TMA.  A CTA (512 threads) owns a 64 (x) x 16 (y) column bundle of `zc` planes at a time; every
+// thread owns 2 adjacent cells of one row and walks along z with s'[z-1], s'[z], s'[z+1] of its two cells in registers.
+//   * Planes arrive through a FOUR-STAGE ring of TMA boxes (cp.async.bulk.tensor.3d, one elected thread, mbarrier completion):
+//     an 18 x 68 box brings a plane of the tile WITH its one-cell ring (and two pad columns that keep the box start 16-byte
+//     aligned; outside the grid TMA fills zeros), 16 x 64 boxes bring x and r.  Plane z+3 is requested while plane z is
+//     evaluated, no register holds data in flight, one __syncthreads per plane.
+//   * P1 turns the raw r, s of plane z+1 into s' = r + beta s IN PLACE (own pair + one ring cell for the first 160 threads, the
+//     owner's expression: the same bits) one step before the plane is evaluated, so the four lateral neighbours are plain
+//     shared-memory reads (or the thread's own registers); P2 stages s' (with ring), x and r.
+//   * Tiles are claimed from a counter (first tile static) in x-fastest order, so neighbouring columns of a slab run at the same
+//     time and their rings meet in L2; every tile leaves its own partial sums, and after the grid barrier every CTA adds the
+//     per-TILE partials in tile order: the scalars do not depend on which CTA ran which tile -- deterministic.
 //   * Tiles that no wall and no obstacle face touches skip the open/closed flags, tiles at a wall only compare coordinates.
-//   Measured and rejected (B200, 256^3 / 512^3 solves of 59 / 100 iterations, this kernel 12.9 / 129 ms): static equal shares of a
-//   plane stream whose cp.async ring never drains across tile changes -- 15.3 / 154 ms (the per-slot role dispatch costs more than
-//   the pipeline fills it removes); the same with column-major shares 17.1 / 174 ms (ring cells and z-neighbour planes then miss L2).
-//   Also rejected: a tile's last two request slots fetching the first two planes of the CTA's next tile (12.7 / 126 ms: the second
-//   CTA of the SM already covers a tile's pipeline fill).
+//   Measured and rejected (B200, 256^3 / 512^3, the cp.async form of this kernel 12.9 / 129 ms per solve): static equal shares of a
+//   plane stream whose ring never drains across tile changes -- 15.3 / 154 ms (the per-slot role dispatch costs more than the
+//   pipeline fills it removes); the same with column-major shares 17.1 / 174 ms (ring cells and z-neighbour planes then miss L2);
+//   a tile's last two request slots fetching the first two planes of the CTA's next tile (12.7 / 126 ms: the second CTA of the SM
+//   already covers a tile's pipeline fill).
+using pano_sm100::mbar_arrive;
+using pano_sm100::mbar_arrive_expect_tx;
+using pano_sm100::mbar_init;
+using pano_sm100::mbar_wait;
+using pano_sm100::smem_u32;
+
 constexpr int kTileThreads = 512;
 constexpr int kTX = 64, kTY = 16;
-constexpr int kSW = kTX + 4;                  // row stride: interior from column 2 (pairs stay 16-byte aligned), ring in columns 1 and kTX + 2
-constexpr int kSPlane = (kTY + 2) * kSW;      // a plane with its ring
+constexpr int kSW = kTX + 4;                  // row stride = box width: interior from column 2, ring in columns 1 and kTX + 2
+constexpr int kRingBoxBytes = (kTY + 2) * kSW * 8;        // 9792: what one ringed box transfers
+constexpr int kSPlane = 1232;                 // doubles reserved for a ringed plane (9856 B, a multiple of 128)
+constexpr int kIntBoxBytes = kTX * kTY * 8;   // 8192
 constexpr int kStages = 4;
 constexpr int kStageDoubles = kSPlane + 2 * kTX * kTY;   // P2: s' (ring) | x | r;  P1: r (ring) | s (ring) = 2 kSPlane, smaller
-constexpr size_t kTileSmemBytes = (size_t)kStages * kStageDoubles * sizeof(double);
-static_assert(2 * kSPlane <= kStageDoubles, "P1 stage must fit");
+constexpr size_t kTileSmemBytes = (size_t)kStages * kStageDoubles * sizeof(double) + 128;   // + slack to align the ring to 128 B
+static_assert(2 * kSPlane <= kStageDoubles && (kSPlane * 8) % 128 == 0 && (kStageDoubles * 8) % 128 == 0, "stage layout");
+static_assert((kTY + 2) * kSW <= kSPlane, "ringed plane must fit");
 
 struct Cg3TileArgs {
     Cg3Args c;
     unsigned long long *claim;   // zero at launch
+    // (w, h, d) tensors: ringed 68 x 18 x 1 boxes of b, r, s0, s1; interior 64 x 16 x 1 boxes of x, r, b
+    CUtensorMap mr_b, mr_r, mr_s0, mr_s1, mi_x, mi_r, mi_b;
 };
+
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct TileGeo {
     int x0, y0, z0, z1;
@@ -381,11 +403,11 @@ __device__ __forceinline__ TileGeo tile_geo(const Cg3Args &a, int t) {
 struct Own3 {        // this thread's share of a plane tile (offsets in elements; every array holds fewer than 2^31)
     int xa, ya;      // cells (ya, xa) and (ya, xa + 1)
     bool v;          // inside the grid
-    bool ring, ring_in;   // this thread also carries one ring cell; it lies inside the grid
+    bool ring;       // this thread also transforms one ring cell
     int so;          // shared-memory offset of (ya, xa) in a ringed plane
     int xo;          // ... in an interior-only 16 x 64 plane
     int rso;         // shared-memory offset of the ring cell
-    unsigned j, rj;  // offsets of (ya, xa) / the ring cell inside a plane of the grid
+    unsigned j;      // offset of (ya, xa) inside a plane of the grid
 };
 __device__ __forceinline__ Own3 own_of(const Cg3Args &a, const TileGeo &g) {
     Own3 o;
@@ -396,32 +418,17 @@ __device__ __forceinline__ Own3 own_of(const Cg3Args &a, const TileGeo &g) {
     o.so = (ty + 1) * kSW + 2 + 2 * tx;
     o.xo = ty * kTX + 2 * tx;
     o.j = o.v ? (unsigned)o.ya * (unsigned)a.w + (unsigned)o.xa : 0u;
-    int gy = 0, gx = 0;
     o.ring = tid < 2 * kTX + 2 * kTY;
     o.rso = 0;
-    if (tid < kTX) { gy = g.y0 - 1; gx = g.x0 + tid; o.rso = 2 + tid; }
-    else if (tid < 2 * kTX) { gy = g.y0 + kTY; gx = g.x0 + tid - kTX; o.rso = (kTY + 1) * kSW + 2 + tid - kTX; }
-    else if (tid < 2 * kTX + kTY) { gy = g.y0 + tid - 2 * kTX; gx = g.x0 - 1; o.rso = (tid - 2 * kTX + 1) * kSW + 1; }
-    else if (o.ring) { gy = g.y0 + tid - 2 * kTX - kTY; gx = g.x0 + kTX; o.rso = (tid - 2 * kTX - kTY + 1) * kSW + kTX + 2; }
-    o.ring_in = o.ring && gy >= 0 && gy < a.h && gx >= 0 && gx < a.w;
-    o.rj = o.ring_in ? (unsigned)gy * (unsigned)a.w + (unsigned)gx : 0u;
+    if (tid < kTX) o.rso = 2 + tid;                                                     // row y0 - 1
+    else if (tid < 2 * kTX) o.rso = (kTY + 1) * kSW + 2 + tid - kTX;                    // row y0 + 16
+    else if (tid < 2 * kTX + kTY) o.rso = (tid - 2 * kTX + 1) * kSW + 1;                // column x0 - 1
+    else if (o.ring) o.rso = (tid - 2 * kTX - kTY + 1) * kSW + kTX + 2;                 // column x0 + 64
     return o;
 }
 
 __device__ __forceinline__ double2 ldv2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ void stv2(double *p, double x, double y) { *reinterpret_cast<double2 *>(p) = make_double2(x, y); }
-// asynchronous global -> shared copies; `ok` false writes zeros (source size 0)
-__device__ __forceinline__ void cp16(double *smem_dst, const double *gsrc, bool ok) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), n = ok ? 16u : 0u;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp8(double *smem_dst, const double *gsrc, bool ok) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), n = ok ? 8u : 0u;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // z = A s' on the two cells of plane z; c = s'[z], f = s'[z-1], k = s'[z+1] in registers, the plane with its ring in `buf`
 template <int kMode>
@@ -450,29 +457,52 @@ __device__ __forceinline__ double2 lap_pair(const Cg3Args &a, const Own3 &o, con
     return out;
 }
 
-// request plane p of the tile's arrays into `st` (nothing for a plane outside [0, plast], plast = the last plane the tile reads;
-// the caller commits the group either way)
-__device__ __forceinline__ void issue_p1(const Cg3Args &a, const Own3 &o, double *st, int p, int plast, const double *r_src, const double *s_old,
-                                         bool ws) {
-    if (p < 0 || p > plast) return;
-    const unsigned pz = (unsigned)p * (unsigned)(a.h * a.w);
-    cp16(st + o.so, r_src + pz + o.j, o.v);
-    if (ws) cp16(st + kSPlane + o.so, s_old + pz + o.j, o.v);
-    if (o.ring) {
-        cp8(st + o.rso, r_src + pz + o.rj, o.ring_in);
-        if (ws) cp8(st + kSPlane + o.rso, s_old + pz + o.rj, o.ring_in);
+// The stage ring of one CTA: slot number L (counted over the CTA's whole life) uses stage L & 3, and its mbarrier completes phase
+// (L >> 2) & 1.  EVERY slot completes its phase -- with the bytes of the boxes it requested, or at once if its plane lies outside
+// [0, plast] -- so the parity bookkeeping never depends on the geometry.
+struct Ring3 {
+    double *smem;
+    uint64_t *full;
+    volatile unsigned int *err;
+    unsigned L;          // the next slot to be requested
+};
+__device__ __forceinline__ double *stage_of(const Ring3 &rg, unsigned slot) { return rg.smem + (slot & 3u) * kStageDoubles; }
+__device__ __forceinline__ bool wait_slot(const Ring3 &rg, unsigned slot) { return mbar_wait(&rg.full[slot & 3u], (slot >> 2) & 1u, rg.err); }
+
+// thread 0: request plane p of the tile for P1 into the next slot
+__device__ __forceinline__ void request_p1(Ring3 &rg, const TileGeo &g, int p, int plast, const CUtensorMap *m_r, const CUtensorMap *m_s) {
+    if (threadIdx.x == 0) {
+        uint64_t *bar = &rg.full[rg.L & 3u];
+        double *st = stage_of(rg, rg.L);
+        if (p < 0 || p > plast) {
+            mbar_arrive(bar);
+        } else {
+            mbar_arrive_expect_tx(bar, m_s ? 2 * kRingBoxBytes : kRingBoxBytes);
+            tma_load_3d(st, m_r, bar, g.x0 - 2, g.y0 - 1, p);
+            if (m_s) tma_load_3d(st + kSPlane, m_s, bar, g.x0 - 2, g.y0 - 1, p);
+        }
     }
+    ++rg.L;
 }
-__device__ __forceinline__ void issue_p2(const Cg3Args &a, const Own3 &o, double *st, int p, int plast, const double *s_rd, const double *r_src,
-                                         bool first, bool with_xr) {
-    if (p < 0 || p > plast) return;
-    const unsigned pz = (unsigned)p * (unsigned)(a.h * a.w);
-    cp16(st + o.so, s_rd + pz + o.j, o.v);
-    if (o.ring) cp8(st + o.rso, s_rd + pz + o.rj, o.ring_in);
-    if (with_xr) {
-        if (!first) cp16(st + kSPlane + o.xo, a.x + pz + o.j, o.v);
-        cp16(st + kSPlane + kTX * kTY + o.xo, r_src + pz + o.j, o.v);
+// thread 0: request plane p for P2 (s' with ring; x and r of the planes the tile evaluates)
+__device__ __forceinline__ void request_p2(Ring3 &rg, const TileGeo &g, int p, int plast, const CUtensorMap *m_s, const CUtensorMap *m_x,
+                                           const CUtensorMap *m_r) {
+    if (threadIdx.x == 0) {
+        uint64_t *bar = &rg.full[rg.L & 3u];
+        double *st = stage_of(rg, rg.L);
+        if (p < 0 || p > plast) {
+            mbar_arrive(bar);
+        } else {
+            const bool xr = p >= g.z0 && p < g.z1;
+            mbar_arrive_expect_tx(bar, kRingBoxBytes + (xr ? (m_x ? 2 : 1) * kIntBoxBytes : 0));
+            tma_load_3d(st, m_s, bar, g.x0 - 2, g.y0 - 1, p);
+            if (xr) {
+                if (m_x) tma_load_3d(st + kSPlane, m_x, bar, g.x0, g.y0, p);
+                tma_load_3d(st + kSPlane + kTX * kTY, m_r, bar, g.x0, g.y0, p);
+            }
+        }
     }
+    ++rg.L;
 }
 // s' = r + beta s (pcg.rs:75-77) of the own pair and the ring cell of a landed plane, in place; returns the own pair
 __device__ __forceinline__ double2 transform_p1(const Own3 &o, double *st, bool ws, double beta) {
@@ -482,45 +512,43 @@ __device__ __forceinline__ double2 transform_p1(const Own3 &o, double *st, bool 
         rv = make_double2(rv.x + beta * sv.x, rv.y + beta * sv.y);
         stv2(st + o.so, rv.x, rv.y);
         if (o.ring) st[o.rso] = st[o.rso] + beta * st[kSPlane + o.rso];
+        fence_async_smem();                            // generic writes now, TMA writes to the same stage four slots later
     }
     return rv;
 }
 
-// P1 over one tile (ws: s' = r + beta s_old, stored to s_cur; else the opening pass on b: max|b| and b.b too).  out: zs, bb, bmax
+// P1 over one tile (m_s: s' = r + beta s_old, stored to s_cur; null: the opening pass on b, max|b| and b.b too).  false: a wait expired
 template <int kMode>
-__device__ __forceinline__ void p1_tile(const Cg3Args &a, const TileGeo &g, double *smem, const double *r_src, const double *s_old, double *s_cur,
-                                        bool ws, double beta, double &zs, double &bb, double &bmax) {
+__device__ __forceinline__ bool p1_tile(const Cg3Args &a, const TileGeo &g, Ring3 &rg, const CUtensorMap *m_r, const CUtensorMap *m_s, double *s_cur,
+                                        double beta, double &zs, double &bb, double &bmax) {
     const Own3 o = own_of(a, g);
+    const bool ws = m_s != nullptr;
     const unsigned plane = (unsigned)(a.h * a.w);
     const int plast = g.z1 < a.d ? g.z1 : a.d - 1;
-    // planes z0-1 .. z0+2 into stages 0 .. 3; plane p lives in stage (p - z0 + 1) & 3
+    const unsigned L0 = rg.L;                          // slot of plane z0 - 1; plane p of the tile lives in slot L0 + (p - z0 + 1)
 #pragma unroll
-    for (int q = 0; q < kStages; ++q) {
-        issue_p1(a, o, smem + q * kStageDoubles, g.z0 - 1 + q, plast, r_src, s_old, ws);
-        cp_commit();
-    }
-    cp_wait<2>();
-    __syncthreads();
+    for (int q = 0; q < kStages; ++q) request_p1(rg, g, g.z0 - 1 + q, plast, m_r, m_s);
+    if (!wait_slot(rg, L0) || !wait_slot(rg, L0 + 1)) return false;
     double2 f = make_double2(0.0, 0.0);
     if (g.z0 > 0) {
-        const double *st = smem;   // plane z0 - 1: only this thread's pair is ever needed, nothing is written back
+        const double *st = stage_of(rg, L0);           // plane z0 - 1: only this thread's pair is ever needed, nothing is written back
         f = ldv2(st + o.so);
         if (ws) {
             const double2 sv = ldv2(st + kSPlane + o.so);
             f = make_double2(f.x + beta * sv.x, f.y + beta * sv.y);
         }
     }
-    double2 c = transform_p1(o, smem + kStageDoubles, ws, beta);
+    double2 c = transform_p1(o, stage_of(rg, L0 + 1), ws, beta);
     unsigned pz = (unsigned)g.z0 * plane;
     for (int z = g.z0; z < g.z1; ++z, pz += plane) {
-        const int q = z - g.z0 + 1;                    // stage index of plane z (mod 4)
-        cp_wait<1>();                                  // plane z + 1 has landed (this thread's copies) ...
-        __syncthreads();                               // ... and everybody's; plane z is transformed; plane z - 1 is no longer read
-        issue_p1(a, o, smem + ((q + 3) & 3) * kStageDoubles, z + 3, plast, r_src, s_old, ws);   // into the stage of plane z - 1
-        cp_commit();
+        const unsigned q = L0 + (unsigned)(z - g.z0 + 1);   // slot of plane z
+        const bool more = z + 1 < a.d;
+        if (more && !wait_slot(rg, q + 1)) return false;    // plane z + 1 has landed
+        __syncthreads();                               // plane z is transformed by everybody; plane z - 1 is no longer read
+        request_p1(rg, g, z + 3, plast, m_r, m_s);     // slot q + 3 = the stage of plane z - 1
         double2 k = make_double2(0.0, 0.0);
-        if (z + 1 < a.d) k = transform_p1(o, smem + ((q + 1) & 3) * kStageDoubles, ws, beta);
-        const double2 zv = lap_pair<kMode>(a, o, smem + (q & 3) * kStageDoubles, z, c, f, k);
+        if (more) k = transform_p1(o, stage_of(rg, q + 1), ws, beta);
+        const double2 zv = lap_pair<kMode>(a, o, stage_of(rg, q), z, c, f, k);
         if (o.v) {
             if (ws) stv2(s_cur + pz + o.j, c.x, c.y);
             zs = zs + zv.x * c.x;
@@ -536,38 +564,35 @@ __device__ __forceinline__ void p1_tile(const Cg3Args &a, const TileGeo &g, doub
         f = c;
         c = k;
     }
-    cp_wait<0>();
+    return true;
 }
 
-// P2 over one tile: z recomputed from s', x += alpha s', r -= alpha z, r.r and max|r|
+// P2 over one tile: z recomputed from s', x += alpha s', r -= alpha z, r.r and max|r|.  m_x null: the first pass (x = 0)
 template <int kMode>
-__device__ __forceinline__ void p2_tile(const Cg3Args &a, const TileGeo &g, double *smem, const double *s_rd, const double *r_src, bool first,
-                                        double alpha, double &rr, double &rmax) {
+__device__ __forceinline__ bool p2_tile(const Cg3Args &a, const TileGeo &g, Ring3 &rg, const CUtensorMap *m_s, const CUtensorMap *m_x,
+                                        const CUtensorMap *m_r, double alpha, double &rr, double &rmax) {
     const Own3 o = own_of(a, g);
+    const bool first = m_x == nullptr;
     const unsigned plane = (unsigned)(a.h * a.w);
     const double nalpha = -alpha;
     const int plast = g.z1 < a.d ? g.z1 : a.d - 1;
+    const unsigned L0 = rg.L;
 #pragma unroll
-    for (int q = 0; q < kStages; ++q) {
-        const int p = g.z0 - 1 + q;
-        issue_p2(a, o, smem + q * kStageDoubles, p, plast, s_rd, r_src, first, p >= g.z0 && p < g.z1);
-        cp_commit();
-    }
-    cp_wait<2>();
-    __syncthreads();
+    for (int q = 0; q < kStages; ++q) request_p2(rg, g, g.z0 - 1 + q, plast, m_s, m_x, m_r);
+    if (!wait_slot(rg, L0) || !wait_slot(rg, L0 + 1)) return false;
     double2 f = make_double2(0.0, 0.0);
-    if (g.z0 > 0) f = ldv2(smem + o.so);
-    double2 c = ldv2(smem + kStageDoubles + o.so);
+    if (g.z0 > 0) f = ldv2(stage_of(rg, L0) + o.so);
+    double2 c = ldv2(stage_of(rg, L0 + 1) + o.so);
     unsigned pz = (unsigned)g.z0 * plane;
     for (int z = g.z0; z < g.z1; ++z, pz += plane) {
-        const int q = z - g.z0 + 1;
-        cp_wait<1>();
+        const unsigned q = L0 + (unsigned)(z - g.z0 + 1);
+        const bool more = z + 1 < a.d;
+        if (more && !wait_slot(rg, q + 1)) return false;
         __syncthreads();
-        issue_p2(a, o, smem + ((q + 3) & 3) * kStageDoubles, z + 3, plast, s_rd, r_src, first, z + 3 < g.z1);
-        cp_commit();
-        const double *st = smem + (q & 3) * kStageDoubles;
+        request_p2(rg, g, z + 3, plast, m_s, m_x, m_r);
+        const double *st = stage_of(rg, q);
         double2 k = make_double2(0.0, 0.0);
-        if (z + 1 < a.d) k = ldv2(smem + ((q + 1) & 3) * kStageDoubles + o.so);
+        if (more) k = ldv2(stage_of(rg, q + 1) + o.so);
         const double2 zv = lap_pair<kMode>(a, o, st, z, c, f, k);
         if (o.v) {
             double2 xv = make_double2(0.0, 0.0);
@@ -586,14 +611,15 @@ __device__ __forceinline__ void p2_tile(const Cg3Args &a, const TileGeo &g, doub
         f = c;
         c = k;
     }
-    cp_wait<0>();
+    return true;
 }
 
-__global__ void __launch_bounds__(kTileThreads, 2) k3_cg_tile(Cg3TileArgs ta) {
-    extern __shared__ __align__(16) double smem[];
+__global__ void __launch_bounds__(kTileThreads, 2) k3_cg_tile(const __grid_constant__ Cg3TileArgs ta) {
+    extern __shared__ unsigned char smem_raw[];
     __shared__ double scratch[32];
     __shared__ int s_flag;
     __shared__ int s_next[2];
+    __shared__ __align__(8) uint64_t full[kStages];
     const Cg3Args &a = ta.c;
     const int G = gridDim.x;
     const int ntiles = a.tiles_x * a.tiles_y * a.tiles_z;   // >= G
@@ -603,23 +629,36 @@ __global__ void __launch_bounds__(kTileThreads, 2) k3_cg_tile(Cg3TileArgs ta) {
     int it = 0, applies = 0;
     bool converged = false;
     double *s_cur = a.s0, *s_old = a.s1;
+    const CUtensorMap *ms_cur = &ta.mr_s0, *ms_old = &ta.mr_s1;
     const size_t n = (size_t)a.d * a.h * a.w;
+    Ring3 rg;
+    rg.smem = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    rg.full = full;
+    rg.err = &a.ctl->error;
+    rg.L = 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        pano_sm100::fence_mbar_init();
+    }
+    __syncthreads();
 
     for (it = 0; it < a.max_iter; ++it) {
         const bool first = it == 0;
-        const double *r_src = first ? a.b : a.r;
         // ---------------------------------------------------------------- P1
         {
             const unsigned long long base = phase * (unsigned long long)ntiles;
+            const CUtensorMap *m_r = first ? &ta.mr_b : &ta.mr_r, *m_s = first ? nullptr : ms_old;
             int t = blockIdx.x;
             for (int i = 0; t < ntiles; ++i) {
                 if (threadIdx.x == 0) s_next[i & 1] = G + (int)(atomicAdd(ta.claim, 1ULL) - base);   // claimed a tile ahead
                 const TileGeo g = tile_geo(a, t);
                 double zs = 0, bb = 0, bm = 0;
-                if (g.mode == 0) p1_tile<0>(a, g, smem, r_src, s_old, s_cur, !first, beta, zs, bb, bm);
-                else if (g.mode == 1) p1_tile<1>(a, g, smem, r_src, s_old, s_cur, !first, beta, zs, bb, bm);
-                else p1_tile<2>(a, g, smem, r_src, s_old, s_cur, !first, beta, zs, bb, bm);
-                const double v = block_sum(zs, scratch);     // (its barriers also fence the stages against the next tile's copies)
+                bool ok;
+                if (g.mode == 0) ok = p1_tile<0>(a, g, rg, m_r, m_s, s_cur, beta, zs, bb, bm);
+                else if (g.mode == 1) ok = p1_tile<1>(a, g, rg, m_r, m_s, s_cur, beta, zs, bb, bm);
+                else ok = p1_tile<2>(a, g, rg, m_r, m_s, s_cur, beta, zs, bb, bm);
+                if (!ok) return;
+                const double v = block_sum(zs, scratch);     // (its barriers also fence the stages against the next tile's requests)
                 if (threadIdx.x == 0) pA[t] = v;
                 if (first) {
                     const double v2 = block_sum(bb, scratch), v3 = block_max(bm, scratch);
@@ -654,16 +693,18 @@ __global__ void __launch_bounds__(kTileThreads, 2) k3_cg_tile(Cg3TileArgs ta) {
         alpha = sigma / zs_all;                                  // pcg.rs:53
         // ---------------------------------------------------------------- P2
         {
-            const double *s_rd = first ? a.b : s_cur;
+            const CUtensorMap *m_s = first ? &ta.mr_b : ms_cur, *m_x = first ? nullptr : &ta.mi_x, *m_r = first ? &ta.mi_b : &ta.mi_r;
             const unsigned long long base = phase * (unsigned long long)ntiles;
             int t = blockIdx.x;
             for (int i = 0; t < ntiles; ++i) {
                 if (threadIdx.x == 0) s_next[i & 1] = G + (int)(atomicAdd(ta.claim, 1ULL) - base);
                 const TileGeo g = tile_geo(a, t);
                 double rr = 0, rm = 0;
-                if (g.mode == 0) p2_tile<0>(a, g, smem, s_rd, r_src, first, alpha, rr, rm);
-                else if (g.mode == 1) p2_tile<1>(a, g, smem, s_rd, r_src, first, alpha, rr, rm);
-                else p2_tile<2>(a, g, smem, s_rd, r_src, first, alpha, rr, rm);
+                bool ok;
+                if (g.mode == 0) ok = p2_tile<0>(a, g, rg, m_s, m_x, m_r, alpha, rr, rm);
+                else if (g.mode == 1) ok = p2_tile<1>(a, g, rg, m_s, m_x, m_r, alpha, rr, rm);
+                else ok = p2_tile<2>(a, g, rg, m_s, m_x, m_r, alpha, rr, rm);
+                if (!ok) return;
                 const double v = block_sum(rr, scratch), v2 = block_max(rm, scratch);
                 if (threadIdx.x == 0) {
                     pD[t] = v;
@@ -686,6 +727,9 @@ __global__ void __launch_bounds__(kTileThreads, 2) k3_cg_tile(Cg3TileArgs ta) {
         double *tmp = s_cur;
         s_cur = s_old;
         s_old = tmp;
+        const CUtensorMap *tm = ms_cur;
+        ms_cur = ms_old;
+        ms_old = tm;
     }
     const double *s_fin = converged ? s_cur : s_old;
     if (a.max_iter > 0 && (!converged || s_fin != a.s0)) {       // what the reference leaves in `search` (pcg.rs:72-77), as k3_cg
@@ -700,6 +744,32 @@ __global__ void __launch_bounds__(kTileThreads, 2) k3_cg_tile(Cg3TileArgs ta) {
         a.ctl->final_residual = rmax;
         a.ctl->rhs_max = bmax;
     }
+}
+
+// (w, h, d) f64 tensor, boxes of box_w x box_h x 1 elements
+int make_tensor_map_3d(CUtensorMap *map, const void *base, uint64_t w, uint64_t h, uint64_t d, uint32_t box_w, uint32_t box_h) {
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        PANO_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) PANO_FAIL(PANO_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        encode = (EncodeFn)fn;
+    }
+    const cuuint64_t dims[3] = {w, h, d};
+    const cuuint64_t strides[2] = {w * 8, w * h * 8};
+    const cuuint32_t box[3] = {box_w, box_h, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS)
+        PANO_FAIL(PANO_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d (%llu x %llu x %llu, box %u x %u)", (int)rc,
+                  (unsigned long long)d, (unsigned long long)h, (unsigned long long)w, box_w, box_h);
+    return PANO_OK;
 }
 
 // ---------------------------------------------------------------------------------- host side
@@ -839,7 +909,17 @@ int cg3_solve_raw(pano_ctx *ctx, double *x, const double *b, double *r, double *
     if (tiled) {
         if (!ctx->d_claim) PANO_CUDA(cudaMalloc((void **)&ctx->d_claim, 4 * sizeof(unsigned long long)));
         PANO_CUDA(cudaMemsetAsync(ctx->d_claim, 0, 4 * sizeof(unsigned long long), ctx->stream));
-        Cg3TileArgs ta{a, ctx->d_claim};
+        Cg3TileArgs ta;
+        memset(&ta, 0, sizeof(ta));
+        ta.c = a;
+        ta.claim = ctx->d_claim;
+        PANO_TRY(make_tensor_map_3d(&ta.mr_b, b, w, h, d, kSW, kTY + 2));
+        PANO_TRY(make_tensor_map_3d(&ta.mr_r, r, w, h, d, kSW, kTY + 2));
+        PANO_TRY(make_tensor_map_3d(&ta.mr_s0, s0, w, h, d, kSW, kTY + 2));
+        PANO_TRY(make_tensor_map_3d(&ta.mr_s1, s1, w, h, d, kSW, kTY + 2));
+        PANO_TRY(make_tensor_map_3d(&ta.mi_x, x, w, h, d, kTX, kTY));
+        PANO_TRY(make_tensor_map_3d(&ta.mi_r, r, w, h, d, kTX, kTY));
+        PANO_TRY(make_tensor_map_3d(&ta.mi_b, b, w, h, d, kTX, kTY));
         void *kargs[] = {(void *)&ta};
         PANO_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)G), dim3(nthreads), kargs, dyn_smem, ctx->stream));
     } else {
