@@ -685,7 +685,7 @@ def run_ours(args, rank, world, local_rank):
             extra["grid3d_256"] = {"value": c3 / (median(lp3) * 1e-3) / 1e6, "unit": UNIT, "median_ms_per_step": median(lp3), "steps": 10, "warmup": 21,
                                    "grid": [n3, n3, n3], "cg_iterations_per_step": i3b["applies"], "cg_applies_per_timed_step": ap3,
                                    "cg_info_before_timing": i3, "kernels": k3,
-                                   "kernel": "k3_cg_tile (persistent 7-point CG: cp.async plane ring, dynamic tiles)",
+                                   "kernel": "k3_cg_tile (persistent 7-point CG: ring of 3-D TMA boxes, dynamic tiles)",
                                    "note": "3-D smoke plume, 7-point Laplacian, identity preconditioner, converging solves (threshold 0.1); parity "
                                            "unpinned: the reference holds only the struct Grid3d and the unused trilinear (DESIGN.md 5c)"}
             del s3

@@ -457,9 +457,9 @@ __device__ __forceinline__ double2 lap_pair(const Cg3Args &a, const Own3 &o, con
     return out;
 }
 
-// The stage ring of one CTA: slot number L (counted over the CTA's whole life) uses stage L & 3, and its mbarrier completes phase
-// (L >> 2) & 1.  EVERY slot completes its phase -- with the bytes of the boxes it requested, or at once if its plane lies outside
-// [0, plast] -- so the parity bookkeeping never depends on the geometry.
+// The stage ring of one CTA: request number L (counted over the CTA's whole life) uses stage L & 3, and its mbarrier completes
+// phase (L >> 2) & 1.  Only planes inside the grid are requested, and every requested plane is waited for by every thread before
+// its stage comes round again, so no phase of a barrier ever completes unobserved.
 struct Ring3 {
     double *smem;
     uint64_t *full;
@@ -469,37 +469,28 @@ struct Ring3 {
 __device__ __forceinline__ double *stage_of(const Ring3 &rg, unsigned slot) { return rg.smem + (slot & 3u) * kStageDoubles; }
 __device__ __forceinline__ bool wait_slot(const Ring3 &rg, unsigned slot) { return mbar_wait(&rg.full[slot & 3u], (slot >> 2) & 1u, rg.err); }
 
-// thread 0: request plane p of the tile for P1 into the next slot
-__device__ __forceinline__ void request_p1(Ring3 &rg, const TileGeo &g, int p, int plast, const CUtensorMap *m_r, const CUtensorMap *m_s) {
+// thread 0: request plane p (inside the grid) of the tile for P1 into the next slot
+__device__ __forceinline__ void request_p1(Ring3 &rg, const TileGeo &g, int p, const CUtensorMap *m_r, const CUtensorMap *m_s) {
     if (threadIdx.x == 0) {
         uint64_t *bar = &rg.full[rg.L & 3u];
         double *st = stage_of(rg, rg.L);
-        if (p < 0 || p > plast) {
-            mbar_arrive(bar);
-        } else {
-            mbar_arrive_expect_tx(bar, m_s ? 2 * kRingBoxBytes : kRingBoxBytes);
-            tma_load_3d(st, m_r, bar, g.x0 - 2, g.y0 - 1, p);
-            if (m_s) tma_load_3d(st + kSPlane, m_s, bar, g.x0 - 2, g.y0 - 1, p);
-        }
+        mbar_arrive_expect_tx(bar, m_s ? 2 * kRingBoxBytes : kRingBoxBytes);
+        tma_load_3d(st, m_r, bar, g.x0 - 2, g.y0 - 1, p);
+        if (m_s) tma_load_3d(st + kSPlane, m_s, bar, g.x0 - 2, g.y0 - 1, p);
     }
     ++rg.L;
 }
 // thread 0: request plane p for P2 (s' with ring; x and r of the planes the tile evaluates)
-__device__ __forceinline__ void request_p2(Ring3 &rg, const TileGeo &g, int p, int plast, const CUtensorMap *m_s, const CUtensorMap *m_x,
-                                           const CUtensorMap *m_r) {
+__device__ __forceinline__ void request_p2(Ring3 &rg, const TileGeo &g, int p, const CUtensorMap *m_s, const CUtensorMap *m_x, const CUtensorMap *m_r) {
     if (threadIdx.x == 0) {
         uint64_t *bar = &rg.full[rg.L & 3u];
         double *st = stage_of(rg, rg.L);
-        if (p < 0 || p > plast) {
-            mbar_arrive(bar);
-        } else {
-            const bool xr = p >= g.z0 && p < g.z1;
-            mbar_arrive_expect_tx(bar, kRingBoxBytes + (xr ? (m_x ? 2 : 1) * kIntBoxBytes : 0));
-            tma_load_3d(st, m_s, bar, g.x0 - 2, g.y0 - 1, p);
-            if (xr) {
-                if (m_x) tma_load_3d(st + kSPlane, m_x, bar, g.x0, g.y0, p);
-                tma_load_3d(st + kSPlane + kTX * kTY, m_r, bar, g.x0, g.y0, p);
-            }
+        const bool xr = p >= g.z0 && p < g.z1;
+        mbar_arrive_expect_tx(bar, kRingBoxBytes + (xr ? (m_x ? 2 : 1) * kIntBoxBytes : 0));
+        tma_load_3d(st, m_s, bar, g.x0 - 2, g.y0 - 1, p);
+        if (xr) {
+            if (m_x) tma_load_3d(st + kSPlane, m_x, bar, g.x0, g.y0, p);
+            tma_load_3d(st + kSPlane + kTX * kTY, m_r, bar, g.x0, g.y0, p);
         }
     }
     ++rg.L;
@@ -524,28 +515,28 @@ __device__ __forceinline__ bool p1_tile(const Cg3Args &a, const TileGeo &g, Ring
     const Own3 o = own_of(a, g);
     const bool ws = m_s != nullptr;
     const unsigned plane = (unsigned)(a.h * a.w);
-    const int plast = g.z1 < a.d ? g.z1 : a.d - 1;
-    const unsigned L0 = rg.L;                          // slot of plane z0 - 1; plane p of the tile lives in slot L0 + (p - z0 + 1)
-#pragma unroll
-    for (int q = 0; q < kStages; ++q) request_p1(rg, g, g.z0 - 1 + q, plast, m_r, m_s);
-    if (!wait_slot(rg, L0) || !wait_slot(rg, L0 + 1)) return false;
+    const int plast = g.z1 < a.d ? g.z1 : a.d - 1, pfirst = g.z0 > 0 ? g.z0 - 1 : 0;
+    const unsigned L0 = rg.L - (unsigned)pfirst;       // plane p of the tile lives in slot L0 + p
+    for (int pq = pfirst; pq <= g.z0 + 2 && pq <= plast; ++pq) request_p1(rg, g, pq, m_r, m_s);
     double2 f = make_double2(0.0, 0.0);
     if (g.z0 > 0) {
-        const double *st = stage_of(rg, L0);           // plane z0 - 1: only this thread's pair is ever needed, nothing is written back
+        if (!wait_slot(rg, L0 + g.z0 - 1)) return false;
+        const double *st = stage_of(rg, L0 + g.z0 - 1);   // plane z0 - 1: only this thread's pair is ever needed, nothing is written back
         f = ldv2(st + o.so);
         if (ws) {
             const double2 sv = ldv2(st + kSPlane + o.so);
             f = make_double2(f.x + beta * sv.x, f.y + beta * sv.y);
         }
     }
-    double2 c = transform_p1(o, stage_of(rg, L0 + 1), ws, beta);
+    if (!wait_slot(rg, L0 + g.z0)) return false;
+    double2 c = transform_p1(o, stage_of(rg, L0 + g.z0), ws, beta);
     unsigned pz = (unsigned)g.z0 * plane;
     for (int z = g.z0; z < g.z1; ++z, pz += plane) {
-        const unsigned q = L0 + (unsigned)(z - g.z0 + 1);   // slot of plane z
+        const unsigned q = L0 + (unsigned)z;           // slot of plane z
         const bool more = z + 1 < a.d;
         if (more && !wait_slot(rg, q + 1)) return false;    // plane z + 1 has landed
         __syncthreads();                               // plane z is transformed by everybody; plane z - 1 is no longer read
-        request_p1(rg, g, z + 3, plast, m_r, m_s);     // slot q + 3 = the stage of plane z - 1
+        if (z + 3 <= plast) request_p1(rg, g, z + 3, m_r, m_s);   // slot q + 3 = the stage of plane z - 1
         double2 k = make_double2(0.0, 0.0);
         if (more) k = transform_p1(o, stage_of(rg, q + 1), ws, beta);
         const double2 zv = lap_pair<kMode>(a, o, stage_of(rg, q), z, c, f, k);
@@ -575,21 +566,23 @@ __device__ __forceinline__ bool p2_tile(const Cg3Args &a, const TileGeo &g, Ring
     const bool first = m_x == nullptr;
     const unsigned plane = (unsigned)(a.h * a.w);
     const double nalpha = -alpha;
-    const int plast = g.z1 < a.d ? g.z1 : a.d - 1;
-    const unsigned L0 = rg.L;
-#pragma unroll
-    for (int q = 0; q < kStages; ++q) request_p2(rg, g, g.z0 - 1 + q, plast, m_s, m_x, m_r);
-    if (!wait_slot(rg, L0) || !wait_slot(rg, L0 + 1)) return false;
+    const int plast = g.z1 < a.d ? g.z1 : a.d - 1, pfirst = g.z0 > 0 ? g.z0 - 1 : 0;
+    const unsigned L0 = rg.L - (unsigned)pfirst;
+    for (int pq = pfirst; pq <= g.z0 + 2 && pq <= plast; ++pq) request_p2(rg, g, pq, m_s, m_x, m_r);
     double2 f = make_double2(0.0, 0.0);
-    if (g.z0 > 0) f = ldv2(stage_of(rg, L0) + o.so);
-    double2 c = ldv2(stage_of(rg, L0 + 1) + o.so);
+    if (g.z0 > 0) {
+        if (!wait_slot(rg, L0 + g.z0 - 1)) return false;
+        f = ldv2(stage_of(rg, L0 + g.z0 - 1) + o.so);
+    }
+    if (!wait_slot(rg, L0 + g.z0)) return false;
+    double2 c = ldv2(stage_of(rg, L0 + g.z0) + o.so);
     unsigned pz = (unsigned)g.z0 * plane;
     for (int z = g.z0; z < g.z1; ++z, pz += plane) {
-        const unsigned q = L0 + (unsigned)(z - g.z0 + 1);
+        const unsigned q = L0 + (unsigned)z;
         const bool more = z + 1 < a.d;
         if (more && !wait_slot(rg, q + 1)) return false;
         __syncthreads();
-        request_p2(rg, g, z + 3, plast, m_s, m_x, m_r);
+        if (z + 3 <= plast) request_p2(rg, g, z + 3, m_s, m_x, m_r);
         const double *st = stage_of(rg, q);
         double2 k = make_double2(0.0, 0.0);
         if (more) k = ldv2(stage_of(rg, q + 1) + o.so);
