@@ -10,9 +10,10 @@
 // Kernels (all HBM-bound; algorithmic bytes per cell in f64):
 //   k3_advect        q, vz, vy, vx advected in ONE pass                      64 B   (4 reads + 4 writes)
 //   k3_neg_div       hodge -> box zero -> d2 -> negate fused, z-marching      32 B
-//   k3_cg            the WHOLE pcg.rs:14-82 loop, one persistent cooperative kernel, two phases per
-//                    iteration as pano_cg.cu, columns marching along z with s'[z-1], s'[z], s'[z+1] in
-//                    registers                                                64 B per iteration
+//   k3_cg_tile       the WHOLE pcg.rs:14-82 loop, one persistent cooperative kernel, two phases per iteration as
+//                    pano_cg.cu; 64 x 16 x zc tiles whose planes arrive as 3-D TMA boxes through a four-stage mbarrier
+//                    ring, s'[z-1], s'[z], s'[z+1] in registers (even widths)                 64 B per iteration
+//   k3_cg            the same loop, one column per thread, neighbours through L1 (any shape)
 //   k3_project       gradient + axpy + walls fused, z-marching                56 B   (p, 3 faces read; 3 faces written)
 #include "pano_cell_math.h"
 #include "pano_gridsync.cuh"
