@@ -343,6 +343,9 @@ PANO_API int pano_pcg3_solve(int precond, pano_field *x, const pano_field *b, in
 PANO_API int pano_fluid3_step(const pano_step3_params *params, pano_field *density, pano_field *vel, pano_field *pressure,
                               pano_field *temp, pano_field *vel_temp, pano_field *residual, pano_field *auxiliary,
                               pano_field *search, pano_pcg_info *info);
+/* pano_fluid_step_host on a Grid3d: host density (d*h*w) and vel (flat face layout) in and out, the pressure unless NULL */
+PANO_API int pano_fluid3_step_host(pano_ctx *ctx, const pano_step3_params *params, size_t d, size_t h, size_t w, double *density,
+                                   double *vel, double *pressure, pano_pcg_info *info);
 
 #ifdef __cplusplus
 }

@@ -141,6 +141,7 @@ _SIGS = {
     "pano_project3": (C.c_int, [_P, _P, C.c_double]),
     "pano_pcg3_solve": (C.c_int, [C.c_int, _P, _P, C.c_int32, C.c_double, _P, _P, _P, C.c_double, Box, C.POINTER(PcgInfo)]),
     "pano_fluid3_step": (C.c_int, [C.POINTER(Step3Params), _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(PcgInfo)]),
+    "pano_fluid3_step_host": (C.c_int, [_P, C.POINTER(Step3Params), C.c_size_t, C.c_size_t, C.c_size_t, _P, _P, _P, C.POINTER(PcgInfo)]),
 }
 IPC_HANDLE_BYTES = 64
 

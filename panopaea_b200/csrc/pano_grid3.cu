@@ -1105,8 +1105,11 @@ int pano_pcg3_solve(int precond, pano_field *x, const pano_field *b, int32_t max
                          x->dep, x->h, x->w, max_iterations, threshold, timestep, obstacle, info);
 }
 
-int pano_fluid3_step(const pano_step3_params *params, pano_field *density, pano_field *vel, pano_field *pressure, pano_field *temp,
-                     pano_field *vel_temp, pano_field *residual, pano_field *auxiliary, pano_field *search, pano_pcg_info *info) {
+// after_advect (nullable) runs once the new density is final: the host-buffer entry point starts its download there
+typedef int (*Step3Hook)(pano_ctx *ctx, void *user);
+static int fluid3_step_impl(const pano_step3_params *params, pano_field *density, pano_field *vel, pano_field *pressure, pano_field *temp,
+                            pano_field *vel_temp, pano_field *residual, pano_field *auxiliary, pano_field *search, pano_pcg_info *info,
+                            Step3Hook after_advect, void *user) {
     if (!params) PANO_FAIL(PANO_ERR_INVALID, "pano_fluid3_step: null params");
     const pano_field *c3[] = {density, pressure, temp, residual, auxiliary, search};
     const char *n3[] = {"density", "pressure", "temp", "residual", "auxiliary", "search"};
@@ -1139,6 +1142,7 @@ int pano_fluid3_step(const pano_step3_params *params, pano_field *density, pano_
     PANO_TRY(advect3_launch(ctx, true, true, (double *)temp->d, vel_temp, (const double *)density->d, vel, vel, dt));   // :59-60
     PANO_TRY(pano_field_swap(density, temp));                                                          // :62-63
     PANO_TRY(pano_field_swap(vel, vel_temp));
+    if (after_advect) PANO_TRY(after_advect(ctx, user));
     PANO_TRY(pano_phase_mark(ctx, 2));
     PANO_TRY(neg_div3_launch(ctx, (double *)temp->d, vel, params->obstacle));                           // :69-83
     PANO_TRY(pano_phase_mark(ctx, 3));
@@ -1159,6 +1163,79 @@ int pano_fluid3_step(const pano_step3_params *params, pano_field *density, pano_
         PANO_CUDA(cudaStreamSynchronize(ctx->stream));
         PANO_TRY(pano_check_device_error(ctx, "pano_fluid3_step"));
         *info = pano_pcg_info{ctx->h_cg->iterations, ctx->h_cg->applies, ctx->h_cg->final_residual, ctx->h_cg->rhs_max};
+    }
+    return PANO_OK;
+}
+
+int pano_fluid3_step(const pano_step3_params *params, pano_field *density, pano_field *vel, pano_field *pressure, pano_field *temp,
+                     pano_field *vel_temp, pano_field *residual, pano_field *auxiliary, pano_field *search, pano_pcg_info *info) {
+    return fluid3_step_impl(params, density, vel, pressure, temp, vel_temp, residual, auxiliary, search, info, nullptr, nullptr);
+}
+
+struct Host3Copy {
+    PanoWorkspace *ws;
+    double *density_host;
+    size_t bytes;
+};
+static int start_density3_download(pano_ctx *ctx, void *user) {
+    Host3Copy *c = static_cast<Host3Copy *>(user);
+    PANO_CUDA(cudaEventRecord(ctx->ev_advect, ctx->stream));
+    PANO_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_advect, 0));
+    PANO_CUDA(cudaMemcpyAsync(c->density_host, c->ws->density->d, c->bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    PANO_CUDA(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+    return PANO_OK;
+}
+static int get_workspace3(pano_ctx *ctx, size_t d, size_t h, size_t w, PanoWorkspace **out) {
+    const auto key = std::make_pair(d, std::make_pair(h, w));
+    auto it = ctx->workspaces3.find(key);
+    if (it != ctx->workspaces3.end()) {
+        *out = it->second;
+        return PANO_OK;
+    }
+    PanoWorkspace *ws = new PanoWorkspace();
+    ws->dep = d; ws->h = h; ws->w = w;
+    struct { pano_field **f; int kind; } want[] = {
+        {&ws->density, PANO_CELL3}, {&ws->vel, PANO_FACE3}, {&ws->pressure, PANO_CELL3}, {&ws->temp, PANO_CELL3},
+        {&ws->vel_temp, PANO_FACE3}, {&ws->residual, PANO_CELL3}, {&ws->auxiliary, PANO_CELL3}, {&ws->search, PANO_CELL3}};
+    for (auto &wf : want) {          // cached only when complete, as the 2-D workspace
+        const int rc = pano_field3_new(ctx, wf.kind, d, h, w, wf.f);
+        if (rc != PANO_OK) {
+            for (auto &g : want) pano_field_free(*g.f);
+            delete ws;
+            return rc;
+        }
+    }
+    ctx->workspaces3[key] = ws;
+    *out = ws;
+    return PANO_OK;
+}
+
+int pano_fluid3_step_host(pano_ctx *ctx, const pano_step3_params *params, size_t d, size_t h, size_t w, double *density, double *vel,
+                          double *pressure, pano_pcg_info *info) {
+    if (!ctx || !params || !density || !vel) PANO_FAIL(PANO_ERR_INVALID, "pano_fluid3_step_host: null argument");
+    PANO_TRY(pano_activate(ctx));
+    PanoWorkspace *ws = nullptr;
+    PANO_TRY(get_workspace3(ctx, d, h, w, &ws));
+    const size_t nc = ws->density->n * sizeof(double), nf = ws->vel->n * sizeof(double);
+    PANO_CUDA(cudaMemcpyAsync(ws->density->d, density, nc, cudaMemcpyHostToDevice, ctx->stream));
+    PANO_CUDA(cudaMemcpyAsync(ws->vel->d, vel, nf, cudaMemcpyHostToDevice, ctx->stream));
+    Host3Copy hook{ws, density, nc};
+    PANO_TRY(fluid3_step_impl(params, ws->density, ws->vel, ws->pressure, ws->temp, ws->vel_temp, ws->residual, ws->auxiliary, ws->search,
+                              nullptr, start_density3_download, &hook));      // the density goes home under the solve
+    PANO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+    PANO_CUDA(cudaMemcpyAsync(vel, ws->vel->d, nf, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pressure) PANO_CUDA(cudaMemcpyAsync(pressure, ws->pressure->d, nc, cudaMemcpyDeviceToHost, ctx->stream));
+    PANO_CUDA(cudaMemcpyAsync(ctx->h_cg, ctx->d_cg, sizeof(PanoCgControl), cudaMemcpyDeviceToHost, ctx->stream));
+    PANO_CUDA(cudaStreamSynchronize(ctx->stream));
+    PANO_TRY(pano_check_device_error(ctx, "pano_fluid3_step_host"));
+    if (info) {
+        if (params->max_iterations <= 0) {
+            double bmax = 0.0;
+            PANO_TRY(pano_norm_max_raw(ctx, PANO_F64, ws->temp->d, ws->temp->n, &bmax));
+            *info = pano_pcg_info{bmax < params->threshold ? -1 : 0, 0, bmax, bmax};
+        } else {
+            *info = pano_pcg_info{ctx->h_cg->iterations, ctx->h_cg->applies, ctx->h_cg->final_residual, ctx->h_cg->rhs_max};
+        }
     }
     return PANO_OK;
 }

@@ -57,7 +57,13 @@ struct PanoCgControl {
 
 constexpr size_t kPanoInboxBytes = (size_t)2 * 192 * 3 * 192 * 16;   // = pano_sm100::kInboxUnits * sizeof(ReduceUnit)
 
-struct PanoWorkspace;   // cached scratch of pano_fluid_step_host
+struct pano_field;
+// cached device fields of pano_fluid_step_host (per (h, w)) and pano_fluid3_step_host (per (d, h, w))
+struct PanoWorkspace {
+    size_t dep = 0, h = 0, w = 0;
+    pano_field *density = nullptr, *vel = nullptr, *pressure = nullptr;
+    pano_field *temp = nullptr, *vel_temp = nullptr, *residual = nullptr, *auxiliary = nullptr, *search = nullptr;
+};
 struct pano_mg;         // multigrid preconditioner (pano_mg.cu)
 
 struct pano_ctx {
@@ -103,6 +109,7 @@ struct pano_ctx {
     int64_t phase_steps = 0;
     std::map<std::string, int64_t> options;
     std::map<std::pair<size_t, size_t>, PanoWorkspace *> workspaces;
+    std::map<std::pair<size_t, std::pair<size_t, size_t>>, PanoWorkspace *> workspaces3;
     std::vector<pano_mg *> mg_cache;             // preconditioners built on this context (pano_mg_create)
     // handles may be released in any order (garbage-collected hosts): fields keep the context alive
     int64_t live_fields = 0;

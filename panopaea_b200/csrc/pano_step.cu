@@ -19,12 +19,6 @@ int pano_project_launch(pano_ctx *ctx, int dtype, void *vel, const void *p, size
 int pano_cg_solve_raw(pano_ctx *ctx, int dtype, void *x, const void *b, void *r, void *s0, void *s1, size_t h, size_t w,
                       int max_iterations, double threshold, double timestep, pano_rect obstacle, pano_pcg_info *info);
 
-struct PanoWorkspace {
-    size_t h = 0, w = 0;
-    pano_field *density = nullptr, *vel = nullptr, *pressure = nullptr;
-    pano_field *temp = nullptr, *vel_temp = nullptr, *residual = nullptr, *auxiliary = nullptr, *search = nullptr;
-};
-
 void pano_workspace_free_all(pano_ctx *ctx) {
     for (auto &kv : ctx->workspaces) {
         PanoWorkspace *ws = kv.second;
@@ -33,6 +27,13 @@ void pano_workspace_free_all(pano_ctx *ctx) {
         delete ws;
     }
     ctx->workspaces.clear();
+    for (auto &kv : ctx->workspaces3) {
+        PanoWorkspace *ws = kv.second;
+        pano_field *fs[] = {ws->density, ws->vel, ws->pressure, ws->temp, ws->vel_temp, ws->residual, ws->auxiliary, ws->search};
+        for (pano_field *f : fs) pano_field_free(f);
+        delete ws;
+    }
+    ctx->workspaces3.clear();
 }
 
 static int get_workspace(pano_ctx *ctx, size_t h, size_t w, PanoWorkspace **out) {

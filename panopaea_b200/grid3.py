@@ -158,3 +158,14 @@ class DecFluid3:
                                        self.temp.handle, self.vel_temp.handle, self.residual.handle, self.auxiliary.handle,
                                        self.search.handle, C.byref(info) if want_info else None))
         return info.as_dict() if want_info else None
+
+
+def fluid3_step_host(ctx, params, d, h, w, density, vel, pressure=None, want_info=True):
+    """pano_fluid3_step_host: the host owns the fields (contiguous float64 arrays: density (d,h,w), vel flat faces, optional pressure);
+    they are updated in place.  Use pinned buffers (pano_host_alloc) for speed; any contiguous array works."""
+    info = PcgInfo()
+    check(_lib.load().pano_fluid3_step_host(ctx.handle, C.byref(params), d, h, w, density.ctypes.data_as(C.c_void_p),
+                                            vel.ctypes.data_as(C.c_void_p),
+                                            pressure.ctypes.data_as(C.c_void_p) if pressure is not None else None,
+                                            C.byref(info) if want_info else None))
+    return info.as_dict() if want_info else None

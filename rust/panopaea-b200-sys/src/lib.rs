@@ -231,6 +231,8 @@ extern "C" {
                             pressure: *mut pano_field, temp: *mut pano_field, vel_temp: *mut pano_field,
                             residual: *mut pano_field, auxiliary: *mut pano_field, search: *mut pano_field,
                             info: *mut pano_pcg_info) -> c_int;
+    pub fn pano_fluid3_step_host(ctx: *mut pano_ctx, params: *const pano_step3_params, d: usize, h: usize, w: usize, density: *mut f64,
+                                 vel: *mut f64, pressure: *mut f64, info: *mut pano_pcg_info) -> c_int;
 }
 
 /// The reference panics on shape mismatches (`ndarray` `Zip`/`assign`) and on `unimplemented!()`; so does the shim.

@@ -209,3 +209,23 @@ def test_step3_256_vs_oracle():
         assert _close(sim.vel.view_linear(), ref.field("vel"), 1e-5)
         assert g["final_residual"] == pytest.approx(o["final_residual"], rel=1e-5)
     ref.close()
+
+
+def test_fluid3_step_host_matches_resident_step():
+    """pano_fluid3_step_host (host arrays in and out, density download under the solve) against the device-resident step: same bits."""
+    from panopaea_b200 import grid3
+    from tests import gpu_util as U
+    n = 64
+    prm = grid3.smoke_params(n)
+    sim = grid3.DecFluid3(**prm, ctx=U.ctx())
+    d = np.zeros((n, n, n))
+    v = np.zeros(sim.grid.num_faces())
+    p = np.zeros((n, n, n))
+    for i in range(5):
+        want = sim.step()
+        got = grid3.fluid3_step_host(U.ctx(), sim.params, n, n, n, d, v, p if i % 2 == 0 else None)
+        assert got == want, (i, got, want)
+        assert np.array_equal(d, sim.density.to_host()) and np.array_equal(v, sim.vel.view_linear())
+        if i % 2 == 0:
+            assert np.array_equal(p, sim.pressure.to_host())
+    assert d.max() > 0.5
