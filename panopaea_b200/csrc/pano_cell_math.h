@@ -353,35 +353,48 @@ PANO_HD double advect3_cell(int z, int y, int x, int d, int h, int w, double dt,
     if (kFast) return advect3_cell_fast(z, y, x, d, h, w, dt, ucx, ucy, ucz, q);
     return advect3_cell_uv<double>(z, y, x, d, h, w, dt, ucx, ucy, ucz, q);
 }
+// *_uv forms: the sampled velocity is passed in, so that a kernel can share velocity loads between the four quantities
+template <bool kFast, class Q>
+PANO_HD double advect3_mac_x_uv(int z, int y, int x, int d, int h, int w, double dt, double vvx, double vvy, double vvz, const Q &qx) {
+    const double ndt = -dt;
+    const double ppx = ((double)x + 0.0) + ndt * vvx, ppy = ((double)y + 0.5) + ndt * vvy, ppz = ((double)z + 0.5) + ndt * vvz;
+    return mac3_gather<kFast>(ppx - 0.0, ppy - 0.5, ppz - 0.5, d, h, w + 1, qx);
+}
+template <bool kFast, class Q>
+PANO_HD double advect3_mac_y_uv(int z, int y, int x, int d, int h, int w, double dt, double vvx, double vvy, double vvz, const Q &qy) {
+    const double ndt = -dt;
+    const double ppx = ((double)x + 0.5) + ndt * vvx, ppy = ((double)y + 0.0) + ndt * vvy, ppz = ((double)z + 0.5) + ndt * vvz;
+    return mac3_gather<kFast>(ppx - 0.5, ppy - 0.0, ppz - 0.5, d, h + 1, w, qy);
+}
+template <bool kFast, class Q>
+PANO_HD double advect3_mac_z_uv(int z, int y, int x, int d, int h, int w, double dt, double vvx, double vvy, double vvz, const Q &qz) {
+    const double ndt = -dt;
+    const double ppx = ((double)x + 0.5) + ndt * vvx, ppy = ((double)y + 0.5) + ndt * vvy, ppz = ((double)z + 0.0) + ndt * vvz;
+    return mac3_gather<kFast>(ppx - 0.5, ppy - 0.5, ppz - 0.0, d + 1, h, w, qz);
+}
 template <bool kFast, class Q, class VZ, class VY, class VX>
 PANO_HD double advect3_mac_x(int z, int y, int x, int d, int h, int w, double dt, const Q &qx, const VZ &vz, const VY &vy, const VX &vx) {
     const int xc = x < w - 1 ? x : w - 1, xm = x > 0 ? x - 1 : 0;   // (z, y, x) in (d, h, w+1), :218-253
-    const double ndt = -dt;
     const double vvx = vx(z, y, x);
     const double vvy = (vy(z, y, xc) + vy(z, y + 1, xc) + vy(z, y, xm) + vy(z, y + 1, xm)) / 4.0;
     const double vvz = (vz(z, y, xc) + vz(z + 1, y, xc) + vz(z, y, xm) + vz(z + 1, y, xm)) / 4.0;
-    const double ppx = ((double)x + 0.0) + ndt * vvx, ppy = ((double)y + 0.5) + ndt * vvy, ppz = ((double)z + 0.5) + ndt * vvz;
-    return mac3_gather<kFast>(ppx - 0.0, ppy - 0.5, ppz - 0.5, d, h, w + 1, qx);
+    return advect3_mac_x_uv<kFast>(z, y, x, d, h, w, dt, vvx, vvy, vvz, qx);
 }
 template <bool kFast, class Q, class VZ, class VY, class VX>
 PANO_HD double advect3_mac_y(int z, int y, int x, int d, int h, int w, double dt, const Q &qy, const VZ &vz, const VY &vy, const VX &vx) {
     const int yc = y < h - 1 ? y : h - 1, ym = y > 0 ? y - 1 : 0;   // (z, y, x) in (d, h+1, w), :255-290
-    const double ndt = -dt;
     const double vvx = (vx(z, yc, x) + vx(z, yc, x + 1) + vx(z, ym, x) + vx(z, ym, x + 1)) / 4.0;
     const double vvy = vy(z, y, x);
     const double vvz = (vz(z, yc, x) + vz(z + 1, yc, x) + vz(z, ym, x) + vz(z + 1, ym, x)) / 4.0;
-    const double ppx = ((double)x + 0.5) + ndt * vvx, ppy = ((double)y + 0.0) + ndt * vvy, ppz = ((double)z + 0.5) + ndt * vvz;
-    return mac3_gather<kFast>(ppx - 0.5, ppy - 0.0, ppz - 0.5, d, h + 1, w, qy);
+    return advect3_mac_y_uv<kFast>(z, y, x, d, h, w, dt, vvx, vvy, vvz, qy);
 }
 template <bool kFast, class Q, class VZ, class VY, class VX>
 PANO_HD double advect3_mac_z(int z, int y, int x, int d, int h, int w, double dt, const Q &qz, const VZ &vz, const VY &vy, const VX &vx) {
     const int zc = z < d - 1 ? z : d - 1, zm = z > 0 ? z - 1 : 0;   // (z, y, x) in (d+1, h, w)
-    const double ndt = -dt;
     const double vvx = (vx(zc, y, x) + vx(zc, y, x + 1) + vx(zm, y, x) + vx(zm, y, x + 1)) / 4.0;
     const double vvy = (vy(zc, y, x) + vy(zc, y + 1, x) + vy(zm, y, x) + vy(zm, y + 1, x)) / 4.0;
     const double vvz = vz(z, y, x);
-    const double ppx = ((double)x + 0.5) + ndt * vvx, ppy = ((double)y + 0.5) + ndt * vvy, ppz = ((double)z + 0.0) + ndt * vvz;
-    return mac3_gather<kFast>(ppx - 0.5, ppy - 0.5, ppz - 0.0, d + 1, h, w, qz);
+    return advect3_mac_z_uv<kFast>(z, y, x, d, h, w, dt, vvx, vvy, vvz, qz);
 }
 
 // ---- the 7-point closure at one cell (dec_fluid.rs:100-119 with a z pair in front): f / k = p at (z-1) / (z+1)

@@ -63,8 +63,30 @@ k3_advect(double *__restrict__ q_dst, double *__restrict__ vz_dst, double *__res
           const double *__restrict__ mx_src, const double *__restrict__ vz_p, const double *__restrict__ vy_p,
           const double *__restrict__ vx_p, int d, int h, int w, double dt) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), z = blockIdx.z;
-    if (x > w || y > h) return;
     const V3 vz{vz_p, h, w}, vy{vy_p, h + 1, w}, vx{vx_p, h, w + 1};
+    // Blocks away from every wall (block-uniform test): all four quantities exist at every point, the clamped neighbour indices of
+    // dec_fluid.rs:222-228 are plain x-1 / y-1 / z-1, and the 18 distinct velocity samples the four backtraces use are loaded once
+    // (33 loads in the general form).  Same operands in the same order: the same bits.
+    const int bx0 = blockIdx.x * 32, by0 = blockIdx.y * 8;
+    if (kScalar && kMac && bx0 >= 1 && bx0 + 31 <= w - 2 && by0 >= 1 && by0 + 7 <= h - 2 && z >= 1 && z <= d - 2) {
+        const unsigned W = (unsigned)w, H = (unsigned)h, HW = H * W;
+        const unsigned ic = ((unsigned)z * H + (unsigned)y) * W + (unsigned)x;                 // cell and vz arrays
+        const unsigned iy = ((unsigned)z * (H + 1u) + (unsigned)y) * W + (unsigned)x;          // vy array
+        const unsigned ix = ((unsigned)z * H + (unsigned)y) * (W + 1u) + (unsigned)x;          // vx array
+        const double a0 = __ldg(vx_p + ix), a1 = __ldg(vx_p + ix + 1), b0 = __ldg(vx_p + ix - (W + 1u)), b1 = __ldg(vx_p + ix - W),
+                     c0 = __ldg(vx_p + ix - H * (W + 1u)), c1 = __ldg(vx_p + ix - H * (W + 1u) + 1);
+        const double p0 = __ldg(vy_p + iy), p1 = __ldg(vy_p + iy + W), q0 = __ldg(vy_p + iy - 1), q1 = __ldg(vy_p + iy + W - 1),
+                     r0 = __ldg(vy_p + iy - (H + 1u) * W), r1 = __ldg(vy_p + iy - (H + 1u) * W + W);
+        const double u0 = __ldg(vz_p + ic), u1 = __ldg(vz_p + ic + HW), s0 = __ldg(vz_p + ic - 1), s1 = __ldg(vz_p + ic + HW - 1),
+                     t0 = __ldg(vz_p + ic - W), t1 = __ldg(vz_p + ic + HW - W);
+        const double sa = a0 + a1, sp = p0 + p1, su = u0 + u1;     // the leading partial sums the reference's left-to-right sums share
+        q_dst[ic] = pano::advect3_cell_fast(z, y, x, d, h, w, dt, sa / 2.0, sp / 2.0, su / 2.0, V3{q_src, h, w});
+        vx_dst[ix] = pano::advect3_mac_x_uv<true>(z, y, x, d, h, w, dt, a0, (sp + q0 + q1) / 4.0, (su + s0 + s1) / 4.0, V3{mx_src, h, w + 1});
+        vy_dst[iy] = pano::advect3_mac_y_uv<true>(z, y, x, d, h, w, dt, (sa + b0 + b1) / 4.0, p0, (su + t0 + t1) / 4.0, V3{my_src, h + 1, w});
+        vz_dst[ic] = pano::advect3_mac_z_uv<true>(z, y, x, d, h, w, dt, (sa + c0 + c1) / 4.0, (sp + r0 + r1) / 4.0, u0, V3{mz_src, h, w});
+        return;
+    }
+    if (x > w || y > h) return;
     const bool xin = x < w, yin = y < h, zin = z < d;
     if (kScalar && xin && yin && zin)
         q_dst[((size_t)z * h + y) * w + x] = pano::advect3_cell<true>(z, y, x, d, h, w, dt, V3{q_src, h, w}, vz, vy, vx);
