@@ -83,6 +83,10 @@ def test_no_cpu_fallback(lib):
     # null handles are rejected, not dereferenced
     assert lib.pano_field_fill(None, 1.0) == 1
     assert lib.pano_fluid_step(None, None, None, None, None, None, None, None, None, None) == 1
+    # the Grid3d family too
+    assert lib.pano_fluid3_step(None, None, None, None, None, None, None, None, None, None) == 1
+    assert lib.pano_field3_new(None, 3, 4, 4, 4, None) == 1
+    assert lib.pano_trilinear(0.0, 1.0, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0, 0.25, 0.5, 0.75) == 0.25   # host arithmetic: no device needed
 
 
 def test_product_never_imports_oracle():
